@@ -1,0 +1,324 @@
+"""bshot_b200 -- Python (ctypes) binding of the B200-native B-SHOT front end.
+
+The product is the C-ABI shared library `libbshot_b200.so` (include/bshot_b200.h) built from the
+sm_100a CUDA sources in csrc/.  This module only marshals numpy / torch buffers to that ABI for the
+tests and bench.py.  There is NO CPU fallback: if the library is missing or no B200 is present the
+calls raise.  Reference-named host C++ shims live in host/ (see INTEGRATION.md).
+
+The directory name `b-shot-slam_b200` is not an importable identifier; load this package with
+`importlib` under the name `bshot_b200` (tests/conftest.py, bench.py and __graft_entry__.py do so).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbshot_b200.so")
+_LIB = None
+
+SR_CV, SR_CVS, SR_CVSN = 0, 1, 2
+NORMALS_REFERENCE, NORMALS_FULL = 0, 1
+
+EXPORTS = [
+    "bshot_params_default", "bshot_version", "bshot_last_error", "bshot_ctx_create",
+    "bshot_ctx_destroy", "bshot_ctx_stream", "bshot_ctx_sync", "bshot_set_cloud",
+    "bshot_detect_keypoints", "bshot_seg_ratio", "bshot_set_keypoints", "bshot_compute_normals",
+    "bshot_query_normals", "bshot_set_normals", "bshot_compute_shot", "bshot_compute_lrf",
+    "bshot_binarize", "bshot_compute_descriptors", "bshot_match", "bshot_match_mutual",
+    "bshot_process_frame", "bshot_process_frame_resident", "bshot_map_reset", "bshot_map_append",
+    "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
+    "bshot_match_map", "bshot_launch_count", "bshot_popc_peak",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("kp_radius", C.c_float), ("kp_max_nn", C.c_int), ("sr_type", C.c_int),
+                ("top_k", C.c_int), ("normal_radius", C.c_float), ("normal_max_nn", C.c_int),
+                ("normals_mode", C.c_int), ("shot_radius", C.c_float)]
+
+
+CAND_DTYPE = np.dtype([("k1", "<u8"), ("k2", "<u8"), ("rq", "<u4"), ("pad", "<u4")])
+NONE_KEY = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+class BshotError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libbshot_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], stdout=out, stderr=out)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise BshotError(f"{LIB_PATH} is missing: build it with `make -C b-shot-slam_b200/csrc` "
+                             "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, ci, cf = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+        L.bshot_last_error.restype = C.c_char_p
+        L.bshot_version.restype = ci
+        L.bshot_params_default.argtypes = [C.POINTER(Params)]
+        L.bshot_ctx_create.argtypes = [C.POINTER(vp), ci, sz, sz, sz]
+        L.bshot_ctx_destroy.argtypes = [vp]
+        L.bshot_ctx_destroy.restype = None
+        L.bshot_ctx_stream.argtypes = [vp]
+        L.bshot_ctx_stream.restype = vp
+        L.bshot_ctx_sync.argtypes = [vp]
+        L.bshot_set_cloud.argtypes = [vp, vp, sz, sz]
+        L.bshot_detect_keypoints.argtypes = [vp, cf, ci, ci, ci, vp, vp, vp, vp]
+        L.bshot_seg_ratio.argtypes = [vp, cf, ci, ci, vp]
+        L.bshot_set_keypoints.argtypes = [vp, vp, sz, sz]
+        L.bshot_compute_normals.argtypes = [vp, ci, cf, ci, vp]
+        L.bshot_query_normals.argtypes = [vp, vp, sz, cf, ci, vp]
+        L.bshot_set_normals.argtypes = [vp, vp, sz]
+        L.bshot_compute_shot.argtypes = [vp, cf, vp, vp, vp, vp, vp]
+        L.bshot_compute_lrf.argtypes = [vp, cf, vp, vp]
+        L.bshot_binarize.argtypes = [vp, vp, sz, sz, vp]
+        L.bshot_compute_descriptors.argtypes = [vp, C.POINTER(Params), vp]
+        L.bshot_match.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp, vp]
+        L.bshot_match_mutual.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
+        L.bshot_process_frame.argtypes = [vp, C.POINTER(Params), vp, sz, sz, vp, vp, vp, vp, vp]
+        L.bshot_process_frame_resident.argtypes = [vp, C.POINTER(Params)]
+        L.bshot_map_reset.argtypes = [vp]
+        L.bshot_map_append.argtypes = [vp, vp, sz]
+        L.bshot_map_size.argtypes = [vp, C.POINTER(sz)]
+        L.bshot_match_shard_dev.argtypes = [vp, vp, sz, C.c_uint64, ci, vp]
+        L.bshot_match_dev.argtypes = [vp, vp, sz, vp, sz, C.c_uint64, ci, vp]
+        L.bshot_merge_cands_dev.argtypes = [vp, vp, sz, sz, vp]
+        L.bshot_match_map.argtypes = [vp, vp, sz, C.c_uint64, vp]
+        L.bshot_launch_count.argtypes = [vp]
+        L.bshot_launch_count.restype = C.c_ulonglong
+        L.bshot_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def _chk(rc):
+    if rc != 0:
+        raise BshotError(f"bshot error {rc}: {lib().bshot_last_error().decode()}")
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def default_params(**kw):
+    p = Params()
+    lib().bshot_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def unpack_cands(cand):
+    """structured candidate records -> dict of int arrays (idx/dist, -1 = none)"""
+    k1, k2 = cand["k1"], cand["k2"]
+    h1, h2 = k1 != NONE_KEY, k2 != NONE_KEY
+    out = dict(
+        idx1=np.where(h1, (k1 & np.uint64(0xFFFFFFFF)).astype(np.int64), -1),
+        dist1=np.where(h1, (k1 >> np.uint64(32)).astype(np.int64), -1),
+        idx2=np.where(h2, (k2 & np.uint64(0xFFFFFFFF)).astype(np.int64), -1),
+        dist2=np.where(h2, (k2 >> np.uint64(32)).astype(np.int64), -1),
+        rq=np.where(cand["rq"] != 0xFFFFFFFF, cand["rq"].astype(np.int64), -1))
+    return out
+
+
+class Context:
+    """One bshot_ctx: device buffers + one stream (mirrors the `bshot cb` member of LidarOdometry,
+    include/lidar_odometry.h:57)."""
+
+    def __init__(self, device=0, max_points=131072, max_keypoints=16384, max_targets=0):
+        h = C.c_void_p()
+        _chk(lib().bshot_ctx_create(C.byref(h), device, max_points, max_keypoints, max_targets))
+        self.h = h
+        self.max_points, self.max_keypoints = max_points, max_keypoints
+        self.n_points = 0
+        self.n_kp = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().bshot_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self):
+        return lib().bshot_ctx_stream(self.h)
+
+    def sync(self):
+        _chk(lib().bshot_ctx_sync(self.h))
+
+    def launch_count(self):
+        return int(lib().bshot_launch_count(self.h))
+
+    def popc_peak(self):
+        v = C.c_double()
+        _chk(lib().bshot_popc_peak(self.h, C.byref(v)))
+        return v.value
+
+    # a1
+    def set_cloud(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        assert xyz.ndim == 2 and xyz.shape[1] in (3, 4)
+        _chk(lib().bshot_set_cloud(self.h, _p(xyz), xyz.shape[0], xyz.shape[1] * 4))
+        self.n_points = xyz.shape[0]
+
+    # a2 / a3
+    def seg_ratio(self, radius=3000.0, max_nn=300, sr_type=SR_CV):
+        out = np.empty(self.n_points, np.float32)
+        _chk(lib().bshot_seg_ratio(self.h, radius, max_nn, sr_type, _p(out)))
+        return out
+
+    def detect_keypoints(self, radius=3000.0, max_nn=300, sr_type=SR_CV, top_k=600):
+        idx = np.empty(top_k, np.int32)
+        ratio = np.empty(top_k, np.float32)
+        xyz = np.empty((top_k, 3), np.float32)
+        cnt = C.c_int()
+        _chk(lib().bshot_detect_keypoints(self.h, radius, max_nn, sr_type, top_k, _p(idx), _p(ratio),
+                                          _p(xyz), C.byref(cnt)))
+        k = cnt.value
+        self.n_kp = k
+        return idx[:k].copy(), ratio[:k].copy(), xyz[:k].copy()
+
+    def set_keypoints(self, kp):
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(-1, 3)
+        _chk(lib().bshot_set_keypoints(self.h, _p(kp), kp.shape[0], 12))
+        self.n_kp = kp.shape[0]
+
+    # a4
+    def compute_normals(self, mode=NORMALS_REFERENCE, radius=3000.0, max_nn=300):
+        out = np.empty((self.n_points, 4), np.float32)
+        _chk(lib().bshot_compute_normals(self.h, mode, radius, max_nn, _p(out)))
+        return out
+
+    def query_normals(self, q, radius=3000.0, max_nn=300):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((q.shape[0], 4), np.float32)
+        _chk(lib().bshot_query_normals(self.h, _p(q), q.shape[0], radius, max_nn, _p(out)))
+        return out
+
+    def set_normals(self, normals4):
+        normals4 = np.ascontiguousarray(normals4, dtype=np.float32).reshape(-1, 4)
+        _chk(lib().bshot_set_normals(self.h, _p(normals4), normals4.shape[0]))
+
+    # a5..a7
+    def compute_lrf(self, radius=3000.0):
+        rf = np.empty((self.n_kp, 9), np.float32)
+        nn = np.empty(self.n_kp, np.int32)
+        _chk(lib().bshot_compute_lrf(self.h, radius, _p(rf), _p(nn)))
+        return rf, nn
+
+    def compute_shot(self, radius=3000.0, want_shot=True):
+        k = self.n_kp
+        bits = np.empty((k, 6), np.uint64)
+        shot = np.empty((k, 352), np.float32) if want_shot else None
+        rf = np.empty((k, 9), np.float32)
+        nn = np.empty(k, np.int32)
+        tot = C.c_longlong()
+        _chk(lib().bshot_compute_shot(self.h, radius, _p(bits), _p(shot), _p(rf), _p(nn), C.byref(tot)))
+        return dict(bits=bits, shot=shot, rf=rf, nn=nn, sum_neighbours=tot.value)
+
+    def binarize(self, shot, stride_floats=None):
+        shot = np.ascontiguousarray(shot, dtype=np.float32)
+        if stride_floats is None:
+            shot = shot.reshape(-1, 352)
+            stride_floats = 352
+        k = shot.size // stride_floats
+        bits = np.empty((k, 6), np.uint64)
+        _chk(lib().bshot_binarize(self.h, _p(shot), k, stride_floats, _p(bits)))
+        return bits
+
+    def compute_descriptors(self, params=None):
+        bits = np.empty((self.n_kp, 6), np.uint64)
+        _chk(lib().bshot_compute_descriptors(self.h, C.byref(params) if params else None, _p(bits)))
+        return bits
+
+    # a10 / a11
+    def match(self, q, t, want_right=True):
+        q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+        t = np.ascontiguousarray(t, dtype=np.uint64).reshape(-1, 6)
+        nq, nt = q.shape[0], t.shape[0]
+        li, ld, li2, ld2 = (np.empty(nq, np.int32) for _ in range(4))
+        ri = np.empty(nt, np.int32) if want_right else None
+        _chk(lib().bshot_match(self.h, _p(q), nq, _p(t), nt, _p(li), _p(ld), _p(li2), _p(ld2), _p(ri)))
+        return dict(left_idx=li, left_dist=ld, left_idx2=li2, left_dist2=ld2, right_idx=ri)
+
+    def match_mutual(self, q, t):
+        q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+        t = np.ascontiguousarray(t, dtype=np.uint64).reshape(-1, 6)
+        nq = q.shape[0]
+        pairs = np.empty((max(nq, 1), 2), np.int32)
+        dist = np.empty(max(nq, 1), np.int32)
+        cnt = C.c_int()
+        _chk(lib().bshot_match_mutual(self.h, _p(q), nq, _p(t), t.shape[0], _p(pairs), _p(dist), C.byref(cnt)))
+        return pairs[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    # whole frame
+    def process_frame(self, xyz, params):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        k = params.top_k
+        kp_idx = np.empty(k, np.int32)
+        bits = np.empty((k, 6), np.uint64)
+        pairs = np.empty((k, 2), np.int32)
+        nk, npairs = C.c_int(), C.c_int()
+        _chk(lib().bshot_process_frame(self.h, C.byref(params), _p(xyz), xyz.shape[0], xyz.shape[1] * 4,
+                                       _p(kp_idx), _p(bits), C.byref(nk), _p(pairs), C.byref(npairs)))
+        self.n_points = xyz.shape[0]
+        self.n_kp = nk.value
+        return dict(kp_idx=kp_idx[:nk.value].copy(), bits=bits[:nk.value].copy(),
+                    pairs=pairs[:npairs.value].copy())
+
+    def process_frame_raw(self, xyz_ptr, n, stride_bytes, params, kp_idx_ptr, bits_ptr, pairs_ptr):
+        """pointer-level variant for bench.py (pinned host buffers, no numpy allocation)"""
+        nk, npairs = C.c_int(), C.c_int()
+        _chk(lib().bshot_process_frame(self.h, C.byref(params), xyz_ptr, n, stride_bytes, kp_idx_ptr,
+                                       bits_ptr, C.byref(nk), pairs_ptr, C.byref(npairs)))
+        return nk.value, npairs.value
+
+    def process_frame_resident(self, params):
+        _chk(lib().bshot_process_frame_resident(self.h, C.byref(params)))
+
+    # sharded map
+    def map_reset(self):
+        _chk(lib().bshot_map_reset(self.h))
+
+    def map_append(self, desc):
+        desc = np.ascontiguousarray(desc, dtype=np.uint64).reshape(-1, 6)
+        _chk(lib().bshot_map_append(self.h, _p(desc), desc.shape[0]))
+
+    def map_size(self):
+        n = C.c_size_t()
+        _chk(lib().bshot_map_size(self.h, C.byref(n)))
+        return n.value
+
+    def match_map(self, q, global_base=0):
+        q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+        cand = np.empty(q.shape[0], CAND_DTYPE)
+        _chk(lib().bshot_match_map(self.h, _p(q), q.shape[0], global_base, _p(cand)))
+        return cand
+
+    def match_shard_dev(self, d_q_ptr, nq, global_base, with_rq, d_cand_ptr):
+        _chk(lib().bshot_match_shard_dev(self.h, d_q_ptr, nq, global_base, int(with_rq), d_cand_ptr))
+
+    def match_dev(self, d_q_ptr, nq, d_t_ptr, nt, global_base, with_rq, d_cand_ptr):
+        _chk(lib().bshot_match_dev(self.h, d_q_ptr, nq, d_t_ptr, nt, global_base, int(with_rq), d_cand_ptr))
+
+    def merge_cands_dev(self, d_cands_ptr, nranks, nq, d_out_ptr):
+        _chk(lib().bshot_merge_cands_dev(self.h, d_cands_ptr, nranks, nq, d_out_ptr))

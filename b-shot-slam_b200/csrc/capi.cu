@@ -1,0 +1,531 @@
+// capi.cu -- the extern "C" boundary declared in include/bshot_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "stages.h"
+
+namespace bshot {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return BSHOT_E_CUDA;
+    }
+    return BSHOT_OK;
+}
+
+template <typename T>
+static int dmalloc(T** p, size_t count) {
+    BSHOT_CUDA_TRY(cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)));
+    return BSHOT_OK;
+}
+
+static int sync(Ctx* c) {
+    BSHOT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return BSHOT_OK;
+}
+
+static int h2d(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return BSHOT_OK;
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return BSHOT_OK;
+}
+static int d2h(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0 || dst == nullptr) return BSHOT_OK;
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return BSHOT_OK;
+}
+
+}  // namespace bshot
+
+using namespace bshot;
+
+#define CHECK_CTX(ctx)                          \
+    do {                                        \
+        if ((ctx) == nullptr) {                 \
+            set_error("null context");          \
+            return BSHOT_E_INVALID;             \
+        }                                       \
+        cudaError_t _e = cudaSetDevice((ctx)->device); \
+        if (_e != cudaSuccess) {                \
+            set_error("cudaSetDevice failed: %s", cudaGetErrorString(_e)); \
+            return BSHOT_E_CUDA;                \
+        }                                       \
+    } while (0)
+
+extern "C" {
+
+void bshot_params_default(bshot_params* p) {
+    if (!p) return;
+    p->kp_radius = 3000.0f;
+    p->kp_max_nn = 300;
+    p->sr_type = BSHOT_SR_CV;
+    p->top_k = 600;
+    p->normal_radius = 3000.0f;
+    p->normal_max_nn = 300;
+    p->normals_mode = BSHOT_NORMALS_REFERENCE;
+    p->shot_radius = 3000.0f;
+}
+
+int bshot_version(void) { return BSHOT_B200_VERSION; }
+const char* bshot_last_error(void) { return g_err; }
+
+int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_keypoints, size_t max_targets) {
+    if (!out || max_points == 0 || max_keypoints == 0) {
+        set_error("bshot_ctx_create: bad arguments");
+        return BSHOT_E_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: this library has no CPU fallback");
+        return BSHOT_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range (%d devices)", device, ndev);
+        return BSHOT_E_INVALID;
+    }
+    BSHOT_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BSHOT_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return BSHOT_E_CUDA;
+    }
+    bshot_ctx* c = new (std::nothrow) bshot_ctx();
+    if (!c) {
+        set_error("out of host memory");
+        return BSHOT_E_INVALID;
+    }
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (max_targets < max_keypoints) max_targets = max_keypoints;
+    c->max_points = max_points;
+    c->max_kp = max_keypoints;
+    c->max_targets = max_targets;
+    const size_t N = max_points, K = max_keypoints, T = max_targets;
+    const size_t QN = std::max(N, K);
+    int r = BSHOT_OK;
+    auto A = [&](int rr) { if (r == BSHOT_OK) r = rr; };
+    cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { set_error("cudaStreamCreate failed: %s", cudaGetErrorString(se)); delete c; return BSHOT_E_CUDA; }
+    A(dmalloc(&c->d_raw, N * 4));
+    A(dmalloc(&c->d_pts, N));
+    A(dmalloc(&c->d_sorted, N));
+    A(dmalloc(&c->d_cell_of, N));
+    A(dmalloc(&c->d_cell_start, (size_t)kMaxCells + 1));
+    A(dmalloc(&c->d_cell_cursor, (size_t)kMaxCells));
+    A(dmalloc(&c->d_block_sums, 4096));
+    A(dmalloc(&c->d_grid, 1));
+    A(dmalloc(&c->d_bbox, 8));
+    A(dmalloc(&c->d_ratio, N));
+    A(dmalloc(&c->d_keys, N));
+    A(dmalloc(&c->d_kp_idx, K));
+    A(dmalloc(&c->d_kp_ratio, K));
+    A(dmalloc(&c->d_kp, K));
+    A(dmalloc(&c->d_kp_count, 4));
+    A(dmalloc(&c->d_normals, N));
+    A(dmalloc(&c->d_qnormals, QN));
+    A(dmalloc(&c->d_shot, K * 352));
+    A(dmalloc(&c->d_rf, K * 9));
+    A(dmalloc(&c->d_nn, K));
+    A(dmalloc(&c->d_sum_nn, 2));
+    A(dmalloc(&c->d_bits, K * 6));
+    A(dmalloc(&c->d_prev_bits, K * 6));
+    A(dmalloc(&c->d_prev_count, 4));
+    A(dmalloc(&c->d_q, K * 6));
+    A(dmalloc(&c->d_t, T * 6));
+    A(dmalloc(&c->d_map, T * 6));
+    c->partial_cap = std::max(K * 2 * 256, T * 2 + 1024);
+    A(dmalloc(&c->d_partial, c->partial_cap));
+    A(dmalloc(&c->d_cand, std::max(K, T)));
+    A(dmalloc(&c->d_cand2, std::max(K, T)));
+    A(dmalloc(&c->d_gather, K * 6));
+    A(dmalloc(&c->d_left, K * 4));
+    A(dmalloc(&c->d_right, T));
+    A(dmalloc(&c->d_pairs, K * 3));
+    A(dmalloc(&c->d_pair_count, 4));
+    if (r == BSHOT_OK && cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(int)) != cudaSuccess) {
+        set_error("cudaMallocHost failed");
+        r = BSHOT_E_CUDA;
+    }
+    if (r == BSHOT_OK) {
+        // pcl::Normal default-constructs to (0,0,0): the persistent normals array starts zeroed
+        cudaError_t e = cudaMemsetAsync(c->d_normals, 0, sizeof(float4) * N, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_prev_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_kp_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("context init failed: %s", cudaGetErrorString(e)); r = BSHOT_E_CUDA; }
+    }
+    if (r != BSHOT_OK) {
+        bshot_ctx_destroy(c);
+        return r;
+    }
+    *out = c;
+    return BSHOT_OK;
+}
+
+void bshot_ctx_destroy(bshot_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
+                    c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
+                    c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
+                    c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
+                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* bshot_ctx_stream(bshot_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int bshot_ctx_sync(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    return sync(ctx);
+}
+
+unsigned long long bshot_launch_count(bshot_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+int bshot_popc_peak(bshot_ctx* ctx, double* out) {
+    CHECK_CTX(ctx);
+    if (!out) { set_error("null output"); return BSHOT_E_INVALID; }
+    return popc_peak(ctx, out);
+}
+
+// ---- a1 ---------------------------------------------------------------------------------------
+int bshot_set_cloud(bshot_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes) {
+    CHECK_CTX(ctx);
+    if (!xyz && n) { set_error("bshot_set_cloud: null cloud"); return BSHOT_E_INVALID; }
+    if (stride_bytes != 12 && stride_bytes != 16) { set_error("bshot_set_cloud: stride must be 12 or 16 bytes"); return BSHOT_E_INVALID; }
+    if (n > ctx->max_points) { set_error("bshot_set_cloud: %zu points > capacity %zu", n, ctx->max_points); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
+    BSHOT_TRY(grid_build(ctx, n, (int)(stride_bytes / 4)));
+    return sync(ctx);
+}
+
+// ---- a2 + a3 ----------------------------------------------------------------------------------
+int bshot_seg_ratio(bshot_ctx* ctx, float radius, int max_nn, int sr_type, float* ratio_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud) { set_error("bshot_seg_ratio: no cloud"); return BSHOT_E_STATE; }
+    BSHOT_TRY(detect_seg_ratio(ctx, radius, max_nn, sr_type));
+    BSHOT_TRY(d2h(ctx, ratio_out, ctx->d_ratio, sizeof(float) * ctx->n_points));
+    return sync(ctx);
+}
+
+int bshot_detect_keypoints(bshot_ctx* ctx, float radius, int max_nn, int sr_type, int top_k, int* idx_out,
+                           float* ratio_out, float* kp_xyz_out, int* count_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud) { set_error("bshot_detect_keypoints: no cloud"); return BSHOT_E_STATE; }
+    if (top_k <= 0 || (size_t)top_k > ctx->max_kp) { set_error("bshot_detect_keypoints: top_k %d outside (0, %zu]", top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(detect_seg_ratio(ctx, radius, max_nn, sr_type));
+    BSHOT_TRY(detect_topk(ctx, top_k));
+    BSHOT_TRY(d2h(ctx, ctx->h_scratch, ctx->d_kp_count, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    const int k = ctx->h_scratch[0];
+    ctx->n_kp = (size_t)k;
+    ctx->have_kp = true;
+    if (count_out) *count_out = k;
+    BSHOT_TRY(d2h(ctx, idx_out, ctx->d_kp_idx, sizeof(int) * k));
+    BSHOT_TRY(d2h(ctx, ratio_out, ctx->d_kp_ratio, sizeof(float) * k));
+    if (kp_xyz_out && k) {
+        BSHOT_CUDA_TRY(cudaMemcpy2DAsync(kp_xyz_out, 12, ctx->d_kp, 16, 12, k, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return sync(ctx);
+}
+
+int bshot_set_keypoints(bshot_ctx* ctx, const float* kp_xyz, size_t k, size_t stride_bytes) {
+    CHECK_CTX(ctx);
+    if (!kp_xyz && k) { set_error("bshot_set_keypoints: null keypoints"); return BSHOT_E_INVALID; }
+    if (stride_bytes != 12 && stride_bytes != 16) { set_error("bshot_set_keypoints: stride must be 12 or 16 bytes"); return BSHOT_E_INVALID; }
+    if (k > ctx->max_kp) { set_error("bshot_set_keypoints: %zu keypoints > capacity %zu", k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    if (k) {
+        BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_kp, 0, sizeof(float4) * k, ctx->stream));
+        BSHOT_CUDA_TRY(cudaMemcpy2DAsync(ctx->d_kp, 16, kp_xyz, stride_bytes, 12, k, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->h_scratch[8] = (int)k;
+    BSHOT_TRY(h2d(ctx, ctx->d_kp_count, &ctx->h_scratch[8], sizeof(int)));
+    ctx->n_kp = k;
+    ctx->have_kp = true;
+    return sync(ctx);
+}
+
+// ---- a4 ---------------------------------------------------------------------------------------
+int bshot_compute_normals(bshot_ctx* ctx, int mode, float radius, int max_nn, float* normals_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud) { set_error("bshot_compute_normals: no cloud"); return BSHOT_E_STATE; }
+    if (mode == BSHOT_NORMALS_REFERENCE && !ctx->have_kp) { set_error("bshot_compute_normals: REFERENCE mode needs keypoints"); return BSHOT_E_STATE; }
+    if (mode != BSHOT_NORMALS_REFERENCE && mode != BSHOT_NORMALS_FULL) { set_error("bshot_compute_normals: bad mode"); return BSHOT_E_INVALID; }
+    BSHOT_TRY(normals_compute(ctx, mode, radius, max_nn));
+    BSHOT_TRY(d2h(ctx, normals_out, ctx->d_normals, sizeof(float4) * ctx->n_points));
+    return sync(ctx);
+}
+
+int bshot_query_normals(bshot_ctx* ctx, const float* q_xyz, size_t nq, float radius, int max_nn, float* normals_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud) { set_error("bshot_query_normals: no cloud"); return BSHOT_E_STATE; }
+    if (nq > std::max(ctx->max_points, ctx->max_kp)) { set_error("bshot_query_normals: too many queries"); return BSHOT_E_CAPACITY; }
+    if (nq == 0) return BSHOT_OK;
+    // stage the queries in d_qnormals (float4) then overwrite in place
+    BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_qnormals, 0, sizeof(float4) * nq, ctx->stream));
+    BSHOT_CUDA_TRY(cudaMemcpy2DAsync(ctx->d_qnormals, 16, q_xyz, 12, 12, nq, cudaMemcpyHostToDevice, ctx->stream));
+    BSHOT_TRY(normals_query(ctx, ctx->d_qnormals, nq, radius, max_nn, ctx->d_qnormals));
+    BSHOT_TRY(d2h(ctx, normals_out, ctx->d_qnormals, sizeof(float4) * nq));
+    return sync(ctx);
+}
+
+int bshot_set_normals(bshot_ctx* ctx, const float* normals4, size_t n) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud || n != ctx->n_points) { set_error("bshot_set_normals: need a cloud with exactly n points"); return BSHOT_E_STATE; }
+    BSHOT_TRY(h2d(ctx, ctx->d_normals, normals4, sizeof(float4) * n));
+    ctx->have_normals = true;
+    ctx->normals_valid = std::max(ctx->normals_valid, n);
+    return sync(ctx);
+}
+
+// ---- a5 + a6 + a7 -----------------------------------------------------------------------------
+int bshot_compute_lrf(bshot_ctx* ctx, float radius, float* rf_out, int* valid_nn_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud || !ctx->have_kp) { set_error("bshot_compute_lrf: need cloud and keypoints"); return BSHOT_E_STATE; }
+    BSHOT_TRY(shot_compute(ctx, radius, /*lrf_only=*/true, /*write_shot=*/false));
+    BSHOT_TRY(d2h(ctx, rf_out, ctx->d_rf, sizeof(float) * 9 * ctx->n_kp));
+    BSHOT_TRY(d2h(ctx, valid_nn_out, ctx->d_nn, sizeof(int) * ctx->n_kp));
+    return sync(ctx);
+}
+
+int bshot_compute_shot(bshot_ctx* ctx, float radius, uint64_t* bits_out, float* shot_out, float* rf_out, int* nn_out,
+                       long long* sum_nn_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_cloud || !ctx->have_kp) { set_error("bshot_compute_shot: need cloud and keypoints"); return BSHOT_E_STATE; }
+    if (!ctx->have_normals) { set_error("bshot_compute_shot: no normals (call bshot_compute_normals / bshot_set_normals)"); return BSHOT_E_STATE; }
+    BSHOT_TRY(shot_compute(ctx, radius, /*lrf_only=*/false, /*write_shot=*/shot_out != nullptr));
+    const size_t k = ctx->n_kp;
+    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * k));
+    BSHOT_TRY(d2h(ctx, shot_out, ctx->d_shot, sizeof(float) * 352 * k));
+    BSHOT_TRY(d2h(ctx, rf_out, ctx->d_rf, sizeof(float) * 9 * k));
+    BSHOT_TRY(d2h(ctx, nn_out, ctx->d_nn, sizeof(int) * k));
+    unsigned long long* h_sum = reinterpret_cast<unsigned long long*>(&ctx->h_scratch[16]);
+    BSHOT_TRY(d2h(ctx, h_sum, ctx->d_sum_nn, sizeof(unsigned long long)));
+    BSHOT_TRY(sync(ctx));
+    if (sum_nn_out) *sum_nn_out = (long long)*h_sum;
+    return BSHOT_OK;
+}
+
+int bshot_binarize(bshot_ctx* ctx, const float* shot, size_t k, size_t stride_floats, uint64_t* bits_out) {
+    CHECK_CTX(ctx);
+    if ((!shot || !bits_out) && k) { set_error("bshot_binarize: null buffer"); return BSHOT_E_INVALID; }
+    if (stride_floats < 352) { set_error("bshot_binarize: stride < 352 floats"); return BSHOT_E_INVALID; }
+    if (k > ctx->max_kp) { set_error("bshot_binarize: %zu descriptors > capacity %zu", k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    if (k == 0) return BSHOT_OK;
+    BSHOT_CUDA_TRY(cudaMemcpy2DAsync(ctx->d_shot, 352 * sizeof(float), shot, stride_floats * sizeof(float),
+                                     352 * sizeof(float), k, cudaMemcpyHostToDevice, ctx->stream));
+    BSHOT_TRY(binarize(ctx, ctx->d_shot, k, ctx->d_bits));
+    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * k));
+    return sync(ctx);
+}
+
+int bshot_compute_descriptors(bshot_ctx* ctx, const bshot_params* p, uint64_t* bits_out) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (!ctx->have_cloud || !ctx->have_kp) { set_error("bshot_compute_descriptors: need cloud and keypoints"); return BSHOT_E_STATE; }
+    BSHOT_TRY(normals_compute(ctx, p->normals_mode, p->normal_radius, p->normal_max_nn));
+    BSHOT_TRY(shot_compute(ctx, p->shot_radius, false, false));
+    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * ctx->n_kp));
+    return sync(ctx);
+}
+
+// ---- a10 + a11 --------------------------------------------------------------------------------
+static int upload_qt(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint64_t* t, size_t nt, const char* who) {
+    if ((!q && nq) || (!t && nt)) { set_error("%s: null descriptors", who); return BSHOT_E_INVALID; }
+    if (nq > ctx->max_kp) { set_error("%s: %zu queries > capacity %zu", who, nq, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    if (nt > ctx->max_targets) { set_error("%s: %zu targets > capacity %zu", who, nt, ctx->max_targets); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_q, q, nq * 48));
+    BSHOT_TRY(h2d(ctx, ctx->d_t, t, nt * 48));
+    return BSHOT_OK;
+}
+
+int bshot_match(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint64_t* t, size_t nt, int* left_idx,
+                int* left_dist, int* left_idx2, int* left_dist2, int* right_idx) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(upload_qt(ctx, q, nq, t, nt, "bshot_match"));
+    if (nq && (left_idx || left_dist || left_idx2 || left_dist2)) {
+        if (nt == 0) {
+            for (size_t i = 0; i < nq; ++i) {
+                if (left_idx) left_idx[i] = -1;
+                if (left_dist) left_dist[i] = -1;
+                if (left_idx2) left_idx2[i] = -1;
+                if (left_dist2) left_dist2[i] = -1;
+            }
+        } else {
+            BSHOT_TRY(hamming_top2(ctx, ctx->d_q, nq, ctx->d_t, nt, 0, ctx->d_cand));
+            int* L = ctx->d_left;
+            BSHOT_TRY(hamming_unpack(ctx, ctx->d_cand, nq, L, L + nq, L + 2 * nq, L + 3 * nq));
+            BSHOT_TRY(d2h(ctx, left_idx, L, sizeof(int) * nq));
+            BSHOT_TRY(d2h(ctx, left_dist, L + nq, sizeof(int) * nq));
+            BSHOT_TRY(d2h(ctx, left_idx2, L + 2 * nq, sizeof(int) * nq));
+            BSHOT_TRY(d2h(ctx, left_dist2, L + 3 * nq, sizeof(int) * nq));
+        }
+    }
+    if (right_idx && nt) {
+        if (nq == 0) {
+            for (size_t i = 0; i < nt; ++i) right_idx[i] = -1;
+        } else {
+            // the reference's second loop (src/lidar_odometry.cpp:226-232): roles swapped
+            BSHOT_TRY(hamming_top2(ctx, ctx->d_t, nt, ctx->d_q, nq, 0, ctx->d_cand2));
+            BSHOT_TRY(hamming_unpack(ctx, ctx->d_cand2, nt, ctx->d_right, nullptr, nullptr, nullptr));
+            BSHOT_TRY(d2h(ctx, right_idx, ctx->d_right, sizeof(int) * nt));
+        }
+    }
+    return sync(ctx);
+}
+
+int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint64_t* t, size_t nt, int* pairs_out,
+                       int* dist_out, int* count_out) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(upload_qt(ctx, q, nq, t, nt, "bshot_match_mutual"));
+    if (count_out) *count_out = 0;
+    if (nq == 0 || nt == 0) return sync(ctx);
+    BSHOT_TRY(hamming_top2(ctx, ctx->d_q, nq, ctx->d_t, nt, 0, ctx->d_cand));
+    BSHOT_TRY(hamming_reverse(ctx, ctx->d_q, nq, ctx->d_t, 0, ctx->d_cand));
+    BSHOT_TRY(hamming_mutual_pairs(ctx, ctx->d_cand, nq, ctx->d_pairs, ctx->d_pair_count));
+    BSHOT_TRY(d2h(ctx, ctx->h_scratch, ctx->d_pair_count, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    const int n = ctx->h_scratch[0];
+    if (count_out) *count_out = n;
+    if (n > 0 && (pairs_out || dist_out)) {
+        std::vector<int> tmp((size_t)n * 3);
+        BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_pairs, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        BSHOT_TRY(sync(ctx));
+        for (int i = 0; i < n; ++i) {
+            if (pairs_out) { pairs_out[2 * i] = tmp[3 * i]; pairs_out[2 * i + 1] = tmp[3 * i + 1]; }
+            if (dist_out) dist_out[i] = tmp[3 * i + 2];
+        }
+    }
+    return BSHOT_OK;
+}
+
+// ---- whole frame --------------------------------------------------------------------------------
+int bshot_process_frame_resident(bshot_ctx* ctx, const bshot_params* p) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (!ctx->have_cloud) { set_error("bshot_process_frame_resident: no cloud"); return BSHOT_E_STATE; }
+    if (p->top_k <= 0 || (size_t)p->top_k > ctx->max_kp) { set_error("top_k %d outside (0, %zu]", p->top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    return frame_run(ctx, p);
+}
+
+int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n, size_t stride_bytes,
+                        int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out, int* n_pairs_out) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (!xyz && n) { set_error("bshot_process_frame: null cloud"); return BSHOT_E_INVALID; }
+    if (stride_bytes != 12 && stride_bytes != 16) { set_error("bshot_process_frame: stride must be 12 or 16 bytes"); return BSHOT_E_INVALID; }
+    if (n > ctx->max_points) { set_error("bshot_process_frame: %zu points > capacity %zu", n, ctx->max_points); return BSHOT_E_CAPACITY; }
+    if (p->top_k <= 0 || (size_t)p->top_k > ctx->max_kp) { set_error("top_k %d outside (0, %zu]", p->top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
+    BSHOT_TRY(grid_build(ctx, n, (int)(stride_bytes / 4)));
+    BSHOT_TRY(frame_run(ctx, p));
+    // one small D2H for the counts, then the payload
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[1], ctx->d_pair_count, sizeof(int)));
+    const size_t kmax = (size_t)p->top_k;
+    BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * kmax));
+    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * kmax));
+    std::vector<int> tmp;
+    if (pairs_out) {
+        tmp.resize(kmax * 3);
+        BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_pairs, sizeof(int) * 3 * kmax, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    BSHOT_TRY(sync(ctx));
+    const int k = ctx->h_scratch[0], np = ctx->h_scratch[1];
+    ctx->n_kp = (size_t)k;
+    if (n_kp_out) *n_kp_out = k;
+    if (n_pairs_out) *n_pairs_out = np;
+    if (pairs_out)
+        for (int i = 0; i < np; ++i) { pairs_out[2 * i] = tmp[3 * i]; pairs_out[2 * i + 1] = tmp[3 * i + 1]; }
+    return BSHOT_OK;
+}
+
+// ---- sharded map --------------------------------------------------------------------------------
+int bshot_map_reset(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    ctx->n_map = 0;
+    return BSHOT_OK;
+}
+
+int bshot_map_append(bshot_ctx* ctx, const uint64_t* desc, size_t n) {
+    CHECK_CTX(ctx);
+    if (!desc && n) { set_error("bshot_map_append: null descriptors"); return BSHOT_E_INVALID; }
+    if (ctx->n_map + n > ctx->max_targets) { set_error("bshot_map_append: shard would hold %zu > capacity %zu", ctx->n_map + n, ctx->max_targets); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_map + ctx->n_map * 6, desc, n * 48));
+    ctx->n_map += n;
+    return sync(ctx);
+}
+
+int bshot_map_size(bshot_ctx* ctx, size_t* n_out) {
+    if (!ctx || !n_out) { set_error("bshot_map_size: null argument"); return BSHOT_E_INVALID; }
+    *n_out = ctx->n_map;
+    return BSHOT_OK;
+}
+
+int bshot_match_dev(bshot_ctx* ctx, const void* d_q, size_t nq, const void* d_t, size_t nt, uint64_t global_base,
+                    int with_rq, void* d_cand_out) {
+    CHECK_CTX(ctx);
+    if (!d_q || !d_cand_out || (!d_t && nt)) { set_error("bshot_match_dev: null device pointer"); return BSHOT_E_INVALID; }
+    if (nq > std::max(ctx->max_kp, ctx->max_targets)) { set_error("bshot_match_dev: %zu queries > capacity", nq); return BSHOT_E_CAPACITY; }
+    bshot_cand* out = reinterpret_cast<bshot_cand*>(d_cand_out);
+    if (nt == 0) {
+        BSHOT_CUDA_TRY(cudaMemsetAsync(out, 0xFF, sizeof(bshot_cand) * nq, ctx->stream));
+        return BSHOT_OK;
+    }
+    BSHOT_TRY(hamming_top2(ctx, d_q, nq, d_t, nt, global_base, out));
+    if (with_rq) {
+        if (nq > ctx->max_kp) { set_error("bshot_match_dev: reverse pass needs nq <= max_keypoints"); return BSHOT_E_CAPACITY; }
+        BSHOT_TRY(hamming_reverse(ctx, d_q, nq, d_t, global_base, out));
+    }
+    return BSHOT_OK;
+}
+
+int bshot_match_shard_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, int with_rq, void* d_cand_out) {
+    if (!ctx) { set_error("null context"); return BSHOT_E_INVALID; }
+    return bshot_match_dev(ctx, d_q, nq, ctx->d_map, ctx->n_map, global_base, with_rq, d_cand_out);
+}
+
+int bshot_merge_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nranks, size_t nq, void* d_out) {
+    CHECK_CTX(ctx);
+    if (!d_cands || !d_out || nranks == 0) { set_error("bshot_merge_cands_dev: bad arguments"); return BSHOT_E_INVALID; }
+    return hamming_merge_cands(ctx, d_cands, nranks, nq, d_out);
+}
+
+int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base, bshot_cand* cand_out) {
+    CHECK_CTX(ctx);
+    if ((!q || !cand_out) && nq) { set_error("bshot_match_map: null buffer"); return BSHOT_E_INVALID; }
+    if (nq > ctx->max_kp) { set_error("bshot_match_map: %zu queries > capacity %zu", nq, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_q, q, nq * 48));
+    BSHOT_TRY(bshot_match_shard_dev(ctx, ctx->d_q, nq, global_base, 1, ctx->d_cand));
+    BSHOT_TRY(d2h(ctx, cand_out, ctx->d_cand, sizeof(bshot_cand) * nq));
+    return sync(ctx);
+}
+
+}  // extern "C"

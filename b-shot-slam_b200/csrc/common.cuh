@@ -1,0 +1,155 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/bshot_b200.h"
+
+namespace bshot {
+
+void set_error(const char* fmt, ...);
+
+#define BSHOT_CUDA_TRY(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::bshot::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                               __LINE__);                                                      \
+            return BSHOT_E_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define BSHOT_TRY(expr)          \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != BSHOT_OK) return _r; \
+    } while (0)
+
+// voxel grid parameters, computed on the device (no host round trip)
+struct GridParams {
+    float ox, oy, oz;   // origin = bbox min
+    float cell;         // cell edge (mm)
+    float inv_cell;
+    int nx, ny, nz;
+    unsigned int ncells;
+    unsigned int npoints;  // finite points that were binned
+};
+
+constexpr unsigned int kMaxCells = 1u << 23;       // cell_start capacity (32 MB of u32)
+constexpr int kDescWords = 12;                      // 48-byte record as u32 words (11 used)
+constexpr float kDefaultCell = 375.0f;              // R/8 for the reference radius 3000 mm
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    unsigned long long launches = 0;
+    size_t max_points = 0, max_kp = 0, max_targets = 0;
+
+    // cloud + voxel grid
+    size_t n_points = 0;
+    bool have_cloud = false;
+    float* d_raw = nullptr;            // staging of caller layout (stride 12 or 16)
+    float4* d_pts = nullptr;           // original order, w = 1
+    float4* d_sorted = nullptr;        // cell order, w = bit pattern of the original index
+    unsigned int* d_cell_of = nullptr; // cell id per point (0xFFFFFFFF = not binned)
+    unsigned int* d_cell_start = nullptr;  // kMaxCells + 1
+    unsigned int* d_cell_cursor = nullptr; // kMaxCells
+    unsigned int* d_block_sums = nullptr;
+    GridParams* d_grid = nullptr;
+    float* d_bbox = nullptr;           // 6 floats as ordered ints
+
+    // detector
+    float* d_ratio = nullptr;                // N
+    unsigned long long* d_keys = nullptr;    // N sortable keys
+    int* d_kp_idx = nullptr;                 // K surface indices (-1 = not a surface point)
+    float* d_kp_ratio = nullptr;             // K
+    float4* d_kp = nullptr;                  // K keypoint positions (w = index bits)
+    int* d_kp_count = nullptr;               // device-side keypoint count
+    size_t n_kp = 0;                         // host-side count (upper bound when detector ran async)
+    bool have_kp = false;
+
+    // normals
+    float4* d_normals = nullptr;   // N, persistent across frames (reference quirk)
+    float4* d_qnormals = nullptr;  // max(N) query normals scratch
+    size_t normals_valid = 0;      // entries of d_normals that have ever been written
+    bool have_normals = false;
+
+    // SHOT / B-SHOT
+    float* d_shot = nullptr;            // K x 352
+    float* d_rf = nullptr;              // K x 9
+    int* d_nn = nullptr;                // K
+    unsigned long long* d_sum_nn = nullptr;
+    uint64_t* d_bits = nullptr;         // K x 6
+    uint64_t* d_prev_bits = nullptr;    // K x 6 (previous frame)
+    size_t n_prev = 0;
+    int* d_prev_count = nullptr;
+
+    // matching
+    uint64_t* d_q = nullptr;            // max_kp x 6
+    uint64_t* d_t = nullptr;            // max_targets x 6 (host-API staging)
+    uint64_t* d_map = nullptr;          // max_targets x 6 resident shard
+    size_t n_map = 0;
+    unsigned long long* d_partial = nullptr;  // [nsplit][nq][2]
+    size_t partial_cap = 0;                   // in u64
+    bshot_cand* d_cand = nullptr;       // max(max_kp, ...) records
+    bshot_cand* d_cand2 = nullptr;
+    uint64_t* d_gather = nullptr;       // max_kp x 6 gathered targets for the reverse pass
+    int* d_left = nullptr;              // 4 x max_kp ints (idx, dist, idx2, dist2)
+    int* d_right = nullptr;             // max_targets ints
+    int* d_pairs = nullptr;             // 3 x max_kp (q, m, dist)
+    int* d_pair_count = nullptr;
+
+    // pinned host scratch
+    int* h_scratch = nullptr;           // 64 ints
+};
+
+inline void count_launch(Ctx* c, unsigned n = 1) { c->launches += n; }
+
+int check_launch(const char* what);
+
+}  // namespace bshot
+
+struct bshot_ctx : public bshot::Ctx {};
+
+// ---- device helpers --------------------------------------------------------------------------
+namespace bshot {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// FLANN L2_Simple in fp32 without FMA contraction
+__device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    float d = __fsub_rn(ax, bx);
+    float r = __fmul_rn(d, d);
+    d = __fsub_rn(ay, by);
+    r = __fadd_rn(r, __fmul_rn(d, d));
+    d = __fsub_rn(az, bz);
+    r = __fadd_rn(r, __fmul_rn(d, d));
+    return r;
+}
+
+// (a0*b0 + a1*b1) + a2*b2 in fp32 without contraction
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+
+}  // namespace bshot

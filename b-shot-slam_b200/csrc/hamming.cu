@@ -1,0 +1,408 @@
+// hamming.cu -- brute-force Hamming correspondence search.
+//
+// Replaces src/lidar_odometry.cpp:212-242 + minVect (include/bshot_bits.h:6-20) of the reference.
+// One distance matrix pass: every thread keeps QPT query descriptors (11 x u32 each) in registers,
+// the target descriptors are streamed through shared memory by TMA bulk copies
+// (cp.async.bulk + mbarrier, SASS UBLKCP) in a 4-stage ring; per (query,target) pair the kernel
+// issues 11 XOR + 11 POPC and folds the distance into a packed key (distance << 23 | local index)
+// so that a min/max pair keeps the top-2 with the reference's first-minimum (lowest index)
+// tie-break.  Target ranges are split over blockIdx.y; a small merge kernel combines the
+// per-split candidates (and, across GPUs, the all-gathered per-rank candidates).
+#include "common.cuh"
+
+namespace bshot {
+
+constexpr int HM_THREADS = 256;
+constexpr int HM_TILE = 128;   // targets per pipeline stage (6 KB)
+constexpr int HM_STAGES = 4;
+constexpr unsigned HM_IDX_BITS = 23;
+constexpr unsigned long long HM_NONE = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int QPT>
+__device__ __forceinline__ void pair_update(const uint32_t (&qw)[QPT][11], const uint4 a, const uint4 b,
+                                            const uint4 c, unsigned idx, uint32_t (&k1)[QPT],
+                                            uint32_t (&k2)[QPT]) {
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+        unsigned d = __popc(qw[j][0] ^ a.x) + __popc(qw[j][1] ^ a.y) + __popc(qw[j][2] ^ a.z) +
+                     __popc(qw[j][3] ^ a.w) + __popc(qw[j][4] ^ b.x) + __popc(qw[j][5] ^ b.y) +
+                     __popc(qw[j][6] ^ b.z) + __popc(qw[j][7] ^ b.w) + __popc(qw[j][8] ^ c.x) +
+                     __popc(qw[j][9] ^ c.y) + __popc(qw[j][10] ^ c.z);
+        const uint32_t key = (d << HM_IDX_BITS) | idx;
+        const uint32_t hi = max(k1[j], key);
+        k1[j] = min(k1[j], key);
+        k2[j] = min(k2[j], hi);
+    }
+}
+
+// grid = (query blocks, target splits). partial[(split * nq + qi) * 2 + {0,1}] = packed
+// (distance << 32 | global target index), HM_NONE when the split saw fewer than 1/2 targets.
+template <int QPT>
+__global__ void __launch_bounds__(HM_THREADS)
+hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __restrict__ t, unsigned nt,
+                    unsigned chunk, unsigned long long global_base,
+                    unsigned long long* __restrict__ partial) {
+    __shared__ __align__(128) uint4 tile[HM_STAGES][HM_TILE * 3];
+    __shared__ __align__(8) unsigned long long full[HM_STAGES];
+
+    const unsigned tid = threadIdx.x;
+    const unsigned split = blockIdx.y;
+    const unsigned t0 = split * chunk;
+    const unsigned tcount = (t0 < nt) ? min(chunk, nt - t0) : 0u;
+    const int ntiles = (int)((tcount + HM_TILE - 1) / HM_TILE);
+    const uint4* tbase = t + (size_t)t0 * 3;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < HM_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int s = it % HM_STAGES;
+        const unsigned cnt = min((unsigned)HM_TILE, tcount - (unsigned)it * HM_TILE);
+        const unsigned bytes = cnt * 48u;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(&tile[s][0], tbase + (size_t)it * HM_TILE * 3, bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int it = 0; it < HM_STAGES && it < ntiles; ++it) issue(it);
+    }
+
+    uint32_t qw[QPT][11];
+    uint32_t k1[QPT], k2[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+        const unsigned qi = (blockIdx.x * QPT + j) * HM_THREADS + tid;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
+        if (qi < nq) {
+            a = __ldg(q + (size_t)qi * 3);
+            b = __ldg(q + (size_t)qi * 3 + 1);
+            c = __ldg(q + (size_t)qi * 3 + 2);
+        }
+        qw[j][0] = a.x; qw[j][1] = a.y; qw[j][2] = a.z; qw[j][3] = a.w;
+        qw[j][4] = b.x; qw[j][5] = b.y; qw[j][6] = b.z; qw[j][7] = b.w;
+        qw[j][8] = c.x; qw[j][9] = c.y; qw[j][10] = c.z;
+        k1[j] = 0xFFFFFFFFu;
+        k2[j] = 0xFFFFFFFFu;
+    }
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int s = it % HM_STAGES;
+        mbar_wait(&full[s], (unsigned)(it / HM_STAGES) & 1u);
+        const uint4* tp = &tile[s][0];
+        const unsigned base = (unsigned)it * HM_TILE;
+        const unsigned cnt = min((unsigned)HM_TILE, tcount - base);
+        if (cnt == HM_TILE) {
+#pragma unroll 4
+            for (int tt = 0; tt < HM_TILE; ++tt)
+                pair_update<QPT>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2);
+        } else {
+            for (unsigned tt = 0; tt < cnt; ++tt)
+                pair_update<QPT>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2);
+        }
+        __syncthreads();  // every warp is done with slot s before it is refilled
+        if (tid == 0 && it + HM_STAGES < ntiles) issue(it + HM_STAGES);
+    }
+
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+        const unsigned qi = (blockIdx.x * QPT + j) * HM_THREADS + tid;
+        if (qi >= nq) continue;
+        unsigned long long o1 = HM_NONE, o2 = HM_NONE;
+        const unsigned long long gb = global_base + t0;
+        if (k1[j] != 0xFFFFFFFFu)
+            o1 = ((unsigned long long)(k1[j] >> HM_IDX_BITS) << 32) | (gb + (k1[j] & ((1u << HM_IDX_BITS) - 1)));
+        if (k2[j] != 0xFFFFFFFFu)
+            o2 = ((unsigned long long)(k2[j] >> HM_IDX_BITS) << 32) | (gb + (k2[j] & ((1u << HM_IDX_BITS) - 1)));
+        unsigned long long* p = partial + ((size_t)split * nq + qi) * 2;
+        p[0] = o1;
+        p[1] = o2;
+    }
+}
+
+__device__ __forceinline__ void top2_insert(unsigned long long key, unsigned long long& k1, unsigned long long& k2) {
+    const unsigned long long hi = max(k1, key);
+    k1 = min(k1, key);
+    k2 = min(k2, hi);
+}
+
+// merge nsrc candidate pairs per query: src[(s * nq + qi) * stride_u64 + {0,1}]
+__global__ void merge_top2_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
+                                  unsigned stride_u64, bshot_cand* __restrict__ out) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+    for (unsigned s = 0; s < nsrc; ++s) {
+        const unsigned long long* p = src + ((size_t)s * nq + qi) * stride_u64;
+        top2_insert(p[0], k1, k2);
+        top2_insert(p[1], k1, k2);
+    }
+    bshot_cand c;
+    c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
+    out[qi] = c;
+}
+
+// merge per-rank candidate RECORDS (all-gather result, rank-major): keeps rq of the winning rank
+__global__ void merge_cands_kernel(const bshot_cand* __restrict__ src, unsigned nranks, unsigned nq,
+                                   bshot_cand* __restrict__ out) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+    unsigned rq = 0xFFFFFFFFu;
+    for (unsigned r = 0; r < nranks; ++r) {
+        const bshot_cand c = src[(size_t)r * nq + qi];
+        if (c.k1 < k1) rq = c.rq;
+        top2_insert(c.k1, k1, k2);
+        top2_insert(c.k2, k1, k2);
+    }
+    bshot_cand c;
+    c.k1 = k1; c.k2 = k2; c.rq = rq; c.pad = 0;
+    out[qi] = c;
+}
+
+// gather the 48-byte record of every query's best target (reverse pass input)
+__global__ void gather_best_kernel(const bshot_cand* __restrict__ cand, unsigned nq, const uint4* __restrict__ t,
+                                   unsigned long long global_base, uint4* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * 3) return;
+    const unsigned qi = i / 3, w = i % 3;
+    const unsigned long long k = cand[qi].k1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (k != HM_NONE) v = __ldg(t + (size_t)((k & 0xFFFFFFFFull) - global_base) * 3 + w);
+    out[i] = v;
+}
+
+__global__ void set_rq_kernel(bshot_cand* __restrict__ cand, const bshot_cand* __restrict__ rev, unsigned nq) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const bool has = cand[qi].k1 != HM_NONE && rev[qi].k1 != HM_NONE;
+    cand[qi].rq = has ? (unsigned)(rev[qi].k1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+}
+
+// unpack candidate records into the reference's int arrays (left_nn etc.)
+__global__ void unpack_cands_kernel(const bshot_cand* __restrict__ cand, unsigned nq, int* __restrict__ idx1,
+                                    int* __restrict__ d1, int* __restrict__ idx2, int* __restrict__ d2) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const bshot_cand c = cand[qi];
+    const bool h1 = c.k1 != HM_NONE, h2 = c.k2 != HM_NONE;
+    if (idx1) idx1[qi] = h1 ? (int)(c.k1 & 0xFFFFFFFFull) : -1;
+    if (d1) d1[qi] = h1 ? (int)(c.k1 >> 32) : -1;
+    if (idx2) idx2[qi] = h2 ? (int)(c.k2 & 0xFFFFFFFFull) : -1;
+    if (d2) d2[qi] = h2 ? (int)(c.k2 >> 32) : -1;
+}
+
+// mutual-NN filter (src/lidar_odometry.cpp:234-242): single CTA, ordered compaction
+__global__ void mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq, int* __restrict__ pairs,
+                                    int* __restrict__ count) {
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned running;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < nq; base += blockDim.x) {
+        const unsigned qi = base + tid;
+        bool keep = false;
+        bshot_cand c;
+        if (qi < nq) {
+            c = cand[qi];
+            keep = (c.k1 != HM_NONE) && (c.rq == qi);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        unsigned off = running;
+        for (unsigned w = 0; w < wid; ++w) off += warp_tot[w];
+        if (keep) {
+            const unsigned pos = off + __popc(m & ((1u << lane) - 1));
+            pairs[3 * pos] = (int)qi;
+            pairs[3 * pos + 1] = (int)(c.k1 & 0xFFFFFFFFull);
+            pairs[3 * pos + 2] = (int)(c.k1 >> 32);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned tot = 0;
+            for (unsigned w = 0; w < (blockDim.x >> 5); ++w) tot += warp_tot[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *count = (int)running;
+}
+
+// ---- host side ----------------------------------------------------------------------------
+
+static int pick_qpt(size_t nq) {
+    int best = 1;
+    size_t best_pad = ~(size_t)0;
+    const int opts[3] = {4, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+        const size_t per = (size_t)HM_THREADS * opts[k];
+        const size_t pad = (nq + per - 1) / per * per;
+        if (pad < best_pad) { best_pad = pad; best = opts[k]; }
+    }
+    return best;
+}
+
+// d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
+int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                 bshot_cand* d_out) {
+    if (nq == 0) return BSHOT_OK;
+    if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
+        set_error("hamming_top2: sizes exceed 32-bit index range");
+        return BSHOT_E_INVALID;
+    }
+    const int qpt = pick_qpt(nq);
+    const unsigned qblocks = (unsigned)((nq + (size_t)HM_THREADS * qpt - 1) / ((size_t)HM_THREADS * qpt));
+    const size_t tiles = (nt + HM_TILE - 1) / HM_TILE;
+    size_t want = ((size_t)c->sm_count * 4 + qblocks - 1) / qblocks;  // ~4 CTAs per SM in flight
+    if (want < 1) want = 1;
+    if (want > tiles) want = tiles ? tiles : 1;
+    const size_t cap_splits = c->partial_cap / (nq * 2);
+    if (cap_splits == 0) {
+        set_error("hamming_top2: partial buffer too small for %zu queries", nq);
+        return BSHOT_E_CAPACITY;
+    }
+    if (want > cap_splits) want = cap_splits;
+    if (want > 65535) want = 65535;
+    size_t chunk = (nt + want - 1) / want;
+    chunk = (chunk + HM_TILE - 1) / HM_TILE * HM_TILE;
+    if (chunk == 0) chunk = HM_TILE;
+    if (chunk > (1u << HM_IDX_BITS)) {
+        set_error("hamming_top2: %zu targets per split exceed the packed index range", chunk);
+        return BSHOT_E_CAPACITY;
+    }
+    unsigned nsplit = (unsigned)((nt + chunk - 1) / chunk);
+    if (nsplit == 0) nsplit = 1;
+    dim3 grid(qblocks, nsplit);
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_q);
+    const uint4* t4 = reinterpret_cast<const uint4*>(d_t);
+    switch (qpt) {
+        case 4:
+            hamming_top2_kernel<4><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
+                                                                        (unsigned)chunk, global_base, c->d_partial);
+            break;
+        case 2:
+            hamming_top2_kernel<2><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
+                                                                        (unsigned)chunk, global_base, c->d_partial);
+            break;
+        default:
+            hamming_top2_kernel<1><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
+                                                                        (unsigned)chunk, global_base, c->d_partial);
+            break;
+    }
+    count_launch(c);
+    BSHOT_TRY(check_launch("hamming_top2_kernel"));
+    merge_top2_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, 2, d_out);
+    count_launch(c);
+    return check_launch("merge_top2_kernel");
+}
+
+// fills d_cand[i].rq = best query (index into d_q) for the target d_cand[i].k1
+int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
+                    bshot_cand* d_cand) {
+    if (nq == 0) return BSHOT_OK;
+    gather_best_kernel<<<(unsigned)((nq * 3 + 255) / 256), 256, 0, c->stream>>>(
+        d_cand, (unsigned)nq, reinterpret_cast<const uint4*>(d_t), global_base, reinterpret_cast<uint4*>(c->d_gather));
+    count_launch(c);
+    BSHOT_TRY(check_launch("gather_best_kernel"));
+    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2));
+    set_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, c->d_cand2, (unsigned)nq);
+    count_launch(c);
+    return check_launch("set_rq_kernel");
+}
+
+int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, void* d_out) {
+    if (nq == 0) return BSHOT_OK;
+    merge_cands_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(
+        reinterpret_cast<const bshot_cand*>(d_cands), (unsigned)nranks, (unsigned)nq, reinterpret_cast<bshot_cand*>(d_out));
+    count_launch(c);
+    return check_launch("merge_cands_kernel");
+}
+
+int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* d1, int* idx2, int* d2) {
+    if (nq == 0) return BSHOT_OK;
+    unpack_cands_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, (unsigned)nq, idx1, d1, idx2, d2);
+    count_launch(c);
+    return check_launch("unpack_cands_kernel");
+}
+
+int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count) {
+    mutual_pairs_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (unsigned)nq, d_pairs3, d_count);
+    count_launch(c);
+    return check_launch("mutual_pairs_kernel");
+}
+
+// ---- POPC pipe microbenchmark (roofline denominator for the matcher) -----------------
+__global__ void popc_peak_kernel(unsigned* out, int iters) {
+    unsigned x0 = threadIdx.x * 2654435761u + blockIdx.x, x1 = x0 ^ 0x9E3779B9u, x2 = x0 + 0x7F4A7C15u,
+             x3 = x0 * 3u + 1u, x4 = ~x0, x5 = x0 ^ 0xDEADBEEFu, x6 = x0 + 12345u, x7 = x0 ^ 0x55555555u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __popc(x0) | 0x10000u; x1 = __popc(x1) | 0x20000u; x2 = __popc(x2) | 0x40000u; x3 = __popc(x3) | 0x80000u;
+            x4 = __popc(x4) | 0x100000u; x5 = __popc(x5) | 0x200000u; x6 = __popc(x6) | 0x400000u; x7 = __popc(x7) | 0x800000u;
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int popc_peak(Ctx* c, double* out) {
+    const int blocks = c->sm_count * 8, threads = 256, iters = 2048;
+    unsigned* d = nullptr;
+    BSHOT_CUDA_TRY(cudaMalloc(&d, sizeof(unsigned) * blocks * threads));
+    cudaEvent_t e0, e1;
+    BSHOT_CUDA_TRY(cudaEventCreate(&e0));
+    BSHOT_CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        BSHOT_CUDA_TRY(cudaEventRecord(e0, c->stream));
+        popc_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters);
+        count_launch(c);
+        BSHOT_CUDA_TRY(cudaEventRecord(e1, c->stream));
+        BSHOT_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        BSHOT_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *out = (double)blocks * threads * iters * 64.0 / (best * 1e-3);
+    return BSHOT_OK;
+}
+
+}  // namespace bshot

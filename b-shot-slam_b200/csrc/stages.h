@@ -1,0 +1,35 @@
+// stages.h -- internal stage entry points (one per SURVEY 8a row); all asynchronous on ctx->stream.
+#pragma once
+#include "common.cuh"
+
+namespace bshot {
+
+// a1: caller layout in d_raw (stride 3 or 4 floats) -> d_pts, voxel grid, d_sorted   (grid.cu)
+int grid_build(Ctx* c, size_t n, int stride_floats);
+
+// a2/a3: seg-ratio for every point -> d_ratio, d_keys ; top-K -> d_kp_idx/d_kp_ratio/d_kp/d_kp_count (detect.cu)
+int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type);
+int detect_topk(Ctx* c, int top_k);
+
+// a4: normals (normals.cu). normals_query: q (float4 xyz_) -> out (nx,ny,nz,curvature); in-place allowed
+int normals_query(Ctx* c, const float4* d_q, size_t nq, float radius, int max_nn, float4* d_out);
+int normals_compute(Ctx* c, int mode, float radius, int max_nn);
+
+// a5/a6/a7: LRF + SHOT352 + B-SHOT for the current keypoints (shot.cu)
+int shot_compute(Ctx* c, float radius, bool lrf_only, bool write_shot);
+int binarize(Ctx* c, const float* d_shot, size_t k, uint64_t* d_bits);
+
+// a10/a11 (hamming.cu)
+int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                 bshot_cand* d_out);
+int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
+                    bshot_cand* d_cand);
+int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, void* d_out);
+int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* d1, int* idx2, int* d2);
+int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count);
+int popc_peak(Ctx* c, double* out);
+
+// whole frame on the resident cloud (frame.cu)
+int frame_run(Ctx* c, const bshot_params* p);
+
+}  // namespace bshot

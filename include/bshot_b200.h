@@ -1,0 +1,193 @@
+/*
+ * bshot_b200.h -- C ABI of the B200-native (sm_100a) B-SHOT feature front end.
+ *
+ * Drop-in boundary for the per-frame front end of TingKaiChen/B-SHOT-SLAM.  The reference has no
+ * FFI layer: control enters the path through C++ member calls on `class bshot`
+ * (include/bshot_bits.h:30-281) made by LidarOdometry::extractKeypoints / computeDescriptors /
+ * featureMatching (src/lidar_odometry.cpp:51,173,186).  Every entry point below names the
+ * reference code it replaces.  The reference-named host C++ shims (b-shot-slam_b200/host/*.h:
+ * `bshot`, `bshot_descriptor`, `minVect`, `Frame`, `Keypoint`, `Map`) forward to this ABI; see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all functions return 0 on success, a negative BSHOT_E_* code
+ *     otherwise and never throw.  bshot_last_error() returns a thread-local message.
+ *   - units are millimetres (reference: src/preprocess.cpp:46).
+ *   - a descriptor record is 48 bytes = std::bitset<352> of libstdc++ (6 x u64 little endian, bit i
+ *     in word i/64 at position i%64, bits 352..383 zero) == bshot_descriptor
+ *     (include/bshot_bits.h:23-27), so std::vector<bshot_descriptor>::data() can be passed as is.
+ *   - a context owns its device buffers (sized at creation, no per-frame allocation) and ONE
+ *     CUDA stream.  It is not thread safe.  Host-buffer calls are synchronous on return.
+ *     *_dev / *_resident calls take device pointers / use resident data and are asynchronous on
+ *     the context stream.
+ *   - there is NO CPU fallback: every call fails with BSHOT_E_CUDA when no sm_100 device is
+ *     usable.
+ */
+#ifndef BSHOT_B200_H
+#define BSHOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSHOT_B200_VERSION 100
+
+enum {
+    BSHOT_OK = 0,
+    BSHOT_E_INVALID = -1,   /* bad argument */
+    BSHOT_E_CAPACITY = -2,  /* input larger than the context was created for */
+    BSHOT_E_CUDA = -3,      /* CUDA runtime / launch failure, or no usable device */
+    BSHOT_E_STATE = -4      /* call order violated (e.g. descriptors before a cloud) */
+};
+
+/* seg-ratio variants, LidarOdometry::sr_type_ "CV"/"CVS"/"CVSN" (src/lidar_odometry.cpp:83,98,109) */
+enum { BSHOT_SR_CV = 0, BSHOT_SR_CVS = 1, BSHOT_SR_CVSN = 2 };
+
+/* normals placement.  REFERENCE reproduces include/bshot_bits.h:58-59,79-81: the K keypoint
+ * normals are stored at indices 0..K-1 of an N-sized, zero-initialised, persistent array that
+ * SHOT then indexes by SURFACE point.  FULL computes a normal for every surface point (what the
+ * commented-out lines include/bshot_bits.h:89-90 did). */
+enum { BSHOT_NORMALS_REFERENCE = 0, BSHOT_NORMALS_FULL = 1 };
+
+typedef struct bshot_ctx bshot_ctx;
+
+/* one frame's parameters; bshot_params_default() fills the reference's literals */
+typedef struct bshot_params {
+    float kp_radius;     /* 3000  src/lidar_odometry.cpp:68 */
+    int kp_max_nn;       /* 300   src/lidar_odometry.cpp:70 */
+    int sr_type;         /* CV    src/lidar_odometry.cpp:6  */
+    int top_k;           /* 600   src/lidar_odometry.cpp:138-142 */
+    float normal_radius; /* 3000  src/lidar_odometry.cpp:174 */
+    int normal_max_nn;   /* 300   include/bshot_bits.h:68 */
+    int normals_mode;    /* BSHOT_NORMALS_REFERENCE */
+    float shot_radius;   /* 3000  src/lidar_odometry.cpp:175 */
+} bshot_params;
+
+void bshot_params_default(bshot_params* p);
+
+int bshot_version(void);
+const char* bshot_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* replaces the `bshot cb` member of LidarOdometry (include/lidar_odometry.h:57) */
+int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_keypoints,
+                     size_t max_targets);
+void bshot_ctx_destroy(bshot_ctx* ctx);
+/* the context's cudaStream_t (for CUDA-event timing by the caller) */
+void* bshot_ctx_stream(bshot_ctx* ctx);
+int bshot_ctx_sync(bshot_ctx* ctx);
+
+/* ---- a1: cloud upload + voxel-hash build -------------------------------------------------- */
+/* replaces LidarOdometry::setSrcFrame (src/lidar_odometry.cpp:29-41) + `cb.cloud1 = src_pcl_`
+ * (:159) and the three pcl::KdTreeFLANN builds (:53-54, include/bshot_bits.h:52-53, PCL SHOT).
+ * stride_bytes is 12 (Eigen::Vector3f) or 16 (pcl::PointXYZ). */
+int bshot_set_cloud(bshot_ctx* ctx, const float* xyz, size_t n, size_t stride_bytes);
+
+/* ---- a2+a3: seg-ratio keypoint detector ---------------------------------------------------- */
+/* replaces LidarOdometry::extractKeypoints loop + sort + top-K (src/lidar_odometry.cpp:61-153).
+ * Keypoints come out in ascending-ratio order (ties: descending point index), the top_k highest.
+ * idx_out / ratio_out / kp_xyz_out (3 floats each) may be NULL; *count_out <= top_k.
+ * The selected keypoints become the context's current keypoints (cb.cloud1_keypoints, :161). */
+int bshot_detect_keypoints(bshot_ctx* ctx, float radius, int max_nn, int sr_type, int top_k,
+                           int* idx_out, float* ratio_out, float* kp_xyz_out, int* count_out);
+/* all N seg-ratios (NaN where the reference skips the point, :63,:121) */
+int bshot_seg_ratio(bshot_ctx* ctx, float radius, int max_nn, int sr_type, float* ratio_out);
+/* explicit keypoints instead of the detector: `cb.cloud1_keypoints = ...` (:161) */
+int bshot_set_keypoints(bshot_ctx* ctx, const float* kp_xyz, size_t k, size_t stride_bytes);
+
+/* ---- a4: normals ---------------------------------------------------------------------------- */
+/* replaces bshot::calculate_normals (include/bshot_bits.h:43-94).  normals_out (may be NULL):
+ * N x 4 floats (nx,ny,nz,curvature) indexed by surface point, i.e. cloud1_normals. */
+int bshot_compute_normals(bshot_ctx* ctx, int mode, float radius, int max_nn, float* normals_out);
+/* normals of arbitrary query points (Q x 4), no placement; the per-query body of :61-88 */
+int bshot_query_normals(bshot_ctx* ctx, const float* q_xyz, size_t nq, float radius, int max_nn,
+                        float* normals_out);
+/* upload cloud1_normals verbatim (N x 4 floats) */
+int bshot_set_normals(bshot_ctx* ctx, const float* normals4, size_t n);
+
+/* ---- a5+a6+a7: SHOT LRF, SHOT352 histogram, B-SHOT bits ------------------------------------ */
+/* replaces bshot::calculate_SHOT (include/bshot_bits.h:113-135) and bshot::compute_bshot (:138-142)
+ * for the current keypoints and normals.  Any output may be NULL:
+ *   bits_out  K x 6 u64 (bshot_descriptor)       shot_out  K x 352 f32 (pcl::SHOT352::descriptor)
+ *   rf_out    K x 9 f32 (pcl::SHOT352::rf)        nn_out    K ints, neighbours within radius
+ * sum_nn_out = sum of nn_out (the algorithmic-bytes unit of SURVEY 8d). */
+int bshot_compute_shot(bshot_ctx* ctx, float radius, uint64_t* bits_out, float* shot_out,
+                       float* rf_out, int* nn_out, long long* sum_nn_out);
+/* LRF only (PCL SHOTLocalReferenceFrameEstimation behind include/bshot_bits.h:117-128) */
+int bshot_compute_lrf(bshot_ctx* ctx, float radius, float* rf_out, int* valid_nn_out);
+/* replaces bshot::compute_bshot_from_SHOT (include/bshot_bits.h:144-278) on caller floats.
+ * shot: k records of 352 floats, stride_floats apart (361 for pcl::SHOT352). */
+int bshot_binarize(bshot_ctx* ctx, const float* shot, size_t k, size_t stride_floats,
+                   uint64_t* bits_out);
+/* replaces LidarOdometry::computeDescriptors (src/lidar_odometry.cpp:173-184): normals + SHOT +
+ * B-SHOT for the current keypoints in one call. */
+int bshot_compute_descriptors(bshot_ctx* ctx, const bshot_params* p, uint64_t* bits_out);
+
+/* ---- a10+a11: Hamming correspondence search ------------------------------------------------ */
+/* replaces the two brute-force loops + minVect (src/lidar_odometry.cpp:212-232,
+ * include/bshot_bits.h:6-20): left_idx[i] = argmin_k popcount(q_i ^ t_k) (first minimum wins),
+ * right_idx[k] = argmin_i popcount(t_k ^ q_i).  Also returns the runner-up (second by
+ * (distance, index)).  Any output may be NULL; right_idx == NULL skips the T x Q pass. */
+int bshot_match(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint64_t* t, size_t nt,
+                int* left_idx, int* left_dist, int* left_idx2, int* left_dist2, int* right_idx);
+/* replaces the mutual-NN filter (src/lidar_odometry.cpp:234-242) fused with the search: writes
+ * (index_query, index_match) pairs in ascending index_query; *count_out <= nq. Only the targets
+ * that are some query's nearest neighbour get their reverse search (Q x Q instead of T x Q). */
+int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint64_t* t, size_t nt,
+                       int* pairs_out, int* dist_out, int* count_out);
+
+/* ---- whole frame (the reference's extractKeypoints -> computeDescriptors -> featureMatching) */
+/* Runs detector, normals, SHOT, B-SHOT on `xyz` and matches the new descriptors against the
+ * previous frame's descriptors kept in the context (first frame: against itself,
+ * src/lidar_odometry.cpp:187-194).  One H2D copy in, one D2H copy out.  Outputs may be NULL.
+ * pairs_out: up to top_k (query,match) pairs. */
+int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n,
+                        size_t stride_bytes, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out,
+                        int* pairs_out, int* n_pairs_out);
+/* same work on the cloud already resident in the context (after bshot_set_cloud); asynchronous,
+ * no host copies -- the kernel-only timing leg of bench.py. */
+int bshot_process_frame_resident(bshot_ctx* ctx, const bshot_params* p);
+
+/* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
+/* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
+ * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first
+ * record in the global target array. */
+int bshot_map_reset(bshot_ctx* ctx);
+int bshot_map_append(bshot_ctx* ctx, const uint64_t* desc, size_t n);
+int bshot_map_size(bshot_ctx* ctx, size_t* n_out);
+/* candidate record per query produced by one shard: packed keys (distance << 32 | global index),
+ * 0xFFFFFFFFFFFFFFFF = none; rq = best query for target k1 among this call's queries. */
+typedef struct bshot_cand {
+    uint64_t k1;
+    uint64_t k2;
+    uint32_t rq;
+    uint32_t pad;
+} bshot_cand;
+/* device pointers, asynchronous on the context stream: d_q (nq x 48 B) against the resident shard
+ * -> d_cand_out (nq records).  with_rq != 0 also fills rq (Q x Q reverse pass). */
+int bshot_match_shard_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
+                          int with_rq, void* d_cand_out);
+/* generic device-pointer matcher against caller-owned targets */
+int bshot_match_dev(bshot_ctx* ctx, const void* d_q, size_t nq, const void* d_t, size_t nt,
+                    uint64_t global_base, int with_rq, void* d_cand_out);
+/* merge `nranks` candidate arrays (rank-major, nranks x nq records, e.g. an all-gather result)
+ * by (distance, global index); d_out: nq merged records. mutual iff merged rq == query index. */
+int bshot_merge_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nranks, size_t nq,
+                          void* d_out);
+/* host-buffer convenience over the three calls above for a single rank */
+int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base,
+                    bshot_cand* cand_out);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of kernels this library launched on the context since creation (bench.py gpu_launches) */
+unsigned long long bshot_launch_count(bshot_ctx* ctx);
+/* POPC-pipe microbenchmark: returns measured POPC32 instructions/s over the whole GPU */
+int bshot_popc_peak(bshot_ctx* ctx, double* popc_per_s_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

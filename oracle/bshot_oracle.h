@@ -1,0 +1,97 @@
+/*
+ * bshot_oracle.h -- C interface of the CPU ORACLE for the B-SHOT front end.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
+ * (b-shot-slam_b200/csrc, include/bshot_b200.h) never links, loads or calls anything in oracle/.
+ *
+ * PARITY UNPINNED: the reference (TingKaiChen/B-SHOT-SLAM) ships no golden vectors, known-answer
+ * tests or fixtures, and its arithmetic lives in PCL (>= 1.7.2, unvendored, not installable
+ * here), so the reference itself cannot be executed in this environment.  The oracle restates
+ *   - the reference's own code: include/bshot_bits.h:6-20,43-94,144-278 and
+ *     src/lidar_odometry.cpp:61-153,186-242 (exactly), and
+ *   - the published PCL 1.8 algorithms it calls (kd-tree radius search, computeCentroid,
+ *     computePointNormal/eigen33, SHOTLocalReferenceFrameEstimation, SHOTEstimation) as
+ *     recorded in SURVEY.md Appendix A.
+ * It is pinned only by truth tables derived from the reference source, analytic cases,
+ * numpy.linalg.eigh / scipy cKDTree cross-checks and an independent numpy restatement
+ * (tests/test_oracle_*.py).
+ */
+#ifndef BSHOT_ORACLE_H
+#define BSHOT_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_cloud orc_cloud;
+
+enum { ORC_SR_CV = 0, ORC_SR_CVS = 1, ORC_SR_CVSN = 2 };
+enum { ORC_TIE_STDSORT = 0, ORC_TIE_DETERMINISTIC = 1 };
+
+/* surface cloud + uniform grid (replaces the three pcl::KdTreeFLANN builds,
+ * src/lidar_odometry.cpp:53-54, include/bshot_bits.h:52-53 and PCL-internal in SHOT) */
+orc_cloud* orc_cloud_create(const float* xyz, size_t n, size_t stride_floats);
+void orc_cloud_destroy(orc_cloud* c);
+size_t orc_cloud_size(const orc_cloud* c);
+
+/* pcl::KdTreeFLANN::radiusSearch semantics: all points with fp32
+ * squared distance < radius^2, ascending by (sqd, index); max_nn > 0 keeps the max_nn nearest.
+ * Returns the count (<= cap written). */
+int orc_radius_search(const orc_cloud* c, const float q[3], float radius, int max_nn,
+                      int* out_idx, float* out_sqd, int cap);
+
+/* src/lidar_odometry.cpp:61-126 : seg-ratio per point (NaN where the reference skips). */
+void orc_seg_ratio(const orc_cloud* c, float radius, int max_nn, int sr_type, float* ratio_out,
+                   int threads);
+
+/* src/lidar_odometry.cpp:131-153 : sort ascending, keep last top_k. Returns count. */
+int orc_select_keypoints(const float* ratio, size_t n, int top_k, int tie_mode, int* idx_out,
+                         float* ratio_out);
+
+/* include/bshot_bits.h:61-88 loop body: normal (nx,ny,nz,curvature) per query point. */
+void orc_normals(const orc_cloud* c, const float* q_xyz, size_t nq, float radius, int max_nn,
+                 float* normal4_out, int threads);
+
+/* PCL SHOTLocalReferenceFrameEstimation::getLocalRF (Appendix A.4). rf = [x;y;z] rows. */
+void orc_lrf(const orc_cloud* c, const float* kp_xyz, size_t nk, float radius, float* rf9_out,
+             int* valid_nn_out, int threads);
+
+/* PCL SHOTEstimation::computePointSHOT (Appendix A.5).  normals4 is indexed by SURFACE index
+ * (size n*4). rf9_in may be NULL (then the LRF is computed). Returns sum of neighbour counts. */
+long long orc_shot(const orc_cloud* c, const float* kp_xyz, size_t nk, float radius,
+                   const float* normals4, const float* rf9_in, float* shot352_out,
+                   float* rf9_out, int* nn_out, int threads);
+
+/* include/bshot_bits.h:144-278 */
+void orc_bshot(const float* shot352, size_t nk, uint64_t* bits6_out);
+
+/* src/lidar_odometry.cpp:212-232 + minVect include/bshot_bits.h:6-20 (first minimum wins).
+ * Any output pointer may be NULL. top-2: second best by (distance, index) order. */
+void orc_match(const uint64_t* q, size_t nq, const uint64_t* t, size_t nt, int* left_idx,
+               int* left_dist, int* left_idx2, int* left_dist2, int* right_idx, int threads);
+
+/* src/lidar_odometry.cpp:234-242 ; writes (index_query,index_match) pairs, returns count */
+int orc_mutual(const int* left_idx, size_t nq, const int* right_idx, int* pairs_out);
+
+/* whole computeDescriptors (src/lidar_odometry.cpp:173-184) in the reference's REFERENCE
+ * normals mode (quirk: keypoint normals stored at indices 0..K-1 of an N-sized zero array,
+ * include/bshot_bits.h:58-59,79-81) or FULL mode (normals for every surface point).
+ * mode: 0 = REFERENCE, 1 = FULL.  Outputs may be NULL. Returns sum of SHOT neighbour counts. */
+long long orc_compute_descriptors(const orc_cloud* c, const float* kp_xyz, size_t nk,
+                                  float radius, int max_nn, int mode, uint64_t* bits6_out,
+                                  float* shot352_out, float* rf9_out, float* normals4_out,
+                                  int threads);
+
+/* symmetric 3x3 eigen decomposition used by orc_lrf (double, ascending), exposed for tests */
+void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]);
+/* pcl::eigen33 smallest-eigenpair (fp32), exposed for tests */
+void orc_eigen33_smallest(const float m[9], float* eval, float evec[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,198 @@
+"""ctypes binding of the CPU oracle (oracle/bshot_oracle.{h,cpp}).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+PARITY UNPINNED -- see the header of oracle/bshot_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SR_CV, SR_CVS, SR_CVSN = 0, 1, 2
+TIE_STDSORT, TIE_DETERMINISTIC = 0, 1
+MODE_REFERENCE, MODE_FULL = 0, 1
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libbshot_oracle.so")
+    src = os.path.join(_HERE, "bshot_oracle.cpp")
+    hdr = os.path.join(_HERE, "bshot_oracle.h")
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libbshot_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        fp = C.POINTER(C.c_float)
+        ip = C.POINTER(C.c_int)
+        up = C.POINTER(C.c_uint64)
+        L.orc_cloud_create.restype = C.c_void_p
+        L.orc_cloud_create.argtypes = [fp, C.c_size_t, C.c_size_t]
+        L.orc_cloud_destroy.argtypes = [C.c_void_p]
+        L.orc_cloud_size.restype = C.c_size_t
+        L.orc_cloud_size.argtypes = [C.c_void_p]
+        L.orc_radius_search.restype = C.c_int
+        L.orc_radius_search.argtypes = [C.c_void_p, fp, C.c_float, C.c_int, ip, fp, C.c_int]
+        L.orc_seg_ratio.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, fp, C.c_int]
+        L.orc_select_keypoints.restype = C.c_int
+        L.orc_select_keypoints.argtypes = [fp, C.c_size_t, C.c_int, C.c_int, ip, fp]
+        L.orc_normals.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_float, C.c_int, fp, C.c_int]
+        L.orc_lrf.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_float, fp, ip, C.c_int]
+        L.orc_shot.restype = C.c_longlong
+        L.orc_shot.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_float, fp, fp, fp, fp, ip, C.c_int]
+        L.orc_bshot.argtypes = [fp, C.c_size_t, up]
+        L.orc_match.argtypes = [up, C.c_size_t, up, C.c_size_t, ip, ip, ip, ip, ip, C.c_int]
+        L.orc_mutual.restype = C.c_int
+        L.orc_mutual.argtypes = [ip, C.c_size_t, ip, ip]
+        L.orc_compute_descriptors.restype = C.c_longlong
+        L.orc_compute_descriptors.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_float, C.c_int,
+                                              C.c_int, up, fp, fp, fp, C.c_int]
+        L.orc_eigh3.argtypes = [C.POINTER(C.c_double)] * 3
+        L.orc_eigen33_smallest.argtypes = [fp, fp, fp]
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _u(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+class Cloud:
+    """surface cloud (N,3) float32 in mm + search grid"""
+
+    def __init__(self, xyz):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        self.h = lib().orc_cloud_create(_f(self.xyz), self.xyz.shape[0], 3)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_cloud_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return self.xyz.shape[0]
+
+    def radius_search(self, q, radius, max_nn=0):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        cap = len(self)
+        idx = np.empty(cap, np.int32)
+        sqd = np.empty(cap, np.float32)
+        n = lib().orc_radius_search(self.h, _f(q), radius, max_nn, _i(idx), _f(sqd), cap)
+        return idx[:n].copy(), sqd[:n].copy()
+
+    def seg_ratio(self, radius=3000.0, max_nn=300, sr_type=SR_CV, threads=0):
+        out = np.empty(len(self), np.float32)
+        lib().orc_seg_ratio(self.h, radius, max_nn, sr_type, _f(out), threads)
+        return out
+
+    def normals(self, q, radius=3000.0, max_nn=300, threads=0):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((q.shape[0], 4), np.float32)
+        lib().orc_normals(self.h, _f(q), q.shape[0], radius, max_nn, _f(out), threads)
+        return out
+
+    def lrf(self, kp, radius=3000.0, threads=0):
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(-1, 3)
+        rf = np.empty((kp.shape[0], 9), np.float32)
+        valid = np.empty(kp.shape[0], np.int32)
+        lib().orc_lrf(self.h, _f(kp), kp.shape[0], radius, _f(rf), _i(valid), threads)
+        return rf, valid
+
+    def shot(self, kp, normals4, radius=3000.0, rf_in=None, threads=0):
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(-1, 3)
+        normals4 = np.ascontiguousarray(normals4, dtype=np.float32).reshape(len(self), 4)
+        shot = np.empty((kp.shape[0], 352), np.float32)
+        rf = np.empty((kp.shape[0], 9), np.float32)
+        nn = np.empty(kp.shape[0], np.int32)
+        rfi = None
+        if rf_in is not None:
+            rf_in = np.ascontiguousarray(rf_in, dtype=np.float32).reshape(-1, 9)
+            rfi = _f(rf_in)
+        total = lib().orc_shot(self.h, _f(kp), kp.shape[0], radius, _f(normals4), rfi, _f(shot),
+                               _f(rf), _i(nn), threads)
+        return shot, rf, nn, total
+
+    def compute_descriptors(self, kp, radius=3000.0, max_nn=300, mode=MODE_REFERENCE, threads=0,
+                            want_normals=False):
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(-1, 3)
+        k = kp.shape[0]
+        bits = np.empty((k, 6), np.uint64)
+        shot = np.empty((k, 352), np.float32)
+        rf = np.empty((k, 9), np.float32)
+        normals = np.empty((len(self), 4), np.float32) if want_normals else None
+        total = lib().orc_compute_descriptors(
+            self.h, _f(kp), k, radius, max_nn, mode, _u(bits), _f(shot), _f(rf),
+            _f(normals) if want_normals else None, threads)
+        return dict(bits=bits, shot=shot, rf=rf, normals=normals, sum_neighbours=total)
+
+
+def select_keypoints(ratio, top_k=600, tie_mode=TIE_DETERMINISTIC):
+    ratio = np.ascontiguousarray(ratio, dtype=np.float32)
+    idx = np.empty(max(top_k, 1), np.int32)
+    rat = np.empty(max(top_k, 1), np.float32)
+    n = lib().orc_select_keypoints(_f(ratio), ratio.shape[0], top_k, tie_mode, _i(idx), _f(rat))
+    return idx[:n].copy(), rat[:n].copy()
+
+
+def bshot(shot):
+    shot = np.ascontiguousarray(shot, dtype=np.float32).reshape(-1, 352)
+    bits = np.empty((shot.shape[0], 6), np.uint64)
+    lib().orc_bshot(_f(shot), shot.shape[0], _u(bits))
+    return bits
+
+
+def match(q, t, want_right=True, threads=0):
+    q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+    t = np.ascontiguousarray(t, dtype=np.uint64).reshape(-1, 6)
+    li = np.empty(q.shape[0], np.int32)
+    ld = np.empty(q.shape[0], np.int32)
+    li2 = np.empty(q.shape[0], np.int32)
+    ld2 = np.empty(q.shape[0], np.int32)
+    ri = np.empty(t.shape[0], np.int32) if want_right else None
+    lib().orc_match(_u(q), q.shape[0], _u(t), t.shape[0], _i(li), _i(ld), _i(li2), _i(ld2),
+                    _i(ri) if want_right else None, threads)
+    return dict(left_idx=li, left_dist=ld, left_idx2=li2, left_dist2=ld2, right_idx=ri)
+
+
+def mutual(left_idx, right_idx):
+    left_idx = np.ascontiguousarray(left_idx, dtype=np.int32)
+    right_idx = np.ascontiguousarray(right_idx, dtype=np.int32)
+    pairs = np.empty((left_idx.shape[0], 2), np.int32)
+    n = lib().orc_mutual(_i(left_idx), left_idx.shape[0], _i(right_idx), _i(pairs))
+    return pairs[:n].copy()
+
+
+def eigh3(m):
+    m = np.ascontiguousarray(m, dtype=np.float64).reshape(9)
+    w = np.empty(3, np.float64)
+    v = np.empty(9, np.float64)
+    dp = C.POINTER(C.c_double)
+    lib().orc_eigh3(m.ctypes.data_as(dp), w.ctypes.data_as(dp), v.ctypes.data_as(dp))
+    return w, v.reshape(3, 3)
+
+
+def eigen33_smallest(m):
+    m = np.ascontiguousarray(m, dtype=np.float32).reshape(9)
+    ev = np.empty(1, np.float32)
+    vec = np.empty(3, np.float32)
+    lib().orc_eigen33_smallest(_f(m), _f(ev), _f(vec))
+    return float(ev[0]), vec

@@ -1,0 +1,150 @@
+"""a10/a11 parity: CUDA Hamming search (through the C ABI) vs the oracle restatement of
+src/lidar_odometry.cpp:212-242 + minVect (include/bshot_bits.h:6-20). Bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, oracle, q, t):
+    g = ctx.match(q, t, want_right=True)
+    o = oracle.match(q, t, want_right=True)
+    for k in ("left_idx", "left_dist", "left_idx2", "left_dist2", "right_idx"):
+        assert np.array_equal(g[k], o[k]), k
+    pairs, dist = ctx.match_mutual(q, t)
+    opairs = oracle.mutual(o["left_idx"], o["right_idx"])
+    assert np.array_equal(pairs, opairs)
+    assert np.array_equal(dist, o["left_dist"][opairs[:, 0]])
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (7, 5), (600, 600), (600, 1337), (2048, 2048),
+                                   (257, 129), (1025, 4097), (3000, 20000)])
+def test_random(gpu_ctx, oracle, synth, nq, nt):
+    q = synth.random_descriptors(nq, seed=nq)
+    t = synth.random_descriptors(nt, seed=1000 + nt)
+    _check(gpu_ctx, oracle, q, t)
+
+
+def test_sparse_reference_like(gpu_ctx, oracle, synth):
+    # <= 40 bits set (what the reference's normals quirk yields): many distance ties
+    q = synth.random_descriptors(2048, seed=3, density=33)
+    t = synth.random_descriptors(5000, seed=4, density=33)
+    _check(gpu_ctx, oracle, q, t)
+
+
+def test_duplicates_and_ties(gpu_ctx, oracle, synth):
+    rng = np.random.default_rng(11)
+    t = synth.random_descriptors(4096, seed=5)
+    # planted exact duplicates at several indices: lowest index must win
+    t[100] = t[3000]
+    t[101] = t[3000]
+    t[4095] = t[7]
+    q = t[rng.integers(0, 4096, 900)].copy()
+    # near duplicates: flip 1-3 bits
+    bits = synth.unpack_bits(q)
+    for i in range(0, 900, 3):
+        for b in rng.integers(0, 352, rng.integers(1, 4)):
+            bits[i, b] ^= True
+    q = synth.pack_bits(bits)
+    _check(gpu_ctx, oracle, q, t)
+
+
+def test_self_match_initial_frame(gpu_ctx, oracle, synth):
+    # src/lidar_odometry.cpp:187-194: the first frame is matched against itself
+    d = synth.random_descriptors(600, seed=9, density=33)
+    _check(gpu_ctx, oracle, d, d)
+
+
+def test_all_ones_invalid_descriptors(gpu_ctx, oracle, synth):
+    # NaN SHOT binarises to all 352 bits set (include/bshot_bits.h:166-260)
+    q = synth.random_descriptors(300, seed=21)
+    t = synth.random_descriptors(700, seed=22)
+    ones = np.full(6, 0xFFFFFFFFFFFFFFFF, np.uint64)
+    ones[5] = 0xFFFFFFFF
+    q[5] = ones
+    t[17] = ones
+    t[400] = ones
+    _check(gpu_ctx, oracle, q, t)
+
+
+def test_empty_inputs(gpu_ctx, synth):
+    q = synth.random_descriptors(10, seed=1)
+    e = np.zeros((0, 6), np.uint64)
+    g = gpu_ctx.match(q, e)
+    assert (g["left_idx"] == -1).all() and (g["left_dist"] == -1).all()
+    g = gpu_ctx.match(e, q)
+    assert (g["right_idx"] == -1).all()
+    pairs, dist = gpu_ctx.match_mutual(q, e)
+    assert pairs.shape[0] == 0
+
+
+def test_single_target_has_no_runner_up(gpu_ctx, synth):
+    q = synth.random_descriptors(33, seed=1)
+    t = synth.random_descriptors(1, seed=2)
+    g = gpu_ctx.match(q, t)
+    assert (g["left_idx"] == 0).all() and (g["left_idx2"] == -1).all() and (g["left_dist2"] == -1).all()
+
+
+def test_sharded_merge_equals_single(gpu_ctx, bshot, oracle, synth):
+    """8 emulated shards on one GPU: per-shard candidates + merge == single-pass result."""
+    import torch
+    nq, nt, shards = 1000, 40000, 8
+    q = synth.random_descriptors(nq, seed=31)
+    t = synth.random_descriptors(nt, seed=32)
+    t[12345] = t[222]     # cross-shard tie: lowest global index must win
+    t[39999] = q[5]
+    t[77] = q[5]
+    dq = torch.from_numpy(q.view(np.int64)).cuda()
+    dt = torch.from_numpy(t.view(np.int64)).cuda()
+    cands = torch.empty((shards, nq, 3), dtype=torch.int64, device="cuda")
+    merged = torch.empty((nq, 3), dtype=torch.int64, device="cuda")
+    per = (nt + shards - 1) // shards
+    torch.cuda.synchronize()
+    for r in range(shards):
+        lo, hi = r * per, min(nt, (r + 1) * per)
+        gpu_ctx.match_dev(dq.data_ptr(), nq, dt[lo:hi].data_ptr(), hi - lo, lo, True, cands[r].data_ptr())
+    gpu_ctx.merge_cands_dev(cands.data_ptr(), shards, nq, merged.data_ptr())
+    gpu_ctx.sync()
+    rec = merged.cpu().numpy().view(bshot.CAND_DTYPE).reshape(nq)
+    u = bshot.unpack_cands(rec)
+    o = oracle.match(q, t, want_right=True)
+    assert np.array_equal(u["idx1"], o["left_idx"])
+    assert np.array_equal(u["dist1"], o["left_dist"])
+    assert np.array_equal(u["idx2"], o["left_idx2"])
+    assert np.array_equal(u["dist2"], o["left_dist2"])
+    mutual_gpu = np.nonzero(u["rq"] == np.arange(nq))[0]
+    opairs = oracle.mutual(o["left_idx"], o["right_idx"])
+    assert np.array_equal(mutual_gpu, opairs[:, 0])
+
+
+def test_full_size_properties(gpu_ctx, bshot, synth):
+    """C4-sized shard (Q=10000 x T=1M): size-independent properties instead of the O(QT) oracle."""
+    nq, nt = 10000, 1 << 20
+    t = synth.random_descriptors(nt, seed=7)
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, nt, nq)
+    q = t[src].copy()
+    bits = synth.unpack_bits(q[: nq // 2])
+    flip = rng.integers(0, 352, nq // 2)
+    bits[np.arange(nq // 2), flip] ^= True          # first half: one bit flipped
+    q[: nq // 2] = synth.pack_bits(bits)
+    gpu_ctx.map_reset()
+    gpu_ctx.map_append(t)
+    u = bshot.unpack_cands(gpu_ctx.match_map(q, 0))
+    # random 352-bit words: the planted source is the unique nearest neighbour
+    assert np.array_equal(u["idx1"], src)
+    assert (u["dist1"][: nq // 2] == 1).all() and (u["dist1"][nq // 2:] == 0).all()
+    assert (u["dist2"] >= u["dist1"]).all() and (u["dist2"] > 100).all()
+    # reverse check: each planted target's best query is the lowest query index that copied it
+    first = {}
+    for i, s in enumerate(src):
+        first.setdefault(int(s), i)
+    exp_rq = np.array([first[int(s)] for s in src])
+    d_exp = np.where(exp_rq < nq // 2, 1, 0)
+    # a later exact copy (dist 0) beats an earlier 1-bit-flipped copy
+    for i, s in enumerate(src):
+        if d_exp[i] == 1:
+            later = [j for j in np.nonzero(src == s)[0] if j >= nq // 2]
+            if later:
+                exp_rq[i] = later[0]
+    assert np.array_equal(u["rq"], exp_rq)
