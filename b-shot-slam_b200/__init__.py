@@ -23,7 +23,7 @@ NORMALS_REFERENCE, NORMALS_FULL = 0, 1
 
 EXPORTS = [
     "bshot_params_default", "bshot_version", "bshot_last_error", "bshot_ctx_create",
-    "bshot_ctx_destroy", "bshot_ctx_stream", "bshot_ctx_sync", "bshot_set_cloud",
+    "bshot_ctx_destroy", "bshot_ctx_stream", "bshot_ctx_sync", "bshot_ctx_reset", "bshot_set_cloud",
     "bshot_detect_keypoints", "bshot_seg_ratio", "bshot_set_keypoints", "bshot_compute_normals",
     "bshot_query_normals", "bshot_set_normals", "bshot_compute_shot", "bshot_compute_lrf",
     "bshot_binarize", "bshot_compute_descriptors", "bshot_match", "bshot_match_mutual",
@@ -71,6 +71,7 @@ def lib():
         L.bshot_ctx_stream.argtypes = [vp]
         L.bshot_ctx_stream.restype = vp
         L.bshot_ctx_sync.argtypes = [vp]
+        L.bshot_ctx_reset.argtypes = [vp]
         L.bshot_set_cloud.argtypes = [vp, vp, sz, sz]
         L.bshot_detect_keypoints.argtypes = [vp, cf, ci, ci, ci, vp, vp, vp, vp]
         L.bshot_seg_ratio.argtypes = [vp, cf, ci, ci, vp]
@@ -164,6 +165,9 @@ class Context:
 
     def sync(self):
         _chk(lib().bshot_ctx_sync(self.h))
+
+    def reset(self):
+        _chk(lib().bshot_ctx_reset(self.h))
 
     def launch_count(self):
         return int(lib().bshot_launch_count(self.h))

@@ -204,6 +204,17 @@ int bshot_ctx_sync(bshot_ctx* ctx) {
     return sync(ctx);
 }
 
+int bshot_ctx_reset(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_normals, 0, sizeof(float4) * ctx->max_points, ctx->stream));
+    BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_prev_count, 0, sizeof(int), ctx->stream));
+    ctx->normals_valid = 0;
+    ctx->have_normals = false;
+    ctx->n_prev = 0;
+    ctx->n_map = 0;
+    return sync(ctx);
+}
+
 unsigned long long bshot_launch_count(bshot_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 
 int bshot_popc_peak(bshot_ctx* ctx, double* out) {

@@ -1,0 +1,38 @@
+// frame.cu -- the reference's per-frame call order on the resident cloud, fully asynchronous:
+// extractKeypoints -> computeDescriptors -> featureMatching (test/odometry_test.cpp:174-194,
+// src/lidar_odometry.cpp:51-265 up to the RANSAC call).
+#include "stages.h"
+
+namespace bshot {
+
+__global__ void copy_prev_kernel(const uint64_t* __restrict__ bits, const int* __restrict__ count, unsigned cap,
+                                 uint64_t* __restrict__ prev, int* __restrict__ prev_count) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = *count;
+    if (i < cap * 6 && (int)(i / 6) < k) prev[i] = bits[i];
+    if (i == 0) *prev_count = k;
+}
+
+int frame_run(Ctx* c, const bshot_params* p) {
+    BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type));
+    BSHOT_TRY(detect_topk(c, p->top_k));
+    BSHOT_TRY(normals_compute(c, p->normals_mode, p->normal_radius, p->normal_max_nn));
+    BSHOT_TRY(shot_compute(c, p->shot_radius, false, false));
+    // featureMatching: the initial frame is matched against itself (src/lidar_odometry.cpp:187-194),
+    // later frames against the previous frame's descriptors.  Host-side counts are upper bounds
+    // (top_k); kernels read the device-side counts.
+    const size_t k = (size_t)p->top_k;
+    const bool initial = (c->n_prev == 0);
+    const uint64_t* tgt = initial ? c->d_bits : c->d_prev_bits;
+    const size_t nt = initial ? k : c->n_prev;
+    BSHOT_TRY(hamming_top2(c, c->d_bits, k, tgt, nt, 0, c->d_cand));
+    BSHOT_TRY(hamming_reverse(c, c->d_bits, k, tgt, 0, c->d_cand));
+    BSHOT_TRY(hamming_mutual_pairs(c, c->d_cand, k, c->d_pairs, c->d_pair_count));
+    copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp_count, (unsigned)k,
+                                                                            c->d_prev_bits, c->d_prev_count);
+    count_launch(c);
+    c->n_prev = k;
+    return check_launch("copy_prev_kernel");
+}
+
+}  // namespace bshot

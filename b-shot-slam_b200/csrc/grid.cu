@@ -1,0 +1,257 @@
+// grid.cu -- cloud ingest + voxel table build (SURVEY 8a row a1 + the kd-tree builds it replaces).
+//
+// Replaces LidarOdometry::setSrcFrame (src/lidar_odometry.cpp:29-41: Vector3f -> PointXYZ copy) and
+// the three pcl::KdTreeFLANN builds per frame (src/lidar_odometry.cpp:53-54,
+// include/bshot_bits.h:52-53, PCL-internal in SHOT).  The search structure is a perfect spatial
+// hash: cell (ix,iy,iz) of edge `cell` over the cloud's bounding box, linearised x-fastest, so that
+// the cells of one (iy,iz) row that a radius query needs are ONE contiguous range of the
+// cell-sorted point array (float4, w = original index) -> coalesced float4 row-segment gathers.
+// Everything is sized on the device (no host round trip): bbox reduce -> grid params -> count ->
+// 3-kernel exclusive scan -> scatter.
+#include "common.cuh"
+#include "nbr.cuh"
+
+namespace bshot {
+
+constexpr int GB_THREADS = 256;
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 8;                        // cells per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS; // 8192 cells per block
+constexpr int SCAN_BLOCKS = kMaxCells / SCAN_TILE;   // 1024
+
+__global__ void bbox_init_kernel(float* bbox) {
+    if (threadIdx.x < 3) bbox[threadIdx.x] = __int_as_float(0x7F800000);       // +inf
+    else if (threadIdx.x < 6) bbox[threadIdx.x] = __int_as_float(0xFF800000);  // -inf
+}
+
+__device__ __forceinline__ void atomic_min_float(float* a, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* a, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+// raw caller layout -> float4 (x,y,z,1) + bounding box of the finite points
+__global__ void __launch_bounds__(GB_THREADS)
+convert_bbox_kernel(const float* __restrict__ raw, unsigned n, int stride, float4* __restrict__ pts,
+                    float* __restrict__ bbox) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float inf = __int_as_float(0x7F800000);
+    float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
+    if (i < n) {
+        float x, y, z;
+        if (stride == 4) {
+            const float4 v = reinterpret_cast<const float4*>(raw)[i];
+            x = v.x; y = v.y; z = v.z;
+        } else {
+            x = raw[(size_t)i * 3]; y = raw[(size_t)i * 3 + 1]; z = raw[(size_t)i * 3 + 2];
+        }
+        pts[i] = make_float4(x, y, z, 1.0f);
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            mn[0] = mx[0] = x; mn[1] = mx[1] = y; mn[2] = mx[2] = z;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    __shared__ float smn[GB_THREADS / 32][3], smx[GB_THREADS / 32][3];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { smn[wid][k] = mn[k]; smx[wid][k] = mx[k]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        float a = inf, b = -inf;
+        for (int w = 0; w < GB_THREADS / 32; ++w) { a = fminf(a, smn[w][k]); b = fmaxf(b, smx[w][k]); }
+        if (a <= b) { atomic_min_float(&bbox[k], a); atomic_max_float(&bbox[3 + k], b); }
+    }
+}
+
+__global__ void grid_params_kernel(const float* __restrict__ bbox, unsigned n, float cell0, GridParams* g) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    GridParams p;
+    float mn[3] = {bbox[0], bbox[1], bbox[2]}, mx[3] = {bbox[3], bbox[4], bbox[5]};
+    if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.0f; mx[0] = mx[1] = mx[2] = 0.0f; }  // empty cloud
+    float cell = cell0;
+    for (;;) {
+        const double cells = (floor((double)(mx[0] - mn[0]) / cell) + 1.0) * (floor((double)(mx[1] - mn[1]) / cell) + 1.0) *
+                             (floor((double)(mx[2] - mn[2]) / cell) + 1.0);
+        if (cells <= (double)kMaxCells) break;
+        cell *= 1.25f;
+    }
+    p.ox = mn[0]; p.oy = mn[1]; p.oz = mn[2];
+    p.cell = cell;
+    p.inv_cell = 1.0f / cell;
+    p.nx = cell_coord(mx[0], p.ox, p.inv_cell) + 1;
+    p.ny = cell_coord(mx[1], p.oy, p.inv_cell) + 1;
+    p.nz = cell_coord(mx[2], p.oz, p.inv_cell) + 1;
+    // cell_coord rounds in fp32; shrink until the table fits (never triggers in practice)
+    while ((double)p.nx * p.ny * p.nz > (double)kMaxCells) {
+        if (p.nx >= p.ny && p.nx >= p.nz) p.nx--; else if (p.ny >= p.nz) p.ny--; else p.nz--;
+    }
+    p.ncells = (unsigned)p.nx * (unsigned)p.ny * (unsigned)p.nz;
+    p.npoints = n;
+    *g = p;
+}
+
+__global__ void zero_cells_kernel(const GridParams* __restrict__ g, unsigned* __restrict__ cursor) {
+    const unsigned n = g->ncells;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cursor[i] = 0;
+}
+
+__global__ void __launch_bounds__(GB_THREADS)
+count_kernel(const float4* __restrict__ pts, unsigned n, const GridParams* __restrict__ gp,
+             unsigned* __restrict__ cell_of, unsigned* __restrict__ cursor) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridParams g = *gp;
+    const float4 p = pts[i];
+    unsigned cid = 0xFFFFFFFFu;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int ix = min(max(cell_coord(p.x, g.ox, g.inv_cell), 0), g.nx - 1);
+        const int iy = min(max(cell_coord(p.y, g.oy, g.inv_cell), 0), g.ny - 1);
+        const int iz = min(max(cell_coord(p.z, g.oz, g.inv_cell), 0), g.nz - 1);
+        cid = ((unsigned)iz * g.ny + iy) * g.nx + ix;
+        atomicAdd(&cursor[cid], 1u);
+    }
+    cell_of[i] = cid;
+}
+
+// exclusive scan of cursor[0..ncells) -> cell_start[0..ncells], three kernels
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cnt, unsigned* __restrict__ block_sums) {
+    const unsigned n = gp->ncells;
+    const unsigned base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
+        if (i < n) s += cnt[i];
+    }
+    s = (unsigned)warp_sum((int)s);
+    __shared__ unsigned ws[32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned v = ws[threadIdx.x];
+        v = (unsigned)warp_sum((int)v);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_blocks_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ block_sums, unsigned* __restrict__ cell_start) {
+    const unsigned n = gp->ncells;
+    const unsigned nb = (n + SCAN_TILE - 1) / SCAN_TILE;  // <= 1024
+    __shared__ unsigned sh[SCAN_THREADS];
+    const unsigned t = threadIdx.x;
+    const unsigned v = (t < nb) ? block_sums[t] : 0u;
+    sh[t] = v;
+    __syncthreads();
+    for (unsigned o = 1; o < SCAN_THREADS; o <<= 1) {
+        const unsigned add = (t >= o) ? sh[t - o] : 0u;
+        __syncthreads();
+        sh[t] += add;
+        __syncthreads();
+    }
+    if (t < nb) block_sums[t] = sh[t] - v;  // exclusive
+    if (t == SCAN_THREADS - 1) cell_start[n] = sh[t];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ cursor, const unsigned* __restrict__ block_sums,
+                  unsigned* __restrict__ cell_start) {
+    const unsigned n = gp->ncells;
+    const unsigned base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    unsigned v[SCAN_ITEMS];
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
+        v[k] = (i < n) ? cursor[i] : 0u;
+        s += v[k];
+    }
+    // block-exclusive prefix of the per-thread sums
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += up;
+    }
+    __shared__ unsigned ws[32];
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned w = ws[lane];
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o) winc += up;
+        }
+        ws[lane] = winc - w;
+    }
+    __syncthreads();
+    unsigned run = block_sums[blockIdx.x] + ws[wid] + (inc - s);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
+        if (i < n) {
+            cell_start[i] = run;
+            cursor[i] = run;  // scatter cursor starts at the cell's first slot
+        }
+        run += v[k];
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS)
+scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __restrict__ cell_of,
+               unsigned* __restrict__ cursor, float4* __restrict__ sorted) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned cid = cell_of[i];
+    if (cid == 0xFFFFFFFFu) return;
+    const unsigned pos = atomicAdd(&cursor[cid], 1u);
+    float4 p = pts[i];
+    p.w = __uint_as_float(i);
+    sorted[pos] = p;
+}
+
+int grid_build(Ctx* c, size_t n, int stride_floats) {
+    const unsigned nn = (unsigned)n;
+    const unsigned pb = (nn + GB_THREADS - 1) / GB_THREADS;
+    bbox_init_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox);
+    if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
+    grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->d_grid);
+    zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor);
+    if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor);
+    scan_reduce_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums);
+    scan_blocks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_block_sums, c->d_cell_start);
+    scan_final_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums, c->d_cell_start);
+    if (pb) scatter_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_cell_of, c->d_cell_cursor, c->d_sorted);
+    count_launch(c, pb ? 9 : 6);
+    BSHOT_TRY(check_launch("grid_build"));
+    // vector::resize semantics of cloud1_normals (include/bshot_bits.h:59): entries beyond the new
+    // size are dropped, so stale keypoint normals above n must not survive a smaller cloud
+    if (c->normals_valid > n) {
+        BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_normals + n, 0, sizeof(float4) * (c->normals_valid - n), c->stream));
+        c->normals_valid = n;
+    }
+    c->n_points = n;
+    c->have_cloud = true;
+    c->have_kp = false;
+    c->have_normals = c->normals_valid > 0;
+    return BSHOT_OK;
+}
+
+}  // namespace bshot

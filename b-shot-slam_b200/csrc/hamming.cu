@@ -265,15 +265,25 @@ __global__ void mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigne
 
 // ---- host side ----------------------------------------------------------------------------
 
-static int pick_qpt(size_t nq) {
+constexpr unsigned HM_MIN_CHUNK = 32;  // smallest target range per CTA (split granularity 16)
+
+static unsigned qblocks_for(size_t nq, int qpt) {
+    const size_t per = (size_t)HM_THREADS * qpt;
+    return (unsigned)((nq + per - 1) / per);
+}
+
+// queries per thread: least padding first (ties -> more queries per thread), then fewer while the
+// launch could not fill the GPU (small frame-to-frame problems are spread over many small CTAs)
+static int pick_qpt(size_t nq, size_t nt, int sm_count) {
     int best = 1;
     size_t best_pad = ~(size_t)0;
     const int opts[3] = {4, 2, 1};
     for (int k = 0; k < 3; ++k) {
-        const size_t per = (size_t)HM_THREADS * opts[k];
-        const size_t pad = (nq + per - 1) / per * per;
+        const size_t pad = (size_t)qblocks_for(nq, opts[k]) * HM_THREADS * opts[k];
         if (pad < best_pad) { best_pad = pad; best = opts[k]; }
     }
+    const size_t max_splits = (nt + HM_MIN_CHUNK - 1) / HM_MIN_CHUNK;
+    while (best > 1 && (size_t)qblocks_for(nq, best) * max_splits < (size_t)sm_count * 2) best >>= 1;
     return best;
 }
 
@@ -285,12 +295,12 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
         set_error("hamming_top2: sizes exceed 32-bit index range");
         return BSHOT_E_INVALID;
     }
-    const int qpt = pick_qpt(nq);
-    const unsigned qblocks = (unsigned)((nq + (size_t)HM_THREADS * qpt - 1) / ((size_t)HM_THREADS * qpt));
-    const size_t tiles = (nt + HM_TILE - 1) / HM_TILE;
+    const int qpt = pick_qpt(nq, nt, c->sm_count);
+    const unsigned qblocks = qblocks_for(nq, qpt);
+    const size_t max_splits = (nt + HM_MIN_CHUNK - 1) / HM_MIN_CHUNK;
     size_t want = ((size_t)c->sm_count * 4 + qblocks - 1) / qblocks;  // ~4 CTAs per SM in flight
     if (want < 1) want = 1;
-    if (want > tiles) want = tiles ? tiles : 1;
+    if (want > max_splits) want = max_splits ? max_splits : 1;
     const size_t cap_splits = c->partial_cap / (nq * 2);
     if (cap_splits == 0) {
         set_error("hamming_top2: partial buffer too small for %zu queries", nq);
@@ -299,8 +309,8 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     if (want > cap_splits) want = cap_splits;
     if (want > 65535) want = 65535;
     size_t chunk = (nt + want - 1) / want;
-    chunk = (chunk + HM_TILE - 1) / HM_TILE * HM_TILE;
-    if (chunk == 0) chunk = HM_TILE;
+    chunk = (chunk + 15) / 16 * 16;
+    if (chunk < HM_MIN_CHUNK) chunk = HM_MIN_CHUNK;
     if (chunk > (1u << HM_IDX_BITS)) {
         set_error("hamming_top2: %zu targets per split exceed the packed index range", chunk);
         return BSHOT_E_CAPACITY;

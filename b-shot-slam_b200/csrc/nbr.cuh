@@ -1,0 +1,120 @@
+// nbr.cuh -- radius-neighbourhood iteration over the voxel table (device side).
+//
+// A query sphere (p, R) touches a rectangle of (iy,iz) rows; inside one row the needed cells are a
+// contiguous range of the cell-sorted float4 array.  A CTA (or warp) first turns the rows into a
+// list of non-empty SEGMENTS (start,len) + exclusive prefix in shared memory, then strides over the
+// flattened candidate index so that consecutive lanes read consecutive float4s (coalesced, 16 B
+// vector loads) regardless of how ragged the segments are.
+#pragma once
+#include "common.cuh"
+
+namespace bshot {
+
+__host__ __device__ __forceinline__ int cell_coord(float v, float o, float inv) {
+    return (int)floorf((v - o) * inv);
+}
+
+struct RowRange {
+    int iy_lo, iz_lo, ny_span, nrows;
+};
+
+__device__ __forceinline__ RowRange row_range(const GridParams& g, float py, float pz, float R) {
+    RowRange r;
+    const float pad = R + 1e-3f * g.cell;
+    const int iy_lo = max(cell_coord(py - pad, g.oy, g.inv_cell), 0);
+    const int iy_hi = min(cell_coord(py + pad, g.oy, g.inv_cell), g.ny - 1);
+    const int iz_lo = max(cell_coord(pz - pad, g.oz, g.inv_cell), 0);
+    const int iz_hi = min(cell_coord(pz + pad, g.oz, g.inv_cell), g.nz - 1);
+    r.iy_lo = iy_lo;
+    r.iz_lo = iz_lo;
+    r.ny_span = iy_hi - iy_lo + 1;
+    r.nrows = (iy_hi >= iy_lo && iz_hi >= iz_lo) ? r.ny_span * (iz_hi - iz_lo + 1) : 0;
+    return r;
+}
+
+// point range [start,end) of row (iy,iz) that can hold points within R of (px,py,pz); conservative
+__device__ __forceinline__ bool row_segment(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
+                                            float py, float pz, float R, int iy, int iz, unsigned& start,
+                                            unsigned& end) {
+    const float eps = 1e-3f * g.cell;
+    const float y0 = g.oy + (float)iy * g.cell, z0 = g.oz + (float)iz * g.cell;
+    float dy = fmaxf(fmaxf(y0 - py, py - (y0 + g.cell)), 0.0f);
+    float dz = fmaxf(fmaxf(z0 - pz, pz - (z0 + g.cell)), 0.0f);
+    dy = fmaxf(dy - eps, 0.0f);
+    dz = fmaxf(dz - eps, 0.0f);
+    const float rem = R * R - dy * dy - dz * dz;
+    if (rem < 0.0f) return false;
+    const float xr = sqrtf(rem) + eps + R * 1e-6f;
+    const int ix_lo = max(cell_coord(px - xr, g.ox, g.inv_cell), 0);
+    const int ix_hi = min(cell_coord(px + xr, g.ox, g.inv_cell), g.nx - 1);
+    if (ix_lo > ix_hi) return false;
+    const unsigned row = ((unsigned)iz * g.ny + iy) * g.nx;
+    start = __ldg(cell_start + row + ix_lo);
+    end = __ldg(cell_start + row + ix_hi + 1);
+    return end > start;
+}
+
+template <int MAXSEG>
+struct SegList {
+    unsigned start[MAXSEG];
+    unsigned off[MAXSEG + 1];  // exclusive prefix of the lengths (len kept in off[] before the scan)
+    unsigned nseg;
+    unsigned total;
+};
+
+// Build the segment list for rows [row0, row0 + MAXSEG) of the query's row rectangle.
+// All NT threads of the group call it. GROUP_SYNC: functor that synchronises the group.
+template <int NT, int MAXSEG, typename Sync>
+__device__ __forceinline__ void build_segments(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
+                                               float py, float pz, float R, const RowRange& rr, int row0,
+                                               SegList<MAXSEG>& sl, unsigned tid, Sync&& group_sync) {
+    if (tid == 0) sl.nseg = 0;
+    group_sync();
+    const int row1 = min(rr.nrows, row0 + MAXSEG);
+    for (int r = row0 + (int)tid; r < row1; r += NT) {
+        const int iy = rr.iy_lo + r % rr.ny_span;
+        const int iz = rr.iz_lo + r / rr.ny_span;
+        unsigned s, e;
+        if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
+            const unsigned slot = atomicAdd(&sl.nseg, 1u);
+            sl.start[slot] = s;
+            sl.off[slot] = e - s;
+        }
+    }
+    group_sync();
+    // exclusive scan of the lengths by the first 32 threads (nseg <= MAXSEG)
+    if (tid < 32) {
+        const unsigned n = sl.nseg;
+        const unsigned per = (n + 31) / 32;
+        const unsigned b = tid * per, e = min(n, b + per);
+        unsigned s = 0;
+        for (unsigned i = b; i < e; ++i) s += sl.off[i];
+        unsigned inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= (unsigned)o) inc += up;
+        }
+        unsigned run = inc - s;
+        for (unsigned i = b; i < e; ++i) {
+            const unsigned len = sl.off[i];
+            sl.off[i] = run;
+            run += len;
+        }
+        if (tid == 31) { sl.off[n] = inc; sl.total = inc; }
+    }
+    group_sync();
+}
+
+// candidate j of the flattened list -> index into the cell-sorted array
+template <int MAXSEG>
+__device__ __forceinline__ unsigned seg_lookup(const SegList<MAXSEG>& sl, unsigned j) {
+    unsigned lo = 0, hi = sl.nseg;  // find largest s with off[s] <= j
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (sl.off[mid] <= j) lo = mid; else hi = mid;
+    }
+    return sl.start[lo] + (j - sl.off[lo]);
+}
+
+}  // namespace bshot

@@ -1,0 +1,479 @@
+// shot.cu -- SHOT local reference frame, SHOT352 histogram and B-SHOT bits.
+//
+// Replaces bshot::calculate_SHOT (include/bshot_bits.h:113-135; PCL SHOTEstimationOMP +
+// SHOTLocalReferenceFrameEstimation) and bshot::compute_bshot_from_SHOT
+// (include/bshot_bits.h:144-278).  One CTA per keypoint:
+//   phase A  weighted covariance about the keypoint in fp64 (weight R - d), CTA reduce,
+//            3x3 symmetric eigen-solve (cyclic Jacobi, fp64)
+//   phase B  sign disambiguation votes (exact-tie median rule via a CTA-wide radix select)
+//   phase C  quadrilinear interpolation into a 352-float shared-memory histogram (<= 5 atomics
+//            per neighbour), fp64 intermediates like PCL
+//   phase D  L2 normalisation, optional float output, 88 nibbles -> packed 352-bit record
+// The float histogram never has to touch HBM when only the bits are wanted.
+#include "nbr.cuh"
+#include "stages.h"
+
+namespace bshot {
+
+constexpr int SH_THREADS = 128;
+constexpr int SH_WARPS = SH_THREADS / 32;
+constexpr int SH_MAXSEG = 1024;
+
+struct ShotSmem {
+    SegList<SH_MAXSEG> sl;
+    float hist[352];
+    double red[SH_WARPS][8];
+    int redi[SH_WARPS][4];
+    double v1[3], v3[3];
+    float rf[9];
+    unsigned words[12];
+    int valid, count_all;
+    int tie1, tie3;
+    int ok;
+    unsigned cnt;
+    double norm;
+};
+
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (fp64); ascending eigenvalues, columns of V
+__device__ void eigh3_jacobi(const double m[6] /*xx,xy,xz,yy,yz,zz*/, double w[3], double V[3][3]) {
+    double a[3][3] = {{m[0], m[1], m[2]}, {m[1], m[3], m[4]}, {m[2], m[4], m[5]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (!(off > 1e-40 * diag)) break;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = a[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = cs * akp - sn * akq;
+                    a[k][q] = sn * akp + cs * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = cs * apk - sn * aqk;
+                    a[q][k] = sn * apk + cs * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = cs * vkp - sn * vkq;
+                    v[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+        }
+    }
+    int o0 = 0, o1 = 1, o2 = 2;
+    double d0 = a[0][0], d1 = a[1][1], d2 = a[2][2];
+    if (d0 > d1) { double t = d0; d0 = d1; d1 = t; int ti = o0; o0 = o1; o1 = ti; }
+    if (d1 > d2) { double t = d1; d1 = d2; d2 = t; int ti = o1; o1 = o2; o2 = ti; }
+    if (d0 > d1) { double t = d0; d0 = d1; d1 = t; int ti = o0; o0 = o1; o1 = ti; }
+    w[0] = d0; w[1] = d1; w[2] = d2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        V[r][0] = (o0 == 0) ? v[r][0] : (o0 == 1 ? v[r][1] : v[r][2]);
+        V[r][1] = (o1 == 0) ? v[r][0] : (o1 == 1 ? v[r][1] : v[r][2]);
+        V[r][2] = (o2 == 0) ? v[r][0] : (o2 == 1 ? v[r][1] : v[r][2]);
+    }
+}
+
+// include/bshot_bits.h:160-260 : 4 floats -> nibble (bit k = element k)
+__device__ __forceinline__ unsigned bshot_nibble(float v0, float v1, float v2, float v3) {
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(v0, v1), v2), v3);
+    const double t = 0.9 * (double)sum;
+    if (v0 == 0.0f && v1 == 0.0f && v2 == 0.0f && v3 == 0.0f) return 0x0u;
+    if ((double)v0 > t) return 0x1u;
+    if ((double)v1 > t) return 0x2u;
+    if ((double)v2 > t) return 0x4u;
+    if ((double)v3 > t) return 0x8u;
+    if ((double)__fadd_rn(v0, v1) > t) return 0x3u;
+    if ((double)__fadd_rn(v1, v2) > t) return 0x6u;
+    if ((double)__fadd_rn(v2, v3) > t) return 0xCu;
+    if ((double)__fadd_rn(v0, v3) > t) return 0x9u;
+    if ((double)__fadd_rn(v1, v3) > t) return 0xAu;
+    if ((double)__fadd_rn(v0, v2) > t) return 0x5u;
+    if ((double)__fadd_rn(__fadd_rn(v0, v1), v2) > t) return 0x7u;
+    if ((double)__fadd_rn(__fadd_rn(v1, v2), v3) > t) return 0xEu;
+    if ((double)__fadd_rn(__fadd_rn(v0, v2), v3) > t) return 0xDu;
+    if ((double)__fadd_rn(__fadd_rn(v0, v1), v3) > t) return 0xBu;
+    return 0xFu;
+}
+
+// hist (352 floats in smem) -> 12 u32 words (smem) ; threads 0..87 active, all threads sync
+__device__ __forceinline__ void pack_bits_block(const float* hist, unsigned* words, unsigned tid) {
+    if (tid < 12) words[tid] = 0u;
+    __syncthreads();
+    if (tid < 88) {
+        const unsigned nib = bshot_nibble(hist[4 * tid], hist[4 * tid + 1], hist[4 * tid + 2], hist[4 * tid + 3]);
+        if (nib) atomicOr(&words[tid >> 3], nib << ((tid & 7) * 4));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SH_THREADS)
+shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
+            const float4* __restrict__ sorted, const float4* __restrict__ kp, const int* __restrict__ kp_count,
+            const float4* __restrict__ normals, unsigned normals_limit, float radius, int lrf_only,
+            float* __restrict__ rf_out, int* __restrict__ nn_out, float* __restrict__ shot_out,
+            uint64_t* __restrict__ bits_out, unsigned long long* __restrict__ sum_nn) {
+    __shared__ ShotSmem sm;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = blockIdx.x;
+    if (k >= *kp_count) return;
+    const GridParams g = *gp;
+    const float4 q = kp[k];
+    const float R = radius;
+    const float R2 = (float)((double)R * (double)R);
+    const bool q_finite = isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+    const float nanf_ = __int_as_float(0x7FC00000);
+
+    RowRange rr = row_range(g, q.y, q.z, R);
+    if (!q_finite) rr.nrows = 0;
+    bool cached = false;
+    auto sync = [] { __syncthreads(); };
+    auto for_each = [&](auto&& f) {
+        for (int row0 = 0; row0 < rr.nrows; row0 += SH_MAXSEG) {
+            if (!(cached && rr.nrows <= SH_MAXSEG)) {
+                build_segments<SH_THREADS, SH_MAXSEG>(g, cell_start, q.x, q.y, q.z, R, rr, row0, sm.sl, tid, sync);
+                cached = true;
+            }
+            const unsigned total = sm.sl.total;
+            for (unsigned j = tid; j < total; j += SH_THREADS) f(__ldg(sorted + seg_lookup(sm.sl, j)));
+            if (rr.nrows > SH_MAXSEG) __syncthreads();
+        }
+    };
+
+    // ---- phase A: weighted covariance about the keypoint (Appendix A.4) -------------------------
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    int valid = 0, count_all = 0;
+    for_each([&](const float4 p) {
+        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (!(sqd < R2)) return;
+        ++count_all;
+        if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+        const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
+        const double w = (double)R - sqrt((double)sqd);
+        acc[0] += w * (vx * vx); acc[1] += w * (vx * vy); acc[2] += w * (vx * vz);
+        acc[3] += w * (vy * vy); acc[4] += w * (vy * vz); acc[5] += w * (vz * vz);
+        acc[6] += w;
+        ++valid;
+    });
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]);
+    valid = warp_sum(valid);
+    count_all = warp_sum(count_all);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sm.red[wid][i] = acc[i];
+        sm.redi[wid][0] = valid;
+        sm.redi[wid][1] = count_all;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double m[7];
+        int nv = 0, na = 0;
+        for (int i = 0; i < 7; ++i) { m[i] = 0; for (int w = 0; w < SH_WARPS; ++w) m[i] += sm.red[w][i]; }
+        for (int w = 0; w < SH_WARPS; ++w) { nv += sm.redi[w][0]; na += sm.redi[w][1]; }
+        sm.valid = nv;
+        sm.count_all = na;
+        int ok = (nv >= 5) ? 1 : 0;
+        if (ok) {
+            double c[6];
+            for (int i = 0; i < 6; ++i) c[i] = m[i] / m[6];
+            double w[3], V[3][3];
+            eigh3_jacobi(c, w, V);
+            if (!isfinite(w[0]) || !isfinite(w[1]) || !isfinite(w[2])) ok = 0;
+            for (int r = 0; r < 3; ++r) { sm.v1[r] = V[r][2]; sm.v3[r] = V[r][0]; }
+        }
+        sm.ok = ok;
+    }
+    __syncthreads();
+    const int ok = sm.ok;
+    const int n_valid = sm.valid, n_all = sm.count_all;
+
+    // ---- phase B: sign disambiguation ---------------------------------------------------------
+    if (ok) {
+        const double v1x = sm.v1[0], v1y = sm.v1[1], v1z = sm.v1[2];
+        const double v3x = sm.v3[0], v3y = sm.v3[1], v3z = sm.v3[2];
+        int plus_t = 0, plus_n = 0;
+        for_each([&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!(sqd < R2)) return;
+            if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+            const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
+            if (vx * v1x + vy * v1y + vz * v1z >= 0) ++plus_t;
+            if (vx * v3x + vy * v3y + vz * v3z >= 0) ++plus_n;
+        });
+        plus_t = warp_sum(plus_t);
+        plus_n = warp_sum(plus_n);
+        __syncthreads();
+        if (lane == 0) { sm.redi[wid][0] = plus_t; sm.redi[wid][1] = plus_n; }
+        __syncthreads();
+        if (tid == 0) {
+            int pt = 0, pn = 0;
+            for (int w = 0; w < SH_WARPS; ++w) { pt += sm.redi[w][0]; pn += sm.redi[w][1]; }
+            const int st = 2 * pt - n_valid, sn = 2 * pn - n_valid;
+            sm.tie1 = (st == 0);
+            sm.tie3 = (sn == 0);
+            if (st < 0) { sm.v1[0] = -sm.v1[0]; sm.v1[1] = -sm.v1[1]; sm.v1[2] = -sm.v1[2]; }
+            if (sn < 0) { sm.v3[0] = -sm.v3[0]; sm.v3[1] = -sm.v3[1]; sm.v3[2] = -sm.v3[2]; }
+        }
+        __syncthreads();
+        if (sm.tie1 || sm.tie3) {
+            // exact tie: votes of the 5 neighbours at sorted positions median-2..median+2 of the valid
+            // list ordered by (sqd, index).  CTA-wide MSB-first radix select of the two bounding keys.
+            const int median = n_valid / 2;
+            unsigned long long bound[2];
+            for (int which = 0; which < 2; ++which) {
+                unsigned rank = (unsigned)(median + (which ? 2 : -2));
+                unsigned long long prefix = 0;
+                for (int bit = 62; bit >= 0; --bit) {
+                    unsigned c0 = 0;
+                    for_each([&](const float4 p) {
+                        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                        if (!(sqd < R2)) return;
+                        if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(sqd) << 32) | __float_as_uint(p.w);
+                        if ((key >> (bit + 1)) == (prefix >> (bit + 1)) && !((key >> bit) & 1ull)) ++c0;
+                    });
+                    c0 = (unsigned)warp_sum((int)c0);
+                    __syncthreads();
+                    if (tid == 0) sm.cnt = 0;
+                    __syncthreads();
+                    if (lane == 0) atomicAdd(&sm.cnt, c0);
+                    __syncthreads();
+                    const unsigned tot0 = sm.cnt;
+                    if (rank >= tot0) { rank -= tot0; prefix |= (1ull << bit); }
+                }
+                bound[which] = prefix;
+            }
+            const double a1x = sm.v1[0], a1y = sm.v1[1], a1z = sm.v1[2];
+            const double a3x = sm.v3[0], a3y = sm.v3[1], a3z = sm.v3[2];
+            int p1 = 0, p3 = 0;
+            for_each([&](const float4 p) {
+                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (!(sqd < R2)) return;
+                if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(sqd) << 32) | __float_as_uint(p.w);
+                if (key < bound[0] || key > bound[1]) return;
+                const double vx = (double)__fsub_rn(p.x, q.x), vy = (double)__fsub_rn(p.y, q.y), vz = (double)__fsub_rn(p.z, q.z);
+                if (vx * a1x + vy * a1y + vz * a1z > 0) ++p1;
+                if (vx * a3x + vy * a3y + vz * a3z > 0) ++p3;
+            });
+            p1 = warp_sum(p1);
+            p3 = warp_sum(p3);
+            __syncthreads();
+            if (lane == 0) { sm.redi[wid][0] = p1; sm.redi[wid][1] = p3; }
+            __syncthreads();
+            if (tid == 0) {
+                int c1 = 0, c3 = 0;
+                for (int w = 0; w < SH_WARPS; ++w) { c1 += sm.redi[w][0]; c3 += sm.redi[w][1]; }
+                if (sm.tie1 && c1 < 3) { sm.v1[0] = -sm.v1[0]; sm.v1[1] = -sm.v1[1]; sm.v1[2] = -sm.v1[2]; }
+                if (sm.tie3 && c3 < 3) { sm.v3[0] = -sm.v3[0]; sm.v3[1] = -sm.v3[1]; sm.v3[2] = -sm.v3[2]; }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        if (ok) {
+            const float x0 = (float)sm.v1[0], x1 = (float)sm.v1[1], x2 = (float)sm.v1[2];
+            const float z0 = (float)sm.v3[0], z1 = (float)sm.v3[1], z2 = (float)sm.v3[2];
+            sm.rf[0] = x0; sm.rf[1] = x1; sm.rf[2] = x2;
+            sm.rf[6] = z0; sm.rf[7] = z1; sm.rf[8] = z2;
+            sm.rf[3] = __fsub_rn(__fmul_rn(z1, x2), __fmul_rn(z2, x1));  // y = z x x in fp32
+            sm.rf[4] = __fsub_rn(__fmul_rn(z2, x0), __fmul_rn(z0, x2));
+            sm.rf[5] = __fsub_rn(__fmul_rn(z0, x1), __fmul_rn(z1, x0));
+        } else {
+            for (int i = 0; i < 9; ++i) sm.rf[i] = nanf_;
+        }
+    }
+    __syncthreads();
+    if (tid < 9) rf_out[(size_t)k * 9 + tid] = sm.rf[tid];
+    if (tid == 0) {
+        nn_out[k] = lrf_only ? n_valid : n_all;
+        if (!lrf_only) atomicAdd(sum_nn, (unsigned long long)n_all);
+    }
+    if (lrf_only) return;
+
+    // ---- phase C: SHOT352 quadrilinear histogram (Appendix A.5) ---------------------------------
+    for (unsigned i = tid; i < 352; i += SH_THREADS) sm.hist[i] = 0.0f;
+    __syncthreads();
+    const bool describe = ok && n_all >= 5;
+    if (describe) {
+        const float fx0 = sm.rf[0], fx1 = sm.rf[1], fx2 = sm.rf[2];
+        const float fy0 = sm.rf[3], fy1 = sm.rf[4], fy2 = sm.rf[5];
+        const float fz0 = sm.rf[6], fz1 = sm.rf[7], fz2 = sm.rf[8];
+        const double radius3_4 = ((double)R * 3) / 4, radius1_4 = (double)R / 4, radius1_2 = (double)R / 2;
+        const double RAD_45 = 0.78539816339744830961566084581988, RAD_90 = 1.5707963267948966192313216916398;
+        const double RAD_135 = 2.3561944901923449288469825374596, RAD_PI_7_8 = 2.7488935718910690836548129603691;
+        float* hist = sm.hist;
+        for_each([&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!(sqd < R2)) return;
+            const unsigned sidx = __float_as_uint(p.w);
+            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sidx < normals_limit) nv = __ldg(normals + sidx);
+            if (!isfinite(nv.x) || !isfinite(nv.y) || !isfinite(nv.z)) return;
+            double cosine = (double)dot3_rn(nv.x, nv.y, nv.z, fz0, fz1, fz2);
+            if (cosine > 1.0) cosine = 1.0;
+            if (cosine < -1.0) cosine = -1.0;
+            double bin = ((1.0 + cosine) * 10) / 2;
+            const double distance = sqrt((double)sqd);
+            if (fabs(distance) < 1e-15) return;
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            double xr = (double)dot3_rn(dx, dy, dz, fx0, fx1, fx2);
+            double yr = (double)dot3_rn(dx, dy, dz, fy0, fy1, fy2);
+            double zr = (double)dot3_rn(dx, dy, dz, fz0, fz1, fz2);
+            if (fabs(yr) < 1E-30) yr = 0;
+            if (fabs(xr) < 1E-30) xr = 0;
+            if (fabs(zr) < 1E-30) zr = 0;
+            const int bit4 = ((yr > 0) || ((yr == 0.0) && (xr < 0))) ? 1 : 0;
+            const int bit3 = ((xr > 0) || ((xr == 0.0) && (yr > 0))) ? !bit4 : bit4;
+            int desc_index = ((bit4 << 3) + (bit3 << 2)) << 1;
+            if ((xr * yr > 0) || (xr == 0.0)) desc_index += (fabs(xr) >= fabs(yr)) ? 0 : 4;
+            else desc_index += (fabs(xr) > fabs(yr)) ? 4 : 0;
+            desc_index += zr > 0 ? 1 : 0;
+            desc_index += (distance > radius1_2) ? 2 : 0;
+            const int step_index = (int)floor(bin + 0.5);
+            const int volume_index = desc_index * 11;
+            bin -= step_index;
+            double w = 1 - fabs(bin);
+            {
+                const float fb = (float)bin;
+                if (bin > 0) { if (fb != 0.0f) atomicAdd(&hist[volume_index + ((step_index + 1) % 10)], fb); }
+                else { if (fb != 0.0f) atomicAdd(&hist[volume_index + ((step_index - 1 + 10) % 10)], -fb); }
+            }
+            if (distance > radius1_2) {
+                const double rd = (distance - radius3_4) / radius1_2;
+                if (distance > radius3_4) w += 1 - rd;
+                else { w += 1 + rd; atomicAdd(&hist[(desc_index - 2) * 11 + step_index], -(float)rd); }
+            } else {
+                const double rd = (distance - radius1_4) / radius1_2;
+                if (distance < radius1_4) w += 1 + rd;
+                else { w += 1 - rd; atomicAdd(&hist[(desc_index + 2) * 11 + step_index], (float)rd); }
+            }
+            double inc_cos = zr / distance;
+            if (inc_cos < -1.0) inc_cos = -1.0;
+            if (inc_cos > 1.0) inc_cos = 1.0;
+            const double inc = acos(inc_cos);
+            if (inc > RAD_90 || (fabs(inc - RAD_90) < 1e-30 && zr <= 0)) {
+                const double id = (inc - RAD_135) / RAD_90;
+                if (inc > RAD_135) w += 1 - id;
+                else { w += 1 + id; atomicAdd(&hist[(desc_index + 1) * 11 + step_index], -(float)id); }
+            } else {
+                const double id = (inc - RAD_45) / RAD_90;
+                if (inc < RAD_45) w += 1 + id;
+                else { w += 1 - id; atomicAdd(&hist[(desc_index - 1) * 11 + step_index], (float)id); }
+            }
+            if (yr != 0.0 || xr != 0.0) {
+                const double azimuth = atan2(yr, xr);
+                const int sel = desc_index >> 2;
+                double ad = (azimuth - (-RAD_PI_7_8 + RAD_45 * sel)) / RAD_45;
+                ad = fmax(-0.5, fmin(ad, 0.5));
+                if (ad > 0) {
+                    w += 1 - ad;
+                    atomicAdd(&hist[((desc_index + 4) % 32) * 11 + step_index], (float)ad);
+                } else {
+                    w += 1 + ad;
+                    atomicAdd(&hist[((desc_index - 4 + 32) % 32) * 11 + step_index], -(float)ad);
+                }
+            }
+            atomicAdd(&hist[volume_index + step_index], (float)w);
+        });
+    }
+    __syncthreads();
+
+    // ---- phase D: normalise, emit, binarise ----------------------------------------------------
+    {
+        double part = 0.0;
+        for (unsigned i = tid; i < 352; i += SH_THREADS) part += (double)__fmul_rn(sm.hist[i], sm.hist[i]);
+        part = warp_sum(part);
+        if (lane == 0) sm.red[wid][0] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0;
+            for (int w = 0; w < SH_WARPS; ++w) s += sm.red[w][0];
+            sm.norm = sqrt(s);
+        }
+        __syncthreads();
+        const float f = (float)sm.norm;
+        for (unsigned i = tid; i < 352; i += SH_THREADS) {
+            float v = describe ? (sm.hist[i] / f) : nanf_;
+            sm.hist[i] = v;
+            if (shot_out) shot_out[(size_t)k * 352 + i] = v;
+        }
+        __syncthreads();
+        pack_bits_block(sm.hist, sm.words, tid);
+        if (tid < 6) bits_out[(size_t)k * 6 + tid] = ((uint64_t)sm.words[2 * tid + 1] << 32) | sm.words[2 * tid];
+    }
+}
+
+// standalone binarisation of caller-provided SHOT floats: one warp per descriptor
+__global__ void __launch_bounds__(128)
+binarize_kernel(const float* __restrict__ shot, unsigned k, uint64_t* __restrict__ bits) {
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= k) return;
+    const float4* s4 = reinterpret_cast<const float4*>(shot + (size_t)warp * 352);
+    unsigned nib[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const unsigned j = r * 32 + lane;
+        if (j < 88) {
+            const float4 v = __ldg(s4 + j);
+            nib[r] = bshot_nibble(v.x, v.y, v.z, v.w);
+        }
+    }
+    // word w (8 nibbles) = nibbles 8w..8w+7 ; lanes 8a..8a+7 of round r hold word 4r + a
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        unsigned v = nib[r] << ((lane & 7) * 4);
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        nib[r] = v;  // every lane of an 8-group holds the group's word
+    }
+    // words 0..10 (+ word 11 = 0): lane l < 6 assembles u64 l from words 2l, 2l+1
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        // word index 4r + a lives in lanes 8a..8a+7
+        for (int a = 0; a < 4; ++a) {
+            const unsigned wv = __shfl_sync(0xffffffffu, nib[r], 8 * a);
+            const int widx = 4 * r + a;
+            if (widx == 2 * (int)lane) lo = wv;
+            if (widx == 2 * (int)lane + 1) hi = wv;
+        }
+    }
+    if (lane < 6) bits[(size_t)warp * 6 + lane] = ((uint64_t)hi << 32) | lo;
+}
+
+int shot_compute(Ctx* c, float radius, bool lrf_only, bool write_shot) {
+    const size_t k = c->n_kp;
+    if (k == 0) return BSHOT_OK;
+    if (!lrf_only) BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_sum_nn, 0, sizeof(unsigned long long), c->stream));
+    const unsigned limit = (unsigned)std::min(c->normals_valid, c->n_points);
+    shot_kernel<<<(unsigned)k, SH_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count,
+                                                          c->d_normals, limit, radius, lrf_only ? 1 : 0, c->d_rf, c->d_nn,
+                                                          write_shot ? c->d_shot : nullptr, c->d_bits, c->d_sum_nn);
+    count_launch(c);
+    return check_launch("shot_kernel");
+}
+
+int binarize(Ctx* c, const float* d_shot, size_t k, uint64_t* d_bits) {
+    if (k == 0) return BSHOT_OK;
+    const unsigned blocks = (unsigned)((k * 32 + 127) / 128);
+    binarize_kernel<<<blocks, 128, 0, c->stream>>>(d_shot, (unsigned)k, d_bits);
+    count_launch(c);
+    return check_launch("binarize_kernel");
+}
+
+}  // namespace bshot

@@ -5,7 +5,7 @@
  * FFI layer: control enters the path through C++ member calls on `class bshot`
  * (include/bshot_bits.h:30-281) made by LidarOdometry::extractKeypoints / computeDescriptors /
  * featureMatching (src/lidar_odometry.cpp:51,173,186).  Every entry point below names the
- * reference code it replaces.  The reference-named host C++ shims (b-shot-slam_b200/host/*.h:
+ * reference code it replaces.  The reference-named host C++ shims (headers under b-shot-slam_b200/host:
  * `bshot`, `bshot_descriptor`, `minVect`, `Frame`, `Keypoint`, `Map`) forward to this ABI; see
  * INTEGRATION.md.
  *
@@ -79,6 +79,10 @@ void bshot_ctx_destroy(bshot_ctx* ctx);
 /* the context's cudaStream_t (for CUDA-event timing by the caller) */
 void* bshot_ctx_stream(bshot_ctx* ctx);
 int bshot_ctx_sync(bshot_ctx* ctx);
+/* forget all cross-frame state, as if `cb` were freshly constructed: the persistent normals array
+ * (include/bshot_bits.h:59 resize keeps old entries), the previous frame's descriptors and the
+ * map shard.  The cloud, keypoints and capacity stay. */
+int bshot_ctx_reset(bshot_ctx* ctx);
 
 /* ---- a1: cloud upload + voxel-hash build -------------------------------------------------- */
 /* replaces LidarOdometry::setSrcFrame (src/lidar_odometry.cpp:29-41) + `cb.cloud1 = src_pcl_`

@@ -1,0 +1,238 @@
+"""a1-a7 parity: CUDA front end (through the C ABI) vs the oracle on seeded synthetic scans.
+
+Tolerances (BASELINE.json north_star): LRF within 1e-4; >= 99.9 % of B-SHOT bits identical on
+identical inputs; neighbour counts exact (integer work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R = 3000.0
+
+
+@pytest.fixture(scope="module")
+def scan(synth):
+    return synth.make_scan("hdl32e", 0)
+
+
+@pytest.fixture(scope="module")
+def ocloud(oracle, scan):
+    return oracle.Cloud(scan)
+
+
+@pytest.fixture(scope="module")
+def keypoints(oracle, ocloud, scan):
+    ratio = ocloud.seg_ratio(R, 300, oracle.SR_CV)
+    idx, rat = oracle.select_keypoints(ratio, 600, oracle.TIE_DETERMINISTIC)
+    return idx, rat, ratio
+
+
+def test_binarize_truth_table(gpu_ctx, oracle):
+    # every branch of include/bshot_bits.h:166-260 on hand-built 4-vectors, NaN => 0xF, zeros => 0x0
+    groups = [
+        [0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1],
+        [.5, .5, 0, 0], [0, .5, .5, 0], [0, 0, .5, .5], [.5, 0, 0, .5], [0, .5, 0, .5], [.5, 0, .5, 0],
+        [.34, .33, .33, 0], [0, .33, .34, .33], [.33, 0, .33, .34], [.33, .34, 0, .33],
+        [.25, .25, .25, .25], [np.nan, 0, 0, 0], [np.nan] * 4, [0.91, 0.03, 0.03, 0.03],
+        [0.9, 0.1, 0, 0], [-1, 0, 0, 0], [1e-30, 0, 0, 0], [0.45, 0.46, 0.05, 0.04],
+    ]
+    expect = [0x0, 0x1, 0x2, 0x4, 0x8, 0x3, 0x6, 0xC, 0x9, 0xA, 0x5, 0x7, 0xE, 0xD, 0xB, 0xF, 0xF, 0xF,
+              0x1, None, None, 0x1, 0x3]
+    shot = np.zeros((len(groups), 352), np.float32)
+    for i, gvals in enumerate(groups):
+        shot[i, 4 * (i % 88): 4 * (i % 88) + 4] = gvals
+    ob = oracle.bshot(shot)
+    gb = gpu_ctx.binarize(shot)
+    assert np.array_equal(ob, gb)
+    for i, e in enumerate(expect):
+        if e is None:
+            continue
+        j = i % 88
+        nib = (int(gb[i, (4 * j) // 64]) >> ((4 * j) % 64)) & 0xF
+        assert nib == e, (i, groups[i], hex(nib))
+
+
+def test_binarize_random_and_stride(gpu_ctx, oracle):
+    rng = np.random.default_rng(3)
+    shot = rng.random((700, 361)).astype(np.float32)
+    shot[rng.random(shot.shape) < 0.6] = 0.0           # sparse like real SHOT
+    shot[5] = np.nan                                    # invalid descriptor -> all 352 bits set
+    gb = gpu_ctx.binarize(shot, stride_floats=361)     # pcl::SHOT352 layout (descriptor[352], rf[9])
+    ob = oracle.bshot(np.ascontiguousarray(shot[:, :352]))
+    assert np.array_equal(gb, ob)
+    assert gb[5, 0] == np.uint64(0xFFFFFFFFFFFFFFFF) and gb[5, 5] == np.uint64(0xFFFFFFFF)
+
+
+def test_lrf_parity(gpu_ctx, ocloud, scan, keypoints):
+    idx, _, _ = keypoints
+    kp = scan[idx]
+    gpu_ctx.set_cloud(scan)
+    gpu_ctx.set_keypoints(kp)
+    rf_g, valid_g = gpu_ctx.compute_lrf(R)
+    rf_o, valid_o = ocloud.lrf(kp, R)
+    assert np.array_equal(valid_g, valid_o)            # integer neighbour counts: exact
+    nan_g, nan_o = np.isnan(rf_g).any(1), np.isnan(rf_o).any(1)
+    assert np.array_equal(nan_g, nan_o)
+    ok = ~nan_o
+    assert np.abs(rf_g[ok] - rf_o[ok]).max() <= 1e-4
+    # orthonormal, right-handed
+    x, y, z = rf_g[ok, 0:3], rf_g[ok, 3:6], rf_g[ok, 6:9]
+    assert np.abs(np.einsum("ij,ij->i", x, z)).max() < 1e-5
+    assert np.abs(np.cross(z, x) - y).max() < 1e-6
+
+
+def test_lrf_xyzw_stride_and_outside_keypoints(gpu_ctx, ocloud, scan):
+    # pcl::PointXYZ layout (16 B) and keypoints that are not surface points / far away (NaN frame)
+    xyzw = np.concatenate([scan, np.ones((scan.shape[0], 1), np.float32)], axis=1)
+    gpu_ctx.set_cloud(xyzw)
+    kp = np.array([[1e6, 1e6, 1e6], [5000.5, 14000.25, 100.125], [-20000.0, -14900.0, 2000.0]], np.float32)
+    gpu_ctx.set_keypoints(kp)
+    rf_g, valid_g = gpu_ctx.compute_lrf(R)
+    rf_o, valid_o = ocloud.lrf(kp, R)
+    assert np.array_equal(valid_g, valid_o)
+    assert np.isnan(rf_g[0]).all() and np.isnan(rf_o[0]).all()
+    ok = ~np.isnan(rf_o).any(1)
+    assert np.array_equal(ok, ~np.isnan(rf_g).any(1))
+    assert np.abs(rf_g[ok] - rf_o[ok]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["reference", "full"])
+def test_shot_bits_identical_inputs(gpu_ctx, oracle, synth, ocloud, scan, keypoints, mode):
+    """SHOT352 + B-SHOT given the SAME keypoints and the SAME normals array."""
+    idx, _, _ = keypoints
+    kp = scan[idx]
+    if mode == "reference":
+        od = ocloud.compute_descriptors(kp, R, 300, oracle.MODE_REFERENCE, want_normals=True)
+        normals = od["normals"]
+    else:
+        # per-surface-point normals of a subsample radius (cheap for the oracle), FULL layout
+        normals = ocloud.normals(scan, 600.0, 60)
+        shot, rf, nn, total = ocloud.shot(kp, normals, R)
+        od = dict(shot=shot, rf=rf, bits=oracle.bshot(shot), sum_neighbours=total)
+    gpu_ctx.set_cloud(scan)
+    gpu_ctx.set_keypoints(kp)
+    gpu_ctx.set_normals(normals)
+    g = gpu_ctx.compute_shot(R, want_shot=True)
+    assert g["sum_neighbours"] == od["sum_neighbours"]
+    nan_o = np.isnan(od["shot"]).any(1)
+    assert np.array_equal(np.isnan(g["shot"]).any(1), nan_o)
+    ok = ~nan_o
+    assert np.abs(g["rf"][ok] - od["rf"][ok]).max() <= 1e-4
+    assert np.abs(g["shot"][ok] - od["shot"][ok]).max() <= 2e-5
+    bg, bo = synth.unpack_bits(g["bits"]), synth.unpack_bits(od["bits"])
+    same = (bg == bo).mean()
+    assert same >= 0.999, same
+    # padding bits 352..383 stay zero; NaN descriptors are all ones
+    assert (g["bits"][:, 5] >> np.uint64(32) == 0).all()
+    if nan_o.any():
+        assert bg[nan_o].all()
+
+
+def test_normals_plane_and_parity_near_origin(gpu_ctx, oracle):
+    """analytic: points on a tilted plane => normal = plane normal; near-origin cloud => fp32
+    single-pass covariance is well conditioned, so GPU and oracle agree tightly."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    uv = rng.uniform(-4000, 4000, (n, 2))
+    nrm = np.array([0.3, -0.2, 0.933], np.float64)
+    nrm /= np.linalg.norm(nrm)
+    e1 = np.cross(nrm, [1, 0, 0]); e1 /= np.linalg.norm(e1)
+    e2 = np.cross(nrm, e1)
+    pts = (uv[:, :1] * e1 + uv[:, 1:] * e2 + nrm * 700.0 + rng.normal(0, 2.0, (n, 1)) * nrm).astype(np.float32)
+    oc = oracle.Cloud(pts)
+    gpu_ctx.set_cloud(pts)
+    q = pts[:500]
+    ng = gpu_ctx.query_normals(q, 800.0, 300)
+    no = oc.normals(q, 800.0, 300)
+    assert not np.isnan(ng).any()
+    cosang = np.abs(ng[:, :3] @ nrm)
+    assert cosang.min() > 0.9995
+    # flipped towards the origin (viewpoint 0,0,0)
+    assert (np.einsum("ij,ij->i", ng[:, :3], -q) >= 0).all()
+    assert np.abs(ng[:, :3] - no[:, :3]).max() < 2e-2
+    assert np.median(np.abs(ng[:, :3] - no[:, :3]).max(1)) < 1e-3
+
+
+def test_normals_reference_placement(gpu_ctx, ocloud, scan, keypoints):
+    """include/bshot_bits.h:58-59,79-81: keypoint normal i lands at surface index i, rest (0,0,0)."""
+    idx, _, _ = keypoints
+    kp = scan[idx]
+    gpu_ctx.reset()                                    # fresh `bshot cb`: normals array all zero
+    gpu_ctx.set_cloud(scan)
+    gpu_ctx.set_keypoints(kp)
+    ng = gpu_ctx.compute_normals(0, R, 300)
+    k = len(kp)
+    assert (ng[k:] == 0).all()
+    no = ocloud.normals(kp, R, 300)
+    assert np.array_equal(np.isnan(ng[:k]).any(1), np.isnan(no).any(1))
+    # fp32 single-pass covariance at |x| ~ 1e4..7e4 mm is ill conditioned in the reference itself:
+    # compare directions loosely here; tight parity is covered near the origin above
+    cosang = np.abs(np.einsum("ij,ij->i", ng[:k, :3], no[:, :3]))
+    assert np.median(cosang) > 0.999
+
+
+def test_seg_ratio_and_topk(gpu_ctx, oracle, scan, keypoints):
+    idx_o, rat_o, ratio_o = keypoints
+    gpu_ctx.set_cloud(scan)
+    ratio_g = gpu_ctx.seg_ratio(R, 300, 0)
+    assert np.array_equal(np.isnan(ratio_g), np.isnan(ratio_o))
+    ok = ~np.isnan(ratio_o)
+    diff = np.abs(ratio_g[ok] - ratio_o[ok])
+    # counts are integers: a centroid that differs in the last ulps flips at most a vote or two
+    assert (diff == 0).mean() > 0.97, (diff == 0).mean()
+    assert diff.max() < 0.05
+    idx_g, rat_g, xyz_g = gpu_ctx.detect_keypoints(R, 300, 0, 600)
+    assert len(idx_g) == 600
+    assert np.array_equal(xyz_g, scan[idx_g])
+    assert np.array_equal(rat_g, ratio_g[idx_g])
+    assert (np.diff(rat_g) >= 0).all()                 # ascending ratio like the reference's slice
+    # deterministic tie-break == oracle's deterministic mode applied to the GPU's own ratios
+    idx_d, rat_d = oracle.select_keypoints(ratio_g, 600, oracle.TIE_DETERMINISTIC)
+    assert np.array_equal(idx_g, idx_d)
+    # everything strictly above the oracle's K-th ratio must be selected by both
+    kth = rat_o[0]
+    must = set(np.nonzero(ok & (ratio_o > kth + 0.05))[0].tolist())
+    assert must <= set(idx_g.tolist())
+
+
+@pytest.mark.parametrize("sr_type", [1, 2])
+def test_seg_ratio_cvs_cvsn(gpu_ctx, oracle, sr_type):
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-6000, 6000, (6000, 3)).astype(np.float32)
+    pts[:, 2] *= 0.2
+    pts[17] = 0.0                                      # the origin is skipped (:63)
+    oc = oracle.Cloud(pts)
+    gpu_ctx.set_cloud(pts)
+    rg = gpu_ctx.seg_ratio(1500.0, 50, sr_type)
+    ro = oc.seg_ratio(1500.0, 50, sr_type)
+    assert np.isnan(rg[17]) and np.isnan(ro[17])
+    ok = ~np.isnan(ro)
+    assert np.array_equal(np.isnan(rg), np.isnan(ro))
+    assert np.allclose(rg[ok], ro[ok], rtol=2e-4, atol=1e-3 if sr_type == 1 else 1e-6)
+
+
+def test_compute_descriptors_end_to_end(gpu_ctx, bshot, oracle, synth, ocloud, scan, keypoints):
+    """LidarOdometry::computeDescriptors (src/lidar_odometry.cpp:173-184) in REFERENCE mode."""
+    idx, _, _ = keypoints
+    kp = scan[idx]
+    od = ocloud.compute_descriptors(kp, R, 300, oracle.MODE_REFERENCE)
+    gpu_ctx.reset()
+    gpu_ctx.set_cloud(scan)
+    gpu_ctx.set_keypoints(kp)
+    bits = gpu_ctx.compute_descriptors(bshot.default_params())
+    same = (synth.unpack_bits(bits) == synth.unpack_bits(od["bits"])).mean()
+    assert same >= 0.999, same
+
+
+def test_process_frame_sequence(gpu_ctx, bshot, oracle, synth):
+    """two frames through bshot_process_frame: frame 0 self-match, frame 1 vs frame 0; the
+    correspondences must equal the oracle matcher applied to the GPU's own descriptors."""
+    p = bshot.default_params(top_k=600)
+    with bshot.Context(0, 131072, 4096, 8192) as ctx:
+        f0 = ctx.process_frame(synth.make_scan("hdl32e", 0), p)
+        f1 = ctx.process_frame(synth.make_scan("hdl32e", 1), p)
+    assert len(f0["bits"]) == 600 and len(f1["bits"]) == 600
+    m0 = oracle.match(f0["bits"], f0["bits"])
+    assert np.array_equal(f0["pairs"], oracle.mutual(m0["left_idx"], m0["right_idx"]))
+    m1 = oracle.match(f1["bits"], f0["bits"])
+    assert np.array_equal(f1["pairs"], oracle.mutual(m1["left_idx"], m1["right_idx"]))
