@@ -27,7 +27,8 @@ EXPORTS = [
     "bshot_detect_keypoints", "bshot_seg_ratio", "bshot_set_keypoints", "bshot_compute_normals",
     "bshot_query_normals", "bshot_set_normals", "bshot_compute_shot", "bshot_compute_lrf",
     "bshot_binarize", "bshot_compute_descriptors", "bshot_match", "bshot_match_mutual",
-    "bshot_process_frame", "bshot_process_frame_resident", "bshot_map_reset", "bshot_map_append",
+    "bshot_process_frame", "bshot_process_frame_dev", "bshot_fetch_frame", "bshot_ctx_enable_timing",
+    "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_launch_count", "bshot_popc_peak",
 ]
@@ -86,7 +87,11 @@ def lib():
         L.bshot_match.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, vp, vp]
         L.bshot_match_mutual.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp]
         L.bshot_process_frame.argtypes = [vp, C.POINTER(Params), vp, sz, sz, vp, vp, vp, vp, vp]
-        L.bshot_process_frame_resident.argtypes = [vp, C.POINTER(Params)]
+        L.bshot_process_frame_dev.argtypes = [vp, C.POINTER(Params), vp, sz, sz]
+        L.bshot_fetch_frame.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+        L.bshot_ctx_enable_timing.argtypes = [vp, ci]
+        L.bshot_stage_times.argtypes = [vp, C.POINTER(C.c_float * 8)]
+        L.bshot_frame_counters.argtypes = [vp, C.POINTER(C.c_ulonglong * 4)]
         L.bshot_map_reset.argtypes = [vp]
         L.bshot_map_append.argtypes = [vp, vp, sz]
         L.bshot_map_size.argtypes = [vp, C.POINTER(sz)]
@@ -296,8 +301,33 @@ class Context:
                                        bits_ptr, C.byref(nk), pairs_ptr, C.byref(npairs)))
         return nk.value, npairs.value
 
-    def process_frame_resident(self, params):
-        _chk(lib().bshot_process_frame_resident(self.h, C.byref(params)))
+    def process_frame_dev(self, d_xyz_ptr, n, stride_bytes, params):
+        """device-resident cloud (raw device pointer), asynchronous on the context stream"""
+        _chk(lib().bshot_process_frame_dev(self.h, C.byref(params), d_xyz_ptr, n, stride_bytes))
+
+    def fetch_frame(self, top_k):
+        kp_idx = np.empty(top_k, np.int32)
+        bits = np.empty((top_k, 6), np.uint64)
+        pairs = np.empty((top_k, 2), np.int32)
+        nk, npairs = C.c_int(), C.c_int()
+        _chk(lib().bshot_fetch_frame(self.h, top_k, _p(kp_idx), _p(bits), C.byref(nk), _p(pairs), C.byref(npairs)))
+        self.n_kp = nk.value
+        return dict(kp_idx=kp_idx[:nk.value].copy(), bits=bits[:nk.value].copy(), pairs=pairs[:npairs.value].copy())
+
+    def enable_timing(self, on=True):
+        _chk(lib().bshot_ctx_enable_timing(self.h, int(on)))
+
+    def stage_times(self):
+        a = (C.c_float * 8)()
+        _chk(lib().bshot_stage_times(self.h, C.byref(a)))
+        names = ["voxel_build", "seg_ratio", "topk", "normals", "shot_bshot", "match", "frame"]
+        return {k: float(a[i]) for i, k in enumerate(names)}
+
+    def frame_counters(self):
+        a = (C.c_ulonglong * 4)()
+        _chk(lib().bshot_frame_counters(self.h, C.byref(a)))
+        return dict(detector_neighbours=int(a[0]), normals_neighbours=int(a[1]), shot_neighbours=int(a[2]),
+                    keypoints=int(a[3]))
 
     # sharded map
     def map_reset(self):

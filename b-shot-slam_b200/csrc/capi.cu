@@ -161,6 +161,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_right, T));
     A(dmalloc(&c->d_pairs, K * 3));
     A(dmalloc(&c->d_pair_count, 4));
+    A(dmalloc(&c->d_counters, 8));
     if (r == BSHOT_OK && cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(int)) != cudaSuccess) {
         set_error("cudaMallocHost failed");
         r = BSHOT_E_CUDA;
@@ -170,6 +171,9 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
         cudaError_t e = cudaMemsetAsync(c->d_normals, 0, sizeof(float4) * N, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_prev_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_kp_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_sum_nn, 0, 2 * sizeof(unsigned long long), c->stream);
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { set_error("context init failed: %s", cudaGetErrorString(e)); r = BSHOT_E_CUDA; }
     }
@@ -189,10 +193,12 @@ void bshot_ctx_destroy(bshot_ctx* c) {
                     c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
-                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count};
+                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    for (int i = 0; i < 8; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -230,7 +236,7 @@ int bshot_set_cloud(bshot_ctx* ctx, const float* xyz, size_t n, size_t stride_by
     if (stride_bytes != 12 && stride_bytes != 16) { set_error("bshot_set_cloud: stride must be 12 or 16 bytes"); return BSHOT_E_INVALID; }
     if (n > ctx->max_points) { set_error("bshot_set_cloud: %zu points > capacity %zu", n, ctx->max_points); return BSHOT_E_CAPACITY; }
     BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
-    BSHOT_TRY(grid_build(ctx, n, (int)(stride_bytes / 4)));
+    BSHOT_TRY(grid_build(ctx, ctx->d_raw, n, (int)(stride_bytes / 4)));
     return sync(ctx);
 }
 
@@ -436,31 +442,30 @@ int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint6
 }
 
 // ---- whole frame --------------------------------------------------------------------------------
-int bshot_process_frame_resident(bshot_ctx* ctx, const bshot_params* p) {
-    CHECK_CTX(ctx);
-    bshot_params dp;
-    if (!p) { bshot_params_default(&dp); p = &dp; }
-    if (!ctx->have_cloud) { set_error("bshot_process_frame_resident: no cloud"); return BSHOT_E_STATE; }
-    if (p->top_k <= 0 || (size_t)p->top_k > ctx->max_kp) { set_error("top_k %d outside (0, %zu]", p->top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
-    return frame_run(ctx, p);
+static int frame_args_ok(bshot_ctx* ctx, const bshot_params* p, size_t n, size_t stride_bytes, const char* who) {
+    if (stride_bytes != 12 && stride_bytes != 16) { set_error("%s: stride must be 12 or 16 bytes", who); return BSHOT_E_INVALID; }
+    if (n > ctx->max_points) { set_error("%s: %zu points > capacity %zu", who, n, ctx->max_points); return BSHOT_E_CAPACITY; }
+    if (p->top_k <= 0 || (size_t)p->top_k > ctx->max_kp) { set_error("%s: top_k %d outside (0, %zu]", who, p->top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    return BSHOT_OK;
 }
 
-int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n, size_t stride_bytes,
-                        int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out, int* n_pairs_out) {
+int bshot_process_frame_dev(bshot_ctx* ctx, const bshot_params* p, const void* d_xyz, size_t n, size_t stride_bytes) {
     CHECK_CTX(ctx);
     bshot_params dp;
     if (!p) { bshot_params_default(&dp); p = &dp; }
-    if (!xyz && n) { set_error("bshot_process_frame: null cloud"); return BSHOT_E_INVALID; }
-    if (stride_bytes != 12 && stride_bytes != 16) { set_error("bshot_process_frame: stride must be 12 or 16 bytes"); return BSHOT_E_INVALID; }
-    if (n > ctx->max_points) { set_error("bshot_process_frame: %zu points > capacity %zu", n, ctx->max_points); return BSHOT_E_CAPACITY; }
-    if (p->top_k <= 0 || (size_t)p->top_k > ctx->max_kp) { set_error("top_k %d outside (0, %zu]", p->top_k, ctx->max_kp); return BSHOT_E_CAPACITY; }
-    BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
-    BSHOT_TRY(grid_build(ctx, n, (int)(stride_bytes / 4)));
-    BSHOT_TRY(frame_run(ctx, p));
-    // one small D2H for the counts, then the payload
+    if (!d_xyz && n) { set_error("bshot_process_frame_dev: null cloud"); return BSHOT_E_INVALID; }
+    BSHOT_TRY(frame_args_ok(ctx, p, n, stride_bytes, "bshot_process_frame_dev"));
+    return frame_run(ctx, p, reinterpret_cast<const float*>(d_xyz), n, (int)(stride_bytes / 4));
+}
+
+int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out,
+                      int* n_pairs_out) {
+    CHECK_CTX(ctx);
+    if (top_k <= 0 || (size_t)top_k > ctx->max_kp) { set_error("bshot_fetch_frame: bad top_k"); return BSHOT_E_INVALID; }
+    const size_t kmax = (size_t)top_k;
+    // counts + payload in one stream-ordered batch, a single synchronisation
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[1], ctx->d_pair_count, sizeof(int)));
-    const size_t kmax = (size_t)p->top_k;
     BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * kmax));
     BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * kmax));
     std::vector<int> tmp;
@@ -475,6 +480,48 @@ int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz,
     if (n_pairs_out) *n_pairs_out = np;
     if (pairs_out)
         for (int i = 0; i < np; ++i) { pairs_out[2 * i] = tmp[3 * i]; pairs_out[2 * i + 1] = tmp[3 * i + 1]; }
+    return BSHOT_OK;
+}
+
+int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n, size_t stride_bytes,
+                        int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out, int* n_pairs_out) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (!xyz && n) { set_error("bshot_process_frame: null cloud"); return BSHOT_E_INVALID; }
+    BSHOT_TRY(frame_args_ok(ctx, p, n, stride_bytes, "bshot_process_frame"));
+    BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
+    BSHOT_TRY(frame_run(ctx, p, ctx->d_raw, n, (int)(stride_bytes / 4)));
+    return bshot_fetch_frame(ctx, p->top_k, kp_idx_out, bits_out, n_kp_out, pairs_out, n_pairs_out);
+}
+
+int bshot_ctx_enable_timing(bshot_ctx* ctx, int on) {
+    CHECK_CTX(ctx);
+    ctx->timing = on != 0;
+    ctx->ev_valid = false;
+    return BSHOT_OK;
+}
+
+int bshot_stage_times(bshot_ctx* ctx, float ms_out[8]) {
+    CHECK_CTX(ctx);
+    if (!ms_out) { set_error("bshot_stage_times: null output"); return BSHOT_E_INVALID; }
+    if (!ctx->ev_valid) { set_error("bshot_stage_times: no timed frame (call bshot_ctx_enable_timing first)"); return BSHOT_E_STATE; }
+    BSHOT_TRY(sync(ctx));
+    for (int i = 0; i < 6; ++i) BSHOT_CUDA_TRY(cudaEventElapsedTime(&ms_out[i], ctx->ev[i], ctx->ev[i + 1]));
+    BSHOT_CUDA_TRY(cudaEventElapsedTime(&ms_out[6], ctx->ev[0], ctx->ev[6]));
+    ms_out[7] = 0.0f;
+    return BSHOT_OK;
+}
+
+int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]) {
+    CHECK_CTX(ctx);
+    if (!out) { set_error("bshot_frame_counters: null output"); return BSHOT_E_INVALID; }
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(&ctx->h_scratch[32]);
+    BSHOT_TRY(d2h(ctx, h, ctx->d_counters, 2 * sizeof(unsigned long long)));
+    BSHOT_TRY(d2h(ctx, h + 2, ctx->d_sum_nn, sizeof(unsigned long long)));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = (unsigned long long)ctx->h_scratch[0];
     return BSHOT_OK;
 }
 

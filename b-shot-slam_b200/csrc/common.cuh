@@ -105,6 +105,12 @@ struct Ctx {
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints
+
+    // instrumentation
+    unsigned long long* d_counters = nullptr;  // 8 work counters (see bshot_frame_counters)
+    bool timing = false;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
 };
 
 inline void count_launch(Ctx* c, unsigned n = 1) { c->launches += n; }

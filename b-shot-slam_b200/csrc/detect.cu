@@ -18,7 +18,8 @@ constexpr int DT_THREADS = DT_WARPS * 32;
 __global__ void __launch_bounds__(DT_THREADS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, unsigned n_total, float radius, int max_nn, int sr_type,
-                 float* __restrict__ ratio, unsigned long long* __restrict__ keys) {
+                 float* __restrict__ ratio, unsigned long long* __restrict__ keys,
+                 unsigned long long* __restrict__ counters) {
     __shared__ KnnWarpSmem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned j = blockIdx.x * DT_WARPS + wid;
@@ -79,6 +80,7 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
         seg = fabsf((float)sum) / fn;
     }
     if (lane == 0) {
+        atomicAdd(&counters[0], (unsigned long long)res.count);
         ratio[qi] = seg;
         keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
     }
@@ -181,7 +183,7 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
     mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys);
     seg_ratio_kernel<<<(n + DT_WARPS - 1) / DT_WARPS, DT_THREADS, 0, c->stream>>>(
-        c->d_grid, c->d_cell_start, c->d_sorted, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys);
+        c->d_grid, c->d_cell_start, c->d_sorted, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters);
     count_launch(c, 2);
     return check_launch("seg_ratio_kernel");
 }

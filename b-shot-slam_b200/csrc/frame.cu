@@ -13,11 +13,22 @@ __global__ void copy_prev_kernel(const uint64_t* __restrict__ bits, const int* _
     if (i == 0) *prev_count = k;
 }
 
-int frame_run(Ctx* c, const bshot_params* p) {
+int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats) {
+    auto mark = [&](int i) {
+        if (c->timing) cudaEventRecord(c->ev[i], c->stream);
+    };
+    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    mark(0);
+    BSHOT_TRY(grid_build(c, d_raw, n, stride_floats));
+    mark(1);
     BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type));
+    mark(2);
     BSHOT_TRY(detect_topk(c, p->top_k));
+    mark(3);
     BSHOT_TRY(normals_compute(c, p->normals_mode, p->normal_radius, p->normal_max_nn));
+    mark(4);
     BSHOT_TRY(shot_compute(c, p->shot_radius, false, false));
+    mark(5);
     // featureMatching: the initial frame is matched against itself (src/lidar_odometry.cpp:187-194),
     // later frames against the previous frame's descriptors.  Host-side counts are upper bounds
     // (top_k); kernels read the device-side counts.
@@ -31,6 +42,8 @@ int frame_run(Ctx* c, const bshot_params* p) {
     copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp_count, (unsigned)k,
                                                                             c->d_prev_bits, c->d_prev_count);
     count_launch(c);
+    mark(6);
+    c->ev_valid = c->timing;
     c->n_prev = k;
     return check_launch("copy_prev_kernel");
 }

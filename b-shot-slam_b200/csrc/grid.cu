@@ -227,11 +227,11 @@ scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __res
     sorted[pos] = p;
 }
 
-int grid_build(Ctx* c, size_t n, int stride_floats) {
+int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
     const unsigned nn = (unsigned)n;
     const unsigned pb = (nn + GB_THREADS - 1) / GB_THREADS;
     bbox_init_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox);
-    if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
+    if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
     grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->d_grid);
     zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor);
     if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor);

@@ -102,7 +102,7 @@ __device__ void eigen33_smallest(const float mat[9], float& eigenvalue, float ev
 __global__ void __launch_bounds__(NM_THREADS)
 normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                const float4* __restrict__ sorted, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
-               float radius, int max_nn, float4* out) {
+               float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters) {
     __shared__ KnnWarpSmem smem[NM_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned j = blockIdx.x * NM_WARPS + wid;
@@ -135,6 +135,7 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
         }
     }
     if (lane != 0) return;
+    atomicAdd(&counters[1], (unsigned long long)n);
     float4 o = make_float4(nanf_, nanf_, nanf_, nanf_);
     if (finite && n >= 3) {  // n == 0: include/bshot_bits.h:67-74 ; n < 3: computePointNormal guard
         const float fn = (float)n;
@@ -171,7 +172,7 @@ int normals_query(Ctx* c, const float4* d_q, size_t nq, float radius, int max_nn
     if (nq == 0) return BSHOT_OK;
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
     normals_kernel<<<(unsigned)((nq + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-        c->d_grid, c->d_cell_start, c->d_sorted, d_q, nullptr, (unsigned)nq, radius, max_nn, d_out);
+        c->d_grid, c->d_cell_start, c->d_sorted, d_q, nullptr, (unsigned)nq, radius, max_nn, d_out, c->d_counters);
     count_launch(c);
     return check_launch("normals_kernel");
 }
@@ -185,7 +186,7 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
             normals_kernel<<<(unsigned)((k + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-                c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count, (unsigned)k, radius, max_nn, c->d_qnormals);
+                c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count, (unsigned)k, radius, max_nn, c->d_qnormals, c->d_counters);
             place_normals_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(c->d_qnormals, c->d_kp_count, (unsigned)k,
                                                                                      c->d_normals);
             count_launch(c, 2);

@@ -5,7 +5,7 @@
 namespace bshot {
 
 // a1: caller layout in d_raw (stride 3 or 4 floats) -> d_pts, voxel grid, d_sorted   (grid.cu)
-int grid_build(Ctx* c, size_t n, int stride_floats);
+int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats);
 
 // a2/a3: seg-ratio for every point -> d_ratio, d_keys ; top-K -> d_kp_idx/d_kp_ratio/d_kp/d_kp_count (detect.cu)
 int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type);
@@ -30,6 +30,6 @@ int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pai
 int popc_peak(Ctx* c, double* out);
 
 // whole frame on the resident cloud (frame.cu)
-int frame_run(Ctx* c, const bshot_params* p);
+int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);
 
 }  // namespace bshot

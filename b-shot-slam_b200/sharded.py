@@ -1,0 +1,91 @@
+"""Host logic of the sharded frame-to-map Hamming search (north_star multi-GPU piece).
+
+The accumulated map descriptors (what Map::getKeypoints, src/mymap.cpp:28-74, hands to
+featureMatching, src/lidar_odometry.cpp:197-206) are split into contiguous index ranges, one per
+rank.  Per call: every rank matches the (replicated) query set against its resident shard with
+GLOBAL target indices, the per-rank candidate records {k1, k2, rq} (24 B/query) are all-gathered,
+and a merge by (distance, global index) reproduces the single-GPU first-minimum rule bit for bit.
+`rq` (best query for the rank's best target) rides along, so the mutual check needs no second
+exchange.
+
+The compute back end is injected: production uses the C ABI on the GPU (gpu_backend), the CPU
+gloo tests inject an oracle-based back end from tests/ -- this module never imports the oracle.
+"""
+import numpy as np
+
+CAND_DTYPE = np.dtype([("k1", "<u8"), ("k2", "<u8"), ("rq", "<u4"), ("pad", "<u4")])
+NONE_KEY = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def shard_range(total, world, rank):
+    """contiguous split: rank r holds [r * ceil(T/G), min(T, (r+1) * ceil(T/G)))"""
+    per = (total + world - 1) // world
+    lo = min(total, rank * per)
+    return lo, min(total, lo + per)
+
+
+def merge_records(gathered):
+    """numpy mirror of merge_cands_kernel (csrc/hamming.cu): gathered (ranks, Q) records -> (Q,)"""
+    g = np.asarray(gathered)
+    ranks, q = g.shape
+    keys = np.concatenate([g["k1"], g["k2"]], axis=0)                  # (2R, Q)
+    order = np.sort(keys, axis=0)
+    out = np.zeros(q, CAND_DTYPE)
+    out["k1"], out["k2"] = order[0], order[1] if 2 * ranks > 1 else NONE_KEY
+    win = np.argmin(g["k1"], axis=0)                                   # first minimum = lowest rank
+    out["rq"] = g["rq"][win, np.arange(q)]
+    out["rq"][out["k1"] == NONE_KEY] = 0xFFFFFFFF
+    return out
+
+
+class ShardedMap:
+    """one rank's view of the sharded map"""
+
+    def __init__(self, backend, rank=0, world=1, all_gather=None):
+        self.backend, self.rank, self.world = backend, rank, world
+        self.all_gather = all_gather            # callable(local (Q,) records) -> (world, Q) records
+        self.lo = self.hi = 0
+
+    def load(self, global_map):
+        """keep this rank's contiguous shard of the global descriptor array resident"""
+        self.lo, self.hi = shard_range(len(global_map), self.world, self.rank)
+        self.backend.set_shard(global_map[self.lo:self.hi])
+
+    def match(self, queries):
+        local = self.backend.match_shard(queries, self.lo)             # (Q,) records, global indices
+        if self.world == 1 or self.all_gather is None:
+            return self.backend.merge(local[None, :])
+        return self.backend.merge(self.all_gather(local))
+
+    @staticmethod
+    def correspondences(merged):
+        """mutual-NN filter (src/lidar_odometry.cpp:234-242) from merged records"""
+        q = np.arange(len(merged))
+        keep = (merged["k1"] != NONE_KEY) & (merged["rq"] == q)
+        idx = (merged["k1"] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        return np.stack([q[keep], idx[keep]], axis=1).astype(np.int32)
+
+
+class GpuBackend:
+    """production back end: bshot_map_append / bshot_match_map / bshot_merge_cands_dev (C ABI)"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def set_shard(self, desc):
+        self.ctx.map_reset()
+        self.ctx.map_append(desc)
+
+    def match_shard(self, queries, global_base):
+        return self.ctx.match_map(queries, global_base)
+
+    def merge(self, gathered):
+        import torch
+        g = np.ascontiguousarray(gathered)
+        ranks, q = g.shape
+        d = torch.from_numpy(g.view(np.int64).reshape(ranks, q, 3)).cuda()
+        out = torch.empty((q, 3), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        self.ctx.merge_cands_dev(d.data_ptr(), ranks, q, out.data_ptr())
+        self.ctx.sync()
+        return out.cpu().numpy().view(CAND_DTYPE).reshape(q)

@@ -144,16 +144,21 @@ int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint6
                        int* pairs_out, int* dist_out, int* count_out);
 
 /* ---- whole frame (the reference's extractKeypoints -> computeDescriptors -> featureMatching) */
-/* Runs detector, normals, SHOT, B-SHOT on `xyz` and matches the new descriptors against the
- * previous frame's descriptors kept in the context (first frame: against itself,
- * src/lidar_odometry.cpp:187-194).  One H2D copy in, one D2H copy out.  Outputs may be NULL.
- * pairs_out: up to top_k (query,match) pairs. */
+/* Runs voxel build, detector, normals, SHOT, B-SHOT on `xyz` and matches the new descriptors
+ * against the previous frame's descriptors kept in the context (first frame: against itself,
+ * src/lidar_odometry.cpp:187-194), i.e. test/odometry_test.cpp:174-180 up to the RANSAC call.
+ * One H2D copy in, one D2H copy out.  Outputs may be NULL.  kp_idx_out / bits_out hold up to
+ * p->top_k records, pairs_out up to top_k (query,match) pairs. */
 int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n,
                         size_t stride_bytes, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out,
                         int* pairs_out, int* n_pairs_out);
-/* same work on the cloud already resident in the context (after bshot_set_cloud); asynchronous,
- * no host copies -- the kernel-only timing leg of bench.py. */
-int bshot_process_frame_resident(bshot_ctx* ctx, const bshot_params* p);
+/* same work on a cloud that is already in device memory (d_xyz: device pointer); asynchronous on
+ * the context stream, no host copies -- the HBM-resident timing leg of bench.py. */
+int bshot_process_frame_dev(bshot_ctx* ctx, const bshot_params* p, const void* d_xyz, size_t n,
+                            size_t stride_bytes);
+/* download the results of the last bshot_process_frame_dev (synchronous) */
+int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out,
+                      int* pairs_out, int* n_pairs_out);
 
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
@@ -188,6 +193,15 @@ int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t globa
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this library launched on the context since creation (bench.py gpu_launches) */
 unsigned long long bshot_launch_count(bshot_ctx* ctx);
+/* per-stage device times of whole-frame calls.  When enabled, CUDA events are recorded on the
+ * context stream around each stage; bshot_stage_times synchronises and returns the LAST frame's
+ * milliseconds: [0] voxel build, [1] seg-ratio, [2] top-K, [3] normals, [4] SHOT+B-SHOT,
+ * [5] matching, [6] whole frame, [7] unused. */
+int bshot_ctx_enable_timing(bshot_ctx* ctx, int on);
+int bshot_stage_times(bshot_ctx* ctx, float ms_out[8]);
+/* work counters of the last frame: [0] sum over points of min(#neighbours, max_nn) in the detector,
+ * [1] same for the normals queries, [2] sum of SHOT neighbour counts, [3] keypoints */
+int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]);
 /* POPC-pipe microbenchmark: returns measured POPC32 instructions/s over the whole GPU */
 int bshot_popc_peak(bshot_ctx* ctx, double* popc_per_s_out);
 
