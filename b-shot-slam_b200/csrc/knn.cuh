@@ -19,9 +19,10 @@ namespace bshot {
 constexpr int KN_MAXSEG = 640;   // rows of the largest query rectangle kept per warp
 constexpr int KN_BINS = 256;
 constexpr int KN_LIST = 256;
+constexpr int KN_MAXB = 512;     // batch table covers 16384 candidates per query
 
 struct KnnWarpSmem {
-    SegList<KN_MAXSEG> sl;
+    SegList<KN_MAXSEG, KN_MAXB> sl;
     unsigned hist[KN_BINS];
     unsigned long long list[KN_LIST];
     unsigned list_n;
@@ -48,7 +49,7 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
     auto sync = [] { __syncwarp(); };
     for (int row0 = 0; row0 < rr.nrows; row0 += KN_MAXSEG) {
         if (!(cached && rr.nrows <= KN_MAXSEG)) {
-            build_segments<32, KN_MAXSEG>(g, cell_start, q.x, q.y, q.z, rho, rr, row0, sm.sl, lane, sync);
+            build_segments<32, KN_MAXSEG, KN_MAXB>(g, cell_start, q.x, q.y, q.z, rho, rr, row0, sm.sl, lane, sync);
             cached = true;
         }
         const unsigned total = sm.sl.total;

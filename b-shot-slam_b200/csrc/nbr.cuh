@@ -54,20 +54,21 @@ __device__ __forceinline__ bool row_segment(const GridParams& g, const unsigned*
     return end > start;
 }
 
-template <int MAXSEG>
+template <int MAXSEG, int MAXB = 2048>
 struct SegList {
     unsigned start[MAXSEG];
     unsigned off[MAXSEG + 1];  // exclusive prefix of the lengths (len kept in off[] before the scan)
+    unsigned short bseg[MAXB]; // segment that holds flattened candidate 32 * b (one search per 32 lanes)
     unsigned nseg;
     unsigned total;
 };
 
 // Build the segment list for rows [row0, row0 + MAXSEG) of the query's row rectangle.
 // All NT threads of the group call it. GROUP_SYNC: functor that synchronises the group.
-template <int NT, int MAXSEG, typename Sync>
+template <int NT, int MAXSEG, int MAXB, typename Sync>
 __device__ __forceinline__ void build_segments(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
                                                float py, float pz, float R, const RowRange& rr, int row0,
-                                               SegList<MAXSEG>& sl, unsigned tid, Sync&& group_sync) {
+                                               SegList<MAXSEG, MAXB>& sl, unsigned tid, Sync&& group_sync) {
     if (tid == 0) sl.nseg = 0;
     group_sync();
     const int row1 = min(rr.nrows, row0 + MAXSEG);
@@ -104,17 +105,40 @@ __device__ __forceinline__ void build_segments(const GridParams& g, const unsign
         if (tid == 31) { sl.off[n] = inc; sl.total = inc; }
     }
     group_sync();
+    // batch table: segment of every 32nd candidate, so the per-candidate lookup is a short walk
+    {
+        const unsigned nb = min((sl.total + 31u) >> 5, (unsigned)MAXB);
+        const unsigned nseg = sl.nseg;
+        for (unsigned b = tid; b < nb; b += NT) {
+            const unsigned j = b << 5;
+            unsigned lo = 0, hi = nseg;
+            while (hi - lo > 1) {
+                const unsigned mid = (lo + hi) >> 1;
+                if (sl.off[mid] <= j) lo = mid; else hi = mid;
+            }
+            sl.bseg[b] = (unsigned short)lo;
+        }
+    }
+    group_sync();
 }
 
 // candidate j of the flattened list -> index into the cell-sorted array
-template <int MAXSEG>
-__device__ __forceinline__ unsigned seg_lookup(const SegList<MAXSEG>& sl, unsigned j) {
-    unsigned lo = 0, hi = sl.nseg;  // find largest s with off[s] <= j
-    while (hi - lo > 1) {
-        const unsigned mid = (lo + hi) >> 1;
-        if (sl.off[mid] <= j) lo = mid; else hi = mid;
+template <int MAXSEG, int MAXB>
+__device__ __forceinline__ unsigned seg_lookup(const SegList<MAXSEG, MAXB>& sl, unsigned j) {
+    const unsigned b = j >> 5;
+    unsigned s;
+    if (b < (unsigned)MAXB) {
+        s = sl.bseg[b];
+        while (sl.off[s + 1] <= j) ++s;  // at most the segments that start inside this batch of 32
+    } else {                             // beyond the table: plain binary search
+        unsigned lo = 0, hi = sl.nseg;
+        while (hi - lo > 1) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (sl.off[mid] <= j) lo = mid; else hi = mid;
+        }
+        s = lo;
     }
-    return sl.start[lo] + (j - sl.off[lo]);
+    return sl.start[s] + (j - sl.off[s]);
 }
 
 }  // namespace bshot

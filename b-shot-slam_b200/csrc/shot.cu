@@ -18,9 +18,10 @@ namespace bshot {
 constexpr int SH_THREADS = 128;
 constexpr int SH_WARPS = SH_THREADS / 32;
 constexpr int SH_MAXSEG = 1024;
+constexpr int SH_MAXB = 2048;  // batch table covers 65536 candidates per keypoint
 
 struct ShotSmem {
-    SegList<SH_MAXSEG> sl;
+    SegList<SH_MAXSEG, SH_MAXB> sl;
     float hist[352];
     double red[SH_WARPS][8];
     int redi[SH_WARPS][4];
@@ -143,7 +144,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     auto for_each = [&](auto&& f) {
         for (int row0 = 0; row0 < rr.nrows; row0 += SH_MAXSEG) {
             if (!(cached && rr.nrows <= SH_MAXSEG)) {
-                build_segments<SH_THREADS, SH_MAXSEG>(g, cell_start, q.x, q.y, q.z, R, rr, row0, sm.sl, tid, sync);
+                build_segments<SH_THREADS, SH_MAXSEG, SH_MAXB>(g, cell_start, q.x, q.y, q.z, R, rr, row0, sm.sl, tid, sync);
                 cached = true;
             }
             const unsigned total = sm.sl.total;

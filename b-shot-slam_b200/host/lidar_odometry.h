@@ -1,0 +1,116 @@
+// lidar_odometry.h -- the three front-end stage methods of the reference's LidarOdometry
+// (include/lidar_odometry.h:22-25, src/lidar_odometry.cpp:51-265) over the B200 C ABI.  Only the hot
+// path is here: RANSAC rejection, ICP, pose bookkeeping and the viewer stay in the reference's own
+// CPU code and consume `corresp` exactly as before.
+#ifndef BSHOT_B200_HOST_LIDAR_ODOMETRY_H
+#define BSHOT_B200_HOST_LIDAR_ODOMETRY_H
+
+#include "bshot_bits.h"
+#include "frame.h"
+#include "mymap.h"
+
+namespace myslam {
+
+class LidarOdometry {
+public:
+    enum STATUS { INITIAL, RUN };
+    explicit LidarOdometry(int device = 0) : cb(device), status_(INITIAL), sr_type_("CV"), top_k_(600) {}
+
+    void setSrcFrame(Frame::Ptr src) {  // src/lidar_odometry.cpp:29-41
+        src_ = src;
+        Frame::PCPtr p = src_->getPointCloud();
+        src_pcl_.clear();
+        src_pcl_.points.resize(p->size());
+        for (size_t i = 0; i < p->size(); ++i) src_pcl_.points[i] = pcl::PointXYZ((*p)[i][0], (*p)[i][1], (*p)[i][2]);
+        src_pcl_.width = (uint32_t)p->size(); src_pcl_.height = 1;
+    }
+    void passSrc2Ref() { ref_ = src_; ref_pcl_ = src_pcl_; }
+    bool isInitial() { return status_ == INITIAL; }
+    void setSRType(std::string t) { sr_type_ = t; }
+    void setTopK(int k) { top_k_ = k; }
+    void setRun() { status_ = RUN; }
+
+    void extractKeypoints() {  // :51-162 (ISS detection :164-170 is evaluation only and not part of the path)
+        bshot_ctx* ctx = cb.context();
+        const int sr = sr_type_ == "CVS" ? BSHOT_SR_CVS : (sr_type_ == "CVSN" ? BSHOT_SR_CVSN : BSHOT_SR_CV);
+        cb.cloud1 = src_pcl_;
+        last_status_ = bshot_set_cloud(ctx, src_pcl_.points.empty() ? nullptr : src_pcl_.points[0].data, src_pcl_.size(), 16);
+        std::vector<int> idx(top_k_);
+        std::vector<float> ratio(top_k_), xyz(3 * (size_t)top_k_);
+        int k = 0;
+        if (last_status_ == BSHOT_OK)
+            last_status_ = bshot_detect_keypoints(ctx, 3000.0f, 300, sr, top_k_, idx.data(), ratio.data(), xyz.data(), &k);
+        auto kps = std::make_shared<std::vector<Vector3f>>();
+        seg_ratios_.assign(ratio.begin(), ratio.begin() + k);
+        for (int i = 0; i < k; ++i) kps->push_back(Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+        src_->setKeypoints(kps);
+        if (isInitial()) { passSrc2Ref(); ref_->setKeypoints(src_->getKeypoints()); }
+        cb.cloud2 = ref_pcl_;
+        cb.cloud1_keypoints = eigen2pcl(src_->getKeypoints());
+        cb.cloud2_keypoints = eigen2pcl(ref_->getKeypoints());
+    }
+
+    void computeDescriptors() {  // :173-184
+        cb.calculate_normals(3000);
+        cb.calculate_SHOT(3000);
+        cb.compute_bshot();
+        auto d = std::make_shared<std::vector<std::bitset<352>>>();
+        d->reserve(cb.cloud1_bshot.size());
+        for (auto& it : cb.cloud1_bshot) d->push_back(it.bits);
+        src_->setDescriptors(d);
+    }
+
+    void featureMatching() {  // :186-242 ; RANSAC (:251-261) is the caller's next step on `corresp`
+        if (isInitial()) {
+            passSrc2Ref();
+            ref_->setKeypoints(src_->getKeypoints());
+            cb.cloud2 = ref_pcl_;
+            cb.cloud2_bshot = cb.cloud1_bshot;
+            cb.cloud2_keypoints = eigen2pcl(ref_->getKeypoints());
+        } else {
+            Vector3f pos = ref_->getPose().translation();
+            globalMap_.getKeypoints(pos, 100000, cb.cloud2_keypoints, cb.cloud2_bshot);
+            Matrix4f T = ref_->getPose();
+            for (auto& p : *ref_->getKeypoints()) { Vector3f w = T.apply(p); cb.cloud2_keypoints.push_back(pcl::PointXYZ(w[0], w[1], w[2])); }
+            for (auto& b : *ref_->getDescriptors()) { bshot_descriptor d; d.bits = b; cb.cloud2_bshot.push_back(d); }
+        }
+        const size_t nq = cb.cloud1_bshot.size(), nt = cb.cloud2_bshot.size();
+        std::vector<int> pairs(2 * nq + 2);
+        int n = 0;
+        last_status_ = bshot_match_mutual(cb.context(), reinterpret_cast<const uint64_t*>(cb.cloud1_bshot.data()), nq,
+                                          reinterpret_cast<const uint64_t*>(cb.cloud2_bshot.data()), nt, pairs.data(), nullptr, &n);
+        corresp.clear();
+        for (int i = 0; i < n; ++i) {
+            pcl::Correspondence c;
+            c.index_query = pairs[2 * i];
+            c.index_match = pairs[2 * i + 1];
+            corresp.push_back(c);
+        }
+    }
+
+    pcl::PointCloud<pcl::PointXYZ> eigen2pcl(Frame::PCPtr pc) {
+        pcl::PointCloud<pcl::PointXYZ> out;
+        if (pc) for (auto& p : *pc) out.push_back(pcl::PointXYZ(p[0], p[1], p[2]));
+        return out;
+    }
+    Frame::Ptr getRefFrame() { return ref_; }
+    Frame::Ptr getSrcFrame() { return src_; }
+    Map& map() { return globalMap_; }
+    int last_status() const { return last_status_ != BSHOT_OK ? last_status_ : cb.last_status(); }
+
+    bshot cb;
+    pcl::Correspondences corresp;   // output of featureMatching, input of the reference's RANSAC rejector
+    std::vector<float> seg_ratios_;
+
+private:
+    Frame::Ptr ref_, src_;
+    pcl::PointCloud<pcl::PointXYZ> ref_pcl_, src_pcl_;
+    STATUS status_;
+    std::string sr_type_;
+    int top_k_;
+    Map globalMap_;
+    int last_status_ = BSHOT_OK;
+};
+
+}  // namespace myslam
+#endif
