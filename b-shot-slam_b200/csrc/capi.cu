@@ -522,6 +522,15 @@ int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]) {
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
     BSHOT_TRY(sync(ctx));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = (unsigned long long)ctx->h_scratch[0];
+#ifdef BSHOT_TILE_STATS
+    {
+        unsigned long long dbg[8];
+        cudaMemcpy(dbg, ctx->d_counters, sizeof(dbg), cudaMemcpyDeviceToHost);
+        unsigned left = 0;
+        cudaMemcpy(&left, reinterpret_cast<unsigned*>(ctx->d_kp_count) + 2, 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tile stats] groups=%llu lanes=%llu grow_passes=%llu sum_total=%llu leftover=%u\n", dbg[4], dbg[7], dbg[6], dbg[5], left);
+    }
+#endif
     return BSHOT_OK;
 }
 

@@ -16,10 +16,10 @@
 
 namespace bshot {
 
-constexpr int KN_MAXSEG = 640;   // rows of the largest query rectangle kept per warp
+constexpr int KN_MAXSEG = 400;   // rows of the largest query rectangle kept per warp
 constexpr int KN_BINS = 256;
 constexpr int KN_LIST = 256;
-constexpr int KN_MAXB = 512;     // batch table covers 16384 candidates per query
+constexpr int KN_MAXB = 256;     // batch table covers 8192 candidates per query
 
 struct KnnWarpSmem {
     SegList<KN_MAXSEG, KN_MAXB> sl;
@@ -53,7 +53,18 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
             cached = true;
         }
         const unsigned total = sm.sl.total;
-        for (unsigned j = lane; j < total; j += 32) f(__ldg(sorted + seg_lookup(sm.sl, j)));
+        // 4 independent candidate loads in flight per lane before the first use
+        for (unsigned j = lane; j < total; j += 32 * 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned ju = j + 32u * u;
+                p[u] = __ldg(sorted + seg_lookup(sm.sl, ju < total ? ju : j));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + 32u * u < total) f(p[u]);
+        }
         __syncwarp();
     }
 }
@@ -69,14 +80,22 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
     int n = 0;
     bool cached = false;
     RowRange rr;
-    // ---- 1. grow the sphere ---------------------------------------------------------------------
-    for (int m = 1;; m *= 2) {
+    // ---- 1. grow the sphere: rho = cell, 2 cell, 3 cell ... until it holds >= max_nn points ----------
+    auto sync = [] { __syncwarp(); };
+    for (int m = 1;; ++m) {
         const float g_m = (float)m * g.cell * 0.9999f;
         const bool last = (max_nn <= 0) || !(g_m < R);
         rho = last ? R : g_m;
         rho2 = last ? R2 : __fmul_rn(rho, rho);
         rr = row_range(g, q.y, q.z, rho);
         cached = false;
+        if (rr.nrows <= KN_MAXSEG) {
+            // cheap necessary condition first: the candidate rows must hold at least max_nn points
+            const unsigned total = enumerate_segments<32>(g, cell_start, q.x, q.y, q.z, rho, rr, 0, sm.sl, lane, sync);
+            if (!last && total < (unsigned)max_nn) continue;
+            finish_segments<32>(sm.sl, lane, sync);
+            cached = true;
+        }
         int cnt = 0;
         knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
             if (sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z) < rho2) ++cnt;

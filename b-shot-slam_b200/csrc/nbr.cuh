@@ -63,27 +63,9 @@ struct SegList {
     unsigned total;
 };
 
-// Build the segment list for rows [row0, row0 + MAXSEG) of the query's row rectangle.
-// All NT threads of the group call it. GROUP_SYNC: functor that synchronises the group.
+// exclusive scan of the segment lengths (kept in off[]) + batch table. All NT threads call.
 template <int NT, int MAXSEG, int MAXB, typename Sync>
-__device__ __forceinline__ void build_segments(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
-                                               float py, float pz, float R, const RowRange& rr, int row0,
-                                               SegList<MAXSEG, MAXB>& sl, unsigned tid, Sync&& group_sync) {
-    if (tid == 0) sl.nseg = 0;
-    group_sync();
-    const int row1 = min(rr.nrows, row0 + MAXSEG);
-    for (int r = row0 + (int)tid; r < row1; r += NT) {
-        const int iy = rr.iy_lo + r % rr.ny_span;
-        const int iz = rr.iz_lo + r / rr.ny_span;
-        unsigned s, e;
-        if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
-            const unsigned slot = atomicAdd(&sl.nseg, 1u);
-            sl.start[slot] = s;
-            sl.off[slot] = e - s;
-        }
-    }
-    group_sync();
-    // exclusive scan of the lengths by the first 32 threads (nseg <= MAXSEG)
+__device__ __forceinline__ void finish_segments(SegList<MAXSEG, MAXB>& sl, unsigned tid, Sync&& group_sync) {
     if (tid < 32) {
         const unsigned n = sl.nseg;
         const unsigned per = (n + 31) / 32;
@@ -120,6 +102,56 @@ __device__ __forceinline__ void build_segments(const GridParams& g, const unsign
         }
     }
     group_sync();
+}
+
+// Enumerate the non-empty row segments of rows [row0, row0 + MAXSEG) of the query's row rectangle
+// (start[] and the lengths in off[]); returns the number of candidate points. All NT threads call;
+// NT == 32 only (the total is a warp reduction).
+template <int NT, int MAXSEG, int MAXB, typename Sync>
+__device__ __forceinline__ unsigned enumerate_segments(const GridParams& g, const unsigned* __restrict__ cell_start,
+                                                       float px, float py, float pz, float R, const RowRange& rr, int row0,
+                                                       SegList<MAXSEG, MAXB>& sl, unsigned tid, Sync&& group_sync) {
+    static_assert(NT == 32, "enumerate_segments returns a warp-reduced total");
+    if (tid == 0) sl.nseg = 0;
+    group_sync();
+    const int row1 = min(rr.nrows, row0 + MAXSEG);
+    unsigned mine = 0;
+    for (int r = row0 + (int)tid; r < row1; r += NT) {
+        const int iy = rr.iy_lo + r % rr.ny_span;
+        const int iz = rr.iz_lo + r / rr.ny_span;
+        unsigned s, e;
+        if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
+            const unsigned slot = atomicAdd(&sl.nseg, 1u);
+            sl.start[slot] = s;
+            sl.off[slot] = e - s;
+            mine += e - s;
+        }
+    }
+    group_sync();
+    return (unsigned)warp_sum((int)mine);
+}
+
+// Build the segment list for rows [row0, row0 + MAXSEG) of the query's row rectangle.
+// All NT threads of the group call it. GROUP_SYNC: functor that synchronises the group.
+template <int NT, int MAXSEG, int MAXB, typename Sync>
+__device__ __forceinline__ void build_segments(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
+                                               float py, float pz, float R, const RowRange& rr, int row0,
+                                               SegList<MAXSEG, MAXB>& sl, unsigned tid, Sync&& group_sync) {
+    if (tid == 0) sl.nseg = 0;
+    group_sync();
+    const int row1 = min(rr.nrows, row0 + MAXSEG);
+    for (int r = row0 + (int)tid; r < row1; r += NT) {
+        const int iy = rr.iy_lo + r % rr.ny_span;
+        const int iz = rr.iz_lo + r / rr.ny_span;
+        unsigned s, e;
+        if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
+            const unsigned slot = atomicAdd(&sl.nseg, 1u);
+            sl.start[slot] = s;
+            sl.off[slot] = e - s;
+        }
+    }
+    group_sync();
+    finish_segments<NT>(sl, tid, group_sync);
 }
 
 // candidate j of the flattened list -> index into the cell-sorted array

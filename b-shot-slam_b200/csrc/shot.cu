@@ -148,7 +148,13 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                 cached = true;
             }
             const unsigned total = sm.sl.total;
-            for (unsigned j = tid; j < total; j += SH_THREADS) f(__ldg(sorted + seg_lookup(sm.sl, j)));
+            for (unsigned j = tid; j < total; j += SH_THREADS * 2) {  // 2 candidate loads in flight per thread
+                const unsigned j1 = j + SH_THREADS;
+                const float4 p0 = __ldg(sorted + seg_lookup(sm.sl, j));
+                const float4 p1 = __ldg(sorted + seg_lookup(sm.sl, j1 < total ? j1 : j));
+                f(p0);
+                if (j1 < total) f(p1);
+            }
             if (rr.nrows > SH_MAXSEG) __syncthreads();
         }
     };
