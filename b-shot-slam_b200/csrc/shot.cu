@@ -19,10 +19,15 @@ constexpr int SH_THREADS = 128;
 constexpr int SH_WARPS = SH_THREADS / 32;
 constexpr int SH_MAXSEG = 1024;
 constexpr int SH_MAXB = 2048;  // batch table covers 65536 candidates per keypoint
+constexpr int SH_TIE_CAP = 512;
 
 struct ShotSmem {
     SegList<SH_MAXSEG, SH_MAXB> sl;
     float hist[352];
+    unsigned int acc[352];  // fixed-point accumulators (native 32-bit shared atomics)
+    unsigned int tie_hist[256];
+    unsigned long long tie_list[SH_TIE_CAP];
+    unsigned tie_n, tie_below, tie_blo, tie_bhi;
     double red[SH_WARPS][8];
     int redi[SH_WARPS][4];
     double v1[3], v3[3];
@@ -240,6 +245,59 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             // list ordered by (sqd, index).  CTA-wide MSB-first radix select of the two bounding keys.
             const int median = n_valid / 2;
             unsigned long long bound[2];
+            // Fast path: 256-bin histogram of sqd over the valid neighbours, collect the bins that hold ranks
+            // median-2 .. median+2, rank that short list exactly by (sqd, index).
+            for (unsigned i = tid; i < 256; i += SH_THREADS) sm.tie_hist[i] = 0u;
+            if (tid == 0) sm.tie_n = 0;
+            __syncthreads();
+            const float tscale = 256.0f / R2;
+            for_each([&](const float4 p) {
+                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (!(sqd < R2)) return;
+                if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+                atomicAdd(&sm.tie_hist[min(255, (int)(sqd * tscale))], 1u);
+            });
+            __syncthreads();
+            if (tid == 0) {
+                unsigned cum = 0, blo = 255, bhi = 255, below = 0;
+                bool flo = false, fhi = false;
+                for (unsigned bn = 0; bn < 256; ++bn) {
+                    const unsigned h = sm.tie_hist[bn];
+                    if (!flo && cum + h > (unsigned)(median - 2)) { blo = bn; below = cum; flo = true; }
+                    if (!fhi && cum + h > (unsigned)(median + 2)) { bhi = bn; fhi = true; }
+                    cum += h;
+                }
+                sm.tie_blo = blo; sm.tie_bhi = bhi; sm.tie_below = below;
+            }
+            __syncthreads();
+            const int blo = (int)sm.tie_blo, bhi = (int)sm.tie_bhi;
+            for_each([&](const float4 p) {
+                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (!(sqd < R2)) return;
+                if (p.x == q.x && p.y == q.y && p.z == q.z) return;
+                const int bn = min(255, (int)(sqd * tscale));
+                if (bn < blo || bn > bhi) return;
+                const unsigned slot = atomicAdd(&sm.tie_n, 1u);
+                if (slot < (unsigned)SH_TIE_CAP) sm.tie_list[slot] = ((unsigned long long)__float_as_uint(sqd) << 32) | __float_as_uint(p.w);
+            });
+            __syncthreads();
+            const unsigned tn = sm.tie_n;
+            if (tn <= (unsigned)SH_TIE_CAP) {
+                // local ranks median-2-below and median+2-below bound the five keys
+                const unsigned r_lo = (unsigned)(median - 2) - sm.tie_below, r_hi = (unsigned)(median + 2) - sm.tie_below;
+                for (unsigned e = tid; e < tn; e += SH_THREADS) {
+                    const unsigned long long ke = sm.tie_list[e];
+                    unsigned rank = 0;
+                    for (unsigned o = 0; o < tn; ++o) rank += (sm.tie_list[o] < ke) ? 1u : 0u;
+                    if (rank == r_lo) sm.red[0][0] = __longlong_as_double((long long)ke);
+                    if (rank == r_hi) sm.red[0][1] = __longlong_as_double((long long)ke);
+                }
+                __syncthreads();
+                bound[0] = (unsigned long long)__double_as_longlong(sm.red[0][0]);
+                bound[1] = (unsigned long long)__double_as_longlong(sm.red[0][1]);
+                __syncthreads();
+            } else
+            // Slow path (more than SH_TIE_CAP neighbours in the median bins): CTA-wide MSB-first radix select.
             for (int which = 0; which < 2; ++which) {
                 unsigned rank = (unsigned)(median + (which ? 2 : -2));
                 unsigned long long prefix = 0;
@@ -312,9 +370,19 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     if (lrf_only) return;
 
     // ---- phase C: SHOT352 quadrilinear histogram (Appendix A.5) ---------------------------------
-    for (unsigned i = tid; i < 352; i += SH_THREADS) sm.hist[i] = 0.0f;
+    for (unsigned i = tid; i < 352; i += SH_THREADS) sm.acc[i] = 0u;
     __syncthreads();
     const bool describe = ok && n_all >= 5;
+    // Votes are accumulated in 32-bit fixed point: float atomicAdd on shared memory is a CAS spin loop
+    // (SASS ATOMS.CAST.SPIN), integer add is native (ATOMS.ADD).  A bin receives at most 4 per
+    // neighbour, so 2^fx_bits * 4.1 * n_all < 2^32 cannot overflow; the sum is order independent.
+    int fx_bits = 0;
+    {
+        const double room = 4294967295.0 / (4.1 * (double)max(n_all, 1));
+        while (fx_bits < 28 && (double)(2u << fx_bits) <= room) ++fx_bits;
+    }
+    const float fx_scale = (float)(1u << fx_bits);
+    const float fx_inv = 1.0f / fx_scale;
     if (describe) {
         const float fx0 = sm.rf[0], fx1 = sm.rf[1], fx2 = sm.rf[2];
         const float fy0 = sm.rf[3], fy1 = sm.rf[4], fy2 = sm.rf[5];
@@ -322,7 +390,8 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         const double radius3_4 = ((double)R * 3) / 4, radius1_4 = (double)R / 4, radius1_2 = (double)R / 2;
         const double RAD_45 = 0.78539816339744830961566084581988, RAD_90 = 1.5707963267948966192313216916398;
         const double RAD_135 = 2.3561944901923449288469825374596, RAD_PI_7_8 = 2.7488935718910690836548129603691;
-        float* hist = sm.hist;
+        unsigned int* hist = sm.acc;
+        auto vote = [&](int idx, float v) { atomicAdd(&hist[idx], __float2uint_rn(v * fx_scale)); };
         for_each([&](const float4 p) {
             const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
             if (!(sqd < R2)) return;
@@ -354,53 +423,50 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             const int volume_index = desc_index * 11;
             bin -= step_index;
             double w = 1 - fabs(bin);
-            {
-                const float fb = (float)bin;
-                if (bin > 0) { if (fb != 0.0f) atomicAdd(&hist[volume_index + ((step_index + 1) % 10)], fb); }
-                else { if (fb != 0.0f) atomicAdd(&hist[volume_index + ((step_index - 1 + 10) % 10)], -fb); }
+            {   // cosine interpolation: |bin| to the next / previous shape bin
+                const float fb = (float)fabs(bin);
+                const int nb_step = (bin > 0) ? (step_index + 1) % 10 : (step_index + 9) % 10;
+                if (fb != 0.0f) vote(volume_index + nb_step, fb);
             }
-            if (distance > radius1_2) {
-                const double rd = (distance - radius3_4) / radius1_2;
-                if (distance > radius3_4) w += 1 - rd;
-                else { w += 1 + rd; atomicAdd(&hist[(desc_index - 2) * 11 + step_index], -(float)rd); }
-            } else {
-                const double rd = (distance - radius1_4) / radius1_2;
-                if (distance < radius1_4) w += 1 + rd;
-                else { w += 1 - rd; atomicAdd(&hist[(desc_index + 2) * 11 + step_index], (float)rd); }
+            {   // radial interpolation (branches of PCL folded: every case adds 1 - |rd| to the own bin and,
+                // towards the neighbouring husk, |rd|)
+                const bool outer = distance > radius1_2;
+                const double rd = (distance - (outer ? radius3_4 : radius1_4)) / radius1_2;
+                w += 1 - fabs(rd);
+                const bool to_nb = outer ? (rd < 0) : (rd > 0);
+                if (to_nb) vote((desc_index + (outer ? -2 : 2)) * 11 + step_index, (float)fabs(rd));
             }
-            double inc_cos = zr / distance;
-            if (inc_cos < -1.0) inc_cos = -1.0;
-            if (inc_cos > 1.0) inc_cos = 1.0;
-            const double inc = acos(inc_cos);
-            if (inc > RAD_90 || (fabs(inc - RAD_90) < 1e-30 && zr <= 0)) {
-                const double id = (inc - RAD_135) / RAD_90;
-                if (inc > RAD_135) w += 1 - id;
-                else { w += 1 + id; atomicAdd(&hist[(desc_index + 1) * 11 + step_index], -(float)id); }
-            } else {
-                const double id = (inc - RAD_45) / RAD_90;
-                if (inc < RAD_45) w += 1 + id;
-                else { w += 1 - id; atomicAdd(&hist[(desc_index - 1) * 11 + step_index], (float)id); }
+            {   // elevation interpolation. PCL tests `inc > 90deg || (|inc - 90deg| < 1e-30 && z <= 0)`, which for a
+                // monotone acos is exactly z <= 0; the angle itself only enters linearly -> fp32 acos suffices
+                double inc_cos = zr / distance;
+                inc_cos = fmin(1.0, fmax(-1.0, inc_cos));
+                const double inc = (double)acosf((float)inc_cos);
+                const bool lower = !(zr > 0);
+                const double id = (inc - (lower ? RAD_135 : RAD_45)) / RAD_90;
+                w += 1 - fabs(id);
+                const bool to_nb = lower ? !(id > 0) : !(id < 0);
+                const float fv = (float)fabs(id);
+                if (to_nb && fv != 0.0f) vote((desc_index + (lower ? 1 : -1)) * 11 + step_index, fv);
             }
-            if (yr != 0.0 || xr != 0.0) {
-                const double azimuth = atan2(yr, xr);
+            if (yr != 0.0 || xr != 0.0) {  // azimuth interpolation
+                const double azimuth = (double)atan2f((float)yr, (float)xr);
                 const int sel = desc_index >> 2;
                 double ad = (azimuth - (-RAD_PI_7_8 + RAD_45 * sel)) / RAD_45;
                 ad = fmax(-0.5, fmin(ad, 0.5));
-                if (ad > 0) {
-                    w += 1 - ad;
-                    atomicAdd(&hist[((desc_index + 4) % 32) * 11 + step_index], (float)ad);
-                } else {
-                    w += 1 + ad;
-                    atomicAdd(&hist[((desc_index - 4 + 32) % 32) * 11 + step_index], -(float)ad);
-                }
+                w += 1 - fabs(ad);
+                const int nbv = (ad > 0) ? ((desc_index + 4) & 31) : ((desc_index + 28) & 31);
+                const float fv = (float)fabs(ad);
+                if (fv != 0.0f) vote(nbv * 11 + step_index, fv);
             }
-            atomicAdd(&hist[volume_index + step_index], (float)w);
+            vote(volume_index + step_index, (float)w);
         });
     }
     __syncthreads();
 
     // ---- phase D: normalise, emit, binarise ----------------------------------------------------
     {
+        for (unsigned i = tid; i < 352; i += SH_THREADS) sm.hist[i] = (float)sm.acc[i] * fx_inv;
+        __syncthreads();
         double part = 0.0;
         for (unsigned i = tid; i < 352; i += SH_THREADS) part += (double)__fmul_rn(sm.hist[i], sm.hist[i]);
         part = warp_sum(part);
