@@ -20,7 +20,8 @@ constexpr int DT_THREADS = DT_WARPS * 32;
 
 __global__ void __launch_bounds__(DT_THREADS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
-                 const float4* __restrict__ sorted, unsigned n_total, float radius, int max_nn, int sr_type,
+                 const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
+                 int sr_type,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
                  unsigned long long* __restrict__ counters, const unsigned* __restrict__ work_list,
                  const unsigned* __restrict__ work_count) {
@@ -40,15 +41,12 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
         continue;
     }
     RowRange rr;
-    const KnnResult res = knn_select(g, cell_start, sorted, q, radius, max_nn, sm, lane, rr);
-    const float rho = sqrtf(res.rho2) * 1.0001f;
-    bool cached = !res.batched;
     // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
     double sx = 0, sy = 0, sz = 0;
-    knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-        if (knn_selected(res, sqd, p.w)) { sx += p.x; sy += p.y; sz += p.z; }
-    });
+    const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, rr,
+                                     [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
+    const float rho = sqrtf(res.rho2) * 1.0001f;
+    bool cached = !res.batched;
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     const float fn = (float)res.count;
     const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
@@ -506,12 +504,12 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters,
             leftover, leftover_count);
         const unsigned sweep_ctas = std::min((n + DT_WARPS - 1) / DT_WARPS, (unsigned)c->sm_count * 12u);
-        seg_ratio_kernel<<<sweep_ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, n, radius, max_nn, sr_type,
+        seg_ratio_kernel<<<sweep_ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type,
                                                                  c->d_ratio, c->d_keys, c->d_counters, leftover, leftover_count);
         count_launch(c, 3);
     } else {
         seg_ratio_kernel<<<(n + DT_WARPS - 1) / DT_WARPS, DT_THREADS, 0, c->stream>>>(
-            c->d_grid, c->d_cell_start, c->d_sorted, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters, nullptr, nullptr);
+            c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters, nullptr, nullptr);
         count_launch(c, 2);
     }
     return check_launch("seg_ratio kernels");

@@ -5,12 +5,8 @@
 // radius, and when there are more than max_nn of them the max_nn NEAREST, ordered by
 // (fp32 squared distance, point index).  The warp never materialises the list; it computes a
 // THRESHOLD KEY (sqd bits << 32 | index) such that the selected set is {key <= threshold}:
-//   1. grow a search sphere rho = cell, 2 cell, 4 cell ... (<= R) until it holds >= max_nn points
-//      (a cube of m cells around the query's cell contains every point closer than m * cell)
-//   2. 256-bin histogram of sqd in shared memory -> the bin where the cumulative count crosses max_nn
-//      (re-histogrammed inside that bin while it holds more than KN_LIST candidates)
-//   3. collect that bin's candidates, rank them by key, pick the (max_nn - below)-th
-// Callers then sweep the SAME shared-memory segment list with `selected()` as the predicate.
+//   see knn_select() below.
+// Callers then sweep the SAME shared-memory segment list with `knn_selected()` as the predicate.
 #pragma once
 #include "nbr.cuh"
 
@@ -69,62 +65,90 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
     }
 }
 
-// All 32 lanes call. On return sm.sl holds the segment list for radius sqrt(res.rho2) (valid for
-// re-use iff !res.batched) and `rr_out` the matching row rectangle.
+// All 32 lanes call.  Selects the nearest <= max_nn points inside radius R of q and calls acc(p) exactly
+// once (on some lane) for every selected point; the caller reduces its accumulators across the warp.
+// On return sm.sl holds the segment list for radius sqrt(res.rho2) (valid for re-use iff !res.batched),
+// `rr_out` the matching row rectangle and res.thr the threshold key for further sweeps.
+//   1. probe rho = 2 cells; predict the radius that holds max_nn points from the local density and grow
+//      from there (one 256-bin sqd histogram sweep per attempt; a cube of m cells around the query's cell
+//      contains every point closer than m * cell)
+//   2. crossing bin of the histogram (re-histogrammed inside the bin while it holds > KN_LIST candidates)
+//   3. one sweep: accumulate everything below the crossing bin, collect the bin; rank the short list by
+//      key, accumulate its first (max_nn - below) entries (re-read from the original-order array `pts`)
+template <typename Acc>
 __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsigned* __restrict__ cell_start,
-                                                const float4* __restrict__ sorted, const float4& q, float R, int max_nn,
-                                                KnnWarpSmem& sm, unsigned lane, RowRange& rr_out) {
+                                                const float4* __restrict__ sorted, const float4* __restrict__ pts,
+                                                const float4& q, float R, int max_nn, KnnWarpSmem& sm, unsigned lane,
+                                                RowRange& rr_out, Acc&& acc) {
     KnnResult res;
     const float R2 = (float)((double)R * (double)R);
     float rho = R, rho2 = R2;
     int n = 0;
     bool cached = false;
     RowRange rr;
-    // ---- 1. grow the sphere: rho = cell, 2 cell, 3 cell ... until it holds >= max_nn points ----------
     auto sync = [] { __syncwarp(); };
-    for (int m = 1;; ++m) {
+    const int M = max(1, (int)ceilf(R * g.inv_cell)) + 1;  // rho(M) >= R: the loop always terminates at m == M
+    // ---- 1. grow the sphere ---------------------------------------------------------------------
+    for (int m = min(2, M);;) {
         const float g_m = (float)m * g.cell * 0.9999f;
-        const bool last = (max_nn <= 0) || !(g_m < R);
+        const bool last = (max_nn <= 0) || m >= M || !(g_m < R);
         rho = last ? R : g_m;
         rho2 = last ? R2 : __fmul_rn(rho, rho);
         rr = row_range(g, q.y, q.z, rho);
         cached = false;
+        unsigned total = 0xFFFFFFFFu;
         if (rr.nrows <= KN_MAXSEG) {
             // cheap necessary condition first: the candidate rows must hold at least max_nn points
-            const unsigned total = enumerate_segments<32>(g, cell_start, q.x, q.y, q.z, rho, rr, 0, sm.sl, lane, sync);
-            if (!last && total < (unsigned)max_nn) continue;
+            total = enumerate_segments<32>(g, cell_start, q.x, q.y, q.z, rho, rr, 0, sm.sl, lane, sync);
+            if (!last && total < (unsigned)max_nn) {
+                // surface-like density: count ~ r^2  ->  radius that should hold 1.4 * max_nn candidates
+                const float f = sqrtf(1.4f * (float)max_nn / (float)max(total, 1u));
+                m = min(M, max(m + 1, (int)ceilf((float)m * f)));
+                continue;
+            }
             finish_segments<32>(sm.sl, lane, sync);
             cached = true;
         }
+        for (unsigned b = lane; b < KN_BINS; b += 32) sm.hist[b] = 0;
+        __syncwarp();
+        const float scale = (float)KN_BINS / rho2;
         int cnt = 0;
         knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-            if (sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z) < rho2) ++cnt;
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (sqd < rho2) {
+                ++cnt;
+                atomicAdd(&sm.hist[min(KN_BINS - 1, (int)(sqd * scale))], 1u);
+            }
         });
         n = warp_sum(cnt);
         if (last || n >= max_nn) break;
+        const float f = sqrtf(1.15f * (float)max_nn / (float)max(n, 1));
+        m = min(M, max(m + 1, (int)ceilf((float)m * f)));
     }
     rr_out = rr;
     res.rho2 = rho2;
     res.batched = rr.nrows > KN_MAXSEG;
-    if (max_nn <= 0 || n <= max_nn) {
-        res.thr = 0xFFFFFFFFFFFFFFFFull;
+    if (max_nn <= 0 || n <= max_nn) {  // everything inside the sphere is selected
+        res.thr = (((unsigned long long)__float_as_uint(rho2)) << 32) - 1ull;
         res.count = n;
+        knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
+            if (sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z) < rho2) acc(p);
+        });
         return res;
     }
-    // ---- 2. histogram refinement ----------------------------------------------------------------
+    // ---- 2. crossing bin (the level-0 histogram is already in sm.hist) ----------------------------------
     float lo = 0.0f, hi = rho2;
     int below = 0;  // selected-for-sure elements with sqd < lo
     for (int iter = 0; iter < 8; ++iter) {
-        for (unsigned b = lane; b < KN_BINS; b += 32) sm.hist[b] = 0;
-        __syncwarp();
         const float scale = (float)KN_BINS / (hi - lo);
-        knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (sqd >= lo && sqd < hi) {
-                const int b = min(KN_BINS - 1, (int)((sqd - lo) * scale));
-                atomicAdd(&sm.hist[b], 1u);
-            }
-        });
+        if (iter > 0) {
+            for (unsigned b = lane; b < KN_BINS; b += 32) sm.hist[b] = 0;
+            __syncwarp();
+            knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
+                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (sqd >= lo && sqd < hi) atomicAdd(&sm.hist[min(KN_BINS - 1, (int)((sqd - lo) * scale))], 1u);
+            });
+        }
         // locate the crossing bin: lane l owns bins 8l..8l+7
         unsigned h[8], s = 0;
 #pragma unroll
@@ -152,19 +176,18 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
         const int bin = __shfl_sync(0xffffffffu, found_bin, src);
         const unsigned bbelow = __shfl_sync(0xffffffffu, found_below, src);
         const unsigned bcnt = __shfl_sync(0xffffffffu, found_cnt, src);
-        // the bin's value range, using the same arithmetic as the binning above
-        const float blo = lo, bscale = scale;
-        below = (int)bbelow;
-        auto in_bin = [&](float sqd) {
-            return sqd >= blo && sqd < hi && min(KN_BINS - 1, (int)((sqd - blo) * bscale)) == bin;
-        };
+        const float blo = lo, bhi = hi, bscale = scale;
+        auto bin_of = [&](float sqd) { return min(KN_BINS - 1, (int)((sqd - blo) * bscale)); };
         if (bcnt <= KN_LIST || iter == 7) {
-            // ---- 3. collect + rank ------------------------------------------------------------------
+            // ---- 3. accumulate below the bin, collect the bin, rank, accumulate the rest ---------------
             if (lane == 0) sm.list_n = 0;
             __syncwarp();
             knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
                 const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (in_bin(sqd)) {
+                if (!(sqd < bhi)) return;
+                const int b = (sqd >= blo) ? bin_of(sqd) : -1;
+                if (b < bin) acc(p);
+                else if (b == bin) {
                     const unsigned slot = atomicAdd(&sm.list_n, 1u);
                     if (slot < KN_LIST) sm.list[slot] = knn_key(sqd, p.w);
                 }
@@ -178,21 +201,21 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
                 const unsigned long long ke = sm.list[e];
                 unsigned rank = 0;
                 for (unsigned o = 0; o < ln; ++o) rank += (sm.list[o] < ke) ? 1u : 0u;
-                if (rank == need - 1) sm.thr = ke;
+                if (rank < need) {
+                    acc(__ldg(pts + (unsigned)(ke & 0xFFFFFFFFull)));
+                    if (rank == need - 1) sm.thr = ke;
+                }
             }
             __syncwarp();
             res.thr = sm.thr;
             res.count = max_nn;
             return res;
         }
-        // narrow to the crossing bin and histogram again
+        // narrow to the crossing bin and histogram again; `below` is recounted exactly for the new bound
         const float w = (hi - lo) / (float)KN_BINS;
         const float nlo = lo + w * (float)bin, nhi = lo + w * (float)(bin + 1);
-        // keep the bin membership consistent with in_bin(): widen by one ulp-ish margin
         lo = fmaxf(lo, nlo - w * 1e-3f);
         hi = fminf(hi, nhi + w * 1e-3f);
-        // elements of other bins that fall into the widened margin are counted again below, so
-        // recompute `below` exactly for the new lower bound
         int cb = 0;
         const float flo = lo;
         knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
@@ -200,13 +223,13 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
         });
         below = warp_sum(cb);
     }
-    res.thr = 0xFFFFFFFFFFFFFFFFull;  // unreachable
+    res.thr = (((unsigned long long)__float_as_uint(rho2)) << 32) - 1ull;  // unreachable
     res.count = n;
     return res;
 }
 
 __device__ __forceinline__ bool knn_selected(const KnnResult& r, float sqd, float w) {
-    return sqd < r.rho2 && knn_key(sqd, w) <= r.thr;
+    return knn_key(sqd, w) <= r.thr;  // thr < (rho2 bits << 32) by construction
 }
 
 }  // namespace bshot

@@ -101,7 +101,7 @@ __device__ void eigen33_smallest(const float mat[9], float& eigenvalue, float ev
 
 __global__ void __launch_bounds__(NM_THREADS)
 normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
-               const float4* __restrict__ sorted, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
+               const float4* __restrict__ sorted, const float4* __restrict__ pts, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
                float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters) {
     __shared__ KnnWarpSmem smem[NM_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -117,19 +117,14 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (finite) {
         RowRange rr;
-        const KnnResult res = knn_select(g, cell_start, sorted, q, radius, max_nn, sm, lane, rr);
+        const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, rr, [&](const float4 p) {
+            // products rounded to fp32 like PCL's accumulator inputs, summed in fp64
+            s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
+            s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
+            s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
+        });
         n = res.count;
-        if (n >= 3) {
-            const float rho = sqrtf(res.rho2) * 1.0001f;
-            bool cached = !res.batched;
-            knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (!knn_selected(res, sqd, p.w)) return;
-                // products rounded to fp32 like PCL's accumulator inputs, summed in fp64
-                s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
-                s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
-                s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
-            });
+        {
 #pragma unroll
             for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
         }
@@ -172,7 +167,7 @@ int normals_query(Ctx* c, const float4* d_q, size_t nq, float radius, int max_nn
     if (nq == 0) return BSHOT_OK;
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
     normals_kernel<<<(unsigned)((nq + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-        c->d_grid, c->d_cell_start, c->d_sorted, d_q, nullptr, (unsigned)nq, radius, max_nn, d_out, c->d_counters);
+        c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nullptr, (unsigned)nq, radius, max_nn, d_out, c->d_counters);
     count_launch(c);
     return check_launch("normals_kernel");
 }
@@ -186,7 +181,7 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
             normals_kernel<<<(unsigned)((k + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-                c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count, (unsigned)k, radius, max_nn, c->d_qnormals, c->d_counters);
+                c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, c->d_kp, c->d_kp_count, (unsigned)k, radius, max_nn, c->d_qnormals, c->d_counters);
             place_normals_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(c->d_qnormals, c->d_kp_count, (unsigned)k,
                                                                                      c->d_normals);
             count_launch(c, 2);
