@@ -422,8 +422,7 @@ int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint6
     BSHOT_TRY(upload_qt(ctx, q, nq, t, nt, "bshot_match_mutual"));
     if (count_out) *count_out = 0;
     if (nq == 0 || nt == 0) return sync(ctx);
-    BSHOT_TRY(hamming_top2(ctx, ctx->d_q, nq, ctx->d_t, nt, 0, ctx->d_cand));
-    BSHOT_TRY(hamming_reverse(ctx, ctx->d_q, nq, ctx->d_t, 0, ctx->d_cand));
+    BSHOT_TRY(hamming_match_rq(ctx, ctx->d_q, nq, ctx->d_t, nt, 0, ctx->d_cand));
     BSHOT_TRY(hamming_mutual_pairs(ctx, ctx->d_cand, nq, ctx->d_pairs, ctx->d_pair_count));
     BSHOT_TRY(d2h(ctx, ctx->h_scratch, ctx->d_pair_count, sizeof(int)));
     BSHOT_TRY(sync(ctx));
@@ -566,12 +565,11 @@ int bshot_match_dev(bshot_ctx* ctx, const void* d_q, size_t nq, const void* d_t,
         BSHOT_CUDA_TRY(cudaMemsetAsync(out, 0xFF, sizeof(bshot_cand) * nq, ctx->stream));
         return BSHOT_OK;
     }
-    BSHOT_TRY(hamming_top2(ctx, d_q, nq, d_t, nt, global_base, out));
     if (with_rq) {
         if (nq > ctx->max_kp) { set_error("bshot_match_dev: reverse pass needs nq <= max_keypoints"); return BSHOT_E_CAPACITY; }
-        BSHOT_TRY(hamming_reverse(ctx, d_q, nq, d_t, global_base, out));
+        return hamming_match_rq(ctx, d_q, nq, d_t, nt, global_base, out);
     }
-    return BSHOT_OK;
+    return hamming_top2(ctx, d_q, nq, d_t, nt, global_base, out);
 }
 
 int bshot_match_shard_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, int with_rq, void* d_cand_out) {

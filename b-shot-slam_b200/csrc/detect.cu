@@ -415,48 +415,83 @@ topk_kernel(const unsigned long long* __restrict__ keys, unsigned n, int top_k, 
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned s_rank, s_valid, s_fill;
     const unsigned tid = threadIdx.x;
-    // number of valid (non-zero) keys
-    if (tid == 0) { s_valid = 0; s_fill = 0; }
+    // K-th largest key via MSB-first 8-bit radix select (rank counted from the top). The first pass also
+    // counts the valid (non-zero) keys, which fixes k_eff = min(top_k, #valid).
+    if (tid == 0) { s_valid = 0; s_fill = 0; s_prefix = 0ull; s_rank = 0; }
     __syncthreads();
-    unsigned cv = 0;
-    for (unsigned i = tid; i < n; i += TK_THREADS) cv += keys[i] != 0ull;
-    cv = (unsigned)warp_sum((int)cv);
-    if ((tid & 31) == 0) atomicAdd(&s_valid, cv);
-    __syncthreads();
-    const unsigned k_eff = min((unsigned)top_k, s_valid);
-    if (tid == 0) *kp_count = (int)k_eff;
-    if (k_eff == 0) return;
-    // K-th largest key via MSB-first 8-bit radix select (rank counted from the top)
-    if (tid == 0) { s_prefix = 0ull; s_rank = k_eff - 1; }
-    __syncthreads();
+    unsigned k_eff = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (unsigned b = tid; b < 256; b += TK_THREADS) hist[b] = 0;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
         const unsigned long long mask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        for (unsigned i = tid; i < n; i += TK_THREADS) {
-            const unsigned long long key = keys[i];
-            if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        unsigned cv = 0;
+        // one CTA reads all keys in every pass: keep 8 independent 8-byte loads in flight per thread
+        for (unsigned base = 0; base < n; base += TK_THREADS * 8) {
+            unsigned long long kk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned i = base + u * TK_THREADS + tid;
+                kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const unsigned i = base + u * TK_THREADS + tid;
+                cv += kk[u] != 0ull;
+                if (i < n && (kk[u] & mask) == prefix) atomicAdd(&hist[(unsigned)(kk[u] >> shift) & 255u], 1u);
+            }
+        }
+        if (shift == 56) {
+            cv = (unsigned)warp_sum((int)cv);
+            if ((tid & 31) == 0) atomicAdd(&s_valid, cv);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned rank = s_rank;
-            int d = 255;
-            for (; d > 0; --d) {
-                if (rank < hist[d]) break;
-                rank -= hist[d];
+        if (shift == 56) {
+            k_eff = min((unsigned)top_k, s_valid);
+            if (tid == 0) { *kp_count = (int)k_eff; s_rank = k_eff ? k_eff - 1 : 0; }
+            if (k_eff == 0) return;
+            __syncthreads();
+        }
+        if (tid < 32) {  // warp 0: lane l owns digits 255-8l .. 248-8l (descending), suffix scan across lanes
+            unsigned h[8], s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { h[k] = hist[255 - (tid * 8 + k)]; s += h[k]; }
+            unsigned inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= (unsigned)o) inc += up;
             }
-            s_rank = rank;
-            s_prefix = prefix | ((unsigned long long)d << shift);
+            const unsigned rank = s_rank;
+            unsigned run = inc - s;  // keys in digits above this lane's
+            int found = -1;
+            unsigned frank = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (found < 0 && rank >= run && rank < run + h[k]) { found = 255 - (int)(tid * 8 + k); frank = rank - run; }
+                run += h[k];
+            }
+            if (found >= 0) {  // exactly one lane
+                s_rank = frank;
+                s_prefix = prefix | ((unsigned long long)found << shift);
+            }
         }
         __syncthreads();
     }
     const unsigned long long kth = s_prefix;  // keys are distinct: exactly k_eff keys are >= kth
-    for (unsigned i = tid; i < n; i += TK_THREADS) {
-        const unsigned long long key = keys[i];
-        if (key >= kth && key != 0ull) {
-            const unsigned slot = atomicAdd(&s_fill, 1u);
-            if (slot < sort_cap) sbuf[slot] = key;
+    for (unsigned base = 0; base < n; base += TK_THREADS * 8) {
+        unsigned long long kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned i = base + u * TK_THREADS + tid;
+            kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (kk[u] >= kth && kk[u] != 0ull) {
+                const unsigned slot = atomicAdd(&s_fill, 1u);
+                if (slot < sort_cap) sbuf[slot] = kk[u];
+            }
         }
     }
     __syncthreads();

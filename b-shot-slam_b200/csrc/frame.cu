@@ -36,8 +36,7 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
     const bool initial = (c->n_prev == 0);
     const uint64_t* tgt = initial ? c->d_bits : c->d_prev_bits;
     const size_t nt = initial ? k : c->n_prev;
-    BSHOT_TRY(hamming_top2(c, c->d_bits, k, tgt, nt, 0, c->d_cand));
-    BSHOT_TRY(hamming_reverse(c, c->d_bits, k, tgt, 0, c->d_cand));
+    BSHOT_TRY(hamming_match_rq(c, c->d_bits, k, tgt, nt, 0, c->d_cand));
     BSHOT_TRY(hamming_mutual_pairs(c, c->d_cand, k, c->d_pairs, c->d_pair_count));
     copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp_count, (unsigned)k,
                                                                             c->d_prev_bits, c->d_prev_count);

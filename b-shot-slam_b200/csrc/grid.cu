@@ -131,10 +131,14 @@ scan_reduce_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
     const unsigned base = blockIdx.x * SCAN_TILE;
     if (base >= n) return;
     unsigned s = 0;
+    const unsigned i0 = base + threadIdx.x * SCAN_ITEMS;
+    if (i0 + SCAN_ITEMS <= n) {  // 8 consecutive cells = two 16-byte loads (the table is 16-byte aligned)
+        const uint4 a = reinterpret_cast<const uint4*>(cnt + i0)[0], b = reinterpret_cast<const uint4*>(cnt + i0)[1];
+        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
-        if (i < n) s += cnt[i];
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (i0 + k < n) s += cnt[i0 + k];
     }
     s = (unsigned)warp_sum((int)s);
     __shared__ unsigned ws[32];
@@ -174,12 +178,17 @@ scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ curs
     if (base >= n) return;
     unsigned v[SCAN_ITEMS];
     unsigned s = 0;
+    const unsigned i0 = base + threadIdx.x * SCAN_ITEMS;
+    const bool full = i0 + SCAN_ITEMS <= n;
+    if (full) {
+        const uint4 a = reinterpret_cast<const uint4*>(cursor + i0)[0], b = reinterpret_cast<const uint4*>(cursor + i0)[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
-        v[k] = (i < n) ? cursor[i] : 0u;
-        s += v[k];
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (i0 + k < n) ? cursor[i0 + k] : 0u;
     }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
     // block-exclusive prefix of the per-thread sums
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned inc = s;
@@ -203,14 +212,17 @@ scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ curs
     }
     __syncthreads();
     unsigned run = block_sums[blockIdx.x] + ws[wid] + (inc - s);
+    unsigned o[SCAN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const unsigned i = base + threadIdx.x * SCAN_ITEMS + k;
-        if (i < n) {
-            cell_start[i] = run;
-            cursor[i] = run;  // scatter cursor starts at the cell's first slot
-        }
-        run += v[k];
+    for (int k = 0; k < SCAN_ITEMS; ++k) { o[k] = run; run += v[k]; }
+    if (full) {  // scatter cursor starts at the cell's first slot
+        const uint4 a = make_uint4(o[0], o[1], o[2], o[3]), b = make_uint4(o[4], o[5], o[6], o[7]);
+        reinterpret_cast<uint4*>(cell_start + i0)[0] = a; reinterpret_cast<uint4*>(cell_start + i0)[1] = b;
+        reinterpret_cast<uint4*>(cursor + i0)[0] = a; reinterpret_cast<uint4*>(cursor + i0)[1] = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (i0 + k < n) { cell_start[i0 + k] = o[k]; cursor[i0 + k] = o[k]; }
     }
 }
 

@@ -49,10 +49,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-template <int QPT>
-__device__ __forceinline__ void pair_update(const uint32_t (&qw)[QPT][11], const uint4 a, const uint4 b,
-                                            const uint4 c, unsigned idx, uint32_t (&k1)[QPT],
-                                            uint32_t (&k2)[QPT]) {
+// COLMIN: also returns min over the thread's queries of (distance << 23 | query index) for this target
+template <int QPT, bool COLMIN>
+__device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], const uint4 a, const uint4 b,
+                                                const uint4 c, unsigned idx, uint32_t (&k1)[QPT],
+                                                uint32_t (&k2)[QPT], const uint32_t (&qor)[QPT]) {
+    uint32_t ck = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
         unsigned d = __popc(qw[j][0] ^ a.x) + __popc(qw[j][1] ^ a.y) + __popc(qw[j][2] ^ a.z) +
@@ -63,18 +65,24 @@ __device__ __forceinline__ void pair_update(const uint32_t (&qw)[QPT][11], const
         const uint32_t hi = max(k1[j], key);
         k1[j] = min(k1[j], key);
         k2[j] = min(k2[j], hi);
+        if (COLMIN) ck = min(ck, (d << HM_IDX_BITS) | qor[j]);  // qor = 0xFFFFFFFF for padding queries
     }
+    return ck;
 }
 
 // grid = (query blocks, target splits). partial[(split * nq + qi) * 2 + {0,1}] = packed
 // (distance << 32 | global target index), HM_NONE when the split saw fewer than 1/2 targets.
-template <int QPT>
+template <int QPT, bool COLMIN>
 __global__ void __launch_bounds__(HM_THREADS)
 hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __restrict__ t, unsigned nt,
                     unsigned chunk, unsigned long long global_base,
-                    unsigned long long* __restrict__ partial) {
+                    unsigned long long* __restrict__ partial, unsigned* __restrict__ gcol) {
     __shared__ __align__(128) uint4 tile[HM_STAGES][HM_TILE * 3];
     __shared__ __align__(8) unsigned long long full[HM_STAGES];
+    __shared__ unsigned col[COLMIN ? HM_STAGES : 1][COLMIN ? HM_TILE : 1];  // per-target best (distance, query) of this CTA
+    if (COLMIN) {
+        for (unsigned i = threadIdx.x; i < HM_STAGES * HM_TILE; i += HM_THREADS) (&col[0][0])[i] = 0xFFFFFFFFu;
+    }
 
     const unsigned tid = threadIdx.x;
     const unsigned split = blockIdx.y;
@@ -102,10 +110,11 @@ hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __res
     }
 
     uint32_t qw[QPT][11];
-    uint32_t k1[QPT], k2[QPT];
+    uint32_t k1[QPT], k2[QPT], qor[QPT];
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
         const unsigned qi = (blockIdx.x * QPT + j) * HM_THREADS + tid;
+        qor[j] = (qi < nq) ? qi : 0xFFFFFFFFu;
         uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
         if (qi < nq) {
             a = __ldg(q + (size_t)qi * 3);
@@ -127,13 +136,28 @@ hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __res
         const unsigned cnt = min((unsigned)HM_TILE, tcount - base);
         if (cnt == HM_TILE) {
 #pragma unroll 4
-            for (int tt = 0; tt < HM_TILE; ++tt)
-                pair_update<QPT>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2);
+            for (int tt = 0; tt < HM_TILE; ++tt) {
+                const uint32_t ck = pair_update<QPT, COLMIN>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2, qor);
+                if (COLMIN) {
+                    const uint32_t wm = __reduce_min_sync(0xffffffffu, ck);
+                    if ((tid & 31) == 0) atomicMin(&col[s][tt], wm);
+                }
+            }
         } else {
-            for (unsigned tt = 0; tt < cnt; ++tt)
-                pair_update<QPT>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2);
+            for (unsigned tt = 0; tt < cnt; ++tt) {
+                const uint32_t ck = pair_update<QPT, COLMIN>(qw, tp[3 * tt], tp[3 * tt + 1], tp[3 * tt + 2], base + tt, k1, k2, qor);
+                if (COLMIN) {
+                    const uint32_t wm = __reduce_min_sync(0xffffffffu, ck);
+                    if ((tid & 31) == 0) atomicMin(&col[s][tt], wm);
+                }
+            }
         }
         __syncthreads();  // every warp is done with slot s before it is refilled
+        if (COLMIN && tid < cnt) {  // publish this CTA's per-target minima, reset the slot
+            const unsigned v = col[s][tid];
+            if (v != 0xFFFFFFFFu) atomicMin(&gcol[t0 + base + tid], v);
+            col[s][tid] = 0xFFFFFFFFu;
+        }
         if (tid == 0 && it + HM_STAGES < ntiles) issue(it + HM_STAGES);
     }
 
@@ -172,6 +196,27 @@ __global__ void merge_top2_kernel(const unsigned long long* __restrict__ src, un
     }
     bshot_cand c;
     c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
+    out[qi] = c;
+}
+
+// merge + reverse result: rq = best query of the winning target from the fused column minima
+__global__ void merge_top2_rq_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
+                                     const unsigned* __restrict__ gcol, unsigned long long global_base,
+                                     bshot_cand* __restrict__ out) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+    for (unsigned s = 0; s < nsrc; ++s) {
+        const unsigned long long* p = src + ((size_t)s * nq + qi) * 2;
+        top2_insert(p[0], k1, k2);
+        top2_insert(p[1], k1, k2);
+    }
+    bshot_cand c;
+    c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
+    if (k1 != HM_NONE) {
+        const unsigned v = gcol[(size_t)((k1 & 0xFFFFFFFFull) - global_base)];
+        if (v != 0xFFFFFFFFu) c.rq = v & ((1u << HM_IDX_BITS) - 1);
+    }
     out[qi] = c;
 }
 
@@ -289,7 +334,7 @@ static int pick_qpt(size_t nq, size_t nt, int sm_count) {
 
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out) {
+                 bshot_cand* d_out, unsigned* d_colmin) {
     if (nq == 0) return BSHOT_OK;
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
         set_error("hamming_top2: sizes exceed 32-bit index range");
@@ -320,23 +365,27 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     dim3 grid(qblocks, nsplit);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_q);
     const uint4* t4 = reinterpret_cast<const uint4*>(d_t);
-    switch (qpt) {
-        case 4:
-            hamming_top2_kernel<4><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
-                                                                        (unsigned)chunk, global_base, c->d_partial);
-            break;
-        case 2:
-            hamming_top2_kernel<2><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
-                                                                        (unsigned)chunk, global_base, c->d_partial);
-            break;
-        default:
-            hamming_top2_kernel<1><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt,
-                                                                        (unsigned)chunk, global_base, c->d_partial);
-            break;
+    const bool colmin = d_colmin != nullptr;
+    if (colmin) {
+        if (nq > (1u << HM_IDX_BITS)) { set_error("hamming_top2: fused reverse pass needs nq <= 2^23"); return BSHOT_E_CAPACITY; }
+        BSHOT_CUDA_TRY(cudaMemsetAsync(d_colmin, 0xFF, sizeof(unsigned) * nt, c->stream));
     }
+#define BSHOT_LAUNCH_TOP2(QPT, CM)                                                                                    \
+    hamming_top2_kernel<QPT, CM><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt, (unsigned)chunk, \
+                                                                     global_base, c->d_partial, d_colmin)
+    switch (qpt) {
+        case 4: if (colmin) BSHOT_LAUNCH_TOP2(4, true); else BSHOT_LAUNCH_TOP2(4, false); break;
+        case 2: if (colmin) BSHOT_LAUNCH_TOP2(2, true); else BSHOT_LAUNCH_TOP2(2, false); break;
+        default: if (colmin) BSHOT_LAUNCH_TOP2(1, true); else BSHOT_LAUNCH_TOP2(1, false); break;
+    }
+#undef BSHOT_LAUNCH_TOP2
     count_launch(c);
     BSHOT_TRY(check_launch("hamming_top2_kernel"));
-    merge_top2_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, 2, d_out);
+    if (colmin)
+        merge_top2_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, d_colmin,
+                                                                                  global_base, d_out);
+    else
+        merge_top2_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, 2, d_out);
     count_launch(c);
     return check_launch("merge_top2_kernel");
 }
@@ -349,7 +398,7 @@ int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigne
         d_cand, (unsigned)nq, reinterpret_cast<const uint4*>(d_t), global_base, reinterpret_cast<uint4*>(c->d_gather));
     count_launch(c);
     BSHOT_TRY(check_launch("gather_best_kernel"));
-    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2));
+    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2, nullptr));
     set_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, c->d_cand2, (unsigned)nq);
     count_launch(c);
     return check_launch("set_rq_kernel");
@@ -415,4 +464,18 @@ int popc_peak(Ctx* c, double* out) {
     return BSHOT_OK;
 }
 
+}  // namespace bshot
+
+namespace bshot {
+// left top-2 AND the reverse best query in one call. When the target set is not much larger than the
+// query set the column minima are tracked inside the single distance-matrix pass (Q x T pairs instead
+// of Q x T + Q x Q); for map-sized target sets the Q x Q reverse pass is negligible and kept separate.
+int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                     bshot_cand* d_out) {
+    if (nq == 0) return BSHOT_OK;
+    if (nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
+        return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right));
+    BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr));
+    return hamming_reverse(c, d_q, nq, d_t, global_base, d_out);
+}
 }  // namespace bshot

@@ -21,7 +21,9 @@ int binarize(Ctx* c, const float* d_shot, size_t k, uint64_t* d_bits);
 
 // a10/a11 (hamming.cu)
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out);
+                 bshot_cand* d_out, unsigned* d_colmin = nullptr);
+int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                     bshot_cand* d_out);
 int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
                     bshot_cand* d_cand);
 int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, void* d_out);
