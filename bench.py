@@ -12,8 +12,8 @@ the previous frame.  One step = one frame.  metric = B-SHOT descriptors/s throug
  * value : cloud already resident in HBM when the timed region starts (bshot_process_frame_dev).
  * e2e   : the C-ABI call a reference maintainer would make (bshot_process_frame) on pinned HOST
            buffers, H2D + D2H inside the timed region.
- * N > 1 : frame extraction does not shard (replicas only) -> every rank processes its own
-           frames of the sequence, no data-path collective, weak scaling.  The part of the path that
+ * N > 1 : frame extraction does not shard (replicas only) -> every rank processes a replica of
+           the frame stream, no data-path collective, weak scaling.  The part of the path that
            DOES shard -- frame-to-map Hamming search against a map split over the ranks, per-rank
            top-2 candidates merged after one NCCL all-gather -- is timed in the same run and
            reported under "map_match" (C4: Q = 10 000 queries vs T = 1 048 576 map descriptors).
@@ -184,8 +184,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- inputs: this rank's frames of the sequence (replicas: disjoint frame ranges) -----------
-    frames = [synth.make_scan(args.sensor, rank * N_FRAMES + f) for f in range(N_FRAMES)]
+    # ---- inputs ---------------------------------------------------------------------------------
+    # replicas: every rank runs the SAME frames (identical work per GPU keeps the weak-scaling figure clean)
+    frames = [synth.make_scan(args.sensor, f) for f in range(N_FRAMES)]
     npts = [len(f) for f in frames]
     max_n = max(npts)
     mode = bs.NORMALS_REFERENCE if args.normals == "reference" else bs.NORMALS_FULL
