@@ -8,6 +8,8 @@
 // so that a min/max pair keeps the top-2 with the reference's first-minimum (lowest index)
 // tie-break.  Target ranges are split over blockIdx.y; a small merge kernel combines the
 // per-split candidates (and, across GPUs, the all-gathered per-rank candidates).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace bshot {
@@ -49,6 +51,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // COLMIN: also returns min over the thread's queries of (distance << 23 | query index) for this target
 template <int QPT, bool COLMIN>
 __device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], const uint4 a, const uint4 b,
@@ -57,10 +70,19 @@ __device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], c
     uint32_t ck = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
-        unsigned d = __popc(qw[j][0] ^ a.x) + __popc(qw[j][1] ^ a.y) + __popc(qw[j][2] ^ a.z) +
-                     __popc(qw[j][3] ^ a.w) + __popc(qw[j][4] ^ b.x) + __popc(qw[j][5] ^ b.y) +
-                     __popc(qw[j][6] ^ b.z) + __popc(qw[j][7] ^ b.w) + __popc(qw[j][8] ^ c.x) +
-                     __popc(qw[j][9] ^ c.y) + __popc(qw[j][10] ^ c.z);
+        // 352-bit XOR, then a carry-save adder tree (3:2 compressors, one LOP3 each for sum and carry)
+        // folds the 11 words into 1 weight-1 and 5 weight-2 words: 6 POPC instead of 11 on the
+        // quarter-rate POPC pipe, the extra LOP3s go to the full-rate ALU pipe.
+        const uint32_t x0 = qw[j][0] ^ a.x, x1 = qw[j][1] ^ a.y, x2 = qw[j][2] ^ a.z, x3 = qw[j][3] ^ a.w;
+        const uint32_t x4 = qw[j][4] ^ b.x, x5 = qw[j][5] ^ b.y, x6 = qw[j][6] ^ b.z, x7 = qw[j][7] ^ b.w;
+        const uint32_t x8 = qw[j][8] ^ c.x, x9 = qw[j][9] ^ c.y, x10 = qw[j][10] ^ c.z;
+        const uint32_t s1 = xor3(x0, x1, x2), c1 = maj3(x0, x1, x2);
+        const uint32_t s2 = xor3(x3, x4, x5), c2 = maj3(x3, x4, x5);
+        const uint32_t s3 = xor3(x6, x7, x8), c3 = maj3(x6, x7, x8);
+        const uint32_t s4 = xor3(s1, s2, s3), c4 = maj3(s1, s2, s3);
+        const uint32_t s5 = xor3(s4, x9, x10), c5 = maj3(s4, x9, x10);
+        const unsigned twos = __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(c5);
+        const unsigned d = __popc(s5) + 2u * twos;
         const uint32_t key = (d << HM_IDX_BITS) | idx;
         const uint32_t hi = max(k1[j], key);
         k1[j] = min(k1[j], key);
@@ -343,9 +365,25 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);
     const size_t max_splits = (nt + HM_MIN_CHUNK - 1) / HM_MIN_CHUNK;
-    size_t want = ((size_t)c->sm_count * 4 + qblocks - 1) / qblocks;  // ~4 CTAs per SM in flight
-    if (want < 1) want = 1;
-    if (want > max_splits) want = max_splits ? max_splits : 1;
+    // whole waves: the grid is a multiple of (SMs x resident CTAs per SM) whenever the problem is big enough,
+    // otherwise the last partial wave costs as much as a full one
+    static int occ_cache[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    int& occ = occ_cache[d_colmin ? 1 : 0][qpt];
+    if (occ == 0) {
+        cudaError_t e = cudaSuccess;
+        switch (qpt * 2 + (d_colmin ? 1 : 0)) {
+            case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<4, false>, HM_THREADS, 0); break;
+            case 9: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<4, true>, HM_THREADS, 0); break;
+            case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<2, false>, HM_THREADS, 0); break;
+            case 5: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<2, true>, HM_THREADS, 0); break;
+            case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<1, false>, HM_THREADS, 0); break;
+            default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<1, true>, HM_THREADS, 0); break;
+        }
+        if (e != cudaSuccess || occ <= 0) { cudaGetLastError(); occ = 2; }
+    }
+    const size_t slots = (size_t)c->sm_count * (size_t)occ;
+    size_t want = std::max<size_t>(1, (2 * slots) / qblocks);           // two waves
+    if ((nt + want - 1) / want < 4 * (size_t)HM_TILE) want = std::max<size_t>(1, slots / qblocks);  // short ranges: one wave
     const size_t cap_splits = c->partial_cap / (nq * 2);
     if (cap_splits == 0) {
         set_error("hamming_top2: partial buffer too small for %zu queries", nq);
