@@ -550,6 +550,16 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     return check_launch("seg_ratio kernels");
 }
 
+#ifdef BSHOT_KNN_STATS
+void knn_stats_dump() {
+    unsigned long long h[8];
+    cudaMemcpyFromSymbol(h, g_knn_stats, sizeof(h));
+    fprintf(stderr, "[knn stats] attempts=%llu rows=%llu cand=%llu insphere=%llu\n", h[0], h[1], h[2], h[3]);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z));
+}
+#endif
+
 int detect_topk(Ctx* c, int top_k) {
     const unsigned n = (unsigned)c->n_points;
     unsigned cap = 1;
@@ -564,6 +574,10 @@ int detect_topk(Ctx* c, int top_k) {
     topk_kernel<<<1, TK_THREADS, smem, c->stream>>>(c->d_keys, n, top_k, cap, c->d_pts, c->d_kp_idx, c->d_kp_ratio,
                                                    c->d_kp, c->d_kp_count);
     count_launch(c);
+#ifdef BSHOT_KNN_STATS
+    cudaStreamSynchronize(c->stream);
+    knn_stats_dump();
+#endif
     c->n_kp = (size_t)top_k;  // upper bound until the host reads d_kp_count
     c->have_kp = true;
     return check_launch("topk_kernel");

@@ -17,6 +17,10 @@ constexpr int KN_BINS = 256;
 constexpr int KN_LIST = 256;
 constexpr int KN_MAXB = 256;     // batch table covers 8192 candidates per query
 
+#ifdef BSHOT_KNN_STATS
+__device__ unsigned long long g_knn_stats[8];
+#endif
+
 struct KnnWarpSmem {
     SegList<KN_MAXSEG, KN_MAXB> sl;
     unsigned hist[KN_BINS];
@@ -121,6 +125,9 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
             }
         });
         n = warp_sum(cnt);
+#ifdef BSHOT_KNN_STATS
+        if (lane == 0) { atomicAdd(&g_knn_stats[0], 1ull); atomicAdd(&g_knn_stats[1], (unsigned long long)rr.nrows); atomicAdd(&g_knn_stats[2], (unsigned long long)sm.sl.total); atomicAdd(&g_knn_stats[3], (unsigned long long)n); }
+#endif
         if (last || n >= max_nn) break;
         const float f = sqrtf(1.15f * (float)max_nn / (float)max(n, 1));
         m = min(M, max(m + 1, (int)ceilf((float)m * f)));
