@@ -18,6 +18,10 @@ constexpr int HM_THREADS = 256;
 constexpr int HM_TILE = 128;   // targets per pipeline stage (6 KB)
 constexpr int HM_STAGES = 4;
 constexpr unsigned HM_IDX_BITS = 23;
+// packed key = distance * HM_K + index.  HM_K is odd (not a power of two) on purpose: the multiply-adds that
+// build the key then stay IMADs on the FMA pipe instead of being strength-reduced to shifts/LEAs on the ALU
+// pipe, which the XOR/CSA LOP3s already saturate.  353 * HM_K < 2^32.
+constexpr unsigned HM_K = (1u << HM_IDX_BITS) + 1u;
 constexpr unsigned long long HM_NONE = 0xFFFFFFFFFFFFFFFFull;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -81,13 +85,17 @@ __device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], c
         const uint32_t s3 = xor3(x6, x7, x8), c3 = maj3(x6, x7, x8);
         const uint32_t s4 = xor3(s1, s2, s3), c4 = maj3(s1, s2, s3);
         const uint32_t s5 = xor3(s4, x9, x10), c5 = maj3(s4, x9, x10);
-        const unsigned twos = __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(c5);
-        const unsigned d = __popc(s5) + 2u * twos;
-        const uint32_t key = (d << HM_IDX_BITS) | idx;
+        // key = (popc(s5) + 2 * sum popc(c_i)) * HM_K + idx as one IMAD chain (FMA pipe)
+        uint32_t key = __popc(s5) * HM_K + idx;
+        key = __popc(c1) * (2u * HM_K) + key;
+        key = __popc(c2) * (2u * HM_K) + key;
+        key = __popc(c3) * (2u * HM_K) + key;
+        key = __popc(c4) * (2u * HM_K) + key;
+        key = __popc(c5) * (2u * HM_K) + key;
         const uint32_t hi = max(k1[j], key);
         k1[j] = min(k1[j], key);
         k2[j] = min(k2[j], hi);
-        if (COLMIN) ck = min(ck, (d << HM_IDX_BITS) | qor[j]);  // qor = 0xFFFFFFFF for padding queries
+        if (COLMIN) ck = min(ck, key + qor[j] - idx);  // same distance, query index instead of target index
     }
     return ck;
 }
@@ -136,13 +144,9 @@ hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __res
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
         const unsigned qi = (blockIdx.x * QPT + j) * HM_THREADS + tid;
-        qor[j] = (qi < nq) ? qi : 0xFFFFFFFFu;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
-        if (qi < nq) {
-            a = __ldg(q + (size_t)qi * 3);
-            b = __ldg(q + (size_t)qi * 3 + 1);
-            c = __ldg(q + (size_t)qi * 3 + 2);
-        }
+        const unsigned ql = min(qi, nq - 1);  // padding slots replicate the last real query; their results are dropped
+        qor[j] = ql;
+        const uint4 a = __ldg(q + (size_t)ql * 3), b = __ldg(q + (size_t)ql * 3 + 1), c = __ldg(q + (size_t)ql * 3 + 2);
         qw[j][0] = a.x; qw[j][1] = a.y; qw[j][2] = a.z; qw[j][3] = a.w;
         qw[j][4] = b.x; qw[j][5] = b.y; qw[j][6] = b.z; qw[j][7] = b.w;
         qw[j][8] = c.x; qw[j][9] = c.y; qw[j][10] = c.z;
@@ -189,10 +193,8 @@ hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __res
         if (qi >= nq) continue;
         unsigned long long o1 = HM_NONE, o2 = HM_NONE;
         const unsigned long long gb = global_base + t0;
-        if (k1[j] != 0xFFFFFFFFu)
-            o1 = ((unsigned long long)(k1[j] >> HM_IDX_BITS) << 32) | (gb + (k1[j] & ((1u << HM_IDX_BITS) - 1)));
-        if (k2[j] != 0xFFFFFFFFu)
-            o2 = ((unsigned long long)(k2[j] >> HM_IDX_BITS) << 32) | (gb + (k2[j] & ((1u << HM_IDX_BITS) - 1)));
+        if (k1[j] != 0xFFFFFFFFu) o1 = ((unsigned long long)(k1[j] / HM_K) << 32) | (gb + (k1[j] % HM_K));
+        if (k2[j] != 0xFFFFFFFFu) o2 = ((unsigned long long)(k2[j] / HM_K) << 32) | (gb + (k2[j] % HM_K));
         unsigned long long* p = partial + ((size_t)split * nq + qi) * 2;
         p[0] = o1;
         p[1] = o2;
@@ -211,6 +213,7 @@ __global__ void merge_top2_kernel(const unsigned long long* __restrict__ src, un
     const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+#pragma unroll 8
     for (unsigned s = 0; s < nsrc; ++s) {
         const unsigned long long* p = src + ((size_t)s * nq + qi) * stride_u64;
         top2_insert(p[0], k1, k2);
@@ -228,6 +231,7 @@ __global__ void merge_top2_rq_kernel(const unsigned long long* __restrict__ src,
     const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+#pragma unroll 8
     for (unsigned s = 0; s < nsrc; ++s) {
         const unsigned long long* p = src + ((size_t)s * nq + qi) * 2;
         top2_insert(p[0], k1, k2);
@@ -237,7 +241,7 @@ __global__ void merge_top2_rq_kernel(const unsigned long long* __restrict__ src,
     c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
     if (k1 != HM_NONE) {
         const unsigned v = gcol[(size_t)((k1 & 0xFFFFFFFFull) - global_base)];
-        if (v != 0xFFFFFFFFu) c.rq = v & ((1u << HM_IDX_BITS) - 1);
+        if (v != 0xFFFFFFFFu) c.rq = v % HM_K;
     }
     out[qi] = c;
 }
