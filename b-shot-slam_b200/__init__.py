@@ -30,7 +30,7 @@ EXPORTS = [
     "bshot_process_frame", "bshot_process_frame_dev", "bshot_fetch_frame", "bshot_ctx_enable_timing",
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
-    "bshot_match_map", "bshot_launch_count", "bshot_popc_peak",
+    "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_launch_count", "bshot_popc_peak",
 ]
 
 
@@ -99,6 +99,8 @@ def lib():
         L.bshot_match_dev.argtypes = [vp, vp, sz, vp, sz, C.c_uint64, ci, vp]
         L.bshot_merge_cands_dev.argtypes = [vp, vp, sz, sz, vp]
         L.bshot_match_map.argtypes = [vp, vp, sz, C.c_uint64, vp]
+        L.bshot_reverse_owned_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp]
+        L.bshot_apply_rq_dev.argtypes = [vp, vp, vp, sz]
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
         L.bshot_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -353,6 +355,12 @@ class Context:
 
     def match_dev(self, d_q_ptr, nq, d_t_ptr, nt, global_base, with_rq, d_cand_ptr):
         _chk(lib().bshot_match_dev(self.h, d_q_ptr, nq, d_t_ptr, nt, global_base, int(with_rq), d_cand_ptr))
+
+    def reverse_owned_dev(self, d_q_ptr, nq, global_base, d_merged_ptr, d_rq_ptr):
+        _chk(lib().bshot_reverse_owned_dev(self.h, d_q_ptr, nq, global_base, d_merged_ptr, d_rq_ptr))
+
+    def apply_rq_dev(self, d_cands_ptr, d_rq_ptr, nq):
+        _chk(lib().bshot_apply_rq_dev(self.h, d_cands_ptr, d_rq_ptr, nq))
 
     def merge_cands_dev(self, d_cands_ptr, nranks, nq, d_out_ptr):
         _chk(lib().bshot_merge_cands_dev(self.h, d_cands_ptr, nranks, nq, d_out_ptr))

@@ -583,6 +583,20 @@ int bshot_merge_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nranks, si
     return hamming_merge_cands(ctx, d_cands, nranks, nq, d_out);
 }
 
+int bshot_reverse_owned_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, const void* d_merged,
+                            void* d_rq_out) {
+    CHECK_CTX(ctx);
+    if (!d_q || !d_merged || !d_rq_out) { set_error("bshot_reverse_owned_dev: null device pointer"); return BSHOT_E_INVALID; }
+    return hamming_reverse_owned(ctx, d_q, nq, ctx->d_map, ctx->n_map, global_base, reinterpret_cast<const bshot_cand*>(d_merged),
+                                 reinterpret_cast<unsigned*>(d_rq_out));
+}
+
+int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t nq) {
+    CHECK_CTX(ctx);
+    if (!d_cands || !d_rq) { set_error("bshot_apply_rq_dev: null device pointer"); return BSHOT_E_INVALID; }
+    return hamming_apply_rq(ctx, reinterpret_cast<bshot_cand*>(d_cands), reinterpret_cast<const unsigned*>(d_rq), nq);
+}
+
 int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base, bshot_cand* cand_out) {
     CHECK_CTX(ctx);
     if ((!q || !cand_out) && nq) { set_error("bshot_match_map: null buffer"); return BSHOT_E_INVALID; }

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "stages.h"
 
 namespace bshot {
 
@@ -104,9 +105,12 @@ __device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], c
 // (distance << 32 | global target index), HM_NONE when the split saw fewer than 1/2 targets.
 template <int QPT, bool COLMIN>
 __global__ void __launch_bounds__(HM_THREADS)
-hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __restrict__ t, unsigned nt,
-                    unsigned chunk, unsigned long long global_base,
+hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq_cap, const unsigned* __restrict__ nq_dev,
+                    const uint4* __restrict__ t, unsigned nt, unsigned chunk, unsigned long long global_base,
                     unsigned long long* __restrict__ partial, unsigned* __restrict__ gcol) {
+    // nq_cap sizes the grid and the partial layout; an optional device-side count trims the work
+    const unsigned nq = nq_dev ? min(nq_cap, *nq_dev) : nq_cap;
+    if (blockIdx.x * (unsigned)(HM_THREADS * QPT) >= nq) return;
     __shared__ __align__(128) uint4 tile[HM_STAGES][HM_TILE * 3];
     __shared__ __align__(8) unsigned long long full[HM_STAGES];
     __shared__ unsigned col[COLMIN ? HM_STAGES : 1][COLMIN ? HM_TILE : 1];  // per-target best (distance, query) of this CTA
@@ -195,7 +199,7 @@ hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq, const uint4* __res
         const unsigned long long gb = global_base + t0;
         if (k1[j] != 0xFFFFFFFFu) o1 = ((unsigned long long)(k1[j] / HM_K) << 32) | (gb + (k1[j] % HM_K));
         if (k2[j] != 0xFFFFFFFFu) o2 = ((unsigned long long)(k2[j] / HM_K) << 32) | (gb + (k2[j] % HM_K));
-        unsigned long long* p = partial + ((size_t)split * nq + qi) * 2;
+        unsigned long long* p = partial + ((size_t)split * nq_cap + qi) * 2;
         p[0] = o1;
         p[1] = o2;
     }
@@ -360,7 +364,7 @@ static int pick_qpt(size_t nq, size_t nt, int sm_count) {
 
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out, unsigned* d_colmin) {
+                 bshot_cand* d_out, unsigned* d_colmin, const unsigned* d_nq) {
     if (nq == 0) return BSHOT_OK;
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
         set_error("hamming_top2: sizes exceed 32-bit index range");
@@ -413,7 +417,7 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
         BSHOT_CUDA_TRY(cudaMemsetAsync(d_colmin, 0xFF, sizeof(unsigned) * nt, c->stream));
     }
 #define BSHOT_LAUNCH_TOP2(QPT, CM)                                                                                    \
-    hamming_top2_kernel<QPT, CM><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, t4, (unsigned)nt, (unsigned)chunk, \
+    hamming_top2_kernel<QPT, CM><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, d_nq, t4, (unsigned)nt, (unsigned)chunk, \
                                                                      global_base, c->d_partial, d_colmin)
     switch (qpt) {
         case 4: if (colmin) BSHOT_LAUNCH_TOP2(4, true); else BSHOT_LAUNCH_TOP2(4, false); break;
@@ -520,4 +524,81 @@ int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t
     BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr));
     return hamming_reverse(c, d_q, nq, d_t, global_base, d_out);
 }
+}  // namespace bshot
+
+namespace bshot {
+
+// Post-merge reverse pass of the sharded search: select the queries whose merged winner lies in this
+// rank's shard [global_base, global_base + nt), gather those target records, search them against all
+// queries and scatter the best query index to rq_out (0xFFFFFFFF elsewhere).  An all-reduce(MIN) over
+// the ranks' rq_out arrays then gives every rank the full reverse result with Q * Q / ranks pairs of
+// work per rank instead of Q * Q.
+__global__ void select_owned_kernel(const bshot_cand* __restrict__ merged, unsigned nq, unsigned long long lo,
+                                    unsigned long long hi, const uint4* __restrict__ t, uint4* __restrict__ gathered,
+                                    unsigned* __restrict__ owner_q, unsigned* __restrict__ count, unsigned* __restrict__ rq_out) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    bool mine = false;
+    unsigned long long idx = 0;
+    if (qi < nq) {
+        rq_out[qi] = 0xFFFFFFFFu;
+        const unsigned long long k = merged[qi].k1;
+        idx = k & 0xFFFFFFFFull;
+        mine = (k != HM_NONE) && idx >= lo && idx < hi;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m == 0) return;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mine) {
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1));
+        owner_q[slot] = qi;
+        const uint4* src = t + (size_t)(idx - lo) * 3;
+        gathered[(size_t)slot * 3] = __ldg(src);
+        gathered[(size_t)slot * 3 + 1] = __ldg(src + 1);
+        gathered[(size_t)slot * 3 + 2] = __ldg(src + 2);
+    }
+}
+
+__global__ void scatter_rq_kernel(const bshot_cand* __restrict__ rev, const unsigned* __restrict__ owner_q,
+                                  const unsigned* __restrict__ count, unsigned* __restrict__ rq_out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const unsigned long long k = rev[i].k1;
+    rq_out[owner_q[i]] = (k != HM_NONE) ? (unsigned)(k & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+}
+
+__global__ void apply_rq_kernel(bshot_cand* __restrict__ cand, const unsigned* __restrict__ rq, unsigned nq) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) cand[qi].rq = (cand[qi].k1 != HM_NONE) ? rq[qi] : 0xFFFFFFFFu;
+}
+
+int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                          const bshot_cand* d_merged, unsigned* d_rq_out) {
+    if (nq == 0) return BSHOT_OK;
+    if (nq > c->max_kp) { set_error("hamming_reverse_owned: %zu queries > capacity %zu", nq, c->max_kp); return BSHOT_E_CAPACITY; }
+    unsigned* owner_q = reinterpret_cast<unsigned*>(c->d_left);          // max_kp x 4 ints: [0,nq) owner list
+    unsigned* count = reinterpret_cast<unsigned*>(c->d_pair_count) + 1;
+    BSHOT_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(unsigned), c->stream));
+    select_owned_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(
+        d_merged, (unsigned)nq, global_base, global_base + nt, reinterpret_cast<const uint4*>(d_t),
+        reinterpret_cast<uint4*>(c->d_gather), owner_q, count, d_rq_out);
+    count_launch(c);
+    BSHOT_TRY(check_launch("select_owned_kernel"));
+    // gathered targets act as queries, the original queries as targets; the device-side count trims the grid
+    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2, nullptr, count));
+    scatter_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_cand2, owner_q, count, d_rq_out);
+    count_launch(c);
+    return check_launch("scatter_rq_kernel");
+}
+
+int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq) {
+    if (nq == 0) return BSHOT_OK;
+    apply_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, d_rq, (unsigned)nq);
+    count_launch(c);
+    return check_launch("apply_rq_kernel");
+}
+
 }  // namespace bshot

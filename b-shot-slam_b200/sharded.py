@@ -57,6 +57,20 @@ class ShardedMap:
             return self.backend.merge(local[None, :])
         return self.backend.merge(self.all_gather(local))
 
+    def match_sharded_reverse(self, queries, all_reduce_max):
+        """Variant that keeps the reverse (best query per winning target) pass sharded: per-rank records
+        carry no rq; after the merge every rank searches only the winners that live in ITS shard
+        (Q*Q/ranks pairs) and the int32 results (-1 = not mine) are combined by an all-reduce(MAX) --
+        exactly one rank owns each winner."""
+        local = self.backend.match_shard(queries, self.lo, with_rq=False)
+        merged = self.backend.merge(self.all_gather(local) if self.world > 1 else local[None, :])
+        rq = self.backend.reverse_owned(queries, self.lo, merged)      # (Q,) int32, -1 where not owned
+        if self.world > 1:
+            rq = all_reduce_max(rq)
+        merged = merged.copy()
+        merged["rq"] = np.where(merged["k1"] != NONE_KEY, rq.astype(np.int64) & 0xFFFFFFFF, 0xFFFFFFFF).astype(np.uint32)
+        return merged
+
     @staticmethod
     def correspondences(merged):
         """mutual-NN filter (src/lidar_odometry.cpp:234-242) from merged records"""
@@ -76,8 +90,28 @@ class GpuBackend:
         self.ctx.map_reset()
         self.ctx.map_append(desc)
 
-    def match_shard(self, queries, global_base):
-        return self.ctx.match_map(queries, global_base)
+    def match_shard(self, queries, global_base, with_rq=True):
+        if with_rq:
+            return self.ctx.match_map(queries, global_base)
+        import torch
+        q = np.ascontiguousarray(queries, dtype=np.uint64).reshape(-1, 6)
+        dq = torch.from_numpy(q.view(np.int64)).cuda()
+        out = torch.empty((len(q), 3), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        self.ctx.match_shard_dev(dq.data_ptr(), len(q), global_base, False, out.data_ptr())
+        self.ctx.sync()
+        return out.cpu().numpy().view(CAND_DTYPE).reshape(len(q))
+
+    def reverse_owned(self, queries, global_base, merged):
+        import torch
+        q = np.ascontiguousarray(queries, dtype=np.uint64).reshape(-1, 6)
+        dq = torch.from_numpy(q.view(np.int64)).cuda()
+        dm = torch.from_numpy(np.ascontiguousarray(merged).view(np.int64).reshape(len(q), 3)).cuda()
+        rq = torch.empty(len(q), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        self.ctx.reverse_owned_dev(dq.data_ptr(), len(q), global_base, dm.data_ptr(), rq.data_ptr())
+        self.ctx.sync()
+        return rq.cpu().numpy()
 
     def merge(self, gathered):
         import torch

@@ -296,13 +296,22 @@ def main():
         gathered = torch.empty((world, Q, 3), dtype=torch.int64, device="cuda")
         merged = torch.empty((Q, 3), dtype=torch.int64, device="cuda")
 
+        rq = torch.empty(Q, dtype=torch.int32, device="cuda")
+
         def map_step():
-            ctx.match_shard_dev(dq.data_ptr(), Q, lo, True, cand.data_ptr())
             if world > 1:
+                # shard search -> all-gather of 24 B/query records -> merge -> reverse pass only for the winners
+                # this rank owns (Q*Q/ranks pairs) -> all-reduce of the 4 B/query reverse result
+                ctx.match_shard_dev(dq.data_ptr(), Q, lo, False, cand.data_ptr())
                 with torch.cuda.stream(st):
                     dist.all_gather_into_tensor(gathered.view(-1), cand.view(-1))
                 ctx.merge_cands_dev(gathered.data_ptr(), world, Q, merged.data_ptr())
+                ctx.reverse_owned_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), rq.data_ptr())
+                with torch.cuda.stream(st):
+                    dist.all_reduce(rq, op=dist.ReduceOp.MAX)     # one owner per query, others hold -1 (0xFFFFFFFF)
+                ctx.apply_rq_dev(merged.data_ptr(), rq.data_ptr(), Q)
             else:
+                ctx.match_shard_dev(dq.data_ptr(), Q, lo, True, cand.data_ptr())
                 ctx.merge_cands_dev(cand.data_ptr(), 1, Q, merged.data_ptr())
 
         for _ in range(3):
@@ -324,7 +333,7 @@ def main():
                                   "peak": world * popc_peak / 1e12, "unit": "TPOPC32/s",
                                   "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
                                   "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
-                     "collective": "nccl all_gather of 24 B/query candidate records" if world > 1 else "none",
+                     "collective": "nccl all_gather of 24 B/query candidate records + all_reduce of 4 B/query reverse result" if world > 1 else "none",
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------

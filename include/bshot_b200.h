@@ -186,6 +186,13 @@ int bshot_match_dev(bshot_ctx* ctx, const void* d_q, size_t nq, const void* d_t,
  * by (distance, global index); d_out: nq merged records. mutual iff merged rq == query index. */
 int bshot_merge_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nranks, size_t nq,
                           void* d_out);
+/* Post-merge reverse pass, sharded: for the queries whose MERGED winner (d_merged, nq records) lies in this
+ * rank's shard, find the best query of that target; d_rq_out (nq x u32) gets the query index there and
+ * 0xFFFFFFFF elsewhere.  An all-reduce(MIN) of d_rq_out over the ranks followed by bshot_apply_rq_dev
+ * completes the records with Q*Q/ranks pairs of work per rank (vs Q*Q for with_rq = 1 above). */
+int bshot_reverse_owned_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
+                            const void* d_merged, void* d_rq_out);
+int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t nq);
 /* host-buffer convenience over the three calls above for a single rank */
 int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base,
                     bshot_cand* cand_out);

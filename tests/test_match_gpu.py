@@ -117,6 +117,50 @@ def test_sharded_merge_equals_single(gpu_ctx, bshot, oracle, synth):
     assert np.array_equal(mutual_gpu, opairs[:, 0])
 
 
+def test_sharded_reverse_owned_equals_single(bshot, oracle, synth):
+    """4 emulated ranks (4 contexts on one GPU): shard search without rq, merge, reverse pass for the owned
+    winners only, MAX-combine -> records identical to the single-pass oracle result."""
+    import torch
+    nq, nt, ranks = 700, 20000, 4
+    q = synth.random_descriptors(nq, seed=41, density=40)
+    t = synth.random_descriptors(nt, seed=42, density=40)
+    t[19999] = q[3]
+    t[10] = q[3]
+    dq = torch.from_numpy(q.view(np.int64)).cuda()
+    per = (nt + ranks - 1) // ranks
+    ctxs = [bshot.Context(0, 1024, 1024, per) for _ in range(ranks)]
+    try:
+        cands = torch.empty((ranks, nq, 3), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        for r, c in enumerate(ctxs):
+            c.map_append(t[r * per:(r + 1) * per])
+            c.match_shard_dev(dq.data_ptr(), nq, r * per, False, cands[r].data_ptr())
+            c.sync()
+        rqs = []
+        merged_all = []
+        for r, c in enumerate(ctxs):
+            merged = torch.empty((nq, 3), dtype=torch.int64, device="cuda")
+            rq = torch.empty(nq, dtype=torch.int32, device="cuda")
+            c.merge_cands_dev(cands.data_ptr(), ranks, nq, merged.data_ptr())
+            c.reverse_owned_dev(dq.data_ptr(), nq, r * per, merged.data_ptr(), rq.data_ptr())
+            c.sync()
+            rqs.append(rq)
+            merged_all.append(merged)
+        rq = torch.stack(rqs).max(dim=0).values            # the all-reduce(MAX)
+        ctxs[0].apply_rq_dev(merged_all[0].data_ptr(), rq.data_ptr(), nq)
+        ctxs[0].sync()
+        rec = merged_all[0].cpu().numpy().view(bshot.CAND_DTYPE).reshape(nq)
+    finally:
+        for c in ctxs:
+            c.close()
+    u = bshot.unpack_cands(rec)
+    o = oracle.match(q, t, want_right=True)
+    assert np.array_equal(u["idx1"], o["left_idx"]) and np.array_equal(u["dist1"], o["left_dist"])
+    assert np.array_equal(u["idx2"], o["left_idx2"])
+    assert np.array_equal(u["rq"], o["right_idx"][o["left_idx"]])
+    assert u["idx1"][3] == 10
+
+
 def test_full_size_properties(gpu_ctx, bshot, synth):
     """C4-sized shard (Q=10000 x T=1M): size-independent properties instead of the O(QT) oracle."""
     nq, nt = 10000, 1 << 20

@@ -21,7 +21,18 @@ class OracleBackend:
     def set_shard(self, desc):
         self.shard = np.ascontiguousarray(desc)
 
-    def match_shard(self, queries, global_base):
+    def reverse_owned(self, queries, global_base, merged):
+        """oracle mirror of bshot_reverse_owned_dev: best query for the winners that live in this shard"""
+        rq = np.full(len(queries), -1, np.int32)
+        idx = (merged["k1"] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        mine = (merged["k1"] != self.sharded.NONE_KEY) & (idx >= global_base) & (idx < global_base + len(self.shard))
+        if mine.any():
+            tg = self.shard[idx[mine] - global_base]
+            m = self.oracle.match(tg, queries, want_right=False)
+            rq[mine] = m["left_idx"]
+        return rq
+
+    def match_shard(self, queries, global_base, with_rq=True):
         q = len(queries)
         rec = np.zeros(q, self.sharded.CAND_DTYPE)
         rec["k1"] = rec["k2"] = self.sharded.NONE_KEY
@@ -60,9 +71,16 @@ def _worker(rank, world, port, nq, nt, out_dir):
         dist.all_gather(outs, x)
         return np.stack([o.numpy().view(sharded.CAND_DTYPE).reshape(-1) for o in outs])
 
+    def all_reduce_max(local):
+        x = torch.from_numpy(local.copy())
+        dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return x.numpy()
+
     sm = sharded.ShardedMap(OracleBackend(oracle, sharded), rank, world, all_gather)
     sm.load(t)
     merged = sm.match(q)
+    merged2 = sm.match_sharded_reverse(q, all_reduce_max)     # sharded reverse pass: same records
+    assert np.array_equal(merged, merged2), "sharded reverse pass differs from the rq-in-record protocol"
     np.save(os.path.join(out_dir, f"merged_{rank}.npy"), merged)
     dist.barrier()
     dist.destroy_process_group()
