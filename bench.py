@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--map-steps", type=int, default=10)
     ap.add_argument("--no-map", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--map-only", action="store_true", help="debug: print only the map_match object")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -287,41 +288,50 @@ def main():
         T, Q = args.map_t, args.map_q
         per = (T + world - 1) // world
         lo, hi = rank * per, min(T, (rank + 1) * per)
-        tdesc = synth.random_descriptors(T, seed=7)[lo:hi]       # same global map on every rank, own shard kept
+        tfull = synth.random_descriptors(T, seed=7)                # same global map on every rank, own shard kept
         ctx.map_reset()
-        ctx.map_append(tdesc)
+        ctx.map_append(tfull[lo:hi])
         q = synth.random_descriptors(Q, seed=8)
+        planted = np.random.default_rng(9).permutation(T)[:64]     # self-check: 64 queries are exact copies of map entries
+        q[:64] = tfull[planted]
+        del tfull
         dq = torch.from_numpy(q.view(np.int64)).cuda()
         cand = torch.empty((Q, 3), dtype=torch.int64, device="cuda")
-        gathered = torch.empty((world, Q, 3), dtype=torch.int64, device="cuda")
         merged = torch.empty((Q, 3), dtype=torch.int64, device="cuda")
 
+        # Per call at N > 1: shard search (no rq) -> all-gather of 24 B/query records -> merge -> reverse pass only
+        # for the winners this rank owns (Q*Q/ranks pairs) -> all-reduce of the 4 B/query reverse result -> records
+        # completed.  Everything is stream-ordered on the context stream.  (Overlapping the collectives with the next
+        # call's shard kernel was measured and is slower: the NCCL kernels wait for SM slots behind a full-GPU grid.)
+        gathered = torch.empty((world, Q, 3), dtype=torch.int64, device="cuda")
         rq = torch.empty(Q, dtype=torch.int32, device="cuda")
 
-        def map_step():
-            if world > 1:
-                # shard search -> all-gather of 24 B/query records -> merge -> reverse pass only for the winners
-                # this rank owns (Q*Q/ranks pairs) -> all-reduce of the 4 B/query reverse result
+        def map_calls(n):
+            for _ in range(n):
+                if world == 1:
+                    ctx.match_shard_dev(dq.data_ptr(), Q, lo, True, cand.data_ptr())
+                    ctx.merge_cands_dev(cand.data_ptr(), 1, Q, merged.data_ptr())
+                    continue
                 ctx.match_shard_dev(dq.data_ptr(), Q, lo, False, cand.data_ptr())
                 with torch.cuda.stream(st):
                     dist.all_gather_into_tensor(gathered.view(-1), cand.view(-1))
                 ctx.merge_cands_dev(gathered.data_ptr(), world, Q, merged.data_ptr())
                 ctx.reverse_owned_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), rq.data_ptr())
                 with torch.cuda.stream(st):
-                    dist.all_reduce(rq, op=dist.ReduceOp.MAX)     # one owner per query, others hold -1 (0xFFFFFFFF)
+                    dist.all_reduce(rq, op=dist.ReduceOp.MAX)      # one owner per query, the others hold -1
                 ctx.apply_rq_dev(merged.data_ptr(), rq.data_ptr(), Q)
-            else:
-                ctx.match_shard_dev(dq.data_ptr(), Q, lo, True, cand.data_ptr())
-                ctx.merge_cands_dev(cand.data_ptr(), 1, Q, merged.data_ptr())
+            return merged
 
-        for _ in range(3):
-            map_step()
+        last = map_calls(3)
         barrier()
+        rec = last[:64].cpu().numpy().view(bs.CAND_DTYPE).reshape(64)
+        chk = bs.unpack_cands(rec)
+        if not (np.array_equal(chk["idx1"], planted) and (chk["dist1"] == 0).all() and np.array_equal(chk["rq"], np.arange(64))):
+            raise SystemExit("bench.py: sharded map match self-check failed (planted duplicates not recovered)")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count()
         e0.record(st)
-        for _ in range(args.map_steps):
-            map_step()
+        map_calls(args.map_steps)
         e1.record(st)
         barrier()
         mm_ms = max_over_ranks(e0.elapsed_time(e1)) / args.map_steps
@@ -333,7 +343,7 @@ def main():
                                   "peak": world * popc_peak / 1e12, "unit": "TPOPC32/s",
                                   "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
                                   "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
-                     "collective": "nccl all_gather of 24 B/query candidate records + all_reduce of 4 B/query reverse result" if world > 1 else "none",
+                     "collective": "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result" if world > 1 else "none",
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
@@ -352,7 +362,9 @@ def main():
                                                 "detector_match_threads": 1, "normals_shot_threads": min(12, cores),
                                                 "sample": "2 frames"}}
 
-    if rank == 0:
+    if rank == 0 and args.map_only:
+        print(json.dumps(map_match))
+    elif rank == 0:
         line = {
             "metric": "bshot_frontend_descriptors_per_s", "value": value, "unit": "descriptors/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
