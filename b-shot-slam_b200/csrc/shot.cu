@@ -10,13 +10,15 @@
 //            per neighbour), fp64 intermediates like PCL
 //   phase D  L2 normalisation, optional float output, 88 nibbles -> packed 352-bit record
 // The float histogram never has to touch HBM when only the bits are wanted.
+#include <stdlib.h>
+
 #include "nbr.cuh"
 #include "stages.h"
 
 namespace bshot {
 
-constexpr int SH_THREADS = 128;
-constexpr int SH_WARPS = SH_THREADS / 32;
+constexpr int SH_MAX_THREADS = 256;
+constexpr int SH_WARPS = SH_MAX_THREADS / 32;  // smem reduction slots (upper bound)
 constexpr int SH_MAXSEG = 1024;
 constexpr int SH_MAXB = 2048;  // batch table covers 65536 candidates per keypoint
 constexpr int SH_TIE_CAP = 512;
@@ -115,16 +117,18 @@ __device__ __forceinline__ unsigned bshot_nibble(float v0, float v1, float v2, f
 }
 
 // hist (352 floats in smem) -> 12 u32 words (smem) ; threads 0..87 active, all threads sync
+template <int NT>
 __device__ __forceinline__ void pack_bits_block(const float* hist, unsigned* words, unsigned tid) {
     if (tid < 12) words[tid] = 0u;
     __syncthreads();
-    if (tid < 88) {
-        const unsigned nib = bshot_nibble(hist[4 * tid], hist[4 * tid + 1], hist[4 * tid + 2], hist[4 * tid + 3]);
-        if (nib) atomicOr(&words[tid >> 3], nib << ((tid & 7) * 4));
+    for (unsigned j = tid; j < 88; j += NT) {
+        const unsigned nib = bshot_nibble(hist[4 * j], hist[4 * j + 1], hist[4 * j + 2], hist[4 * j + 3]);
+        if (nib) atomicOr(&words[j >> 3], nib << ((j & 7) * 4));
     }
     __syncthreads();
 }
 
+template <int SH_THREADS>
 __global__ void __launch_bounds__(SH_THREADS)
 shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
             const float4* __restrict__ sorted, const float4* __restrict__ kp, const int* __restrict__ kp_count,
@@ -193,8 +197,8 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     if (tid == 0) {
         double m[7];
         int nv = 0, na = 0;
-        for (int i = 0; i < 7; ++i) { m[i] = 0; for (int w = 0; w < SH_WARPS; ++w) m[i] += sm.red[w][i]; }
-        for (int w = 0; w < SH_WARPS; ++w) { nv += sm.redi[w][0]; na += sm.redi[w][1]; }
+        for (int i = 0; i < 7; ++i) { m[i] = 0; for (int w = 0; w < SH_THREADS / 32; ++w) m[i] += sm.red[w][i]; }
+        for (int w = 0; w < SH_THREADS / 32; ++w) { nv += sm.redi[w][0]; na += sm.redi[w][1]; }
         sm.valid = nv;
         sm.count_all = na;
         int ok = (nv >= 5) ? 1 : 0;
@@ -232,7 +236,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         __syncthreads();
         if (tid == 0) {
             int pt = 0, pn = 0;
-            for (int w = 0; w < SH_WARPS; ++w) { pt += sm.redi[w][0]; pn += sm.redi[w][1]; }
+            for (int w = 0; w < SH_THREADS / 32; ++w) { pt += sm.redi[w][0]; pn += sm.redi[w][1]; }
             const int st = 2 * pt - n_valid, sn = 2 * pn - n_valid;
             sm.tie1 = (st == 0);
             sm.tie3 = (sn == 0);
@@ -341,7 +345,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             __syncthreads();
             if (tid == 0) {
                 int c1 = 0, c3 = 0;
-                for (int w = 0; w < SH_WARPS; ++w) { c1 += sm.redi[w][0]; c3 += sm.redi[w][1]; }
+                for (int w = 0; w < SH_THREADS / 32; ++w) { c1 += sm.redi[w][0]; c3 += sm.redi[w][1]; }
                 if (sm.tie1 && c1 < 3) { sm.v1[0] = -sm.v1[0]; sm.v1[1] = -sm.v1[1]; sm.v1[2] = -sm.v1[2]; }
                 if (sm.tie3 && c3 < 3) { sm.v3[0] = -sm.v3[0]; sm.v3[1] = -sm.v3[1]; sm.v3[2] = -sm.v3[2]; }
             }
@@ -474,7 +478,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         __syncthreads();
         if (tid == 0) {
             double s = 0;
-            for (int w = 0; w < SH_WARPS; ++w) s += sm.red[w][0];
+            for (int w = 0; w < SH_THREADS / 32; ++w) s += sm.red[w][0];
             sm.norm = sqrt(s);
         }
         __syncthreads();
@@ -485,7 +489,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             if (shot_out) shot_out[(size_t)k * 352 + i] = v;
         }
         __syncthreads();
-        pack_bits_block(sm.hist, sm.words, tid);
+        pack_bits_block<SH_THREADS>(sm.hist, sm.words, tid);
         if (tid < 6) bits_out[(size_t)k * 6 + tid] = ((uint64_t)sm.words[2 * tid + 1] << 32) | sm.words[2 * tid];
     }
 }
@@ -534,9 +538,15 @@ int shot_compute(Ctx* c, float radius, bool lrf_only, bool write_shot) {
     if (k == 0) return BSHOT_OK;
     if (!lrf_only) BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_sum_nn, 0, sizeof(unsigned long long), c->stream));
     const unsigned limit = (unsigned)std::min(c->normals_valid, c->n_points);
-    shot_kernel<<<(unsigned)k, SH_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count,
-                                                          c->d_normals, limit, radius, lrf_only ? 1 : 0, c->d_rf, c->d_nn,
-                                                          write_shot ? c->d_shot : nullptr, c->d_bits, c->d_sum_nn);
+    static const int nthreads = [] { const char* e = getenv("BSHOT_SHOT_THREADS"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
+#define BSHOT_LAUNCH_SHOT(NT)                                                                                              \
+    shot_kernel<NT><<<(unsigned)k, NT, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count,   \
+                                                      c->d_normals, limit, radius, lrf_only ? 1 : 0, c->d_rf, c->d_nn,   \
+                                                      write_shot ? c->d_shot : nullptr, c->d_bits, c->d_sum_nn)
+    if (nthreads == 64) BSHOT_LAUNCH_SHOT(64);
+    else if (nthreads == 256) BSHOT_LAUNCH_SHOT(256);
+    else BSHOT_LAUNCH_SHOT(128);
+#undef BSHOT_LAUNCH_SHOT
     count_launch(c);
     return check_launch("shot_kernel");
 }
