@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbshot_b200.so")
+LIB_PATH = os.environ.get("BSHOT_LIB") or os.path.join(_HERE, "libbshot_b200.so")  # BSHOT_LIB: tuning builds (tools/build_variant.sh)
 _LIB = None
 
 SR_CV, SR_CVS, SR_CVSN = 0, 1, 2

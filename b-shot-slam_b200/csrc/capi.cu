@@ -140,6 +140,10 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_kp_ratio, K));
     A(dmalloc(&c->d_kp, K));
     A(dmalloc(&c->d_kp_count, 4));
+    A(dmalloc(&c->d_tk_hist, 4096));
+    A(dmalloc(&c->d_tk_state, 16));
+    A(dmalloc(&c->d_tk_sure, K));
+    A(dmalloc(&c->d_tk_tie, N));
     A(dmalloc(&c->d_normals, N));
     A(dmalloc(&c->d_qnormals, QN));
     A(dmalloc(&c->d_shot, K * 352));
@@ -171,6 +175,8 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
         cudaError_t e = cudaMemsetAsync(c->d_normals, 0, sizeof(float4) * N, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_prev_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_kp_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tk_hist, 0, 4096 * sizeof(unsigned), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tk_state, 0, 16 * sizeof(unsigned), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_sum_nn, 0, 2 * sizeof(unsigned long long), c->stream);
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
@@ -191,7 +197,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
                     c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
-                    c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
+                    c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
     for (void* p : ptrs)
@@ -521,15 +527,6 @@ int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]) {
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
     BSHOT_TRY(sync(ctx));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = (unsigned long long)ctx->h_scratch[0];
-#ifdef BSHOT_TILE_STATS
-    {
-        unsigned long long dbg[8];
-        cudaMemcpy(dbg, ctx->d_counters, sizeof(dbg), cudaMemcpyDeviceToHost);
-        unsigned left = 0;
-        cudaMemcpy(&left, reinterpret_cast<unsigned*>(ctx->d_kp_count) + 2, 4, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[tile stats] groups=%llu lanes=%llu grow_passes=%llu sum_total=%llu leftover=%u\n", dbg[4], dbg[7], dbg[6], dbg[5], left);
-    }
-#endif
     return BSHOT_OK;
 }
 

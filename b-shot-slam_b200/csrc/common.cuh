@@ -69,6 +69,10 @@ struct Ctx {
     float* d_kp_ratio = nullptr;             // K
     float4* d_kp = nullptr;                  // K keypoint positions (w = index bits)
     int* d_kp_count = nullptr;               // device-side keypoint count
+    unsigned* d_tk_hist = nullptr;           // top-K: 4096-bin ratio histogram (kept zeroed between frames)
+    unsigned* d_tk_state = nullptr;          // top-K: 16 words of device-side state
+    unsigned long long* d_tk_sure = nullptr; // top-K: keys above the threshold bin (< K)
+    unsigned long long* d_tk_tie = nullptr;  // top-K: keys inside the threshold bin (<= N)
     size_t n_kp = 0;                         // host-side count (upper bound when detector ran async)
     bool have_kp = false;
 

@@ -3,8 +3,8 @@
 // Replaces the per-point loop of LidarOdometry::extractKeypoints (src/lidar_odometry.cpp:61-126)
 // and the sort / keep-last-K that follows (:131-153).  One warp per point (taken in voxel order so
 // neighbouring warps share cache lines): nearest-<=max_nn-inside-R selection (knn.cuh), centroid,
-// then the CV / CVS / CVSN score.  Top-K is a single-CTA MSB radix select over 64-bit keys
-// (ratio bits << 32 | ~index) followed by an in-shared-memory bitonic sort, so keypoints come out
+// then the CV / CVS / CVSN score.  Top-K is a multi-CTA histogram select over 64-bit keys
+// (ratio bits << 32 | ~index) followed by a rank-by-counting scatter, so keypoints come out
 // in ascending ratio order like the reference's `SegRatio.end()-600 .. end()` slice, with a
 // deterministic tie-break (lower point index wins) where std::sort's is unspecified.
 #include <stdlib.h>
@@ -18,507 +18,283 @@ namespace bshot {
 constexpr int DT_WARPS = 4;
 constexpr int DT_THREADS = DT_WARPS * 32;
 
+#ifndef BSHOT_DT_CHUNK
+#define BSHOT_DT_CHUNK 1
+#endif
+#ifndef BSHOT_DT_DYNAMIC
+#define BSHOT_DT_DYNAMIC 0
+#endif
+constexpr int DT_CHUNK = BSHOT_DT_CHUNK;  // consecutive voxel-ordered points per work item (the sphere size of one seeds the next)
+
 __global__ void __launch_bounds__(DT_THREADS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
                  int sr_type,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
-                 unsigned long long* __restrict__ counters, const unsigned* __restrict__ work_list,
-                 const unsigned* __restrict__ work_count) {
+                 unsigned long long* __restrict__ counters, unsigned* __restrict__ work_counter) {
     __shared__ KnnWarpSmem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const GridParams g = *gp;
     KnnWarpSmem& sm = smem[wid];
-    // work items: either every binned point (voxel order) or the tile kernel's leftover list
-    const unsigned n_items = work_list ? min(*work_count, n_total) : min(__ldg(cell_start + g.ncells), n_total);
-    for (unsigned item = blockIdx.x * DT_WARPS + wid; item < n_items; item += gridDim.x * DT_WARPS) {
-    const unsigned j = work_list ? work_list[item] : item;
-    const float4 q = __ldg(sorted + j);
-    const unsigned qi = __float_as_uint(q.w);
+    const unsigned n_items = min(__ldg(cell_start + g.ncells), n_total);  // binned points, voxel order
     const float nanf_ = __int_as_float(0x7FC00000);
-    if (q.x == 0.0f && q.y == 0.0f && q.z == 0.0f) {  // src/lidar_odometry.cpp:63
-        if (lane == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
-        continue;
-    }
-    RowRange rr;
-    // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
-    double sx = 0, sy = 0, sz = 0;
-    const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, rr,
-                                     [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
-    const float rho = sqrtf(res.rho2) * 1.0001f;
-    bool cached = !res.batched;
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    const float fn = (float)res.count;
-    const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
-    const float vx = __fsub_rn(q.x, ctx), vy = __fsub_rn(q.y, cty), vz = __fsub_rn(q.z, ctz);  // :79
-    float seg;
-    if (sr_type == BSHOT_SR_CV) {  // :83-97
-        int pos = 0, neg = 0;
-        knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (!knn_selected(res, sqd, p.w)) return;
-            const float d = dot3_rn(vx, vy, vz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-            if (d > 0.0f) ++pos;
-            else if (d < 0.0f) ++neg;
-        });
-        pos = warp_sum(pos);
-        neg = warp_sum(neg);
-        const float fp = (float)pos, fq = (float)neg;
-        seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);  // 0/0 -> NaN like the reference
-        if (pos == 0 && neg == 0) seg = nanf_;
-    } else {  // CVS :98-108, CVSN :109-119
-        const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
-        double sum = 0.0;
-        knn_for_each(g, cell_start, sorted, q, rho, rr, sm, lane, cached, [&](const float4 p) {
-            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (!knn_selected(res, sqd, p.w)) return;
-            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-            const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
-            if (ctn == 0.0f || dn == 0.0f) return;
-            const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
-            sum += (sr_type == BSHOT_SR_CVS) ? (double)d : (double)(d / __fmul_rn(ctn, dn));
-        });
-        sum = warp_sum(sum);
-        seg = fabsf((float)sum) / fn;
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[0], (unsigned long long)res.count);
-        ratio[qi] = seg;
-        keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
-    }
-    __syncwarp();
-    }  // work items
-}
-
-// =====================================================================================================
-// Tile path: one LANE per query, one CTA (4 warps) per 32 consecutive points of the voxel-sorted array.
-// The 32 points are split into groups that share a row (iy,iz) and an 8-cell x window; a group's
-// candidates (the cells within rho of the group) are staged 32 at a time in shared memory -- each warp
-// takes every 4th tile -- and lane l of every warp evaluates the staged candidates against query l
-// with broadcast LDS.128 reads: no per-candidate search, the candidate loads are amortised over up to
-// 32 queries, and the per-query state (128-bin histogram column, counts, centroid sums) lives in
-// shared memory and is updated with fire-and-forget shared atomics.  The nearest-<=max_nn selection is
-// the same threshold-key construction as knn.cuh.  Groups the tile path cannot take (row rectangle
-// larger than the segment list, > 64 Ki candidates, > 32 exact distance duplicates at the threshold)
-// go to a leftover list that the warp-per-query kernel above finishes.
-constexpr int TL_WARPS = 4;
-constexpr int TL_THREADS = TL_WARPS * 32;
-constexpr int TL_MAXSEG = 400;
-constexpr int TL_MAXB = 256;
-constexpr int TL_BINS = 128;
-constexpr int TL_LCAP = 32;
-constexpr int TL_WINDOW_SHIFT = 3;  // 8-cell x window per group
-
-struct TileSmem {
-    SegList<TL_MAXSEG, TL_MAXB> sl;
-    float4 tile[TL_WARPS][32];
-    union {
-        unsigned hist[TL_BINS][32];                // per-query histogram columns (16 KB)
-        unsigned long long list[TL_LCAP][32];      // per-query candidate keys of the crossing bin (8 KB)
-    } u;
-    double sum[3][32];
-    unsigned n[32];
-    unsigned ln[32];
-    int pos[32], neg[32];
-};
-
-// every warp sweeps the tiles t = warp, warp + 4, ... of the flattened candidate list
-template <typename F>
-__device__ __forceinline__ void tile_pass(const float4* __restrict__ sorted, TileSmem& sm, unsigned lane, unsigned wid,
-                                          bool active, F&& body) {
-    const unsigned total = sm.sl.total;
-    float4* tile = sm.tile[wid];
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned j0 = wid * 32u;
-    if (j0 + lane < total) nxt = __ldg(sorted + seg_lookup(sm.sl, j0 + lane));
-    for (; j0 < total; j0 += 32u * TL_WARPS) {
-        tile[lane] = nxt;
-        __syncwarp();
-        const unsigned jn = j0 + 32u * TL_WARPS + lane;
-        if (jn < total) nxt = __ldg(sorted + seg_lookup(sm.sl, jn));  // prefetch this warp's next tile
-        const unsigned cnt = min(32u, total - j0);
-        if (active) {
-#pragma unroll 4
-            for (unsigned t = 0; t < cnt; ++t) body(tile[t]);
-        }
-        __syncwarp();
-    }
-}
-
-__device__ __forceinline__ float tl_bound(float lo, float w, int k) { return fmaf((float)k, w, lo); }
-
-// bin of sqd in [lo, hi) split into TL_BINS bins of width w, consistent with tl_bound()
-__device__ __forceinline__ int tl_bin(float sqd, float lo, float w, float inv_w) {
-    int b = min(TL_BINS - 1, max(0, (int)((sqd - lo) * inv_w)));
-    if (b > 0 && sqd < tl_bound(lo, w, b)) --b;
-    else if (b < TL_BINS - 1 && sqd >= tl_bound(lo, w, b + 1)) ++b;
-    return b;
-}
-
-__global__ void __launch_bounds__(TL_THREADS)
-seg_ratio_tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
-                      const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius,
-                      int max_nn, int sr_type, float* __restrict__ ratio, unsigned long long* __restrict__ keys,
-                      unsigned long long* __restrict__ counters, unsigned* __restrict__ leftover,
-                      unsigned* __restrict__ leftover_count) {
-    __shared__ TileSmem sm;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned chunk = blockIdx.x;
-    const GridParams g = *gp;
-    const unsigned nb = min(__ldg(cell_start + g.ncells), n_total);
-    if (chunk * 32u >= nb) return;
-    const unsigned j = chunk * 32u + lane;  // every warp holds the same 32 queries
-    const bool have = j < nb;
-    const float4 q = have ? __ldg(sorted + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned qi = __float_as_uint(q.w);
-    const float nanf_ = __int_as_float(0x7FC00000);
-    bool todo = have;
-    if (have && q.x == 0.0f && q.y == 0.0f && q.z == 0.0f) {  // src/lidar_odometry.cpp:63
-        if (wid == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
-        todo = false;
-    }
-    const int cix = min(max(cell_coord(q.x, g.ox, g.inv_cell), 0), g.nx - 1);
-    const int ciy = min(max(cell_coord(q.y, g.oy, g.inv_cell), 0), g.ny - 1);
-    const int ciz = min(max(cell_coord(q.z, g.oz, g.inv_cell), 0), g.nz - 1);
-    const unsigned gkey = ((unsigned)ciz * g.ny + ciy) * ((unsigned)(g.nx >> TL_WINDOW_SHIFT) + 1u) + (unsigned)(cix >> TL_WINDOW_SHIFT);
-    const float R = radius;
-    const float R2 = (float)((double)R * (double)R);
-    const bool tile_ok = max_nn > 0;
-    auto sync = [] { __syncthreads(); };
-
-    auto push_leftover = [&](bool mine) {  // warp 0 only
-        const unsigned m = __ballot_sync(FULL, mine);
-        if (m == 0 || wid != 0) return;
-        unsigned base = 0;
-        const int leader = __ffs(m) - 1;
-        if ((int)lane == leader) base = atomicAdd(leftover_count, (unsigned)__popc(m));
-        base = __shfl_sync(FULL, base, leader);
-        if (mine) leftover[base + __popc(m & ((1u << lane) - 1))] = j;
-    };
-
-    unsigned remaining = __ballot_sync(FULL, todo);
-    while (remaining) {  // uniform across the CTA: every warp computes the same groups
-        const int leader = __ffs(remaining) - 1;
-        const unsigned lkey = __shfl_sync(FULL, gkey, leader);
-        const unsigned gm = __ballot_sync(FULL, todo && gkey == lkey) & remaining;
-        remaining &= ~gm;
-        bool in_g = (gm >> lane) & 1u;
-        if (!tile_ok) {
-            push_leftover(in_g);
+    unsigned long long selected_total = 0;
+#if BSHOT_DT_DYNAMIC
+    // persistent warps take chunks of DT_CHUNK consecutive points from a global counter: a warp that meets
+    // a dense spot (10x the average work) does not hold back the other warps of its CTA
+    for (;;) {
+    unsigned j0 = 0;
+    if (lane == 0) j0 = atomicAdd(work_counter, 1u) * DT_CHUNK;
+    j0 = __shfl_sync(0xffffffffu, j0, 0);
+    if (j0 >= n_items) break;
+#else
+    {
+    const unsigned j0 = (blockIdx.x * DT_WARPS + wid) * DT_CHUNK;
+#endif
+    int m_hint = 0;
+    for (unsigned j = j0; j < min(j0 + DT_CHUNK, n_items); ++j) {
+        const float4 q = __ldg(sorted + j);
+        const unsigned qi = __float_as_uint(q.w);
+        if (q.x == 0.0f && q.y == 0.0f && q.z == 0.0f) {  // src/lidar_odometry.cpp:63
+            if (lane == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
             continue;
         }
-        // ---- grow the shared search region until every query of the group holds >= max_nn -------------
-        float rho2 = R2;
-        unsigned n = 0;
-        bool fail = false;
-        for (int m = 1;; ++m) {
-            const float g_m = (float)m * g.cell * 0.9999f;
-            const bool last = !(g_m < R);
-            const float rho = last ? R : g_m;
-            rho2 = last ? R2 : __fmul_rn(rho, rho);
-            const float pad = rho + 1e-3f * g.cell;
-            const int big = 0x3fffffff;
-            const int X0 = __reduce_min_sync(FULL, in_g ? max(cell_coord(q.x - pad, g.ox, g.inv_cell), 0) : big);
-            const int X1 = __reduce_max_sync(FULL, in_g ? min(cell_coord(q.x + pad, g.ox, g.inv_cell), g.nx - 1) : -1);
-            const int Y0 = __reduce_min_sync(FULL, in_g ? max(cell_coord(q.y - pad, g.oy, g.inv_cell), 0) : big);
-            const int Y1 = __reduce_max_sync(FULL, in_g ? min(cell_coord(q.y + pad, g.oy, g.inv_cell), g.ny - 1) : -1);
-            const int Z0 = __reduce_min_sync(FULL, in_g ? max(cell_coord(q.z - pad, g.oz, g.inv_cell), 0) : big);
-            const int Z1 = __reduce_max_sync(FULL, in_g ? min(cell_coord(q.z + pad, g.oz, g.inv_cell), g.nz - 1) : -1);
-            const int ys = Y1 - Y0 + 1;
-            const int nrows = ys * (Z1 - Z0 + 1);
-            if (nrows > TL_MAXSEG || X1 < X0) { fail = true; break; }
-            // cheap pre-check from the voxel table: not enough points in the whole region -> grow directly
-            __syncthreads();
-            if (tid == 0) { sm.sl.nseg = 0; sm.sl.total = 0; }
-            if (tid < 32) { sm.n[tid] = 0; }
-            __syncthreads();
-            for (int r = (int)tid; r < nrows; r += TL_THREADS) {
-                const unsigned row = ((unsigned)(Z0 + r / ys) * g.ny + (unsigned)(Y0 + r % ys)) * g.nx;
-                const unsigned s = __ldg(cell_start + row + X0), e = __ldg(cell_start + row + X1 + 1);
-                if (e > s) {
-                    const unsigned slot = atomicAdd(&sm.sl.nseg, 1u);
-                    sm.sl.start[slot] = s;
-                    sm.sl.off[slot] = e - s;
-                    atomicAdd(&sm.sl.total, e - s);
-                }
-            }
-            __syncthreads();
-            if (!last && sm.sl.total < (unsigned)max_nn) continue;  // cannot hold max_nn points: next radius
-            finish_segments<TL_THREADS>(sm.sl, tid, sync);
-            const unsigned total = sm.sl.total;
-            for (unsigned i = tid; i < TL_BINS * 32; i += TL_THREADS) (&sm.u.hist[0][0])[i] = 0u;
-            __syncthreads();
-            const float w = rho2 / (float)TL_BINS, inv_w = (float)TL_BINS / rho2;
-            const float lim = rho2;
-            unsigned nl = 0;
-            tile_pass(sorted, sm, lane, wid, in_g, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (sqd < lim) {
-                    ++nl;
-                    atomicAdd(&sm.u.hist[tl_bin(sqd, 0.0f, w, inv_w)][lane], 1u);
-                }
-            });
-            if (in_g && nl) atomicAdd(&sm.n[lane], nl);
-            __syncthreads();
-            n = sm.n[lane];
-            if (last || __all_sync(FULL, !in_g || n >= (unsigned)max_nn)) break;
-        }
-        if (fail) {
-            push_leftover(in_g);
-            continue;
-        }
-        // ---- per-query crossing bin (refined while it holds more than TL_LCAP candidates) ---------------
-        const bool sel_all = n <= (unsigned)max_nn;
-        bool need_sel = in_g && !sel_all;
-        float lo = 0.0f, hi = rho2;
-        unsigned below = 0, cntb = 0;
-        for (int level = 0; level < 4; ++level) {
-            const bool refine = need_sel && (level == 0 || cntb > (unsigned)TL_LCAP);
-            if (level > 0) {
-                if (!__any_sync(FULL, refine)) break;
-                __syncthreads();
-                for (unsigned i = tid; i < TL_BINS * 32; i += TL_THREADS) (&sm.u.hist[0][0])[i] = 0u;
-                __syncthreads();
-                const float w = (hi - lo) / (float)TL_BINS, inv_w = (float)TL_BINS / (hi - lo);
-                const float flo = lo, fhi = hi;
-                tile_pass(sorted, sm, lane, wid, refine, [&](const float4 p) {
-                    const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                    if (sqd >= flo && sqd < fhi) atomicAdd(&sm.u.hist[tl_bin(sqd, flo, w, inv_w)][lane], 1u);
-                });
-                __syncthreads();
-            }
-            if (refine) {  // every warp scans its copy of the column: identical results, no broadcast needed
-                const float w = (hi - lo) / (float)TL_BINS;
-                unsigned cum = below;
-                int b = TL_BINS - 1;
-                unsigned hb = 0;
-                for (int k = 0; k < TL_BINS; ++k) {
-                    const unsigned h = sm.u.hist[k][lane];
-                    if (cum + h >= (unsigned)max_nn) { b = k; hb = h; break; }
-                    cum += h;
-                }
-                below = cum;
-                cntb = hb;
-                const float nlo = tl_bound(lo, w, b);
-                const float nhi = (b == TL_BINS - 1) ? hi : tl_bound(lo, w, b + 1);
-                lo = nlo;
-                hi = nhi;
-            }
-        }
-        // queries whose crossing bin still overflows (exact-distance duplicates) take the exact slow path
-        const bool overflow = need_sel && cntb > (unsigned)TL_LCAP;
-        push_leftover(overflow);
-        if (overflow) { in_g = false; need_sel = false; }
-        // ---- collect the crossing bin + centroid of the surely selected --------------------------------
-        __syncthreads();
-        if (tid < 32) { sm.ln[tid] = 0; sm.pos[tid] = 0; sm.neg[tid] = 0; sm.sum[0][tid] = 0.0; sm.sum[1][tid] = 0.0; sm.sum[2][tid] = 0.0; }
-        __syncthreads();
-        {
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            const float flo = lo, fhi = hi, lim = rho2;
-            tile_pass(sorted, sm, lane, wid, in_g, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (!(sqd < lim)) return;
-                if (sel_all || sqd < flo) { sx += p.x; sy += p.y; sz += p.z; }
-                else if (sqd < fhi) {
-                    const unsigned slot = atomicAdd(&sm.ln[lane], 1u);
-                    if (slot < (unsigned)TL_LCAP) sm.u.list[slot][lane] = knn_key(sqd, p.w);
-                }
-            });
-            if (in_g) { atomicAdd(&sm.sum[0][lane], sx); atomicAdd(&sm.sum[1][lane], sy); atomicAdd(&sm.sum[2][lane], sz); }
-        }
-        __syncthreads();
-        double sx = sm.sum[0][lane], sy = sm.sum[1][lane], sz = sm.sum[2][lane];
-        unsigned long long thr = (((unsigned long long)__float_as_uint(rho2)) << 32) - 1ull;  // sel_all: sqd < rho2
-        int count = (int)n;
-        if (need_sel) {  // redundantly in every warp (identical inputs, identical results)
-            count = max_nn;
-            const unsigned L = min(sm.ln[lane], (unsigned)TL_LCAP);
-            const unsigned need = (unsigned)max_nn - below;  // 1..cntb
-            for (unsigned e = 0; e < L; ++e) {
-                const unsigned long long ke = sm.u.list[e][lane];
-                unsigned rank = 0;
-                for (unsigned o = 0; o < L; ++o) rank += (sm.u.list[o][lane] < ke) ? 1u : 0u;
-                if (rank < need) {
-                    const float4 p = __ldg(pts + (unsigned)(ke & 0xFFFFFFFFull));
-                    sx += p.x; sy += p.y; sz += p.z;
-                    if (rank == need - 1) thr = ke;
-                }
-            }
-        }
-        // ---- score -------------------------------------------------------------------------------------
-        const float fn = (float)count;
+        // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
+        double sx = 0, sy = 0, sz = 0;
+        KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, m_hint, sm, lane,
+                                   [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
+        // next point of the chunk is a voxel neighbour: start from the sphere that should hold 1.15 max_nn there
+        m_hint = (max_nn > 0) ? max(1, (int)ceilf((float)res.m * sqrtf(1.15f * (float)max_nn / (float)max(res.n_in, 1)))) : 0;
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+        const float fn = (float)res.count;
         const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
         const float vx = __fsub_rn(q.x, ctx), vy = __fsub_rn(q.y, cty), vz = __fsub_rn(q.z, ctz);  // :79
         float seg;
         if (sr_type == BSHOT_SR_CV) {  // :83-97
             int pos = 0, neg = 0;
-            tile_pass(sorted, sm, lane, wid, in_g, [&](const float4 p) {
+            knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
                 const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (knn_key(sqd, p.w) > thr) return;
+                if (!knn_selected(res, sqd, p.w)) return;
                 const float d = dot3_rn(vx, vy, vz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
                 if (d > 0.0f) ++pos;
                 else if (d < 0.0f) ++neg;
             });
-            if (in_g) { if (pos) atomicAdd(&sm.pos[lane], pos); if (neg) atomicAdd(&sm.neg[lane], neg); }
-            __syncthreads();
-            const float fp = (float)sm.pos[lane], fq = (float)sm.neg[lane];
-            seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);
-            if (sm.pos[lane] == 0 && sm.neg[lane] == 0) seg = nanf_;
-        } else {  // CVS :98-108, CVSN :109-119 (sum reduced across warps through sm.sum[0], zeroed first)
+            pos = warp_sum(pos);
+            neg = warp_sum(neg);
+            const float fp = (float)pos, fq = (float)neg;
+            seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);  // 0/0 -> NaN like the reference
+            if (pos == 0 && neg == 0) seg = nanf_;
+        } else {  // CVS :98-108, CVSN :109-119
             const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
-            __syncthreads();
-            if (tid < 32) sm.sum[0][tid] = 0.0;
-            __syncthreads();
             double sum = 0.0;
-            tile_pass(sorted, sm, lane, wid, in_g, [&](const float4 p) {
+            knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
                 const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (knn_key(sqd, p.w) > thr) return;
+                if (!knn_selected(res, sqd, p.w)) return;
                 const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
                 const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
                 if (ctn == 0.0f || dn == 0.0f) return;
                 const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
                 sum += (sr_type == BSHOT_SR_CVS) ? (double)d : (double)(d / __fmul_rn(ctn, dn));
             });
-            if (in_g) atomicAdd(&sm.sum[0][lane], sum);
-            __syncthreads();
-            seg = fabsf((float)sm.sum[0][lane]) / fn;
+            sum = warp_sum(sum);
+            seg = fabsf((float)sum) / fn;
         }
-        if (wid == 0) {
-            if (in_g) {
-                ratio[qi] = seg;
-                keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
-            }
-            const int tot = __reduce_add_sync(FULL, in_g ? count : 0);
-            if (lane == 0) atomicAdd(&counters[0], (unsigned long long)tot);
+        selected_total += (unsigned long long)res.count;
+        if (lane == 0) {
+            ratio[qi] = seg;
+            keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
         }
-        __syncthreads();
     }
+    }  // work items
+    if (lane == 0 && selected_total) atomicAdd(&counters[0], selected_total);
 }
 
 __global__ void mark_unbinned_kernel(const unsigned* __restrict__ cell_of, unsigned n, float* __restrict__ ratio,
-                                     unsigned long long* __restrict__ keys) {
+                                     unsigned long long* __restrict__ keys, unsigned* __restrict__ work_counter) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *work_counter = 0u;  // seg_ratio_kernel's chunk dispenser
     if (i < n && cell_of[i] == 0xFFFFFFFFu) { ratio[i] = __int_as_float(0x7FC00000); keys[i] = 0ull; }
 }
 
-// ---- top-K: single CTA radix select + bitonic sort -------------------------------------------------
-constexpr int TK_THREADS = 1024;
+// ---- top-K (a3): multi-CTA histogram select + rank scatter ------------------------------------------
+// keys are (ratio bits << 32 | ~index), 0 = no score.  The K largest keys come out in ASCENDING key
+// order (ascending ratio like the reference's `SegRatio.end()-600 .. end()` slice; equal ratios: lower
+// point index last, i.e. it survives a cut first).
+//   tk_hist_kernel    4096-bin histogram of a monotone bin function of the ratio, privatised per CTA in
+//                     shared memory and flushed with one global atomic per non-empty bin; the last CTA to
+//                     finish (atomic ticket) scans it from the top, finds the bin b* that holds the K-th
+//                     largest key, publishes {k_eff, b*, need = k_eff - #keys above b*} and clears the table
+//   tk_compact_kernel keys above b* -> `sure` list, keys in b* -> `tie` list (warp-aggregated appends)
+//   tk_rank_kernel    rank of every sure key among the sure keys and of every tie key among the tie keys
+//                     by counting (keys are distinct, so ranks are a permutation); the `need` largest
+//                     tie keys and all sure keys are scattered to their final sorted position
+constexpr int TK_THREADS = 256;
+constexpr int TK_BINS = 4096;
+constexpr int TK_TILE = 2048;
+enum { TKS_VALID = 0, TKS_TICKET = 1, TKS_BIN = 2, TKS_KEFF = 3, TKS_NSURE = 4, TKS_NTIE = 5, TKS_NEED = 6 };
+
+// monotone (non-decreasing in the key) bin: ratios in [0,1] -- all CV scores -- are spread uniformly over
+// bins 0..2048, larger ones (CVS / CVSN sums) by exponent and 4 mantissa bits over 2048..4095
+__device__ __forceinline__ unsigned tk_bin(unsigned long long key) {
+    const unsigned bits = (unsigned)(key >> 32);
+    const float r = __uint_as_float(bits);
+    if (!(r > 1.0f)) return (unsigned)(fmaxf(r, 0.0f) * 2048.0f);  // NaN never reaches here (key 0 is skipped)
+    return min(4095u, 2048u + ((bits - 0x3F800000u) >> 19));
+}
 
 __global__ void __launch_bounds__(TK_THREADS)
-topk_kernel(const unsigned long long* __restrict__ keys, unsigned n, int top_k, unsigned sort_cap,
-            const float4* __restrict__ pts, int* __restrict__ kp_idx, float* __restrict__ kp_ratio,
-            float4* __restrict__ kp, int* __restrict__ kp_count) {
-    extern __shared__ unsigned long long sbuf[];  // sort_cap keys
-    __shared__ unsigned hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ unsigned s_rank, s_valid, s_fill;
-    const unsigned tid = threadIdx.x;
-    // K-th largest key via MSB-first 8-bit radix select (rank counted from the top). The first pass also
-    // counts the valid (non-zero) keys, which fixes k_eff = min(top_k, #valid).
-    if (tid == 0) { s_valid = 0; s_fill = 0; s_prefix = 0ull; s_rank = 0; }
+tk_hist_kernel(const unsigned long long* __restrict__ keys, unsigned n, int top_k, unsigned* __restrict__ hist,
+               unsigned* __restrict__ state, int* __restrict__ kp_count) {
+    __shared__ unsigned s_hist[TK_BINS];
+    __shared__ unsigned s_warp[TK_THREADS / 32];
+    __shared__ unsigned s_last, s_found_bin, s_found_above;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (unsigned b = tid; b < TK_BINS; b += TK_THREADS) s_hist[b] = 0u;
     __syncthreads();
-    unsigned k_eff = 0;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        for (unsigned b = tid; b < 256; b += TK_THREADS) hist[b] = 0;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const unsigned long long mask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        unsigned cv = 0;
-        // one CTA reads all keys in every pass: keep 8 independent 8-byte loads in flight per thread
-        for (unsigned base = 0; base < n; base += TK_THREADS * 8) {
-            unsigned long long kk[8];
+    unsigned cv = 0;
+    for (unsigned i0 = blockIdx.x * TK_THREADS * 4; i0 < n; i0 += gridDim.x * TK_THREADS * 4) {
+        unsigned long long k[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const unsigned i = base + u * TK_THREADS + tid;
-                kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const unsigned i = i0 + u * TK_THREADS + tid;
+            k[u] = (i < n) ? __ldg(keys + i) : 0ull;
+        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const unsigned i = base + u * TK_THREADS + tid;
-                cv += kk[u] != 0ull;
-                if (i < n && (kk[u] & mask) == prefix) atomicAdd(&hist[(unsigned)(kk[u] >> shift) & 255u], 1u);
-            }
+        for (int u = 0; u < 4; ++u)
+            if (k[u] != 0ull) { ++cv; atomicAdd(&s_hist[tk_bin(k[u])], 1u); }
+    }
+    cv = (unsigned)warp_sum((int)cv);
+    if (lane == 0 && cv) atomicAdd(&state[TKS_VALID], cv);
+    __syncthreads();
+    for (unsigned b = tid; b < TK_BINS; b += TK_THREADS) {
+        const unsigned h = s_hist[b];
+        if (h) atomicAdd(&hist[b], h);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&state[TKS_TICKET], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- last CTA: thread t owns the 16 bins [4096 - 16 (t + 1), 4096 - 16 t), scanned from the top
+    constexpr int PER = TK_BINS / TK_THREADS;
+    const unsigned valid = __ldcg(state + TKS_VALID);
+    const unsigned k_eff = min((unsigned)max(top_k, 0), valid);
+    const unsigned hi = TK_BINS - tid * PER;  // exclusive upper bin
+    unsigned h[PER], s = 0;
+    {
+        const uint4* h4 = reinterpret_cast<const uint4*>(hist + (hi - PER));
+#pragma unroll
+        for (int v = 0; v < PER / 4; ++v) {
+            const uint4 a = __ldcg(h4 + v);
+            h[4 * v] = a.x; h[4 * v + 1] = a.y; h[4 * v + 2] = a.z; h[4 * v + 3] = a.w;
+            s += a.x + a.y + a.z + a.w;
         }
-        if (shift == 56) {
-            cv = (unsigned)warp_sum((int)cv);
-            if ((tid & 31) == 0) atomicAdd(&s_valid, cv);
+    }
+    unsigned inc = s;  // inclusive scan over threads = keys in this thread's bins and all higher bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += up;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    if (tid == 0) { s_found_bin = 0xFFFFFFFFu; s_found_above = 0; }
+    __syncthreads();
+    unsigned above = inc - s;
+    for (unsigned w = 0; w < wid; ++w) above += s_warp[w];
+    if (k_eff > 0 && above < k_eff && above + s >= k_eff) {  // exactly one thread: the K-th largest key is in its bins
+        unsigned run = above;
+#pragma unroll
+        for (int b = PER - 1; b >= 0; --b) {
+            if (run < k_eff && run + h[b] >= k_eff) { s_found_bin = hi - PER + (unsigned)b; s_found_above = run; }
+            run += h[b];
         }
-        __syncthreads();
-        if (shift == 56) {
-            k_eff = min((unsigned)top_k, s_valid);
-            if (tid == 0) { *kp_count = (int)k_eff; s_rank = k_eff ? k_eff - 1 : 0; }
-            if (k_eff == 0) return;
+    }
+    {   // clear the table for the next frame
+        uint4* z4 = reinterpret_cast<uint4*>(hist + (hi - PER));
+#pragma unroll
+        for (int v = 0; v < PER / 4; ++v) z4[v] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        state[TKS_BIN] = s_found_bin;
+        state[TKS_KEFF] = k_eff;
+        state[TKS_NEED] = k_eff - s_found_above;
+        state[TKS_NSURE] = 0;
+        state[TKS_NTIE] = 0;
+        state[TKS_VALID] = 0;
+        state[TKS_TICKET] = 0;
+        *kp_count = (int)k_eff;
+    }
+}
+
+__device__ __forceinline__ void tk_append(bool mine, unsigned long long key, unsigned* counter, unsigned long long* list,
+                                          unsigned lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mine) list[base + __popc(m & ((1u << lane) - 1u))] = key;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+tk_compact_kernel(const unsigned long long* __restrict__ keys, unsigned n, unsigned* __restrict__ state,
+                  unsigned long long* __restrict__ sure, unsigned long long* __restrict__ tie) {
+    const unsigned i = blockIdx.x * TK_THREADS + threadIdx.x, lane = threadIdx.x & 31;
+    const unsigned bstar = state[TKS_BIN];
+    if (bstar == 0xFFFFFFFFu) return;  // k_eff == 0
+    const unsigned long long k = (i < n) ? __ldg(keys + i) : 0ull;
+    const unsigned bin = tk_bin(k);
+    tk_append(k != 0ull && bin > bstar, k, state + TKS_NSURE, sure, lane);
+    tk_append(k != 0ull && bin == bstar, k, state + TKS_NTIE, tie, lane);
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __restrict__ sure,
+               const unsigned long long* __restrict__ tie, const float4* __restrict__ pts, int* __restrict__ kp_idx,
+               float* __restrict__ kp_ratio, float4* __restrict__ kp) {
+    __shared__ unsigned long long s_keys[TK_TILE];
+    __shared__ unsigned s_cnt[4][64];
+    const unsigned tid = threadIdx.x, slot = tid & 63, part = tid >> 6;
+    const unsigned n_sure = state[TKS_NSURE], n_tie = state[TKS_NTIE], need = state[TKS_NEED];
+    const unsigned nb_a = (n_sure + 63) / 64, nb_b = (n_tie + 63) / 64;
+    for (unsigned ib = blockIdx.x; ib < nb_a + nb_b; ib += gridDim.x) {
+        const bool is_a = ib < nb_a;
+        const unsigned long long* list = is_a ? sure : tie;
+        const unsigned len = is_a ? n_sure : n_tie;
+        const unsigned item = (is_a ? ib : ib - nb_a) * 64 + slot;
+        const unsigned long long x = (item < len) ? list[item] : 0ull;
+        unsigned cnt = 0;
+        for (unsigned t0 = 0; t0 < len; t0 += TK_TILE) {
+            const unsigned tl = min((unsigned)TK_TILE, len - t0);
             __syncthreads();
+            for (unsigned t = tid; t < tl; t += TK_THREADS) s_keys[t] = list[t0 + t];
+            __syncthreads();
+            const unsigned lo = part * (TK_TILE / 4), hi = min(lo + TK_TILE / 4, tl);
+            if (is_a) {  // sure keys: position among the sure keys, ascending
+                for (unsigned j = lo; j < hi; ++j) cnt += (s_keys[j] < x) ? 1u : 0u;
+            } else {     // tie keys: number of larger tie keys
+                for (unsigned j = lo; j < hi; ++j) cnt += (s_keys[j] > x) ? 1u : 0u;
+            }
         }
-        if (tid < 32) {  // warp 0: lane l owns digits 255-8l .. 248-8l (descending), suffix scan across lanes
-            unsigned h[8], s = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { h[k] = hist[255 - (tid * 8 + k)]; s += h[k]; }
-            unsigned inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (tid >= (unsigned)o) inc += up;
-            }
-            const unsigned rank = s_rank;
-            unsigned run = inc - s;  // keys in digits above this lane's
-            int found = -1;
-            unsigned frank = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (found < 0 && rank >= run && rank < run + h[k]) { found = 255 - (int)(tid * 8 + k); frank = rank - run; }
-                run += h[k];
-            }
-            if (found >= 0) {  // exactly one lane
-                s_rank = frank;
-                s_prefix = prefix | ((unsigned long long)found << shift);
+        s_cnt[part][slot] = cnt;
+        __syncthreads();
+        if (part == 0 && item < len) {
+            const unsigned c = s_cnt[0][slot] + s_cnt[1][slot] + s_cnt[2][slot] + s_cnt[3][slot];
+            const bool keep = is_a || c < need;
+            if (keep) {
+                const unsigned pos = is_a ? need + c : need - 1u - c;
+                const unsigned idx = ~(unsigned)(x & 0xFFFFFFFFull);
+                kp_idx[pos] = (int)idx;
+                kp_ratio[pos] = __uint_as_float((unsigned)(x >> 32));
+                float4 p = pts[idx];
+                p.w = __uint_as_float(idx);
+                kp[pos] = p;
             }
         }
         __syncthreads();
-    }
-    const unsigned long long kth = s_prefix;  // keys are distinct: exactly k_eff keys are >= kth
-    for (unsigned base = 0; base < n; base += TK_THREADS * 8) {
-        unsigned long long kk[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const unsigned i = base + u * TK_THREADS + tid;
-            kk[u] = (i < n) ? __ldg(keys + i) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (kk[u] >= kth && kk[u] != 0ull) {
-                const unsigned slot = atomicAdd(&s_fill, 1u);
-                if (slot < sort_cap) sbuf[slot] = kk[u];
-            }
-        }
-    }
-    __syncthreads();
-    unsigned m = 1;
-    while (m < k_eff) m <<= 1;
-    for (unsigned i = k_eff + tid; i < m; i += TK_THREADS) sbuf[i] = ~0ull;  // pad high
-    __syncthreads();
-    for (unsigned size = 2; size <= m; size <<= 1) {
-        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
-            for (unsigned t = tid; t < (m >> 1); t += TK_THREADS) {
-                const unsigned lo = 2 * t - (t & (stride - 1));
-                const unsigned hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const unsigned long long a = sbuf[lo], b = sbuf[hi];
-                if ((a > b) == up) { sbuf[lo] = b; sbuf[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    for (unsigned i = tid; i < k_eff; i += TK_THREADS) {
-        const unsigned long long key = sbuf[i];
-        const unsigned idx = ~(unsigned)(key & 0xFFFFFFFFull);
-        kp_idx[i] = (int)idx;
-        kp_ratio[i] = __uint_as_float((unsigned)(key >> 32));
-        float4 p = pts[idx];
-        p.w = __uint_as_float(idx);
-        kp[i] = p;
     }
 }
 
@@ -527,26 +303,16 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     if (n == 0) return BSHOT_OK;
     if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
-    // leftover list lives in d_cell_of's neighbour buffer d_qnormals (N x 16 B, free during detection)
-    unsigned* leftover = reinterpret_cast<unsigned*>(c->d_qnormals);
-    unsigned* leftover_count = reinterpret_cast<unsigned*>(c->d_kp_count) + 2;
-    BSHOT_CUDA_TRY(cudaMemsetAsync(leftover_count, 0, sizeof(unsigned), c->stream));
-    mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys);
-    static const bool use_tile = [] { const char* e = getenv("BSHOT_DETECTOR"); return e && !strcmp(e, "tile"); }();
-    if (use_tile) {
-        const unsigned chunks = (n + 31) / 32;
-        seg_ratio_tile_kernel<<<chunks, TL_THREADS, 0, c->stream>>>(
-            c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters,
-            leftover, leftover_count);
-        const unsigned sweep_ctas = std::min((n + DT_WARPS - 1) / DT_WARPS, (unsigned)c->sm_count * 12u);
-        seg_ratio_kernel<<<sweep_ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type,
-                                                                 c->d_ratio, c->d_keys, c->d_counters, leftover, leftover_count);
-        count_launch(c, 3);
-    } else {
-        seg_ratio_kernel<<<(n + DT_WARPS - 1) / DT_WARPS, DT_THREADS, 0, c->stream>>>(
-            c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type, c->d_ratio, c->d_keys, c->d_counters, nullptr, nullptr);
-        count_launch(c, 2);
-    }
+    unsigned* work_counter = c->d_tk_state + 8;
+    mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys, work_counter);
+#if BSHOT_DT_DYNAMIC
+    const unsigned ctas = std::min((n + DT_WARPS * DT_CHUNK - 1) / (DT_WARPS * DT_CHUNK), (unsigned)c->sm_count * 8u);
+#else
+    const unsigned ctas = (n + DT_WARPS * DT_CHUNK - 1) / (DT_WARPS * DT_CHUNK);
+#endif
+    seg_ratio_kernel<<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type,
+                                                        c->d_ratio, c->d_keys, c->d_counters, work_counter);
+    count_launch(c, 2);
     return check_launch("seg_ratio kernels");
 }
 
@@ -554,7 +320,7 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
 void knn_stats_dump() {
     unsigned long long h[8];
     cudaMemcpyFromSymbol(h, g_knn_stats, sizeof(h));
-    fprintf(stderr, "[knn stats] attempts=%llu rows=%llu cand=%llu insphere=%llu\n", h[0], h[1], h[2], h[3]);
+    fprintf(stderr, "[knn stats] attempts=%llu rows=%llu cand=%llu insphere=%llu slow=%llu\n", h[0], h[1], h[2], h[3], h[4]);
     unsigned long long z[8] = {0};
     cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z));
 }
@@ -562,25 +328,20 @@ void knn_stats_dump() {
 
 int detect_topk(Ctx* c, int top_k) {
     const unsigned n = (unsigned)c->n_points;
-    unsigned cap = 1;
-    while (cap < (unsigned)top_k) cap <<= 1;
-    const size_t smem = sizeof(unsigned long long) * cap;
-    if (smem > 200 * 1024) { set_error("top_k %d too large for the single-CTA sorter", top_k); return BSHOT_E_CAPACITY; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        BSHOT_CUDA_TRY(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    topk_kernel<<<1, TK_THREADS, smem, c->stream>>>(c->d_keys, n, top_k, cap, c->d_pts, c->d_kp_idx, c->d_kp_ratio,
-                                                   c->d_kp, c->d_kp_count);
-    count_launch(c);
+    if (top_k < 0 || (size_t)top_k > c->max_kp) { set_error("top_k %d exceeds max_keypoints %zu", top_k, c->max_kp); return BSHOT_E_CAPACITY; }
+    const unsigned hist_ctas = std::max(1u, std::min((n + TK_THREADS * 16 - 1) / (TK_THREADS * 16), (unsigned)c->sm_count));
+    tk_hist_kernel<<<hist_ctas, TK_THREADS, 0, c->stream>>>(c->d_keys, n, top_k, c->d_tk_hist, c->d_tk_state, c->d_kp_count);
+    if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie);
+    tk_rank_kernel<<<(unsigned)c->sm_count * 2u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_kp_idx,
+                                                                             c->d_kp_ratio, c->d_kp);
+    count_launch(c, n ? 3 : 2);
 #ifdef BSHOT_KNN_STATS
     cudaStreamSynchronize(c->stream);
     knn_stats_dump();
 #endif
     c->n_kp = (size_t)top_k;  // upper bound until the host reads d_kp_count
     c->have_kp = true;
-    return check_launch("topk_kernel");
+    return check_launch("top-K kernels");
 }
 
 }  // namespace bshot

@@ -211,39 +211,38 @@ __device__ __forceinline__ void top2_insert(unsigned long long key, unsigned lon
     k2 = min(k2, hi);
 }
 
-// merge nsrc candidate pairs per query: src[(s * nq + qi) * stride_u64 + {0,1}]
-__global__ void merge_top2_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
-                                  unsigned stride_u64, bshot_cand* __restrict__ out) {
-    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
-#pragma unroll 8
-    for (unsigned s = 0; s < nsrc; ++s) {
-        const unsigned long long* p = src + ((size_t)s * nq + qi) * stride_u64;
-        top2_insert(p[0], k1, k2);
-        top2_insert(p[1], k1, k2);
-    }
-    bshot_cand c;
-    c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
-    out[qi] = c;
-}
+// merge nsrc candidate pairs per query: src[(s * nq + qi) * 2 + {0,1}].  HM_MERGE_LANES lanes share a
+// query (lane l takes the splits l, l + 8, ...: one round of independent 16-byte loads instead of a serial
+// walk over all splits), then a butterfly merges the partial top-2 sets.  With `gcol` (fused column
+// minima of a frame-sized target set) the reverse result rq = best query of the winning target is attached.
+constexpr int HM_MERGE_LANES = 8;
 
-// merge + reverse result: rq = best query of the winning target from the fused column minima
-__global__ void merge_top2_rq_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
-                                     const unsigned* __restrict__ gcol, unsigned long long global_base,
-                                     bshot_cand* __restrict__ out) {
-    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
+__global__ void __launch_bounds__(256)
+merge_top2_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
+                  const unsigned* __restrict__ gcol, unsigned long long global_base, bshot_cand* __restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned qi = t / HM_MERGE_LANES, sub = t % HM_MERGE_LANES;
     unsigned long long k1 = HM_NONE, k2 = HM_NONE;
-#pragma unroll 8
-    for (unsigned s = 0; s < nsrc; ++s) {
-        const unsigned long long* p = src + ((size_t)s * nq + qi) * 2;
-        top2_insert(p[0], k1, k2);
-        top2_insert(p[1], k1, k2);
+    if (qi < nq) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src);
+#pragma unroll 4
+        for (unsigned sp = sub; sp < nsrc; sp += HM_MERGE_LANES) {
+            const ulonglong2 v = p[(size_t)sp * nq + qi];
+            top2_insert(v.x, k1, k2);
+            top2_insert(v.y, k1, k2);
+        }
     }
+#pragma unroll
+    for (int o = HM_MERGE_LANES / 2; o > 0; o >>= 1) {  // whole warps run this (no early exit above)
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        top2_insert(o1, k1, k2);
+        top2_insert(o2, k1, k2);
+    }
+    if (qi >= nq || sub != 0) return;
     bshot_cand c;
     c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
-    if (k1 != HM_NONE) {
+    if (gcol && k1 != HM_NONE) {
         const unsigned v = gcol[(size_t)((k1 & 0xFFFFFFFFull) - global_base)];
         if (v != 0xFFFFFFFFu) c.rq = v % HM_K;
     }
@@ -427,11 +426,8 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
 #undef BSHOT_LAUNCH_TOP2
     count_launch(c);
     BSHOT_TRY(check_launch("hamming_top2_kernel"));
-    if (colmin)
-        merge_top2_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, d_colmin,
-                                                                                  global_base, d_out);
-    else
-        merge_top2_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, 2, d_out);
+    merge_top2_kernel<<<(unsigned)((nq * HM_MERGE_LANES + 255) / 256), 256, 0, c->stream>>>(
+        c->d_partial, nsplit, (unsigned)nq, colmin ? d_colmin : nullptr, global_base, d_out);
     count_launch(c);
     return check_launch("merge_top2_kernel");
 }

@@ -16,7 +16,16 @@ __host__ __device__ __forceinline__ int cell_coord(float v, float o, float inv) 
 
 struct RowRange {
     int iy_lo, iz_lo, ny_span, nrows;
+    float inv_span;
 };
+
+// row r of the rectangle -> (iy, iz) without an integer division: (r + 0.5) / span is at least
+// 0.5 / span away from an integer, far more than the fp32 error for r < 2^16
+__device__ __forceinline__ void row_coords(const RowRange& rr, int r, int& iy, int& iz) {
+    const int q = (int)(((float)r + 0.5f) * rr.inv_span);
+    iy = rr.iy_lo + (r - q * rr.ny_span);
+    iz = rr.iz_lo + q;
+}
 
 __device__ __forceinline__ RowRange row_range(const GridParams& g, float py, float pz, float R) {
     RowRange r;
@@ -29,6 +38,7 @@ __device__ __forceinline__ RowRange row_range(const GridParams& g, float py, flo
     r.iz_lo = iz_lo;
     r.ny_span = iy_hi - iy_lo + 1;
     r.nrows = (iy_hi >= iy_lo && iz_hi >= iz_lo) ? r.ny_span * (iz_hi - iz_lo + 1) : 0;
+    r.inv_span = 1.0f / (float)max(r.ny_span, 1);
     return r;
 }
 
@@ -117,8 +127,8 @@ __device__ __forceinline__ unsigned enumerate_segments(const GridParams& g, cons
     const int row1 = min(rr.nrows, row0 + MAXSEG);
     unsigned mine = 0;
     for (int r = row0 + (int)tid; r < row1; r += NT) {
-        const int iy = rr.iy_lo + r % rr.ny_span;
-        const int iz = rr.iz_lo + r / rr.ny_span;
+        int iy, iz;
+        row_coords(rr, r, iy, iz);
         unsigned s, e;
         if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
             const unsigned slot = atomicAdd(&sl.nseg, 1u);
@@ -141,8 +151,8 @@ __device__ __forceinline__ void build_segments(const GridParams& g, const unsign
     group_sync();
     const int row1 = min(rr.nrows, row0 + MAXSEG);
     for (int r = row0 + (int)tid; r < row1; r += NT) {
-        const int iy = rr.iy_lo + r % rr.ny_span;
-        const int iz = rr.iz_lo + r / rr.ny_span;
+        int iy, iz;
+        row_coords(rr, r, iy, iz);
         unsigned s, e;
         if (row_segment(g, cell_start, px, py, pz, R, iy, iz, s, e)) {
             const unsigned slot = atomicAdd(&sl.nseg, 1u);

@@ -116,8 +116,7 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
     int n = 0;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (finite) {
-        RowRange rr;
-        const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, rr, [&](const float4 p) {
+        const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, 0, sm, lane, [&](const float4 p) {
             // products rounded to fp32 like PCL's accumulator inputs, summed in fp64
             s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
             s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);

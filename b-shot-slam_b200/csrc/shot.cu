@@ -380,11 +380,8 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     // Votes are accumulated in 32-bit fixed point: float atomicAdd on shared memory is a CAS spin loop
     // (SASS ATOMS.CAST.SPIN), integer add is native (ATOMS.ADD).  A bin receives at most 4 per
     // neighbour, so 2^fx_bits * 4.1 * n_all < 2^32 cannot overflow; the sum is order independent.
-    int fx_bits = 0;
-    {
-        const double room = 4294967295.0 / (4.1 * (double)max(n_all, 1));
-        while (fx_bits < 28 && (double)(2u << fx_bits) <= room) ++fx_bits;
-    }
+    // = largest b <= 28 with 2^b <= room (room >= 2 for any neighbour count below 5e8)
+    const int fx_bits = min(28, max(0, ilogb(4294967295.0 / (4.1 * (double)max(n_all, 1)))));
     const float fx_scale = (float)(1u << fx_bits);
     const float fx_inv = 1.0f / fx_scale;
     if (describe) {
