@@ -18,101 +18,92 @@ namespace bshot {
 constexpr int DT_WARPS = 4;
 constexpr int DT_THREADS = DT_WARPS * 32;
 
-#ifndef BSHOT_DT_CHUNK
-#define BSHOT_DT_CHUNK 1
+#ifndef BSHOT_DT_MINBLOCKS
+#define BSHOT_DT_MINBLOCKS 8
 #endif
-#ifndef BSHOT_DT_DYNAMIC
-#define BSHOT_DT_DYNAMIC 0
-#endif
-constexpr int DT_CHUNK = BSHOT_DT_CHUNK;  // consecutive voxel-ordered points per work item (the sphere size of one seeds the next)
 
-__global__ void __launch_bounds__(DT_THREADS)
+// seg-ratio of one point, all 32 lanes call
+template <int SR>
+__device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsigned* __restrict__ cell_start,
+                                                const float4* __restrict__ sorted, const float4* __restrict__ pts,
+                                                const float4& q, float radius, int max_nn, KnnWarpSmem& sm,
+                                                unsigned lane, float& seg, int& count) {
+    const float nanf_ = __int_as_float(0x7FC00000);
+    // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
+    double sx = 0, sy = 0, sz = 0;
+    KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane,
+                                     [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    const float fn = (float)res.count;
+    const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
+    const float vx = __fsub_rn(q.x, ctx), vy = __fsub_rn(q.y, cty), vz = __fsub_rn(q.z, ctz);  // :79
+    if (SR == BSHOT_SR_CV) {  // :83-97
+        int pos = 0, neg = 0;
+        knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!knn_selected(res, sqd, p.w)) return;
+            const float d = dot3_rn(vx, vy, vz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
+            if (d > 0.0f) ++pos;
+            else if (d < 0.0f) ++neg;
+        });
+        pos = warp_sum(pos);
+        neg = warp_sum(neg);
+        const float fp = (float)pos, fq = (float)neg;
+        seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);  // 0/0 -> NaN like the reference
+        if (pos == 0 && neg == 0) seg = nanf_;
+    } else {  // CVS :98-108, CVSN :109-119
+        const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
+        double sum = 0.0;
+        knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!knn_selected(res, sqd, p.w)) return;
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
+            if (ctn == 0.0f || dn == 0.0f) return;
+            const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
+            sum += (SR == BSHOT_SR_CVS) ? (double)d : (double)(d / __fmul_rn(ctn, dn));
+        });
+        sum = warp_sum(sum);
+        seg = fabsf((float)sum) / fn;
+    }
+    count = res.count;
+}
+
+// SR = score type (compile time: the CV kernel carries no CVS / CVSN code).  One warp per binned point, taken
+// in voxel order so that neighbouring warps share cache lines.
+template <int SR>
+__global__ void __launch_bounds__(DT_THREADS, BSHOT_DT_MINBLOCKS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
-                 int sr_type,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
-                 unsigned long long* __restrict__ counters, unsigned* __restrict__ work_counter) {
+                 unsigned long long* __restrict__ counters) {
     __shared__ KnnWarpSmem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const GridParams g = *gp;
     KnnWarpSmem& sm = smem[wid];
-    const unsigned n_items = min(__ldg(cell_start + g.ncells), n_total);  // binned points, voxel order
+    const unsigned n_items = min(__ldg(cell_start + g.ncells), n_total);
     const float nanf_ = __int_as_float(0x7FC00000);
-    unsigned long long selected_total = 0;
-#if BSHOT_DT_DYNAMIC
-    // persistent warps take chunks of DT_CHUNK consecutive points from a global counter: a warp that meets
-    // a dense spot (10x the average work) does not hold back the other warps of its CTA
-    for (;;) {
-    unsigned j0 = 0;
-    if (lane == 0) j0 = atomicAdd(work_counter, 1u) * DT_CHUNK;
-    j0 = __shfl_sync(0xffffffffu, j0, 0);
-    if (j0 >= n_items) break;
-#else
-    {
-    const unsigned j0 = (blockIdx.x * DT_WARPS + wid) * DT_CHUNK;
-#endif
-    int m_hint = 0;
-    for (unsigned j = j0; j < min(j0 + DT_CHUNK, n_items); ++j) {
+    for (unsigned j = blockIdx.x * DT_WARPS + wid; j < n_items; j += gridDim.x * DT_WARPS) {
         const float4 q = __ldg(sorted + j);
         const unsigned qi = __float_as_uint(q.w);
         if (q.x == 0.0f && q.y == 0.0f && q.z == 0.0f) {  // src/lidar_odometry.cpp:63
             if (lane == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
             continue;
         }
-        // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
-        double sx = 0, sy = 0, sz = 0;
-        KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, m_hint, sm, lane,
-                                   [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
-        // next point of the chunk is a voxel neighbour: start from the sphere that should hold 1.15 max_nn there
-        m_hint = (max_nn > 0) ? max(1, (int)ceilf((float)res.m * sqrtf(1.15f * (float)max_nn / (float)max(res.n_in, 1)))) : 0;
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        const float fn = (float)res.count;
-        const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
-        const float vx = __fsub_rn(q.x, ctx), vy = __fsub_rn(q.y, cty), vz = __fsub_rn(q.z, ctz);  // :79
         float seg;
-        if (sr_type == BSHOT_SR_CV) {  // :83-97
-            int pos = 0, neg = 0;
-            knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (!knn_selected(res, sqd, p.w)) return;
-                const float d = dot3_rn(vx, vy, vz, __fsub_rn(p.x, q.x), __fsub_rn(p.y, q.y), __fsub_rn(p.z, q.z));
-                if (d > 0.0f) ++pos;
-                else if (d < 0.0f) ++neg;
-            });
-            pos = warp_sum(pos);
-            neg = warp_sum(neg);
-            const float fp = (float)pos, fq = (float)neg;
-            seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);  // 0/0 -> NaN like the reference
-            if (pos == 0 && neg == 0) seg = nanf_;
-        } else {  // CVS :98-108, CVSN :109-119
-            const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
-            double sum = 0.0;
-            knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (!knn_selected(res, sqd, p.w)) return;
-                const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
-                const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
-                if (ctn == 0.0f || dn == 0.0f) return;
-                const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
-                sum += (sr_type == BSHOT_SR_CVS) ? (double)d : (double)(d / __fmul_rn(ctn, dn));
-            });
-            sum = warp_sum(sum);
-            seg = fabsf((float)sum) / fn;
-        }
-        selected_total += (unsigned long long)res.count;
+        int count;
+        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, seg, count);
         if (lane == 0) {
+            atomicAdd(&counters[0], (unsigned long long)count);
             ratio[qi] = seg;
             keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
         }
     }
-    }  // work items
-    if (lane == 0 && selected_total) atomicAdd(&counters[0], selected_total);
 }
 
 __global__ void mark_unbinned_kernel(const unsigned* __restrict__ cell_of, unsigned n, float* __restrict__ ratio,
-                                     unsigned long long* __restrict__ keys, unsigned* __restrict__ work_counter) {
+                                     unsigned long long* __restrict__ keys) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *work_counter = 0u;  // seg_ratio_kernel's chunk dispenser
     if (i < n && cell_of[i] == 0xFFFFFFFFu) { ratio[i] = __int_as_float(0x7FC00000); keys[i] = 0ull; }
 }
 
@@ -303,15 +294,15 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     if (n == 0) return BSHOT_OK;
     if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
-    unsigned* work_counter = c->d_tk_state + 8;
-    mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys, work_counter);
-#if BSHOT_DT_DYNAMIC
-    const unsigned ctas = std::min((n + DT_WARPS * DT_CHUNK - 1) / (DT_WARPS * DT_CHUNK), (unsigned)c->sm_count * 8u);
-#else
-    const unsigned ctas = (n + DT_WARPS * DT_CHUNK - 1) / (DT_WARPS * DT_CHUNK);
-#endif
-    seg_ratio_kernel<<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, sr_type,
-                                                        c->d_ratio, c->d_keys, c->d_counters, work_counter);
+    mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys);
+    const unsigned ctas = (n + DT_WARPS - 1) / DT_WARPS;
+#define BSHOT_LAUNCH_SEG(SR)                                                                                                     \
+    seg_ratio_kernel<SR><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, \
+                                                             c->d_ratio, c->d_keys, c->d_counters)
+    if (sr_type == BSHOT_SR_CV) BSHOT_LAUNCH_SEG(BSHOT_SR_CV);
+    else if (sr_type == BSHOT_SR_CVS) BSHOT_LAUNCH_SEG(BSHOT_SR_CVS);
+    else BSHOT_LAUNCH_SEG(BSHOT_SR_CVSN);
+#undef BSHOT_LAUNCH_SEG
     count_launch(c, 2);
     return check_launch("seg_ratio kernels");
 }
@@ -320,7 +311,7 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
 void knn_stats_dump() {
     unsigned long long h[8];
     cudaMemcpyFromSymbol(h, g_knn_stats, sizeof(h));
-    fprintf(stderr, "[knn stats] attempts=%llu rows=%llu cand=%llu insphere=%llu slow=%llu\n", h[0], h[1], h[2], h[3], h[4]);
+    fprintf(stderr, "[knn stats] sweeps=%llu rows=%llu cand=%llu insphere=%llu slow=%llu enumerations=%llu enum_rows=%llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
     unsigned long long z[8] = {0};
     cudaMemcpyToSymbol(g_knn_stats, z, sizeof(z));
 }

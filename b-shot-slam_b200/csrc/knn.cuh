@@ -19,8 +19,19 @@ namespace bshot {
 constexpr int KN_MAXSEG = 400;   // slow path: rows of the largest query rectangle kept per warp
 constexpr int KN_MAXB = 256;     // slow path: batch table covers 8192 candidates per query
 constexpr int KN_CAP = 1024;     // fast path: explicit candidate list
+#ifndef BSHOT_KN_DEPTH
+#define BSHOT_KN_DEPTH 4
+#endif
+#ifndef BSHOT_KN_WLO
+#define BSHOT_KN_WLO 1.45f
+#endif
+#ifndef BSHOT_KN_WHI
+#define BSHOT_KN_WHI 2.2f
+#endif
+constexpr int KN_DEPTH = BSHOT_KN_DEPTH;
 constexpr int KN_BINS = 256;
 constexpr int KN_LIST = 224;
+constexpr int KN_SEGCAP = 2 * KN_LIST;  // fast path: non-empty row segments per sphere (staging aliases `list` and `hist`)
 
 #ifdef BSHOT_KNN_STATS
 __device__ unsigned long long g_knn_stats[8];
@@ -31,12 +42,20 @@ struct KnnWarpSmem {
         unsigned idx[KN_CAP];               // fast path: positions in the cell-sorted array
         SegList<KN_MAXSEG, KN_MAXB> sl;     // slow path
     } u;
-    unsigned hist[KN_BINS];
-    unsigned long long list[KN_LIST];
+    union {
+        unsigned hist[KN_BINS];             // sqd histogram
+        struct { unsigned heads[32]; unsigned short off[KN_SEGCAP]; } x;  // expansion: head masks of the list chunks, segment offsets
+    } h;
+    union {
+        unsigned long long list[KN_LIST];   // crossing-bin keys
+        unsigned seg_start[KN_SEGCAP];      // expansion: first point of every non-empty row segment
+    } v;
     unsigned list_n;
     unsigned long long thr;
 };
 static_assert(sizeof(SegList<KN_MAXSEG, KN_MAXB>) <= sizeof(unsigned) * KN_CAP, "slow path must fit under the index list");
+static_assert(KN_CAP <= 32 * 32, "one head-mask word per lane");
+static_assert(32 * 4 + KN_SEGCAP * 2 <= KN_BINS * 4 && KN_CAP < 65536, "expansion staging must fit under the histogram");
 
 // where the candidates of the current sphere live (warp-uniform)
 struct KnnIter {
@@ -52,7 +71,6 @@ struct KnnResult {
     unsigned long long thr;   // selected <=> sqd < rho2 && key <= thr
     int count;                // size of the selected set
     int n_in;                 // points inside the final sphere (>= count)
-    int m;                    // sphere size (cells) that succeeded: warm start for a nearby query
     KnnIter it;               // candidate set for further sweeps by the caller
 };
 
@@ -60,12 +78,18 @@ __device__ __forceinline__ unsigned long long knn_key(float sqd, float w) {
     return ((unsigned long long)__float_as_uint(sqd) << 32) | __float_as_uint(w);
 }
 
-// Enumerate the row segments of the sphere (q, rho) and expand them into sm.u.idx (entries beyond
-// KN_CAP are dropped but still counted).  Returns the number of candidates.  All 32 lanes call.
+// Enumerate the row segments of the sphere (q, rho) and, when there are at least `fill_lo` and at most
+// `fill_hi` (<= KN_CAP) candidates in at most KN_SEGCAP non-empty segments, expand them into sm.u.idx.  Returns the
+// number of candidates; `filled` says whether sm.u.idx holds them.  All 32 lanes call.
+//   1. rows -> (start, length) of the non-empty segments, compacted with a ballot rank (row order)
+//   2. exclusive scan of the lengths
+//   3. head mask: bit j of word c set iff a segment starts at candidate 32 c + j
+//   4. balanced fill: candidate j belongs to segment #(heads at or before j); every STS writes 32 entries
 __device__ __forceinline__ unsigned knn_expand(const GridParams& g, const unsigned* __restrict__ cell_start,
-                                               const float4& q, float rho, const RowRange& rr, KnnWarpSmem& sm,
-                                               unsigned lane) {
-    unsigned base = 0;
+                                               const float4& q, float rho, const RowRange& rr, unsigned fill_lo,
+                                               unsigned fill_hi, KnnWarpSmem& sm, unsigned lane, bool& filled) {
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned nseg = 0, part = 0;
     __syncwarp();
     for (int r0 = 0; r0 < rr.nrows; r0 += 32) {
         const int r = r0 + (int)lane;
@@ -76,28 +100,67 @@ __device__ __forceinline__ unsigned knn_expand(const GridParams& g, const unsign
             unsigned e;
             if (row_segment(g, cell_start, q.x, q.y, q.z, rho, iy, iz, s, e)) len = e - s;
         }
-        unsigned inc = len;
+        const unsigned m = __ballot_sync(0xffffffffu, len > 0);
+        const unsigned k = nseg + __popc(m & lt_mask);
+        // lengths above 65535 cannot be listed anyway (total > KN_CAP): clamp for the u16 staging
+        if (len > 0 && k < (unsigned)KN_SEGCAP) { sm.v.seg_start[k] = s; sm.h.x.off[k] = (unsigned short)min(len, 65535u); }
+        nseg += __popc(m);
+        part += len;
+    }
+    const unsigned total = (unsigned)warp_sum((int)part);
+    filled = false;
+    if (total < fill_lo || total > fill_hi || nseg > (unsigned)KN_SEGCAP) return total;
+    __syncwarp();
+    {   // 2. exclusive scan (lane l owns a contiguous run of segments)
+        const unsigned per = (nseg + 31) / 32;
+        const unsigned b = lane * per, e = min(nseg, b + per);
+        unsigned sum = 0;
+        for (unsigned i = b; i < e; ++i) sum += sm.h.x.off[i];
+        unsigned inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (unsigned)o) inc += up;
         }
-        const unsigned off = base + inc - len;
-        const unsigned room = (off < (unsigned)KN_CAP) ? (unsigned)KN_CAP - off : 0u;
-        const unsigned wr = min(len, room);
-        // lane-divergent fill, 4 entries per trip (segments are short: a few points per row on lidar data)
-        for (unsigned i = 0; i < wr; i += 4) {
-            unsigned* d = sm.u.idx + off + i;
-            const unsigned v = s + i;
-            d[0] = v;
-            if (i + 1 < wr) d[1] = v + 1;
-            if (i + 2 < wr) d[2] = v + 2;
-            if (i + 3 < wr) d[3] = v + 3;
+        unsigned run = inc - sum;
+        for (unsigned i = b; i < e; ++i) {
+            const unsigned len = sm.h.x.off[i];
+            sm.h.x.off[i] = (unsigned short)run;
+            run += len;
         }
-        base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    const unsigned nchunk = (total + 31) >> 5;  // <= 32
+    sm.h.x.heads[lane] = 0u;
+    __syncwarp();
+    for (unsigned k = lane; k < nseg; k += 32) {  // 3. head masks
+        const unsigned o = sm.h.x.off[k];
+        atomicOr(&sm.h.x.heads[o >> 5], 1u << (o & 31));
     }
     __syncwarp();
-    return base;
+    const unsigned hw = sm.h.x.heads[lane];
+    unsigned pre = __popc(hw);  // -> exclusive prefix of the head counts over the chunks
+    {
+        unsigned inc = pre;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += up;
+        }
+        pre = inc - pre;
+    }
+    const unsigned le_mask = lt_mask | (1u << lane);
+    for (unsigned c = 0; c < nchunk; ++c) {  // 4. balanced fill
+        const unsigned w = __shfl_sync(0xffffffffu, hw, c);
+        const unsigned p0 = __shfl_sync(0xffffffffu, pre, c);
+        const unsigned j = (c << 5) + lane;
+        if (j < total) {
+            const unsigned k = p0 + __popc(w & le_mask) - 1u;  // candidate 0 is a head: k >= 0
+            sm.u.idx[j] = sm.v.seg_start[k] + (j - sm.h.x.off[k]);
+        }
+    }
+    __syncwarp();
+    filled = true;
+    return total;
 }
 
 // iterate all candidates of the current sphere; f(float4 point).
@@ -107,16 +170,16 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
                                              KnnWarpSmem& sm, unsigned lane, F&& f) {
     if (it.list) {
         const unsigned total = it.total;
-        // 4 independent candidate loads in flight per lane before the first use
-        for (unsigned j = lane; j < total; j += 32 * 4) {
-            float4 p[4];
+        // KN_DEPTH independent candidate loads in flight per lane before the first use
+        for (unsigned j = lane; j < total; j += 32 * KN_DEPTH) {
+            float4 p[KN_DEPTH];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < KN_DEPTH; ++u) {
                 const unsigned ju = j + 32u * u;
                 p[u] = __ldg(sorted + sm.u.idx[ju < total ? ju : j]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < KN_DEPTH; ++u)
                 if (j + 32u * u < total) f(p[u]);
         }
         __syncwarp();
@@ -144,44 +207,54 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
 // All 32 lanes call.  Selects the nearest <= max_nn points inside radius R of q and calls acc(p) exactly
 // once (on some lane) for every selected point; the caller reduces its accumulators across the warp.
 // On return res.it describes the candidate set (still in shared memory) for further sweeps with
-// knn_selected() as the predicate.  `m_hint` > 0 starts the sphere growth at that many cells (the size
-// that worked for a nearby query) instead of the 2-cell probe.
-//   1. grow the sphere: candidates are enumerated first (cheap) and a sweep is only spent when the rows
-//      can hold max_nn points; the radius is predicted from the local density (count ~ r^2 on surfaces);
-//      one sweep counts the points inside the sphere and fills a 256-bin sqd histogram
+// knn_selected() as the predicate.
+//   1. size the sphere: candidates are enumerated first (cheap, no point is touched) and the radius is
+//      tuned until their number falls into a window around 1.7 max_nn, each step predicted from the local
+//      density (count ~ r^2 on surfaces); then one sweep counts the points inside the sphere and fills a
+//      256-bin sqd histogram; fewer than max_nn inside -> grow and repeat
 //   2. crossing bin of the histogram (re-histogrammed inside the bin while it holds > KN_LIST candidates)
 //   3. one sweep: accumulate everything below the crossing bin, collect the bin; rank the short list by
 //      key, accumulate its first (max_nn - below) entries (re-read from the original-order array `pts`)
 template <typename Acc>
 __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsigned* __restrict__ cell_start,
                                                 const float4* __restrict__ sorted, const float4* __restrict__ pts,
-                                                const float4& q, float R, int max_nn, int m_hint, KnnWarpSmem& sm,
+                                                const float4& q, float R, int max_nn, KnnWarpSmem& sm,
                                                 unsigned lane, Acc&& acc) {
     KnnResult res;
     KnnIter& it = res.it;
     const float R2 = (float)((double)R * (double)R);
     float rho2 = R2;
     int n = 0;
-    const int M = max(1, (int)ceilf(R * g.inv_cell)) + 1;  // rho(M) >= R: the loop always terminates at m == M
-    int m = (m_hint > 0) ? min(m_hint, M) : min(2, M);
-    // ---- 1. grow the sphere ---------------------------------------------------------------------
+    float rho = 2.0f * g.cell * 0.9999f;  // first probe
+    int tries = 0;
+    // candidate window that is worth a sweep: ~74 % of the candidates of a chord-clipped row set lie inside
+    // the sphere, so 1.45 .. 2.2 max_nn candidates hold max_nn points with little excess
+    const unsigned want_lo = (unsigned)(BSHOT_KN_WLO * (float)max(max_nn, 0)), want_hi = min((unsigned)(BSHOT_KN_WHI * (float)max(max_nn, 0)), (unsigned)KN_CAP);
+    // ---- 1. size the sphere ---------------------------------------------------------------------
     for (;;) {
-        const float g_m = (float)m * g.cell * 0.9999f;
-        const bool last = (max_nn <= 0) || m >= M || !(g_m < R);
-        it.rho = last ? R : g_m;
+        const bool last = (max_nn <= 0) || !(rho < R);
+        it.rho = last ? R : rho;
         rho2 = last ? R2 : __fmul_rn(it.rho, it.rho);
         it.rr = row_range(g, q.y, q.z, it.rho);
-        it.total = knn_expand(g, cell_start, q, it.rho, it.rr, sm, lane);
-        if (!last && it.total < (unsigned)max_nn) {
-            // cheap necessary condition failed (the candidate rows hold fewer than max_nn points).
-            // surface-like density: count ~ r^2  ->  radius that should hold 1.4 * max_nn candidates
-            const float f = sqrtf(1.4f * (float)max_nn / (float)max(it.total, 1u));
-            m = min(M, max(m + 1, (int)ceilf((float)m * f)));
+        const bool settle = last || tries >= 4;  // stop tuning: take whatever holds enough candidates
+        bool filled;
+        it.total = knn_expand(g, cell_start, q, it.rho, it.rr, last ? 0u : want_lo, settle ? (unsigned)KN_CAP : want_hi, sm, lane,
+                              filled);
+        ++tries;
+#ifdef BSHOT_KNN_STATS
+        if (lane == 0) { atomicAdd(&g_knn_stats[5], 1ull); atomicAdd(&g_knn_stats[6], (unsigned long long)it.rr.nrows); }
+#endif
+        if (!last && it.total < want_lo) {  // too few candidates (no point touched yet): grow, count ~ r^2 on surfaces
+            rho *= fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)max(it.total, 1u)), 1.08f), 4.0f);
             continue;
         }
-        it.list = it.total <= (unsigned)KN_CAP;
+        if (!settle && it.total > want_hi) {  // too many (dense spot): shrink
+            rho *= fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)it.total), 0.25f), 0.95f);
+            continue;
+        }
+        it.list = filled;
         it.cached = false;
-        for (unsigned b = lane; b < KN_BINS; b += 32) sm.hist[b] = 0;
+        for (unsigned b = lane; b < KN_BINS; b += 32) sm.h.hist[b] = 0;
         __syncwarp();
         const float scale = (float)KN_BINS / rho2;
         int cnt = 0;
@@ -189,7 +262,7 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
             const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
             if (sqd < rho2) {
                 ++cnt;
-                atomicAdd(&sm.hist[min(KN_BINS - 1, (int)(sqd * scale))], 1u);
+                atomicAdd(&sm.h.hist[min(KN_BINS - 1, (int)(sqd * scale))], 1u);
             }
         });
         n = warp_sum(cnt);
@@ -197,108 +270,108 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
         if (lane == 0) { atomicAdd(&g_knn_stats[0], 1ull); atomicAdd(&g_knn_stats[1], (unsigned long long)it.rr.nrows); atomicAdd(&g_knn_stats[2], (unsigned long long)it.total); atomicAdd(&g_knn_stats[3], (unsigned long long)n); atomicAdd(&g_knn_stats[4], it.list ? 0ull : 1ull); }
 #endif
         if (last || n >= max_nn) break;
-        const float f = sqrtf(1.15f * (float)max_nn / (float)max(n, 1));
-        m = min(M, max(m + 1, (int)ceilf((float)m * f)));
+        rho *= fminf(fmaxf(sqrtf(1.3f * (float)max_nn / (float)max(n, 1)), 1.1f), 4.0f);
+        tries = 4;  // grown after a sweep: no more shrinking
     }
     res.rho2 = rho2;
-    res.m = m;
     res.n_in = n;
-    if (max_nn <= 0 || n <= max_nn) {  // everything inside the sphere is selected
+    // ---- 2. crossing bin (the level-0 histogram is already in sm.hist) ----------------------------------
+    // select-all (n <= max_nn, or no cap) is the same collect sweep with every bin below `bin`
+    const bool select_all = (max_nn <= 0 || n <= max_nn);
+    float lo = 0.0f, hi = rho2, scale = (float)KN_BINS / rho2;
+    int below = 0;  // selected-for-sure elements with sqd < lo
+    int bin = KN_BINS;
+    unsigned bbelow = 0;
+    if (!select_all) {
+        for (int iter = 0;; ++iter) {
+            scale = (float)KN_BINS / (hi - lo);
+            if (iter > 0) {
+                for (unsigned b = lane; b < KN_BINS; b += 32) sm.h.hist[b] = 0;
+                __syncwarp();
+                int cb = 0;
+                const float flo = lo, fhi = hi, fscale = scale;
+                knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
+                    const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                    if (sqd < flo) ++cb;  // `below` is recounted exactly for the narrowed bound
+                    else if (sqd < fhi) atomicAdd(&sm.h.hist[min(KN_BINS - 1, (int)((sqd - flo) * fscale))], 1u);
+                });
+                below = warp_sum(cb);
+            }
+            // locate the crossing bin: lane l owns bins 8l..8l+7
+            unsigned h[8], s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { h[k] = sm.h.hist[lane * 8 + k]; s += h[k]; }
+            unsigned inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (unsigned)o) inc += up;
+            }
+            unsigned run = (unsigned)below + inc - s;
+            int found_bin = -1;
+            unsigned found_below = 0, found_cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (found_bin < 0 && run < (unsigned)max_nn && run + h[k] >= (unsigned)max_nn) {
+                    found_bin = (int)lane * 8 + k;
+                    found_below = run;
+                    found_cnt = h[k];
+                }
+                run += h[k];
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
+            const int src = __ffs(who) - 1;  // exactly one lane finds it (n > max_nn)
+            bin = __shfl_sync(0xffffffffu, found_bin, src);
+            bbelow = __shfl_sync(0xffffffffu, found_below, src);
+            const unsigned bcnt = __shfl_sync(0xffffffffu, found_cnt, src);
+            if (bcnt <= KN_LIST || iter == 7) break;
+            // narrow to the crossing bin and histogram again
+            const float w = (hi - lo) / (float)KN_BINS;
+            const float nlo = lo + w * (float)bin, nhi = lo + w * (float)(bin + 1);
+            lo = fmaxf(lo, nlo - w * 1e-3f);
+            hi = fminf(hi, nhi + w * 1e-3f);
+        }
+    }
+    // ---- 3. accumulate below the bin, collect the bin, rank, accumulate the rest -----------------------
+    {
+        const float blo = lo, bhi = hi, bscale = scale;
+        const int cbin = bin;
+        if (lane == 0) sm.list_n = 0;
+        __syncwarp();
+        knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!(sqd < bhi)) return;
+            const int b = (sqd >= blo) ? min(KN_BINS - 1, (int)((sqd - blo) * bscale)) : -1;
+            if (b < cbin) acc(p);
+            else if (b == cbin) {
+                const unsigned slot = atomicAdd(&sm.list_n, 1u);
+                if (slot < KN_LIST) sm.v.list[slot] = knn_key(sqd, p.w);
+            }
+        });
+        __syncwarp();
+    }
+    if (select_all) {
         res.thr = (((unsigned long long)__float_as_uint(rho2)) << 32) - 1ull;
         res.count = n;
-        knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
-            if (sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z) < rho2) acc(p);
-        });
         return res;
     }
-    // ---- 2. crossing bin (the level-0 histogram is already in sm.hist) ----------------------------------
-    float lo = 0.0f, hi = rho2;
-    int below = 0;  // selected-for-sure elements with sqd < lo
-    for (int iter = 0; iter < 8; ++iter) {
-        const float scale = (float)KN_BINS / (hi - lo);
-        if (iter > 0) {
-            for (unsigned b = lane; b < KN_BINS; b += 32) sm.hist[b] = 0;
-            __syncwarp();
-            int cb = 0;
-            const float flo = lo, fhi = hi;
-            knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (sqd < flo) ++cb;  // `below` is recounted exactly for the narrowed bound
-                else if (sqd < fhi) atomicAdd(&sm.hist[min(KN_BINS - 1, (int)((sqd - flo) * scale))], 1u);
-            });
-            below = warp_sum(cb);
+    const unsigned ln = min(sm.list_n, (unsigned)KN_LIST);
+    const unsigned need = (unsigned)max_nn - bbelow;  // 1..bcnt
+    // fallback threshold (only reachable for > KN_LIST exact distance duplicates)
+    if (lane == 0) sm.thr = (unsigned long long)__float_as_uint(hi) << 32;
+    __syncwarp();
+    for (unsigned e = lane; e < ln; e += 32) {
+        const unsigned long long ke = sm.v.list[e];
+        unsigned rank = 0;
+        for (unsigned o = 0; o < ln; ++o) rank += (sm.v.list[o] < ke) ? 1u : 0u;
+        if (rank < need) {
+            acc(__ldg(pts + (unsigned)(ke & 0xFFFFFFFFull)));
+            if (rank == need - 1) sm.thr = ke;
         }
-        // locate the crossing bin: lane l owns bins 8l..8l+7
-        unsigned h[8], s = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { h[k] = sm.hist[lane * 8 + k]; s += h[k]; }
-        unsigned inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += up;
-        }
-        unsigned run = (unsigned)below + inc - s;
-        int found_bin = -1;
-        unsigned found_below = 0, found_cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (found_bin < 0 && run < (unsigned)max_nn && run + h[k] >= (unsigned)max_nn) {
-                found_bin = (int)lane * 8 + k;
-                found_below = run;
-                found_cnt = h[k];
-            }
-            run += h[k];
-        }
-        const unsigned who = __ballot_sync(0xffffffffu, found_bin >= 0);
-        const int src = __ffs(who) - 1;  // exactly one lane finds it (n > max_nn)
-        const int bin = __shfl_sync(0xffffffffu, found_bin, src);
-        const unsigned bbelow = __shfl_sync(0xffffffffu, found_below, src);
-        const unsigned bcnt = __shfl_sync(0xffffffffu, found_cnt, src);
-        const float blo = lo, bhi = hi, bscale = scale;
-        auto bin_of = [&](float sqd) { return min(KN_BINS - 1, (int)((sqd - blo) * bscale)); };
-        if (bcnt <= KN_LIST || iter == 7) {
-            // ---- 3. accumulate below the bin, collect the bin, rank, accumulate the rest ---------------
-            if (lane == 0) sm.list_n = 0;
-            __syncwarp();
-            knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
-                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (!(sqd < bhi)) return;
-                const int b = (sqd >= blo) ? bin_of(sqd) : -1;
-                if (b < bin) acc(p);
-                else if (b == bin) {
-                    const unsigned slot = atomicAdd(&sm.list_n, 1u);
-                    if (slot < KN_LIST) sm.list[slot] = knn_key(sqd, p.w);
-                }
-            });
-            __syncwarp();
-            const unsigned ln = min(sm.list_n, (unsigned)KN_LIST);
-            const unsigned need = (unsigned)max_nn - bbelow;  // 1..bcnt
-            // fallback threshold (only reachable for > KN_LIST exact distance duplicates)
-            if (lane == 0) sm.thr = (unsigned long long)__float_as_uint(hi) << 32;
-            __syncwarp();
-            for (unsigned e = lane; e < ln; e += 32) {
-                const unsigned long long ke = sm.list[e];
-                unsigned rank = 0;
-                for (unsigned o = 0; o < ln; ++o) rank += (sm.list[o] < ke) ? 1u : 0u;
-                if (rank < need) {
-                    acc(__ldg(pts + (unsigned)(ke & 0xFFFFFFFFull)));
-                    if (rank == need - 1) sm.thr = ke;
-                }
-            }
-            __syncwarp();
-            res.thr = sm.thr;
-            res.count = max_nn;
-            return res;
-        }
-        // narrow to the crossing bin and histogram again
-        const float w = (hi - lo) / (float)KN_BINS;
-        const float nlo = lo + w * (float)bin, nhi = lo + w * (float)(bin + 1);
-        lo = fmaxf(lo, nlo - w * 1e-3f);
-        hi = fminf(hi, nhi + w * 1e-3f);
     }
-    res.thr = (((unsigned long long)__float_as_uint(rho2)) << 32) - 1ull;  // unreachable
-    res.count = n;
+    __syncwarp();
+    res.thr = sm.thr;
+    res.count = max_nn;
     return res;
 }
 

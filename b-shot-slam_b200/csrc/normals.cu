@@ -99,7 +99,20 @@ __device__ void eigen33_smallest(const float mat[9], float& eigenvalue, float ev
     evec[0] = v[0] / inv; evec[1] = v[1] / inv; evec[2] = v[2] / inv;
 }
 
-__global__ void __launch_bounds__(NM_THREADS)
+// the 9 single-pass sums of pcl::computeMeanAndCovarianceMatrix over the selected neighbourhood (lane-partial)
+__device__ __forceinline__ void normal_sums(const GridParams& g, const unsigned* __restrict__ cell_start,
+                                            const float4* __restrict__ sorted, const float4* __restrict__ pts, const float4& q,
+                                            float radius, int max_nn, KnnWarpSmem& sm, unsigned lane, double s[9], int& n) {
+    const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, [&](const float4 p) {
+        // products rounded to fp32 like PCL's accumulator inputs, summed in fp64
+        s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
+        s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
+        s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
+    });
+    n = res.count;
+}
+
+__global__ void __launch_bounds__(NM_THREADS, 8)
 normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                const float4* __restrict__ sorted, const float4* __restrict__ pts, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
                float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters) {
@@ -116,17 +129,9 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
     int n = 0;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (finite) {
-        const KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, 0, sm, lane, [&](const float4 p) {
-            // products rounded to fp32 like PCL's accumulator inputs, summed in fp64
-            s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
-            s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
-            s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
-        });
-        n = res.count;
-        {
+        normal_sums(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, s, n);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
-        }
+        for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
     }
     if (lane != 0) return;
     atomicAdd(&counters[1], (unsigned long long)n);
@@ -162,13 +167,18 @@ __global__ void place_normals_kernel(const float4* __restrict__ src, const int* 
     if (i < cap && (int)i < *count) dst[i] = src[i];
 }
 
+static int normals_launch(Ctx* c, const float4* d_q, const int* nq_dev, size_t nq, float radius, int max_nn, float4* d_out) {
+    const unsigned ctas = (unsigned)((nq + NM_WARPS - 1) / NM_WARPS);
+    normals_kernel<<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
+                                                       radius, max_nn, d_out, c->d_counters);
+    count_launch(c);
+    return check_launch("normals_kernel");
+}
+
 int normals_query(Ctx* c, const float4* d_q, size_t nq, float radius, int max_nn, float4* d_out) {
     if (nq == 0) return BSHOT_OK;
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
-    normals_kernel<<<(unsigned)((nq + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-        c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nullptr, (unsigned)nq, radius, max_nn, d_out, c->d_counters);
-    count_launch(c);
-    return check_launch("normals_kernel");
+    return normals_launch(c, d_q, nullptr, nq, radius, max_nn, d_out);
 }
 
 int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
@@ -179,12 +189,11 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
     } else {
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
-            normals_kernel<<<(unsigned)((k + NM_WARPS - 1) / NM_WARPS), NM_THREADS, 0, c->stream>>>(
-                c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, c->d_kp, c->d_kp_count, (unsigned)k, radius, max_nn, c->d_qnormals, c->d_counters);
+            BSHOT_TRY(normals_launch(c, c->d_kp, c->d_kp_count, k, radius, max_nn, c->d_qnormals));
             place_normals_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(c->d_qnormals, c->d_kp_count, (unsigned)k,
                                                                                      c->d_normals);
-            count_launch(c, 2);
-            BSHOT_TRY(check_launch("normals_kernel"));
+            count_launch(c);
+            BSHOT_TRY(check_launch("place_normals_kernel"));
         }
         c->normals_valid = std::max(c->normals_valid, k);
     }

@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--map-steps", type=int, default=10)
     ap.add_argument("--no-map", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the HDL-64E frame / SHOT-radius sweep (C3) object")
     ap.add_argument("--map-only", action="store_true", help="debug: print only the map_match object")
     args = ap.parse_args()
 
@@ -346,6 +347,50 @@ def main():
                      "collective": "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result" if world > 1 else "none",
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
 
+
+    # ---- C3: HDL-64E-shaped 120 k-point scans, K = 10 000 (rank 0, N = 1 only) --------------------------
+    # (a) the north_star frame: full extraction + match of one 120 k-point scan, REFERENCE normals;
+    # (b) extraction throughput (normals + LRF + SHOT352 + B-SHOT) over the SHOT radius, FULL normals.
+    c3 = None
+    if rank == 0 and world == 1 and not args.no_c3 and not args.map_only:
+        K64, NF64 = 10000, 3
+        f64 = [synth.make_scan("hdl64e", f) for f in range(NF64)]
+        n64 = [len(f) for f in f64]
+        d64 = [torch.from_numpy(f).cuda() for f in f64]
+        ctx64 = bs.Context(local_rank, max_points=max(n64) + 1024, max_keypoints=K64, max_targets=K64)
+        st64 = torch.cuda.ExternalStream(ctx64.stream)
+        ctx64.enable_timing(True)
+
+        def run64(params64, reps):
+            acc, nbr = {}, 0
+            for i in range(2):                                        # warm-up (also fills prev-frame descriptors)
+                ctx64.process_frame_dev(d64[i % NF64].data_ptr(), n64[i % NF64], 12, params64)
+            ctx64.sync()
+            for i in range(reps):
+                with torch.cuda.stream(st64):
+                    flush.fill_(1.0)
+                ctx64.process_frame_dev(d64[i % NF64].data_ptr(), n64[i % NF64], 12, params64)
+                for k, v in ctx64.stage_times().items():
+                    acc[k] = acc.get(k, 0.0) + v / reps
+                nbr += ctx64.frame_counters()["shot_neighbours"] / reps
+            return acc, nbr
+
+        st_ref, _ = run64(bs.default_params(top_k=K64), 12)
+        sweep = []
+        for R in (500.0, 1000.0, 2000.0, 3000.0, 4000.0):
+            ctx64.reset()
+            st_r, nbr = run64(bs.default_params(top_k=K64, normals_mode=bs.NORMALS_FULL, normal_radius=R, shot_radius=R), 6)
+            ext_ms = st_r["normals"] + st_r["shot_bshot"]
+            sweep.append({"radius_mm": R, "normals_ms": st_r["normals"], "shot_bshot_ms": st_r["shot_bshot"],
+                          "descriptors_per_s": K64 / (ext_ms * 1e-3), "shot_neighbours_per_keypoint": nbr / K64,
+                          "shot_algorithmic_GBps": 32.0 * nbr / (st_r["shot_bshot"] * 1e-3) / 1e9})
+        c3 = {"workload": "C3", "sensor": "hdl64e", "points_per_frame": int(np.mean(n64)), "top_k": K64,
+              "frame_reference_normals": {"ms_per_frame": st_ref["frame"], "stages_ms": st_ref,
+                                          "north_star_target_ms": 2.0},
+              "radius_sweep_full_normals": sweep,
+              "note": "stage times from CUDA events on the context stream, L2 flushed before every frame"}
+        ctx64.close()
+
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -376,7 +421,7 @@ def main():
                        "parallelism": "replicas (one frame stream per GPU)" if world > 1 else "single GPU",
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write), per-step CUDA events on the context stream"},
             "stages_ms": stages, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match,
+            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c3": c3,
         }
         print(json.dumps(line))
     ctx.close()

@@ -1,10 +1,10 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-run() { python bench.py --steps 20 --warmup 5 --no-cpu --no-map --sensor $1 --top-k $2 2>/dev/null | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); print('$3 $1', {k: round(x,4) for k,x in d['stages_ms'].items()})"; }
-run hdl32e 2048 default
-run hdl64e 10000 default
-BSHOT_SHOT_THREADS=256 run hdl32e 2048 shot256
-BSHOT_SHOT_THREADS=256 run hdl64e 10000 shot256
-BSHOT_SHOT_THREADS=64 run hdl32e 2048 shot64
-BSHOT_SHOT_THREADS=64 run hdl64e 10000 shot64
+python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+T0=$(date +%s); python bench.py > gpurun_out/bench_r1d.json 2> gpurun_out/bench_r1d.err; echo "bench exit $? in $(( $(date +%s) - T0 )) s"; tail -3 gpurun_out/bench_r1d.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_r1d.json'))
+print({k:d[k] for k in ['value','ms_per_step']}, d['stages_ms'])
+print('e2e', d['e2e']); print('roofline', d['roofline']); print('cpu', d['cpu_baseline']['value'], 'map', d['map_match']['ms_per_call'], d['map_match']['roofline']['frac'])
+print('c3 frame', d['c3']['frame_reference_normals'])
+for r in d['c3']['radius_sweep_full_normals']: print(r)
+PY
