@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "stages.h"
 
 namespace bshot {
@@ -115,6 +117,10 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     }
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("BSHOT_YZ_MUL")) {  // tuning knob: row thickness relative to the cell length
+        const float v = (float)atof(e);
+        if (v >= 1.0f && v <= 8.0f) c->yz_mul = v;
+    }
     if (max_targets < max_keypoints) max_targets = max_keypoints;
     c->max_points = max_points;
     c->max_kp = max_keypoints;

@@ -74,24 +74,27 @@ convert_bbox_kernel(const float* __restrict__ raw, unsigned n, int stride, float
     }
 }
 
-__global__ void grid_params_kernel(const float* __restrict__ bbox, unsigned n, float cell0, GridParams* g) {
+__global__ void grid_params_kernel(const float* __restrict__ bbox, unsigned n, float cell0, float yz_mul, GridParams* g) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     GridParams p;
     float mn[3] = {bbox[0], bbox[1], bbox[2]}, mx[3] = {bbox[3], bbox[4], bbox[5]};
     if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.0f; mx[0] = mx[1] = mx[2] = 0.0f; }  // empty cloud
     float cell = cell0;
     for (;;) {
-        const double cells = (floor((double)(mx[0] - mn[0]) / cell) + 1.0) * (floor((double)(mx[1] - mn[1]) / cell) + 1.0) *
-                             (floor((double)(mx[2] - mn[2]) / cell) + 1.0);
+        const double cyz = (double)cell * (double)yz_mul;
+        const double cells = (floor((double)(mx[0] - mn[0]) / cell) + 1.0) * (floor((double)(mx[1] - mn[1]) / cyz) + 1.0) *
+                             (floor((double)(mx[2] - mn[2]) / cyz) + 1.0);
         if (cells <= (double)kMaxCells) break;
         cell *= 1.25f;
     }
     p.ox = mn[0]; p.oy = mn[1]; p.oz = mn[2];
     p.cell = cell;
     p.inv_cell = 1.0f / cell;
+    p.cell_yz = cell * yz_mul;
+    p.inv_cell_yz = 1.0f / p.cell_yz;
     p.nx = cell_coord(mx[0], p.ox, p.inv_cell) + 1;
-    p.ny = cell_coord(mx[1], p.oy, p.inv_cell) + 1;
-    p.nz = cell_coord(mx[2], p.oz, p.inv_cell) + 1;
+    p.ny = cell_coord(mx[1], p.oy, p.inv_cell_yz) + 1;
+    p.nz = cell_coord(mx[2], p.oz, p.inv_cell_yz) + 1;
     // cell_coord rounds in fp32; shrink until the table fits (never triggers in practice)
     while ((double)p.nx * p.ny * p.nz > (double)kMaxCells) {
         if (p.nx >= p.ny && p.nx >= p.nz) p.nx--; else if (p.ny >= p.nz) p.ny--; else p.nz--;
@@ -116,8 +119,8 @@ count_kernel(const float4* __restrict__ pts, unsigned n, const GridParams* __res
     unsigned cid = 0xFFFFFFFFu;
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
         const int ix = min(max(cell_coord(p.x, g.ox, g.inv_cell), 0), g.nx - 1);
-        const int iy = min(max(cell_coord(p.y, g.oy, g.inv_cell), 0), g.ny - 1);
-        const int iz = min(max(cell_coord(p.z, g.oz, g.inv_cell), 0), g.nz - 1);
+        const int iy = min(max(cell_coord(p.y, g.oy, g.inv_cell_yz), 0), g.ny - 1);
+        const int iz = min(max(cell_coord(p.z, g.oz, g.inv_cell_yz), 0), g.nz - 1);
         cid = ((unsigned)iz * g.ny + iy) * g.nx + ix;
         atomicAdd(&cursor[cid], 1u);
     }
@@ -244,7 +247,7 @@ int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
     const unsigned pb = (nn + GB_THREADS - 1) / GB_THREADS;
     bbox_init_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox);
     if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
-    grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->d_grid);
+    grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->yz_mul, c->d_grid);
     zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor);
     if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor);
     scan_reduce_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums);

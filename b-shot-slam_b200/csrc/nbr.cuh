@@ -29,11 +29,11 @@ __device__ __forceinline__ void row_coords(const RowRange& rr, int r, int& iy, i
 
 __device__ __forceinline__ RowRange row_range(const GridParams& g, float py, float pz, float R) {
     RowRange r;
-    const float pad = R + 1e-3f * g.cell;
-    const int iy_lo = max(cell_coord(py - pad, g.oy, g.inv_cell), 0);
-    const int iy_hi = min(cell_coord(py + pad, g.oy, g.inv_cell), g.ny - 1);
-    const int iz_lo = max(cell_coord(pz - pad, g.oz, g.inv_cell), 0);
-    const int iz_hi = min(cell_coord(pz + pad, g.oz, g.inv_cell), g.nz - 1);
+    const float pad = R + 1e-3f * g.cell_yz;
+    const int iy_lo = max(cell_coord(py - pad, g.oy, g.inv_cell_yz), 0);
+    const int iy_hi = min(cell_coord(py + pad, g.oy, g.inv_cell_yz), g.ny - 1);
+    const int iz_lo = max(cell_coord(pz - pad, g.oz, g.inv_cell_yz), 0);
+    const int iz_hi = min(cell_coord(pz + pad, g.oz, g.inv_cell_yz), g.nz - 1);
     r.iy_lo = iy_lo;
     r.iz_lo = iz_lo;
     r.ny_span = iy_hi - iy_lo + 1;
@@ -46,10 +46,10 @@ __device__ __forceinline__ RowRange row_range(const GridParams& g, float py, flo
 __device__ __forceinline__ bool row_segment(const GridParams& g, const unsigned* __restrict__ cell_start, float px,
                                             float py, float pz, float R, int iy, int iz, unsigned& start,
                                             unsigned& end) {
-    const float eps = 1e-3f * g.cell;
-    const float y0 = g.oy + (float)iy * g.cell, z0 = g.oz + (float)iz * g.cell;
-    float dy = fmaxf(fmaxf(y0 - py, py - (y0 + g.cell)), 0.0f);
-    float dz = fmaxf(fmaxf(z0 - pz, pz - (z0 + g.cell)), 0.0f);
+    const float eps = 1e-3f * g.cell_yz;
+    const float y0 = g.oy + (float)iy * g.cell_yz, z0 = g.oz + (float)iz * g.cell_yz;
+    float dy = fmaxf(fmaxf(y0 - py, py - (y0 + g.cell_yz)), 0.0f);
+    float dz = fmaxf(fmaxf(z0 - pz, pz - (z0 + g.cell_yz)), 0.0f);
     dy = fmaxf(dy - eps, 0.0f);
     dz = fmaxf(dz - eps, 0.0f);
     const float rem = R * R - dy * dy - dz * dz;

@@ -1,10 +1,12 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-T0=$(date +%s); python bench.py > gpurun_out/bench_r1d.json 2> gpurun_out/bench_r1d.err; echo "bench exit $? in $(( $(date +%s) - T0 )) s"; tail -3 gpurun_out/bench_r1d.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_r1d.json'))
-print({k:d[k] for k in ['value','ms_per_step']}, d['stages_ms'])
-print('e2e', d['e2e']); print('roofline', d['roofline']); print('cpu', d['cpu_baseline']['value'], 'map', d['map_match']['ms_per_call'], d['map_match']['roofline']['frac'])
-print('c3 frame', d['c3']['frame_reference_normals'])
-for r in d['c3']['radius_sweep_full_normals']: print(r)
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+run() { python bench.py --steps 30 --warmup 5 --no-cpu --no-map --no-c3 --sensor $1 --top-k $2 2>gpurun_out/err_$3.log | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); s=d['stages_ms']; print('%-10s %s seg %.4f normals %.4f shot %.4f frame %.4f' % ('$3','$1',s['seg_ratio'],s['normals'],s['shot_bshot'],s['frame']))"; }
+for v in default list; do
+  L=$PWD/b-shot-slam_b200/libbshot_b200_$v.so; [ $v = default ] && L=$PWD/b-shot-slam_b200/libbshot_b200.so
+  for m in 1 2 3; do
+  BSHOT_YZ_MUL=$m BSHOT_LIB=$L run hdl32e 2048 $v-yz$m
+  BSHOT_YZ_MUL=$m BSHOT_LIB=$L run hdl64e 10000 $v-yz$m
+  done
+done
+BSHOT_LIB=$PWD/b-shot-slam_b200/libbshot_b200_stats.so python bench.py --steps 1 --warmup 3 --no-cpu --no-map --no-c3 2>&1 >/dev/null | grep "knn stats" | tail -1

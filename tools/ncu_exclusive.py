@@ -40,3 +40,22 @@ print(f"exclusive totals: warp inst {ti}  samples {ts}  (distinct SASS {len(best
 for k, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"{k[0]}:{k[1]:<4} inst {i:>10} ({100.0*i/ti:5.1f}%) samples {100.0*s/max(ts,1):5.1f}%  {src.get(k,'')}")
 print("opcodes:", ", ".join(f"{o} {100.0*c/ti:.1f}%" for o, c in sorted(ops.items(), key=lambda kv: -kv[1])[:24]))
+
+# optional phase buckets: ncu_exclusive.py dump.csv top "file:lo-hi=name,..."
+if len(sys.argv) > 3:
+    buckets = []
+    for spec in sys.argv[3].split(","):
+        rng, name = spec.split("=")
+        f, lh = rng.split(":")
+        lo, hi = lh.split("-")
+        buckets.append((f, int(lo), int(hi), name))
+    tot = defaultdict(int)
+    for (f, l), (i, s) in agg.items():
+        for bf, lo, hi, name in buckets:
+            if f == bf and lo <= l <= hi:
+                tot[name] += i
+                break
+        else:
+            tot["other:" + f] += i
+    for name, i in sorted(tot.items(), key=lambda kv: -kv[1]):
+        print(f"  {name:28s} {i:>11} {100.0*i/ti:5.1f}%  ({i/61079:.0f} per query)")
