@@ -128,8 +128,14 @@ __device__ __forceinline__ void pack_bits_block(const float* hist, unsigned* wor
     __syncthreads();
 }
 
+#ifndef BSHOT_SHOT_FP64_INTERP
+#define BSHOT_SHOT_FP64_INTERP 0  // 1: PCL's double-precision interpolation arithmetic (slower; same bits to >= 99.9 %)
+#endif
+#ifndef BSHOT_SH_MINBLOCKS
+#define BSHOT_SH_MINBLOCKS 9
+#endif
 template <int SH_THREADS>
-__global__ void __launch_bounds__(SH_THREADS)
+__global__ void __launch_bounds__(SH_THREADS, (SH_THREADS == 128) ? BSHOT_SH_MINBLOCKS : 1)
 shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
             const float4* __restrict__ sorted, const float4* __restrict__ kp, const int* __restrict__ kp_count,
             const float4* __restrict__ normals, unsigned normals_limit, float radius, int lrf_only,
@@ -393,6 +399,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         const double RAD_135 = 2.3561944901923449288469825374596, RAD_PI_7_8 = 2.7488935718910690836548129603691;
         unsigned int* hist = sm.acc;
         auto vote = [&](int idx, float v) { atomicAdd(&hist[idx], __float2uint_rn(v * fx_scale)); };
+#if BSHOT_SHOT_FP64_INTERP
         for_each([&](const float4 p) {
             const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
             if (!(sqd < R2)) return;
@@ -461,6 +468,84 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             }
             vote(volume_index + step_index, (float)w);
         });
+#else
+        // Interpolation weights in fp32: every DECISION below (volume index, shape bin, which neighbour bin
+        // receives the second vote) is taken on exactly the values PCL compares -- fp32 dot products, the
+        // fp32 squared distance against (R/2)^2, the double shape bin -- only the weights themselves, which
+        // are rounded to a 2^-fx_bits fixed-point grid anyway, are computed in single precision (relative
+        // error 1e-7 against a grid of ~4e-6).  Saves the fp64 sqrt and five fp64 divisions per neighbour.
+        const float r12 = (float)radius1_2, r34 = (float)radius3_4, r14 = (float)radius1_4;
+        const float inv_r12 = 1.0f / r12;
+        const float R2_4 = (float)(((double)R * (double)R) / 4.0);  // distance > R/2  <=>  sqd > R^2/4 (exact for fp32 sqd)
+        const float F_45 = (float)RAD_45, F_135 = (float)RAD_135, F_78 = (float)RAD_PI_7_8;
+        const float INV_90 = (float)(1.0 / RAD_90), INV_45 = (float)(1.0 / RAD_45);
+        for_each([&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (!(sqd < R2)) return;
+            const unsigned sidx = __float_as_uint(p.w);
+            float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sidx < normals_limit) nv = __ldg(normals + sidx);
+            if (!isfinite(nv.x) || !isfinite(nv.y) || !isfinite(nv.z)) return;
+            double cosine = (double)dot3_rn(nv.x, nv.y, nv.z, fz0, fz1, fz2);
+            if (cosine > 1.0) cosine = 1.0;
+            if (cosine < -1.0) cosine = -1.0;
+            const double bin = ((1.0 + cosine) * 10) / 2;
+            if (sqd < 1e-30f) return;  // |distance| < 1e-15
+            const float dist = __fsqrt_rn(sqd);
+            const float dx = __fsub_rn(p.x, q.x), dy = __fsub_rn(p.y, q.y), dz = __fsub_rn(p.z, q.z);
+            float xr = dot3_rn(dx, dy, dz, fx0, fx1, fx2);
+            float yr = dot3_rn(dx, dy, dz, fy0, fy1, fy2);
+            float zr = dot3_rn(dx, dy, dz, fz0, fz1, fz2);
+            if (fabsf(yr) < 1E-30f) yr = 0.0f;
+            if (fabsf(xr) < 1E-30f) xr = 0.0f;
+            if (fabsf(zr) < 1E-30f) zr = 0.0f;
+            const int bit4 = ((yr > 0.0f) || ((yr == 0.0f) && (xr < 0.0f))) ? 1 : 0;
+            const int bit3 = ((xr > 0.0f) || ((xr == 0.0f) && (yr > 0.0f))) ? !bit4 : bit4;
+            int desc_index = ((bit4 << 3) + (bit3 << 2)) << 1;
+            const bool same_sign = (xr > 0.0f && yr > 0.0f) || (xr < 0.0f && yr < 0.0f);  // xr * yr > 0 without underflow
+            if (same_sign || (xr == 0.0f)) desc_index += (fabsf(xr) >= fabsf(yr)) ? 0 : 4;
+            else desc_index += (fabsf(xr) > fabsf(yr)) ? 4 : 0;
+            desc_index += zr > 0.0f ? 1 : 0;
+            const bool outer = sqd > R2_4;
+            desc_index += outer ? 2 : 0;
+            const int step_index = (int)floor(bin + 0.5);
+            const int volume_index = desc_index * 11;
+            const float fbin = (float)(bin - (double)step_index);
+            float w = 1.0f - fabsf(fbin);
+            {   // cosine interpolation: |bin| to the next / previous shape bin
+                const float fb = fabsf(fbin);
+                const int nb_step = (fbin > 0.0f) ? (step_index + 1) % 10 : (step_index + 9) % 10;
+                if (fb != 0.0f) vote(volume_index + nb_step, fb);
+            }
+            {   // radial interpolation
+                const float rd = (dist - (outer ? r34 : r14)) * inv_r12;
+                w += 1.0f - fabsf(rd);
+                const bool to_nb = outer ? (rd < 0.0f) : (rd > 0.0f);
+                if (to_nb) vote((desc_index + (outer ? -2 : 2)) * 11 + step_index, fabsf(rd));
+            }
+            {   // elevation interpolation (z <= 0 is PCL's `inclination > 90 deg` test, see above)
+                const float inc_cos = fminf(1.0f, fmaxf(-1.0f, zr / dist));
+                const float inc = acosf(inc_cos);
+                const bool lower = !(zr > 0.0f);
+                const float id = (inc - (lower ? F_135 : F_45)) * INV_90;
+                w += 1.0f - fabsf(id);
+                const bool to_nb = lower ? !(id > 0.0f) : !(id < 0.0f);
+                const float fv = fabsf(id);
+                if (to_nb && fv != 0.0f) vote((desc_index + (lower ? 1 : -1)) * 11 + step_index, fv);
+            }
+            if (yr != 0.0f || xr != 0.0f) {  // azimuth interpolation
+                const float azimuth = atan2f(yr, xr);
+                const int sel = desc_index >> 2;
+                float ad = (azimuth - (F_45 * (float)sel - F_78)) * INV_45;
+                ad = fmaxf(-0.5f, fminf(ad, 0.5f));
+                w += 1.0f - fabsf(ad);
+                const int nbv = (ad > 0.0f) ? ((desc_index + 4) & 31) : ((desc_index + 28) & 31);
+                const float fv = fabsf(ad);
+                if (fv != 0.0f) vote(nbv * 11 + step_index, fv);
+            }
+            vote(volume_index + step_index, w);
+        });
+#endif
     }
     __syncthreads();
 
