@@ -146,6 +146,8 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_kp_ratio, K));
     A(dmalloc(&c->d_kp, K));
     A(dmalloc(&c->d_kp_count, 4));
+    A(dmalloc(&c->d_sel_rho2, N));
+    A(dmalloc(&c->d_sel_thr, N));
     A(dmalloc(&c->d_tk_hist, 4096));
     A(dmalloc(&c->d_tk_state, 16));
     A(dmalloc(&c->d_tk_sure, K));
@@ -202,7 +204,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
-                    c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
+                    c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count, c->d_sel_rho2, c->d_sel_thr,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
@@ -295,6 +297,7 @@ int bshot_set_keypoints(bshot_ctx* ctx, const float* kp_xyz, size_t k, size_t st
     BSHOT_TRY(h2d(ctx, ctx->d_kp_count, &ctx->h_scratch[8], sizeof(int)));
     ctx->n_kp = k;
     ctx->have_kp = true;
+    ctx->kp_from_detector = false;
     return sync(ctx);
 }
 

@@ -72,6 +72,12 @@ struct Ctx {
     float* d_kp_ratio = nullptr;             // K
     float4* d_kp = nullptr;                  // K keypoint positions (w = index bits)
     int* d_kp_count = nullptr;               // device-side keypoint count
+    float* d_sel_rho2 = nullptr;             // N: detector neighbourhood of every point = {sqd < rho2, key <= thr} ...
+    unsigned long long* d_sel_thr = nullptr; // N: ... kept so that the keypoint normals re-collect it in one sweep
+    bool sel_valid = false;                  // d_sel_* describe the current cloud for (sel_radius, sel_max_nn)
+    float sel_radius = 0.0f;
+    int sel_max_nn = 0;
+    bool kp_from_detector = false;           // d_kp[i].w is the surface index of keypoint i
     unsigned* d_tk_hist = nullptr;           // top-K: 4096-bin ratio histogram (kept zeroed between frames)
     unsigned* d_tk_state = nullptr;          // top-K: 16 words of device-side state
     unsigned long long* d_tk_sure = nullptr; // top-K: keys above the threshold bin (< K)

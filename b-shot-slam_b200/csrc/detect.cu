@@ -27,7 +27,8 @@ template <int SR>
 __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsigned* __restrict__ cell_start,
                                                 const float4* __restrict__ sorted, const float4* __restrict__ pts,
                                                 const float4& q, float radius, int max_nn, KnnWarpSmem& sm,
-                                                unsigned lane, float& seg, int& count) {
+                                                unsigned lane, float& seg, int& count, float& sel_rho2,
+                                                unsigned long long& sel_thr) {
     const float nanf_ = __int_as_float(0x7FC00000);
     // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
     double sx = 0, sy = 0, sz = 0;
@@ -67,6 +68,8 @@ __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsig
         seg = fabsf((float)sum) / fn;
     }
     count = res.count;
+    sel_rho2 = res.rho2;
+    sel_thr = res.thr;
 }
 
 // SR = score type (compile time: the CV kernel carries no CVS / CVSN code).  One warp per binned point, taken
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(DT_THREADS, BSHOT_DT_MINBLOCKS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
-                 unsigned long long* __restrict__ counters) {
+                 unsigned long long* __restrict__ counters, float* __restrict__ sel_rho2,
+                 unsigned long long* __restrict__ sel_thr) {
     __shared__ KnnWarpSmem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const GridParams g = *gp;
@@ -90,10 +94,14 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
             if (lane == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
             continue;
         }
-        float seg;
+        float seg, rho2;
         int count;
-        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, seg, count);
+        unsigned long long thr;
+        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, seg, count, rho2, thr);
         if (lane == 0) {
+            // the neighbourhood (sphere + threshold key) is kept: normals of the keypoints re-collect it in one sweep
+            sel_rho2[qi] = rho2;
+            sel_thr[qi] = thr;
             atomicAdd(&counters[0], (unsigned long long)count);
             ratio[qi] = seg;
             keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
@@ -247,15 +255,15 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
                const unsigned long long* __restrict__ tie, const float4* __restrict__ pts, int* __restrict__ kp_idx,
                float* __restrict__ kp_ratio, float4* __restrict__ kp) {
     __shared__ unsigned long long s_keys[TK_TILE];
-    __shared__ unsigned s_cnt[4][64];
-    const unsigned tid = threadIdx.x, slot = tid & 63, part = tid >> 6;
+    __shared__ unsigned s_cnt[8][32];
+    const unsigned tid = threadIdx.x, slot = tid & 31, part = tid >> 5;  // 32 items per CTA, every warp counts one eighth of a tile
     const unsigned n_sure = state[TKS_NSURE], n_tie = state[TKS_NTIE], need = state[TKS_NEED];
-    const unsigned nb_a = (n_sure + 63) / 64, nb_b = (n_tie + 63) / 64;
+    const unsigned nb_a = (n_sure + 31) / 32, nb_b = (n_tie + 31) / 32;
     for (unsigned ib = blockIdx.x; ib < nb_a + nb_b; ib += gridDim.x) {
         const bool is_a = ib < nb_a;
         const unsigned long long* list = is_a ? sure : tie;
         const unsigned len = is_a ? n_sure : n_tie;
-        const unsigned item = (is_a ? ib : ib - nb_a) * 64 + slot;
+        const unsigned item = (is_a ? ib : ib - nb_a) * 32 + slot;
         const unsigned long long x = (item < len) ? list[item] : 0ull;
         unsigned cnt = 0;
         for (unsigned t0 = 0; t0 < len; t0 += TK_TILE) {
@@ -263,7 +271,7 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
             __syncthreads();
             for (unsigned t = tid; t < tl; t += TK_THREADS) s_keys[t] = list[t0 + t];
             __syncthreads();
-            const unsigned lo = part * (TK_TILE / 4), hi = min(lo + TK_TILE / 4, tl);
+            const unsigned lo = part * (TK_TILE / 8), hi = min(lo + TK_TILE / 8, tl);
             if (is_a) {  // sure keys: position among the sure keys, ascending
                 for (unsigned j = lo; j < hi; ++j) cnt += (s_keys[j] < x) ? 1u : 0u;
             } else {     // tie keys: number of larger tie keys
@@ -273,7 +281,8 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
         s_cnt[part][slot] = cnt;
         __syncthreads();
         if (part == 0 && item < len) {
-            const unsigned c = s_cnt[0][slot] + s_cnt[1][slot] + s_cnt[2][slot] + s_cnt[3][slot];
+            const unsigned c = s_cnt[0][slot] + s_cnt[1][slot] + s_cnt[2][slot] + s_cnt[3][slot] + s_cnt[4][slot] + s_cnt[5][slot] +
+                               s_cnt[6][slot] + s_cnt[7][slot];
             const bool keep = is_a || c < need;
             if (keep) {
                 const unsigned pos = is_a ? need + c : need - 1u - c;
@@ -298,12 +307,15 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     const unsigned ctas = (n + DT_WARPS - 1) / DT_WARPS;
 #define BSHOT_LAUNCH_SEG(SR)                                                                                                     \
     seg_ratio_kernel<SR><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, \
-                                                             c->d_ratio, c->d_keys, c->d_counters)
+                                                             c->d_ratio, c->d_keys, c->d_counters, c->d_sel_rho2, c->d_sel_thr)
     if (sr_type == BSHOT_SR_CV) BSHOT_LAUNCH_SEG(BSHOT_SR_CV);
     else if (sr_type == BSHOT_SR_CVS) BSHOT_LAUNCH_SEG(BSHOT_SR_CVS);
     else BSHOT_LAUNCH_SEG(BSHOT_SR_CVSN);
 #undef BSHOT_LAUNCH_SEG
     count_launch(c, 2);
+    c->sel_valid = true;
+    c->sel_radius = radius;
+    c->sel_max_nn = max_nn;
     return check_launch("seg_ratio kernels");
 }
 
@@ -323,7 +335,7 @@ int detect_topk(Ctx* c, int top_k) {
     const unsigned hist_ctas = std::max(1u, std::min((n + TK_THREADS * 16 - 1) / (TK_THREADS * 16), (unsigned)c->sm_count));
     tk_hist_kernel<<<hist_ctas, TK_THREADS, 0, c->stream>>>(c->d_keys, n, top_k, c->d_tk_hist, c->d_tk_state, c->d_kp_count);
     if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie);
-    tk_rank_kernel<<<(unsigned)c->sm_count * 2u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_kp_idx,
+    tk_rank_kernel<<<(unsigned)c->sm_count * 4u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_kp_idx,
                                                                              c->d_kp_ratio, c->d_kp);
     count_launch(c, n ? 3 : 2);
 #ifdef BSHOT_KNN_STATS
@@ -332,6 +344,7 @@ int detect_topk(Ctx* c, int top_k) {
 #endif
     c->n_kp = (size_t)top_k;  // upper bound until the host reads d_kp_count
     c->have_kp = true;
+    c->kp_from_detector = true;  // d_kp[i].w carries the surface index
     return check_launch("top-K kernels");
 }
 

@@ -375,6 +375,31 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
     return res;
 }
 
+// Re-collect a neighbourhood that an earlier knn_select() of the SAME query point already determined
+// (rho2 and the threshold key were kept): one enumeration and one sweep instead of the whole sizing /
+// crossing-bin procedure.  Calls acc(p) for exactly the same selected set; returns its size.
+template <typename Acc>
+__device__ __forceinline__ int knn_collect_cached(const GridParams& g, const unsigned* __restrict__ cell_start,
+                                                  const float4* __restrict__ sorted, const float4& q, float rho2,
+                                                  unsigned long long thr, KnnWarpSmem& sm, unsigned lane, Acc&& acc) {
+    KnnIter it;
+    it.rho = sqrtf(rho2) * 1.0001f;  // covers every point with sqd < rho2
+    it.rr = row_range(g, q.y, q.z, it.rho);
+    bool filled;
+    it.total = knn_expand(g, cell_start, q, it.rho, it.rr, 0u, (unsigned)KN_CAP, sm, lane, filled);
+    it.list = filled;
+    it.cached = false;
+    int cnt = 0;
+    knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
+        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+        if (sqd < rho2 && knn_key(sqd, p.w) <= thr) {
+            acc(p);
+            ++cnt;
+        }
+    });
+    return warp_sum(cnt);
+}
+
 __device__ __forceinline__ bool knn_selected(const KnnResult& r, float sqd, float w) {
     return knn_key(sqd, w) <= r.thr;  // thr < (rho2 bits << 32) by construction
 }

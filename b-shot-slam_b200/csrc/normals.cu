@@ -112,10 +112,14 @@ __device__ __forceinline__ void normal_sums(const GridParams& g, const unsigned*
     n = res.count;
 }
 
+// CACHED: the queries are keypoints chosen by the detector (w = surface index) and the detector searched with
+// the same (radius, max_nn): their neighbourhoods are re-collected from the kept (rho2, threshold key).
+template <bool CACHED>
 __global__ void __launch_bounds__(NM_THREADS, 8)
 normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                const float4* __restrict__ sorted, const float4* __restrict__ pts, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
-               float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters) {
+               float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters,
+               const float* __restrict__ sel_rho2, const unsigned long long* __restrict__ sel_thr) {
     __shared__ KnnWarpSmem smem[NM_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned j = blockIdx.x * NM_WARPS + wid;
@@ -129,7 +133,16 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
     int n = 0;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (finite) {
-        normal_sums(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, s, n);
+        if (CACHED) {
+            const unsigned si = __float_as_uint(q.w);
+            n = knn_collect_cached(g, cell_start, sorted, q, sel_rho2[si], sel_thr[si], sm, lane, [&](const float4 p) {
+                s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
+                s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
+                s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
+            });
+        } else {
+            normal_sums(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, s, n);
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k) s[k] = warp_sum(s[k]);
     }
@@ -167,10 +180,15 @@ __global__ void place_normals_kernel(const float4* __restrict__ src, const int* 
     if (i < cap && (int)i < *count) dst[i] = src[i];
 }
 
-static int normals_launch(Ctx* c, const float4* d_q, const int* nq_dev, size_t nq, float radius, int max_nn, float4* d_out) {
+static int normals_launch(Ctx* c, const float4* d_q, const int* nq_dev, size_t nq, float radius, int max_nn, float4* d_out,
+                          bool cached = false) {
     const unsigned ctas = (unsigned)((nq + NM_WARPS - 1) / NM_WARPS);
-    normals_kernel<<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
-                                                       radius, max_nn, d_out, c->d_counters);
+    if (cached)
+        normals_kernel<true><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
+                                                                 radius, max_nn, d_out, c->d_counters, c->d_sel_rho2, c->d_sel_thr);
+    else
+        normals_kernel<false><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
+                                                                  radius, max_nn, d_out, c->d_counters, nullptr, nullptr);
     count_launch(c);
     return check_launch("normals_kernel");
 }
@@ -189,7 +207,9 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
     } else {
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
-            BSHOT_TRY(normals_launch(c, c->d_kp, c->d_kp_count, k, radius, max_nn, c->d_qnormals));
+            // keypoints that came out of the detector with the same search parameters: reuse its neighbourhoods
+            const bool cached = c->sel_valid && c->kp_from_detector && radius == c->sel_radius && max_nn == c->sel_max_nn;
+            BSHOT_TRY(normals_launch(c, c->d_kp, c->d_kp_count, k, radius, max_nn, c->d_qnormals, cached));
             place_normals_kernel<<<(unsigned)((k + 255) / 256), 256, 0, c->stream>>>(c->d_qnormals, c->d_kp_count, (unsigned)k,
                                                                                      c->d_normals);
             count_launch(c);

@@ -101,3 +101,26 @@ def test_row_thickness_knob_does_not_change_results(bshot, synth):
         assert len(np.intersect1d(k, k0)) >= 0.99 * len(k0)
         if np.array_equal(k, k0):
             assert (synth.unpack_bits(b) == synth.unpack_bits(b0)).mean() >= 0.999
+
+
+def test_keypoint_normals_reuse_detector_neighbourhoods(gpu_ctx, synth):
+    """REFERENCE-mode normals of detector keypoints re-collect the neighbourhood the detector kept (sphere +
+    threshold key) instead of selecting it again: same selected set, so the same normals as a fresh search"""
+    scan = synth.make_scan("hdl32e", 4)
+    gpu_ctx.reset()
+    gpu_ctx.set_cloud(scan)
+    idx, _, xyz = gpu_ctx.detect_keypoints(3000.0, 300, 0, 512)
+    cached = gpu_ctx.compute_normals(0, 3000.0, 300)[: len(idx)]       # keypoint ordinal i -> index i (reference quirk)
+    fresh = gpu_ctx.query_normals(xyz, 3000.0, 300)
+    assert np.array_equal(np.isnan(cached), np.isnan(fresh))
+    ok = ~np.isnan(fresh[:, 0])
+    # identical selected sets; only the fp64 summation order differs (then rounded to fp32)
+    assert (cached[ok] == fresh[ok]).all(1).mean() > 0.95
+    assert np.abs(cached[ok] - fresh[ok]).max() < 1e-3
+    # different search parameters must not use the kept neighbourhoods
+    other = gpu_ctx.compute_normals(0, 2000.0, 100)[: len(idx)]
+    fresh2 = gpu_ctx.query_normals(xyz, 2000.0, 100)
+    assert np.array_equal(np.isnan(other), np.isnan(fresh2))
+    ok2 = ~np.isnan(fresh2[:, 0])
+    assert np.abs(other[ok2] - fresh2[ok2]).max() < 1e-3
+    assert not np.array_equal(other[ok & ok2], cached[ok & ok2])       # a smaller neighbourhood gives other normals
