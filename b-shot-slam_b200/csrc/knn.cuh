@@ -28,6 +28,9 @@ constexpr int KN_CAP = 1024;     // fast path: explicit candidate list
 #ifndef BSHOT_KN_WHI
 #define BSHOT_KN_WHI 2.2f
 #endif
+#ifndef BSHOT_KN_PAD
+#define BSHOT_KN_PAD 0.5f  // candidate-count model: count ~ (rho + PAD * row thickness)^2 (rows are taken whole in y and z)
+#endif
 constexpr int KN_DEPTH = BSHOT_KN_DEPTH;
 constexpr int KN_BINS = 256;
 constexpr int KN_LIST = 224;
@@ -227,6 +230,7 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
     int n = 0;
     float rho = 2.0f * g.cell * 0.9999f;  // first probe
     int tries = 0;
+    const float pad = BSHOT_KN_PAD * g.cell_yz;
     // candidate window that is worth a sweep: ~74 % of the candidates of a chord-clipped row set lie inside
     // the sphere, so 1.45 .. 2.2 max_nn candidates hold max_nn points with little excess
     const unsigned want_lo = (unsigned)(BSHOT_KN_WLO * (float)max(max_nn, 0)), want_hi = min((unsigned)(BSHOT_KN_WHI * (float)max(max_nn, 0)), (unsigned)KN_CAP);
@@ -245,11 +249,13 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
         if (lane == 0) { atomicAdd(&g_knn_stats[5], 1ull); atomicAdd(&g_knn_stats[6], (unsigned long long)it.rr.nrows); }
 #endif
         if (!last && it.total < want_lo) {  // too few candidates (no point touched yet): grow, count ~ r^2 on surfaces
-            rho *= fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)max(it.total, 1u)), 1.08f), 4.0f);
+            const float f = fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)max(it.total, 1u)), 1.08f), 4.0f);
+            rho = fmaxf(1.08f * rho, (rho + pad) * f - pad);
             continue;
         }
         if (!settle && it.total > want_hi) {  // too many (dense spot): shrink
-            rho *= fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)it.total), 0.25f), 0.95f);
+            const float f = fminf(fmaxf(sqrtf(1.7f * (float)max_nn / (float)it.total), 0.25f), 0.95f);
+            rho = fminf(0.95f * rho, fmaxf(0.25f * rho, (rho + pad) * f - pad));
             continue;
         }
         it.list = filled;

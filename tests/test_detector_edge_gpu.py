@@ -124,3 +124,20 @@ def test_keypoint_normals_reuse_detector_neighbourhoods(gpu_ctx, synth):
     ok2 = ~np.isnan(fresh2[:, 0])
     assert np.abs(other[ok2] - fresh2[ok2]).max() < 1e-3
     assert not np.array_equal(other[ok & ok2], cached[ok & ok2])       # a smaller neighbourhood gives other normals
+
+
+@pytest.mark.parametrize("sr_type", [1, 2])
+def test_topk_on_unbounded_scores(gpu_ctx, oracle, sr_type):
+    """CVS scores are sums of mm^2 dot products (far above 1), CVSN scores lie in [0,1]: the top-K histogram bins
+    both ranges monotonically, so the kept set must again follow the documented rule on the GPU's own scores"""
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(-5000, 5000, (8000, 3)).astype(np.float32)
+    pts[:, 2] *= 0.15
+    gpu_ctx.set_cloud(pts)
+    ratio = gpu_ctx.seg_ratio(1500.0, 60, sr_type)
+    if sr_type == 1:
+        assert np.nanmax(ratio) > 1e3                        # exercises the exponent-binned range
+    for k in (50, 1000):
+        idx, rat, _ = gpu_ctx.detect_keypoints(1500.0, 60, sr_type, k)
+        idx_d, rat_d = oracle.select_keypoints(ratio, k, oracle.TIE_DETERMINISTIC)
+        assert np.array_equal(idx, idx_d) and np.array_equal(rat, rat_d)

@@ -1,18 +1,9 @@
-python -m pytest tests/test_detector_edge_gpu.py -m gpu -x -q -k reuse 2>&1 | grep -E "^E|assert" | head -20
-python - <<'PY'
-import sys, numpy as np
-sys.path.insert(0,'tests')
-from conftest import load_bshot, load_synth
-bs, synth = load_bshot(), load_synth()
-ctx = bs.Context(0, 131072, 16384, 16384)
-scan = synth.make_scan("hdl32e", 4)
-ctx.set_cloud(scan)
-idx, _, xyz = ctx.detect_keypoints(3000.0, 300, 0, 512)
-cached = ctx.compute_normals(0, 3000.0, 300)[:len(idx)]
-fresh = ctx.query_normals(xyz, 3000.0, 300)
-fresh_b = ctx.query_normals(xyz, 3000.0, 300)
-d = np.abs(cached - fresh).max(1)
-print("cached vs fresh: exact rows", (d == 0).mean(), "max", d.max(), "n>1e-3", (d > 1e-3).sum(), "fresh vs fresh max", np.abs(fresh - fresh_b).max())
-bad = np.argsort(-d)[:5]
-for b in bad: print(b, idx[b], cached[b], fresh[b])
-PY
+run() { python bench.py --steps 30 --warmup 5 --no-cpu --no-map --no-c3 --sensor $1 --top-k $2 2>gpurun_out/err_$3.log | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); s=d['stages_ms']; print('%-10s %s seg %.4f topk %.4f normals %.4f shot %.4f match %.4f frame %.4f' % ('$3','$1',s['seg_ratio'],s['topk'],s['normals'],s['shot_bshot'],s['match'],s['frame']))"; }
+for v in p75 p100; do
+  L=$PWD/b-shot-slam_b200/libbshot_b200_$v.so; [ $v = default ] && L=$PWD/b-shot-slam_b200/libbshot_b200.so
+  BSHOT_LIB=$L run hdl32e 2048 $v
+  BSHOT_LIB=$L run hdl64e 10000 $v
+done
+for v in p75s p100s; do BSHOT_LIB=$PWD/b-shot-slam_b200/libbshot_b200_$v.so python bench.py --steps 1 --warmup 3 --no-cpu --no-map --no-c3 2>&1 >/dev/null | grep "knn stats" | tail -1; done
