@@ -1,9 +1,10 @@
-run() { python bench.py --steps 30 --warmup 5 --no-cpu --no-map --no-c3 --sensor $1 --top-k $2 2>gpurun_out/err_$3.log | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); s=d['stages_ms']; print('%-10s %s seg %.4f topk %.4f normals %.4f shot %.4f match %.4f frame %.4f' % ('$3','$1',s['seg_ratio'],s['topk'],s['normals'],s['shot_bshot'],s['match'],s['frame']))"; }
-for v in p75 p100; do
-  L=$PWD/b-shot-slam_b200/libbshot_b200_$v.so; [ $v = default ] && L=$PWD/b-shot-slam_b200/libbshot_b200.so
-  BSHOT_LIB=$L run hdl32e 2048 $v
-  BSHOT_LIB=$L run hdl64e 10000 $v
-done
-for v in p75s p100s; do BSHOT_LIB=$PWD/b-shot-slam_b200/libbshot_b200_$v.so python bench.py --steps 1 --warmup 3 --no-cpu --no-map --no-c3 2>&1 >/dev/null | grep "knn stats" | tail -1; done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_r1f.json 2> gpurun_out/bench_r1f.err; echo "bench exit $?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1f_ref.json 2>> gpurun_out/bench_r1f.err; echo "ref exit $?"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-c3 --map-steps 2"
+$CMD > gpurun_out/plain_r1f.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_r1f.csv $CMD > gpurun_out/ncu_r1f_a.log 2>&1
+$CMD > gpurun_out/plain_r1f.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'seg_ratio_kernel|shot_kernel|tk_|normals_kernel|hamming_top2_kernel|merge_top2' -s 20 -c 12 -o gpurun_out/prof_r1f $CMD > gpurun_out/ncu_r1f_b.log 2>&1
+tail -n 1 gpurun_out/ncu_r1f_b.log
