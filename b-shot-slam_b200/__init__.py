@@ -30,7 +30,8 @@ EXPORTS = [
     "bshot_process_frame", "bshot_process_frame_dev", "bshot_fetch_frame", "bshot_ctx_enable_timing",
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
-    "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_launch_count", "bshot_popc_peak",
+    "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
+    "bshot_reverse_owned_push_dev", "bshot_launch_count", "bshot_popc_peak",
 ]
 
 
@@ -101,6 +102,8 @@ def lib():
         L.bshot_match_map.argtypes = [vp, vp, sz, C.c_uint64, vp]
         L.bshot_reverse_owned_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp]
         L.bshot_apply_rq_dev.argtypes = [vp, vp, vp, sz]
+        L.bshot_push_cands_dev.argtypes = [vp, vp, sz, vp, ci, ci]
+        L.bshot_reverse_owned_push_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp, ci, ci]
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
         L.bshot_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
@@ -361,6 +364,13 @@ class Context:
 
     def apply_rq_dev(self, d_cands_ptr, d_rq_ptr, nq):
         _chk(lib().bshot_apply_rq_dev(self.h, d_cands_ptr, d_rq_ptr, nq))
+
+    # peer-memory exchange (symmetric buffers): stores into every rank's buffers, the caller adds the barriers
+    def push_cands_dev(self, d_cands_ptr, nq, d_peer_ptrs, nranks, rank):
+        _chk(lib().bshot_push_cands_dev(self.h, d_cands_ptr, nq, d_peer_ptrs, nranks, rank))
+
+    def reverse_owned_push_dev(self, d_q_ptr, nq, global_base, d_merged_ptr, d_peer_rq_ptrs, nranks, rank):
+        _chk(lib().bshot_reverse_owned_push_dev(self.h, d_q_ptr, nq, global_base, d_merged_ptr, d_peer_rq_ptrs, nranks, rank))
 
     def merge_cands_dev(self, d_cands_ptr, nranks, nq, d_out_ptr):
         _chk(lib().bshot_merge_cands_dev(self.h, d_cands_ptr, nranks, nq, d_out_ptr))

@@ -597,6 +597,20 @@ int bshot_reverse_owned_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t
                                  reinterpret_cast<unsigned*>(d_rq_out));
 }
 
+int bshot_push_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nq, const void* d_peer_ptrs, int nranks, int rank) {
+    CHECK_CTX(ctx);
+    if (!d_cands || !d_peer_ptrs || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bshot_push_cands_dev: bad arguments"); return BSHOT_E_INVALID; }
+    return hamming_push_cands(ctx, reinterpret_cast<const bshot_cand*>(d_cands), nq, d_peer_ptrs, (unsigned)nranks, (unsigned)rank);
+}
+
+int bshot_reverse_owned_push_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, const void* d_merged,
+                                 const void* d_peer_rq_ptrs, int nranks, int rank) {
+    CHECK_CTX(ctx);
+    if (!d_q || !d_merged || !d_peer_rq_ptrs || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bshot_reverse_owned_push_dev: bad arguments"); return BSHOT_E_INVALID; }
+    return hamming_reverse_owned(ctx, d_q, nq, ctx->d_map, ctx->n_map, global_base, reinterpret_cast<const bshot_cand*>(d_merged),
+                                 nullptr, d_peer_rq_ptrs, (unsigned)nranks, (unsigned)rank);
+}
+
 int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t nq) {
     CHECK_CTX(ctx);
     if (!d_cands || !d_rq) { set_error("bshot_apply_rq_dev: null device pointer"); return BSHOT_E_INVALID; }

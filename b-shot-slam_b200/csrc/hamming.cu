@@ -536,7 +536,7 @@ __global__ void select_owned_kernel(const bshot_cand* __restrict__ merged, unsig
     bool mine = false;
     unsigned long long idx = 0;
     if (qi < nq) {
-        rq_out[qi] = 0xFFFFFFFFu;
+        if (rq_out) rq_out[qi] = 0xFFFFFFFFu;  // null in push mode: the owners write straight into every rank's array
         const unsigned long long k = merged[qi].k1;
         idx = k & 0xFFFFFFFFull;
         mine = (k != HM_NONE) && idx >= lo && idx < hi;
@@ -566,13 +566,48 @@ __global__ void scatter_rq_kernel(const bshot_cand* __restrict__ rev, const unsi
     rq_out[owner_q[i]] = (k != HM_NONE) ? (unsigned)(k & 0xFFFFFFFFull) : 0xFFFFFFFFu;
 }
 
+// ---- peer-memory exchange (symmetric buffers over NVLink, one barrier instead of a collective) ---------
+// every rank stores its nq candidate records into slot `rank` of EVERY rank's gather buffer
+__global__ void push_cands_kernel(const bshot_cand* __restrict__ src, unsigned nq, bshot_cand* const* __restrict__ peers,
+                                  unsigned nranks, unsigned rank) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const bshot_cand c = src[qi];
+    for (unsigned p = 0; p < nranks; ++p) {
+        bshot_cand* dst = peers[(p + rank) % nranks] + (size_t)rank * nq + qi;  // start at the own buffer, spread the links
+        *dst = c;
+    }
+}
+
+// reverse result of the winners this rank owns -> rq[query] in every rank's array (one owner per query)
+__global__ void push_rq_kernel(const bshot_cand* __restrict__ rev, const unsigned* __restrict__ owner_q,
+                               const unsigned* __restrict__ count, unsigned* const* __restrict__ peers, unsigned nranks,
+                               unsigned rank) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const unsigned long long k = rev[i].k1;
+    const unsigned v = (k != HM_NONE) ? (unsigned)(k & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    const unsigned q = owner_q[i];
+    for (unsigned p = 0; p < nranks; ++p) peers[(p + rank) % nranks][q] = v;
+}
+
 __global__ void apply_rq_kernel(bshot_cand* __restrict__ cand, const unsigned* __restrict__ rq, unsigned nq) {
     const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi < nq) cand[qi].rq = (cand[qi].k1 != HM_NONE) ? rq[qi] : 0xFFFFFFFFu;
 }
 
+int hamming_push_cands(Ctx* c, const bshot_cand* d_cands, size_t nq, const void* d_peer_ptrs, unsigned nranks, unsigned rank) {
+    if (nq == 0) return BSHOT_OK;
+    push_cands_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cands, (unsigned)nq,
+                                                                          reinterpret_cast<bshot_cand* const*>(d_peer_ptrs), nranks, rank);
+    count_launch(c);
+    return check_launch("push_cands_kernel");
+}
+
+// d_rq_out: local array (then combined by the caller's all-reduce) -- or, with d_peer_rq (device array of nranks
+// pointers), the owned results are stored into every rank's array directly and d_rq_out is not touched
 int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                          const bshot_cand* d_merged, unsigned* d_rq_out) {
+                          const bshot_cand* d_merged, unsigned* d_rq_out, const void* d_peer_rq, unsigned nranks, unsigned rank) {
     if (nq == 0) return BSHOT_OK;
     if (nq > c->max_kp) { set_error("hamming_reverse_owned: %zu queries > capacity %zu", nq, c->max_kp); return BSHOT_E_CAPACITY; }
     unsigned* owner_q = reinterpret_cast<unsigned*>(c->d_left);          // max_kp x 4 ints: [0,nq) owner list
@@ -580,12 +615,16 @@ int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, s
     BSHOT_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(unsigned), c->stream));
     select_owned_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(
         d_merged, (unsigned)nq, global_base, global_base + nt, reinterpret_cast<const uint4*>(d_t),
-        reinterpret_cast<uint4*>(c->d_gather), owner_q, count, d_rq_out);
+        reinterpret_cast<uint4*>(c->d_gather), owner_q, count, d_peer_rq ? nullptr : d_rq_out);
     count_launch(c);
     BSHOT_TRY(check_launch("select_owned_kernel"));
     // gathered targets act as queries, the original queries as targets; the device-side count trims the grid
     BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2, nullptr, count));
-    scatter_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_cand2, owner_q, count, d_rq_out);
+    if (d_peer_rq)
+        push_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_cand2, owner_q, count,
+                                                                           reinterpret_cast<unsigned* const*>(d_peer_rq), nranks, rank);
+    else
+        scatter_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->d_cand2, owner_q, count, d_rq_out);
     count_launch(c);
     return check_launch("scatter_rq_kernel");
 }

@@ -23,7 +23,9 @@ int binarize(Ctx* c, const float* d_shot, size_t k, uint64_t* d_bits);
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                  bshot_cand* d_out, unsigned* d_colmin = nullptr, const unsigned* d_nq = nullptr);
 int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                          const bshot_cand* d_merged, unsigned* d_rq_out);
+                          const bshot_cand* d_merged, unsigned* d_rq_out, const void* d_peer_rq = nullptr, unsigned nranks = 1,
+                          unsigned rank = 0);
+int hamming_push_cands(Ctx* c, const bshot_cand* d_cands, size_t nq, const void* d_peer_ptrs, unsigned nranks, unsigned rank);
 int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq);
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                      bshot_cand* d_out);

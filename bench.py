@@ -310,6 +310,32 @@ def main():
         gathered = torch.empty((world, Q, 3), dtype=torch.int64, device="cuda")
         rq = torch.empty(Q, dtype=torch.int32, device="cuda")
 
+        # Preferred exchange at N > 1: symmetric buffers mapped on every rank (torch symmetric memory over NVLink /
+        # NVSwitch).  Every rank STORES its records into slot `rank` of every rank's gather buffer and the owner of a
+        # winner stores rq[query] into every rank's array (bshot_push_cands_dev / bshot_reverse_owned_push_dev); one
+        # cross-rank barrier after each replaces the all-gather and the all-reduce.  Falls back to NCCL collectives if
+        # symmetric memory cannot be set up (BSHOT_EXCHANGE=nccl forces the fallback).
+        peer = None
+        if world > 1 and os.environ.get("BSHOT_EXCHANGE", "peer") != "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                g_sym = symm_mem.empty(world * Q * 3, dtype=torch.int64, device=torch.device("cuda", local_rank))
+                r_sym = symm_mem.empty(Q, dtype=torch.int32, device=torch.device("cuda", local_rank))
+                h_g = symm_mem.rendezvous(g_sym, dist.group.WORLD)
+                h_r = symm_mem.rendezvous(r_sym, dist.group.WORLD)
+                peer = {"g": g_sym, "r": r_sym, "hg": h_g, "hr": h_r, "pg": int(h_g.buffer_ptrs_dev), "pr": int(h_r.buffer_ptrs_dev)}
+                g_sym.zero_(); r_sym.fill_(-1)
+                torch.cuda.synchronize()
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"bench.py: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL collectives", file=sys.stderr)
+                peer = None
+            # all ranks must take the same path
+            flag = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                peer = None
+
         def map_calls(n):
             for _ in range(n):
                 if world == 1:
@@ -317,6 +343,16 @@ def main():
                     ctx.merge_cands_dev(cand.data_ptr(), 1, Q, merged.data_ptr())
                     continue
                 ctx.match_shard_dev(dq.data_ptr(), Q, lo, False, cand.data_ptr())
+                if peer is not None:
+                    ctx.push_cands_dev(cand.data_ptr(), Q, peer["pg"], world, rank)
+                    with torch.cuda.stream(st):
+                        peer["hg"].barrier(channel=0)
+                    ctx.merge_cands_dev(peer["g"].data_ptr(), world, Q, merged.data_ptr())
+                    ctx.reverse_owned_push_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), peer["pr"], world, rank)
+                    with torch.cuda.stream(st):
+                        peer["hr"].barrier(channel=0)
+                    ctx.apply_rq_dev(merged.data_ptr(), peer["r"].data_ptr(), Q)
+                    continue
                 with torch.cuda.stream(st):
                     dist.all_gather_into_tensor(gathered.view(-1), cand.view(-1))
                 ctx.merge_cands_dev(gathered.data_ptr(), world, Q, merged.data_ptr())
@@ -347,7 +383,10 @@ def main():
                                   "peak": world * popc_peak / 1e12, "unit": "TPOPC32/s",
                                   "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
                                   "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
-                     "collective": "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result" if world > 1 else "none",
+                     "collective": ("none" if world == 1 else
+                                    "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the owner) + 2 symmetric-memory barriers"
+                                    if peer is not None else
+                                    "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result"),
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
 
 

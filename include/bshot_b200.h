@@ -193,6 +193,14 @@ int bshot_merge_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nranks, si
 int bshot_reverse_owned_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
                             const void* d_merged, void* d_rq_out);
 int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t nq);
+/* Peer-memory variant of the exchange (symmetric buffers mapped on every rank, e.g. torch symmetric memory over
+ * NVLink / NVSwitch): instead of an all-gather, every rank STORES its nq records into slot `rank` of every rank's
+ * gather buffer (d_peer_ptrs = device array of nranks pointers to buffers of nranks x nq records); instead of an
+ * all-reduce, the owner of a winner stores rq[query] into every rank's rq array (d_peer_rq_ptrs = device array of
+ * nranks pointers to nq x uint32).  The caller places one cross-rank barrier after each of the two calls. */
+int bshot_push_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nq, const void* d_peer_ptrs, int nranks, int rank);
+int bshot_reverse_owned_push_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
+                                 const void* d_merged, const void* d_peer_rq_ptrs, int nranks, int rank);
 /* host-buffer convenience over the three calls above for a single rank */
 int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base,
                     bshot_cand* cand_out);

@@ -161,6 +161,56 @@ def test_sharded_reverse_owned_equals_single(bshot, oracle, synth):
     assert u["idx1"][3] == 10
 
 
+def test_sharded_peer_push_equals_single(bshot, oracle, synth):
+    """the peer-memory exchange on 4 emulated ranks (4 contexts on one GPU, every 'peer' buffer is a local
+    buffer): every rank pushes its records into slot r of every rank's gather buffer, merges its own copy, runs the
+    reverse pass for the winners it owns and pushes rq into every rank's array -> every rank ends with records
+    identical to the single-pass oracle result."""
+    import torch
+    nq, nt, ranks = 700, 20000, 4
+    q = synth.random_descriptors(nq, seed=51, density=40)
+    t = synth.random_descriptors(nt, seed=52, density=40)
+    t[19999] = q[5]
+    t[12] = q[5]
+    dq = torch.from_numpy(q.view(np.int64)).cuda()
+    per = (nt + ranks - 1) // ranks
+    ctxs = [bshot.Context(0, 1024, 1024, per) for _ in range(ranks)]
+    try:
+        gather = [torch.zeros((ranks, nq, 3), dtype=torch.int64, device="cuda") for _ in range(ranks)]
+        rqbuf = [torch.full((nq,), -7, dtype=torch.int32, device="cuda") for _ in range(ranks)]
+        peer_g = torch.tensor([g.data_ptr() for g in gather], dtype=torch.int64, device="cuda")
+        peer_r = torch.tensor([r.data_ptr() for r in rqbuf], dtype=torch.int64, device="cuda")
+        local = torch.empty((nq, 3), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        for r, c in enumerate(ctxs):
+            c.map_append(t[r * per:(r + 1) * per])
+            c.match_shard_dev(dq.data_ptr(), nq, r * per, False, local.data_ptr())
+            c.push_cands_dev(local.data_ptr(), nq, peer_g.data_ptr(), ranks, r)
+            c.sync()
+        for r in range(1, ranks):
+            assert torch.equal(gather[r], gather[0])            # the barrier point: every rank holds all records
+        merged = [torch.empty((nq, 3), dtype=torch.int64, device="cuda") for _ in range(ranks)]
+        for r, c in enumerate(ctxs):
+            c.merge_cands_dev(gather[r].data_ptr(), ranks, nq, merged[r].data_ptr())
+            c.reverse_owned_push_dev(dq.data_ptr(), nq, r * per, merged[r].data_ptr(), peer_r.data_ptr(), ranks, r)
+            c.sync()
+        recs = []
+        for r, c in enumerate(ctxs):                             # second barrier point, then every rank completes its records
+            c.apply_rq_dev(merged[r].data_ptr(), rqbuf[r].data_ptr(), nq)
+            c.sync()
+            recs.append(merged[r].cpu().numpy().view(bshot.CAND_DTYPE).reshape(nq))
+    finally:
+        for c in ctxs:
+            c.close()
+    o = oracle.match(q, t, want_right=True)
+    for rec in recs:
+        u = bshot.unpack_cands(rec)
+        assert np.array_equal(u["idx1"], o["left_idx"]) and np.array_equal(u["dist1"], o["left_dist"])
+        assert np.array_equal(u["idx2"], o["left_idx2"])
+        assert np.array_equal(u["rq"], o["right_idx"][o["left_idx"]])
+    assert bshot.unpack_cands(recs[0])["idx1"][5] == 12
+
+
 def test_full_size_properties(gpu_ctx, bshot, synth):
     """C4-sized shard (Q=10000 x T=1M): size-independent properties instead of the O(QT) oracle."""
     nq, nt = 10000, 1 << 20
