@@ -31,7 +31,7 @@ EXPORTS = [
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
-    "bshot_reverse_owned_push_dev", "bshot_launch_count", "bshot_popc_peak",
+    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
         L.bshot_reverse_owned_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp]
         L.bshot_apply_rq_dev.argtypes = [vp, vp, vp, sz]
         L.bshot_push_cands_dev.argtypes = [vp, vp, sz, vp, ci, ci]
+        L.bshot_peer_barrier_dev.argtypes = [vp, vp, ci, ci]
+        L.bshot_peer_barrier_timeouts.argtypes = [vp, C.POINTER(C.c_uint)]
         L.bshot_reverse_owned_push_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp, ci, ci]
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
@@ -368,6 +370,14 @@ class Context:
     # peer-memory exchange (symmetric buffers): stores into every rank's buffers, the caller adds the barriers
     def push_cands_dev(self, d_cands_ptr, nq, d_peer_ptrs, nranks, rank):
         _chk(lib().bshot_push_cands_dev(self.h, d_cands_ptr, nq, d_peer_ptrs, nranks, rank))
+
+    def peer_barrier_dev(self, d_peer_flag_ptrs, nranks, rank):
+        _chk(lib().bshot_peer_barrier_dev(self.h, d_peer_flag_ptrs, nranks, rank))
+
+    def peer_barrier_timeouts(self):
+        e = C.c_uint()
+        _chk(lib().bshot_peer_barrier_timeouts(self.h, C.byref(e)))
+        return int(e.value)
 
     def reverse_owned_push_dev(self, d_q_ptr, nq, global_base, d_merged_ptr, d_peer_rq_ptrs, nranks, rank):
         _chk(lib().bshot_reverse_owned_push_dev(self.h, d_q_ptr, nq, global_base, d_merged_ptr, d_peer_rq_ptrs, nranks, rank))

@@ -183,6 +183,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
         cudaError_t e = cudaMemsetAsync(c->d_normals, 0, sizeof(float4) * N, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_prev_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_kp_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_pair_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tk_hist, 0, 4096 * sizeof(unsigned), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tk_state, 0, 16 * sizeof(unsigned), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream);
@@ -595,6 +596,21 @@ int bshot_reverse_owned_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t
     if (!d_q || !d_merged || !d_rq_out) { set_error("bshot_reverse_owned_dev: null device pointer"); return BSHOT_E_INVALID; }
     return hamming_reverse_owned(ctx, d_q, nq, ctx->d_map, ctx->n_map, global_base, reinterpret_cast<const bshot_cand*>(d_merged),
                                  reinterpret_cast<unsigned*>(d_rq_out));
+}
+
+int bshot_peer_barrier_dev(bshot_ctx* ctx, const void* d_peer_flag_ptrs, int nranks, int rank) {
+    CHECK_CTX(ctx);
+    if (!d_peer_flag_ptrs || nranks <= 0 || rank < 0 || rank >= nranks) { set_error("bshot_peer_barrier_dev: bad arguments"); return BSHOT_E_INVALID; }
+    return hamming_peer_barrier(ctx, d_peer_flag_ptrs, (unsigned)nranks, (unsigned)rank);
+}
+
+int bshot_peer_barrier_timeouts(bshot_ctx* ctx, unsigned* epoch_out) {
+    CHECK_CTX(ctx);
+    if (!epoch_out) { set_error("bshot_peer_barrier_timeouts: null output"); return BSHOT_E_INVALID; }
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[16], ctx->d_pair_count + 3, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    *epoch_out = (unsigned)ctx->h_scratch[16];
+    return BSHOT_OK;
 }
 
 int bshot_push_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nq, const void* d_peer_ptrs, int nranks, int rank) {

@@ -114,7 +114,8 @@ struct Ctx {
     int* d_left = nullptr;              // 4 x max_kp ints (idx, dist, idx2, dist2)
     int* d_right = nullptr;             // max_targets ints
     int* d_pairs = nullptr;             // 3 x max_kp (q, m, dist)
-    int* d_pair_count = nullptr;
+    int* d_pair_count = nullptr;        // [0] mutual pairs, [1] owned winners, [3] peer-barrier timeout flag
+    unsigned peer_epoch = 0;            // barriers issued on the symmetric flag array so far
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints

@@ -591,9 +591,40 @@ __global__ void push_rq_kernel(const bshot_cand* __restrict__ rev, const unsigne
     for (unsigned p = 0; p < nranks; ++p) peers[(p + rank) % nranks][q] = v;
 }
 
+// Cross-rank barrier over a symmetric flag array (peers[r] = rank r's array of nranks words, zero at start):
+// thread p tells rank p "rank `rank` has reached barrier #epoch" and waits until rank p has said the same here.
+// Release / acquire at system scope order the peer stores of the kernels before it against the kernels after it on
+// every rank.  Epochs only grow, so a peer that is already one barrier ahead still satisfies the wait.  The spin is
+// bounded (about 2 s): a rank that never arrives raises `*timeout_flag` instead of hanging the GPU.
+__global__ void peer_barrier_kernel(unsigned* const* __restrict__ peers, unsigned nranks, unsigned rank, unsigned epoch,
+                                    unsigned* __restrict__ timeout_flag) {
+    const unsigned p = threadIdx.x;
+    if (p >= nranks) return;
+    __threadfence_system();
+    unsigned* theirs = peers[p] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    const unsigned* mine = peers[rank] + p;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 4000000000ll) { *timeout_flag = epoch; break; }
+    }
+}
+
 __global__ void apply_rq_kernel(bshot_cand* __restrict__ cand, const unsigned* __restrict__ rq, unsigned nq) {
     const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi < nq) cand[qi].rq = (cand[qi].k1 != HM_NONE) ? rq[qi] : 0xFFFFFFFFu;
+}
+
+int hamming_peer_barrier(Ctx* c, const void* d_peer_flags, unsigned nranks, unsigned rank) {
+    if (nranks > 32) { set_error("peer barrier: at most 32 ranks"); return BSHOT_E_INVALID; }
+    ++c->peer_epoch;
+    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<unsigned* const*>(d_peer_flags), nranks, rank, c->peer_epoch,
+                                                 reinterpret_cast<unsigned*>(c->d_pair_count) + 3);
+    count_launch(c);
+    return check_launch("peer_barrier_kernel");
 }
 
 int hamming_push_cands(Ctx* c, const bshot_cand* d_cands, size_t nq, const void* d_peer_ptrs, unsigned nranks, unsigned rank) {

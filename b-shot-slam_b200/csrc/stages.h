@@ -25,6 +25,7 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
 int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                           const bshot_cand* d_merged, unsigned* d_rq_out, const void* d_peer_rq = nullptr, unsigned nranks = 1,
                           unsigned rank = 0);
+int hamming_peer_barrier(Ctx* c, const void* d_peer_flags, unsigned nranks, unsigned rank);
 int hamming_push_cands(Ctx* c, const bshot_cand* d_cands, size_t nq, const void* d_peer_ptrs, unsigned nranks, unsigned rank);
 int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq);
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,

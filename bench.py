@@ -321,10 +321,15 @@ def main():
                 import torch.distributed._symmetric_memory as symm_mem
                 g_sym = symm_mem.empty(world * Q * 3, dtype=torch.int64, device=torch.device("cuda", local_rank))
                 r_sym = symm_mem.empty(Q, dtype=torch.int32, device=torch.device("cuda", local_rank))
+                f_sym = symm_mem.empty(64, dtype=torch.int32, device=torch.device("cuda", local_rank))
+                g_sym.zero_(); r_sym.fill_(-1); f_sym.zero_()
+                torch.cuda.synchronize()
                 h_g = symm_mem.rendezvous(g_sym, dist.group.WORLD)
                 h_r = symm_mem.rendezvous(r_sym, dist.group.WORLD)
-                peer = {"g": g_sym, "r": r_sym, "hg": h_g, "hr": h_r, "pg": int(h_g.buffer_ptrs_dev), "pr": int(h_r.buffer_ptrs_dev)}
-                g_sym.zero_(); r_sym.fill_(-1)
+                h_f = symm_mem.rendezvous(f_sym, dist.group.WORLD)
+                peer = {"g": g_sym, "r": r_sym, "f": f_sym, "h": (h_g, h_r, h_f), "pg": int(h_g.buffer_ptrs_dev),
+                        "pr": int(h_r.buffer_ptrs_dev), "pf": int(h_f.buffer_ptrs_dev)}
+                dist.barrier()                                     # every rank's flag array is zero before the first barrier
                 torch.cuda.synchronize()
             except Exception as e:  # noqa: BLE001
                 if rank == 0:
@@ -345,12 +350,10 @@ def main():
                 ctx.match_shard_dev(dq.data_ptr(), Q, lo, False, cand.data_ptr())
                 if peer is not None:
                     ctx.push_cands_dev(cand.data_ptr(), Q, peer["pg"], world, rank)
-                    with torch.cuda.stream(st):
-                        peer["hg"].barrier(channel=0)
+                    ctx.peer_barrier_dev(peer["pf"], world, rank)
                     ctx.merge_cands_dev(peer["g"].data_ptr(), world, Q, merged.data_ptr())
                     ctx.reverse_owned_push_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), peer["pr"], world, rank)
-                    with torch.cuda.stream(st):
-                        peer["hr"].barrier(channel=0)
+                    ctx.peer_barrier_dev(peer["pf"], world, rank)
                     ctx.apply_rq_dev(merged.data_ptr(), peer["r"].data_ptr(), Q)
                     continue
                 with torch.cuda.stream(st):
@@ -375,6 +378,8 @@ def main():
         e1.record(st)
         barrier()
         mm_ms = max_over_ranks(e0.elapsed_time(e1)) / args.map_steps
+        if peer is not None and ctx.peer_barrier_timeouts():
+            raise SystemExit("bench.py: a peer barrier timed out (a rank did not arrive)")
         popc_peak = ctx.popc_peak()
         pairs = float(Q) * float(T)
         map_match = {"workload": "C4", "Q": Q, "T": T, "shards": world, "ms_per_call": mm_ms,
@@ -384,7 +389,7 @@ def main():
                                   "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
                                   "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
                      "collective": ("none" if world == 1 else
-                                    "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the owner) + 2 symmetric-memory barriers"
+                                    "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the owner) + 2 flag barriers over symmetric memory (no NCCL on the data path)"
                                     if peer is not None else
                                     "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result"),
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}

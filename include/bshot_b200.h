@@ -199,6 +199,11 @@ int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t n
  * all-reduce, the owner of a winner stores rq[query] into every rank's rq array (d_peer_rq_ptrs = device array of
  * nranks pointers to nq x uint32).  The caller places one cross-rank barrier after each of the two calls. */
 int bshot_push_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nq, const void* d_peer_ptrs, int nranks, int rank);
+/* the barrier: d_peer_flag_ptrs = device array of nranks pointers to each rank's flag array (>= nranks uint32, zero
+ * before the first barrier).  Every rank must issue the same sequence of barriers.  A rank that never arrives makes the
+ * others give up after ~2 s instead of hanging; bshot_peer_barrier_timeouts then reports the epoch (0 = none). */
+int bshot_peer_barrier_dev(bshot_ctx* ctx, const void* d_peer_flag_ptrs, int nranks, int rank);
+int bshot_peer_barrier_timeouts(bshot_ctx* ctx, unsigned* epoch_out);
 int bshot_reverse_owned_push_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
                                  const void* d_merged, const void* d_peer_rq_ptrs, int nranks, int rank);
 /* host-buffer convenience over the three calls above for a single rank */
