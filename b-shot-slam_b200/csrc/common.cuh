@@ -136,6 +136,15 @@ int check_launch(const char* what);
 struct bshot_ctx : public bshot::Ctx {};
 
 // ---- device helpers --------------------------------------------------------------------------
+// -DBSHOT_DEBUG_BOUNDS: device-side asserts on every shared-memory / list index the kernels compute (the pool has no
+// compute-sanitizer); a violated bound traps the kernel and the next API call reports the CUDA error.
+#ifdef BSHOT_DEBUG_BOUNDS
+#include <assert.h>
+#define BSHOT_ASSERT(cond) assert(cond)
+#else
+#define BSHOT_ASSERT(cond) ((void)0)
+#endif
+
 namespace bshot {
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

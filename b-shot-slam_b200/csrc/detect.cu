@@ -228,26 +228,27 @@ tk_hist_kernel(const unsigned long long* __restrict__ keys, unsigned n, int top_
 }
 
 __device__ __forceinline__ void tk_append(bool mine, unsigned long long key, unsigned* counter, unsigned long long* list,
-                                          unsigned lane) {
+                                          unsigned lane, unsigned cap) {
     const unsigned m = __ballot_sync(0xffffffffu, mine);
     if (m == 0) return;
     const int leader = __ffs(m) - 1;
     unsigned base = 0;
     if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
+    BSHOT_ASSERT(!mine || base + __popc(m & ((1u << lane) - 1u)) < cap);
     if (mine) list[base + __popc(m & ((1u << lane) - 1u))] = key;
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
 tk_compact_kernel(const unsigned long long* __restrict__ keys, unsigned n, unsigned* __restrict__ state,
-                  unsigned long long* __restrict__ sure, unsigned long long* __restrict__ tie) {
+                  unsigned long long* __restrict__ sure, unsigned long long* __restrict__ tie, unsigned sure_cap) {
     const unsigned i = blockIdx.x * TK_THREADS + threadIdx.x, lane = threadIdx.x & 31;
     const unsigned bstar = state[TKS_BIN];
     if (bstar == 0xFFFFFFFFu) return;  // k_eff == 0
     const unsigned long long k = (i < n) ? __ldg(keys + i) : 0ull;
     const unsigned bin = tk_bin(k);
-    tk_append(k != 0ull && bin > bstar, k, state + TKS_NSURE, sure, lane);
-    tk_append(k != 0ull && bin == bstar, k, state + TKS_NTIE, tie, lane);
+    tk_append(k != 0ull && bin > bstar, k, state + TKS_NSURE, sure, lane, sure_cap);
+    tk_append(k != 0ull && bin == bstar, k, state + TKS_NTIE, tie, lane, n);
 }
 
 __global__ void __launch_bounds__(TK_THREADS)
@@ -286,6 +287,7 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
             const bool keep = is_a || c < need;
             if (keep) {
                 const unsigned pos = is_a ? need + c : need - 1u - c;
+                BSHOT_ASSERT(pos < state[TKS_KEFF]);
                 const unsigned idx = ~(unsigned)(x & 0xFFFFFFFFull);
                 kp_idx[pos] = (int)idx;
                 kp_ratio[pos] = __uint_as_float((unsigned)(x >> 32));
@@ -334,7 +336,7 @@ int detect_topk(Ctx* c, int top_k) {
     if (top_k < 0 || (size_t)top_k > c->max_kp) { set_error("top_k %d exceeds max_keypoints %zu", top_k, c->max_kp); return BSHOT_E_CAPACITY; }
     const unsigned hist_ctas = std::max(1u, std::min((n + TK_THREADS * 16 - 1) / (TK_THREADS * 16), (unsigned)c->sm_count));
     tk_hist_kernel<<<hist_ctas, TK_THREADS, 0, c->stream>>>(c->d_keys, n, top_k, c->d_tk_hist, c->d_tk_state, c->d_kp_count);
-    if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie);
+    if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, (unsigned)c->max_kp);
     tk_rank_kernel<<<(unsigned)c->sm_count * 4u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_kp_idx,
                                                                              c->d_kp_ratio, c->d_kp);
     count_launch(c, n ? 3 : 2);

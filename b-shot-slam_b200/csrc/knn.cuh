@@ -137,6 +137,7 @@ __device__ __forceinline__ unsigned knn_expand(const GridParams& g, const unsign
     __syncwarp();
     for (unsigned k = lane; k < nseg; k += 32) {  // 3. head masks
         const unsigned o = sm.h.x.off[k];
+        BSHOT_ASSERT(o < total && (o >> 5) < 32u);
         atomicOr(&sm.h.x.heads[o >> 5], 1u << (o & 31));
     }
     __syncwarp();
@@ -158,6 +159,7 @@ __device__ __forceinline__ unsigned knn_expand(const GridParams& g, const unsign
         const unsigned j = (c << 5) + lane;
         if (j < total) {
             const unsigned k = p0 + __popc(w & le_mask) - 1u;  // candidate 0 is a head: k >= 0
+            BSHOT_ASSERT(j < (unsigned)KN_CAP && k < nseg && sm.h.x.off[k] <= j);
             sm.u.idx[j] = sm.v.seg_start[k] + (j - sm.h.x.off[k]);
         }
     }
@@ -179,6 +181,7 @@ __device__ __forceinline__ void knn_for_each(const GridParams& g, const unsigned
 #pragma unroll
             for (int u = 0; u < KN_DEPTH; ++u) {
                 const unsigned ju = j + 32u * u;
+                BSHOT_ASSERT(total <= (unsigned)KN_CAP);
                 p[u] = __ldg(sorted + sm.u.idx[ju < total ? ju : j]);
             }
 #pragma unroll
