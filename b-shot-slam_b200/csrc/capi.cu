@@ -117,6 +117,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     }
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("BSHOT_EXACT_SUMS")) c->exact_sums = (atoi(e) != 0);
     if (const char* e = getenv("BSHOT_YZ_MUL")) {  // tuning knob: row thickness relative to the cell length
         const float v = (float)atof(e);
         if (v >= 1.0f && v <= 8.0f) c->yz_mul = v;

@@ -47,6 +47,7 @@ constexpr float kDefaultCell = 375.0f;              // R/8 for the reference rad
 struct Ctx {
     int device = 0;
     int sm_count = 148;
+    bool exact_sums = false;  // BSHOT_EXACT_SUMS=1: replay the reference's fp32 running sums in neighbour order (knn.cuh)
     float yz_mul = 1.0f;  // cell_yz / cell (tuning knob BSHOT_YZ_MUL; 2 helps SHOT by ~3 %, costs the detector ~6 %)
     cudaStream_t stream = nullptr;
     unsigned long long launches = 0;

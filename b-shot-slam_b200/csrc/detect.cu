@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "knn.cuh"
 #include "stages.h"
 
@@ -22,13 +24,13 @@ constexpr int DT_THREADS = DT_WARPS * 32;
 #define BSHOT_DT_MINBLOCKS 8
 #endif
 
-// seg-ratio of one point, all 32 lanes call
+// seg-ratio of one point, all 32 lanes call.  skeys != nullptr: exact-order fp32 centroid (knn.cuh)
 template <int SR>
 __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsigned* __restrict__ cell_start,
                                                 const float4* __restrict__ sorted, const float4* __restrict__ pts,
                                                 const float4& q, float radius, int max_nn, KnnWarpSmem& sm,
-                                                unsigned lane, float& seg, int& count, float& sel_rho2,
-                                                unsigned long long& sel_thr) {
+                                                unsigned long long* skeys, unsigned lane, float& seg, int& count,
+                                                float& sel_rho2, unsigned long long& sel_thr) {
     const float nanf_ = __int_as_float(0x7FC00000);
     // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
     double sx = 0, sy = 0, sz = 0;
@@ -36,7 +38,17 @@ __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsig
                                      [&](const float4 p) { sx += p.x; sy += p.y; sz += p.z; });
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     const float fn = (float)res.count;
-    const float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
+    float ctx = (float)sx / fn, cty = (float)sy / fn, ctz = (float)sz / fn;
+    bool exact = false;
+    if (skeys && knn_sorted_selected(g, cell_start, sorted, q, res, sm, skeys, lane)) {
+        // the reference's own arithmetic: fp32 running sums in ascending-distance order
+        float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+        knn_replay_in_order(pts, skeys, res.count, lane, [&](float x, float y, float z) {
+            fx = __fadd_rn(fx, x); fy = __fadd_rn(fy, y); fz = __fadd_rn(fz, z);
+        });
+        ctx = fx / fn; cty = fy / fn; ctz = fz / fn;
+        exact = true;
+    }
     const float vx = __fsub_rn(q.x, ctx), vy = __fsub_rn(q.y, cty), vz = __fsub_rn(q.z, ctz);  // :79
     if (SR == BSHOT_SR_CV) {  // :83-97
         int pos = 0, neg = 0;
@@ -52,6 +64,17 @@ __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsig
         const float fp = (float)pos, fq = (float)neg;
         seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);  // 0/0 -> NaN like the reference
         if (pos == 0 && neg == 0) seg = nanf_;
+    } else if (exact) {  // CVS / CVSN with the reference's fp32 running sum in neighbour order
+        const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
+        float sum = 0.0f;
+        knn_replay_in_order(pts, skeys, res.count, lane, [&](float x, float y, float z) {
+            const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
+            const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
+            if (ctn == 0.0f || dn == 0.0f) return;
+            const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
+            sum = __fadd_rn(sum, (SR == BSHOT_SR_CVS) ? d : d / __fmul_rn(ctn, dn));
+        });
+        seg = fabsf(sum) / fn;
     } else {  // CVS :98-108, CVSN :109-119
         const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
         double sum = 0.0;
@@ -74,17 +97,20 @@ __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsig
 
 // SR = score type (compile time: the CV kernel carries no CVS / CVSN code).  One warp per binned point, taken
 // in voxel order so that neighbouring warps share cache lines.
-template <int SR>
-__global__ void __launch_bounds__(DT_THREADS, BSHOT_DT_MINBLOCKS)
+template <int SR, bool EXACT>
+__global__ void __launch_bounds__(DT_THREADS, EXACT ? 4 : BSHOT_DT_MINBLOCKS)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
                  unsigned long long* __restrict__ counters, float* __restrict__ sel_rho2,
                  unsigned long long* __restrict__ sel_thr) {
-    __shared__ KnnWarpSmem smem[DT_WARPS];
+    using Smem = typename std::conditional<EXACT, KnnExactSmem, KnnWarpSmem>::type;
+    __shared__ Smem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const GridParams g = *gp;
-    KnnWarpSmem& sm = smem[wid];
+    KnnWarpSmem& sm = *reinterpret_cast<KnnWarpSmem*>(&smem[wid]);  // KnnExactSmem starts with its KnnWarpSmem
+    unsigned long long* skeys = nullptr;
+    if constexpr (EXACT) skeys = smem[wid].skeys;
     const unsigned n_items = min(__ldg(cell_start + g.ncells), n_total);
     const float nanf_ = __int_as_float(0x7FC00000);
     for (unsigned j = blockIdx.x * DT_WARPS + wid; j < n_items; j += gridDim.x * DT_WARPS) {
@@ -97,7 +123,7 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
         float seg, rho2;
         int count;
         unsigned long long thr;
-        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, seg, count, rho2, thr);
+        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, skeys, lane, seg, count, rho2, thr);
         if (lane == 0) {
             // the neighbourhood (sphere + threshold key) is kept: normals of the keypoints re-collect it in one sweep
             sel_rho2[qi] = rho2;
@@ -307,9 +333,17 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
     mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys);
     const unsigned ctas = (n + DT_WARPS - 1) / DT_WARPS;
-#define BSHOT_LAUNCH_SEG(SR)                                                                                                     \
-    seg_ratio_kernel<SR><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, \
-                                                             c->d_ratio, c->d_keys, c->d_counters, c->d_sel_rho2, c->d_sel_thr)
+#define BSHOT_LAUNCH_SEG(SR)                                                                                              \
+    do {                                                                                                                  \
+        if (c->exact_sums)                                                                                                \
+            seg_ratio_kernel<SR, true><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, \
+                                                                           max_nn, c->d_ratio, c->d_keys, c->d_counters,  \
+                                                                           c->d_sel_rho2, c->d_sel_thr);                  \
+        else                                                                                                              \
+            seg_ratio_kernel<SR, false><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, \
+                                                                            max_nn, c->d_ratio, c->d_keys, c->d_counters, \
+                                                                            c->d_sel_rho2, c->d_sel_thr);                 \
+    } while (0)
     if (sr_type == BSHOT_SR_CV) BSHOT_LAUNCH_SEG(BSHOT_SR_CV);
     else if (sr_type == BSHOT_SR_CVS) BSHOT_LAUNCH_SEG(BSHOT_SR_CVS);
     else BSHOT_LAUNCH_SEG(BSHOT_SR_CVSN);

@@ -409,6 +409,74 @@ __device__ __forceinline__ int knn_collect_cached(const GridParams& g, const uns
     return warp_sum(cnt);
 }
 
+// ---- exact-order sums (opt-in, BSHOT_EXACT_SUMS=1) --------------------------------------------------------
+// pcl::computeCentroid and pcl::computeMeanAndCovarianceMatrix add their fp32 accumulators in NEIGHBOUR ORDER
+// (ascending distance).  The default kernels sum in fp64 in candidate order -- more accurate than the reference,
+// but not bit-identical to it: a vote next to the dividing plane may flip.  The exact mode materialises the selected
+// set as sorted keys and replays the reference's sequential fp32 additions, so seg-ratios, keypoints and normals
+// come out bit-identical to the oracle.  Sets larger than KN_EXACT_CAP (uncapped searches) keep the default sums.
+constexpr int KN_EXACT_CAP = 512;
+
+struct KnnExactSmem {
+    KnnWarpSmem k;
+    unsigned long long skeys[KN_EXACT_CAP];
+};
+
+// keys of the selected set of `res` in ascending (sqd, index) order in skeys[0..res.count); false if it does not fit
+__device__ __forceinline__ bool knn_sorted_selected(const GridParams& g, const unsigned* __restrict__ cell_start,
+                                                    const float4* __restrict__ sorted, const float4& q, KnnResult& res,
+                                                    KnnWarpSmem& sm, unsigned long long* skeys, unsigned lane) {
+    if (res.count > KN_EXACT_CAP) return false;
+    if (lane == 0) sm.list_n = 0;
+    for (unsigned i = lane; i < (unsigned)KN_EXACT_CAP; i += 32) skeys[i] = ~0ull;  // padding sorts last
+    __syncwarp();
+    const float rho2 = res.rho2;
+    const unsigned long long thr = res.thr;
+    knn_for_each(g, cell_start, sorted, q, res.it, sm, lane, [&](const float4 p) {
+        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+        const unsigned long long key = knn_key(sqd, p.w);
+        if (sqd < rho2 && key <= thr) {
+            const unsigned slot = atomicAdd(&sm.list_n, 1u);
+            if (slot < (unsigned)KN_EXACT_CAP) skeys[slot] = key;
+        }
+    });
+    __syncwarp();
+    BSHOT_ASSERT(sm.list_n == (unsigned)res.count);
+    // bitonic sort of the smallest power of two that holds the set
+    unsigned m = 32;
+    while (m < (unsigned)res.count) m <<= 1;
+    for (unsigned size = 2; size <= m; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = lane; t < (m >> 1); t += 32) {
+                const unsigned lo = 2 * t - (t & (stride - 1));
+                const unsigned hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = skeys[lo], b = skeys[hi];
+                if ((a > b) == up) { skeys[lo] = b; skeys[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    return true;
+}
+
+// replays `for (j in neighbour order) acc(point j)` with every lane holding the same running state: f(x, y, z)
+// is called count times, in order, with the coordinates broadcast from the lane that loaded them
+template <typename F>
+__device__ __forceinline__ void knn_replay_in_order(const float4* __restrict__ pts, const unsigned long long* skeys,
+                                                    int count, unsigned lane, F&& f) {
+#pragma unroll 1
+    for (int base = 0; base < count; base += 32) {
+        const int j = base + (int)lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < count) p = __ldg(pts + (unsigned)(skeys[j] & 0xFFFFFFFFull));
+        const int m = min(32, count - base);
+#pragma unroll 1
+        for (int l = 0; l < m; ++l)
+            f(__shfl_sync(0xffffffffu, p.x, l), __shfl_sync(0xffffffffu, p.y, l), __shfl_sync(0xffffffffu, p.z, l));
+    }
+}
+
 __device__ __forceinline__ bool knn_selected(const KnnResult& r, float sqd, float w) {
     return knn_key(sqd, w) <= r.thr;  // thr < (rho2 bits << 32) by construction
 }

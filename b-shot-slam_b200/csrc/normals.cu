@@ -6,6 +6,8 @@
 // (SURVEY Appendix A.3).  One warp per query.  REFERENCE mode reproduces the reference's placement
 // quirk (normal of keypoint ordinal i stored at index i of the N-sized, persistent, zero-initialised
 // array that SHOT indexes by surface point); FULL mode computes a normal per surface point.
+#include <type_traits>
+
 #include "knn.cuh"
 #include "stages.h"
 
@@ -114,19 +116,20 @@ __device__ __forceinline__ void normal_sums(const GridParams& g, const unsigned*
 
 // CACHED: the queries are keypoints chosen by the detector (w = surface index) and the detector searched with
 // the same (radius, max_nn): their neighbourhoods are re-collected from the kept (rho2, threshold key).
-template <bool CACHED>
-__global__ void __launch_bounds__(NM_THREADS, 8)
+template <bool CACHED, bool EXACT>
+__global__ void __launch_bounds__(NM_THREADS, EXACT ? 4 : 8)
 normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                const float4* __restrict__ sorted, const float4* __restrict__ pts, const float4* queries, const int* __restrict__ nq_dev, unsigned nq,
                float radius, int max_nn, float4* out, unsigned long long* __restrict__ counters,
                const float* __restrict__ sel_rho2, const unsigned long long* __restrict__ sel_thr) {
-    __shared__ KnnWarpSmem smem[NM_WARPS];
+    using Smem = typename std::conditional<EXACT, KnnExactSmem, KnnWarpSmem>::type;
+    __shared__ Smem smem[NM_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned j = blockIdx.x * NM_WARPS + wid;
     if (j >= nq) return;
     if (nq_dev && (int)j >= *nq_dev) return;
     const GridParams g = *gp;
-    KnnWarpSmem& sm = smem[wid];
+    KnnWarpSmem& sm = *reinterpret_cast<KnnWarpSmem*>(&smem[wid]);
     float4 q = queries[j];
     const float nanf_ = __int_as_float(0x7FC00000);
     const bool finite = isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
@@ -140,6 +143,25 @@ normals_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ c
                 s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
                 s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
             });
+        } else if constexpr (EXACT) {
+            // pcl::computeMeanAndCovarianceMatrix as the reference runs it: nine fp32 accumulators, neighbour order
+            KnnResult res = knn_select(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, [&](const float4 p) {
+                s[0] += (double)__fmul_rn(p.x, p.x); s[1] += (double)__fmul_rn(p.x, p.y); s[2] += (double)__fmul_rn(p.x, p.z);
+                s[3] += (double)__fmul_rn(p.y, p.y); s[4] += (double)__fmul_rn(p.y, p.z); s[5] += (double)__fmul_rn(p.z, p.z);
+                s[6] += (double)p.x; s[7] += (double)p.y; s[8] += (double)p.z;
+            });
+            n = res.count;
+            if (knn_sorted_selected(g, cell_start, sorted, q, res, sm, smem[wid].skeys, lane)) {
+                float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                knn_replay_in_order(pts, smem[wid].skeys, res.count, lane, [&](float x, float y, float z) {
+                    a[0] = __fadd_rn(a[0], __fmul_rn(x, x)); a[1] = __fadd_rn(a[1], __fmul_rn(x, y)); a[2] = __fadd_rn(a[2], __fmul_rn(x, z));
+                    a[3] = __fadd_rn(a[3], __fmul_rn(y, y)); a[4] = __fadd_rn(a[4], __fmul_rn(y, z)); a[5] = __fadd_rn(a[5], __fmul_rn(z, z));
+                    a[6] = __fadd_rn(a[6], x); a[7] = __fadd_rn(a[7], y); a[8] = __fadd_rn(a[8], z);
+                });
+                // every lane holds the same sums: hand them to the common tail as lane 0's contribution
+#pragma unroll
+                for (int k = 0; k < 9; ++k) s[k] = (lane == 0) ? (double)a[k] : 0.0;
+            }
         } else {
             normal_sums(g, cell_start, sorted, pts, q, radius, max_nn, sm, lane, s, n);
         }
@@ -183,12 +205,16 @@ __global__ void place_normals_kernel(const float4* __restrict__ src, const int* 
 static int normals_launch(Ctx* c, const float4* d_q, const int* nq_dev, size_t nq, float radius, int max_nn, float4* d_out,
                           bool cached = false) {
     const unsigned ctas = (unsigned)((nq + NM_WARPS - 1) / NM_WARPS);
-    if (cached)
-        normals_kernel<true><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
-                                                                 radius, max_nn, d_out, c->d_counters, c->d_sel_rho2, c->d_sel_thr);
+    if (c->exact_sums)  // exact-order fp32 sums (knn.cuh): always a fresh, sorted selection
+        normals_kernel<false, true><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev,
+                                                                        (unsigned)nq, radius, max_nn, d_out, c->d_counters, nullptr, nullptr);
+    else if (cached)
+        normals_kernel<true, false><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev,
+                                                                        (unsigned)nq, radius, max_nn, d_out, c->d_counters, c->d_sel_rho2,
+                                                                        c->d_sel_thr);
     else
-        normals_kernel<false><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev, (unsigned)nq,
-                                                                  radius, max_nn, d_out, c->d_counters, nullptr, nullptr);
+        normals_kernel<false, false><<<ctas, NM_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, d_q, nq_dev,
+                                                                         (unsigned)nq, radius, max_nn, d_out, c->d_counters, nullptr, nullptr);
     count_launch(c);
     return check_launch("normals_kernel");
 }

@@ -141,3 +141,43 @@ def test_topk_on_unbounded_scores(gpu_ctx, oracle, sr_type):
         idx, rat, _ = gpu_ctx.detect_keypoints(1500.0, 60, sr_type, k)
         idx_d, rat_d = oracle.select_keypoints(ratio, k, oracle.TIE_DETERMINISTIC)
         assert np.array_equal(idx, idx_d) and np.array_equal(rat, rat_d)
+
+
+def test_exact_sums_mode_is_bit_identical_to_the_oracle(bshot, oracle, synth):
+    """BSHOT_EXACT_SUMS=1 replays the reference's fp32 running sums in neighbour (ascending distance) order:
+    seg-ratios of all three score types and the keypoint set then match the oracle bit for bit, the keypoint normals
+    to the last ulp of the device / host trigonometric functions, and the whole REFERENCE-mode descriptor chain to
+    >= 99.95 % of the bits (the default mode sums in fp64, which flips a vote next to the dividing plane for ~3 % of
+    the points)."""
+    scan = synth.make_scan("hdl32e", 5)[::2].copy()
+    oc = oracle.Cloud(scan)
+    os.environ["BSHOT_EXACT_SUMS"] = "1"
+    try:
+        with bshot.Context(0, 65536, 2048, 4096) as ctx:
+            ctx.set_cloud(scan)
+            for sr in (0, 1, 2):
+                rg = ctx.seg_ratio(3000.0, 300, sr)
+                ro = oc.seg_ratio(3000.0, 300, sr)
+                nan = np.isnan(ro)
+                assert np.array_equal(np.isnan(rg), nan)
+                assert np.array_equal(rg[~nan], ro[~nan]), (sr, np.abs(rg[~nan] - ro[~nan]).max())
+            ro = oc.seg_ratio(3000.0, 300, 0)
+            idx_o, rat_o = oracle.select_keypoints(ro, 400, oracle.TIE_DETERMINISTIC)
+            idx_g, rat_g, xyz = ctx.detect_keypoints(3000.0, 300, 0, 400)
+            assert np.array_equal(idx_g, idx_o) and np.array_equal(rat_g, rat_o)
+            ng = ctx.compute_normals(0, 3000.0, 300)[:400]
+            no = oc.normals(scan[idx_o], 3000.0, 300)
+            assert np.array_equal(np.isnan(ng), np.isnan(no))
+            ok = ~np.isnan(no[:, 0])
+            # same sums, same covariance; the closed-form eigen-solver calls atan2f / cosf / sinf, whose device and
+            # host implementations may differ in the last bit
+            assert np.abs(ng[ok] - no[ok]).max() <= 1e-6, np.abs(ng[ok] - no[ok]).max()
+            # whole chain: detector -> normals (reference placement) -> SHOT -> B-SHOT
+            ctx.reset()
+            f = ctx.process_frame(scan, bshot.default_params(top_k=400))
+            od = oc.compute_descriptors(scan[idx_o], 3000.0, 300, oracle.MODE_REFERENCE)
+            assert np.array_equal(f["kp_idx"], idx_o)
+            same = synth.unpack_bits(f["bits"]) == synth.unpack_bits(od["bits"])
+            assert same.mean() >= 0.9995, same.mean()
+    finally:
+        os.environ.pop("BSHOT_EXACT_SUMS", None)
