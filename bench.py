@@ -438,6 +438,25 @@ def main():
               "note": "stage times from CUDA events on the context stream, L2 flushed before every frame"}
         ctx64.close()
 
+    # ---- exact-sums mode (reference summation order, bit-identical seg-ratios / keypoints): same C2 frames ----
+    exact = None
+    if rank == 0 and world == 1 and not args.map_only:
+        os.environ["BSHOT_EXACT_SUMS"] = "1"
+        try:
+            ctxe = bs.Context(local_rank, max_points=max_n + 1024, max_keypoints=args.top_k, max_targets=args.top_k)
+        finally:
+            os.environ.pop("BSHOT_EXACT_SUMS", None)
+        ctxe.enable_timing(True)
+        acc = {}
+        for i in range(3 + 10):
+            ctxe.process_frame_dev(d_frames[i % N_FRAMES].data_ptr(), npts[i % N_FRAMES], 12, params)
+            if i >= 3:
+                for k, v in ctxe.stage_times().items():
+                    acc[k] = acc.get(k, 0.0) + v / 10
+        exact = {"env": "BSHOT_EXACT_SUMS=1", "ms_per_frame": acc["frame"], "stages_ms": acc,
+                 "note": "fp32 running sums replayed in neighbour order: seg-ratios and keypoints bit-identical to the oracle"}
+        ctxe.close()
+
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -468,7 +487,7 @@ def main():
                        "parallelism": "replicas (one frame stream per GPU)" if world > 1 else "single GPU",
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write), per-step CUDA events on the context stream"},
             "stages_ms": stages, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c3": c3,
+            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c3": c3, "exact_mode": exact,
         }
         print(json.dumps(line))
     ctx.close()
