@@ -7,9 +7,6 @@
 // (ratio bits << 32 | ~index) followed by a rank-by-counting scatter, so keypoints come out
 // in ascending ratio order like the reference's `SegRatio.end()-600 .. end()` slice, with a
 // deterministic tie-break (lower point index wins) where std::sort's is unspecified.
-#include <stdlib.h>
-#include <string.h>
-
 #include <type_traits>
 
 #include "knn.cuh"

@@ -371,7 +371,6 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     }
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);
-    const size_t max_splits = (nt + HM_MIN_CHUNK - 1) / HM_MIN_CHUNK;
     // whole waves: the grid is a multiple of (SMs x resident CTAs per SM) whenever the problem is big enough,
     // otherwise the last partial wave costs as much as a full one
     static int occ_cache[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
