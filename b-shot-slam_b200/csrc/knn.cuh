@@ -23,10 +23,10 @@ constexpr int KN_CAP = 1024;     // fast path: explicit candidate list
 #define BSHOT_KN_DEPTH 4
 #endif
 #ifndef BSHOT_KN_WLO
-#define BSHOT_KN_WLO 1.45f
+#define BSHOT_KN_WLO 1.4f
 #endif
 #ifndef BSHOT_KN_WHI
-#define BSHOT_KN_WHI 2.2f
+#define BSHOT_KN_WHI 2.4f
 #endif
 #ifndef BSHOT_KN_PAD
 #define BSHOT_KN_PAD 0.5f  // candidate-count model: count ~ (rho + PAD * row thickness)^2 (rows are taken whole in y and z)
@@ -235,7 +235,7 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
     int tries = 0;
     const float pad = BSHOT_KN_PAD * g.cell_yz;
     // candidate window that is worth a sweep: ~74 % of the candidates of a chord-clipped row set lie inside
-    // the sphere, so 1.45 .. 2.2 max_nn candidates hold max_nn points with little excess
+    // the sphere, so 1.4 .. 2.4 max_nn candidates hold max_nn points with little excess (window chosen by measurement)
     const unsigned want_lo = (unsigned)(BSHOT_KN_WLO * (float)max(max_nn, 0)), want_hi = min((unsigned)(BSHOT_KN_WHI * (float)max(max_nn, 0)), (unsigned)KN_CAP);
     // ---- 1. size the sphere ---------------------------------------------------------------------
     for (;;) {
