@@ -123,3 +123,98 @@ class GpuBackend:
         self.ctx.merge_cands_dev(d.data_ptr(), ranks, q, out.data_ptr())
         self.ctx.sync()
         return out.cpu().numpy().view(CAND_DTYPE).reshape(q)
+
+
+class DeviceShardedMatcher:
+    """Device-resident sharded frame-to-map match of one rank: queries, records and the exchange stay on the GPU and
+    everything is stream-ordered on the context stream (no host synchronisation per call).
+
+    Per call at world > 1: shard search (no rq) -> exchange of the 24 B/query records -> merge by (distance, global
+    index) -> reverse pass only for the winners this rank owns (Q * Q / ranks pairs) -> exchange of the 4 B/query
+    reverse result -> records completed.  Two interchangeable exchanges:
+      * "peer": gather buffer, rq array and a flag array are torch symmetric-memory allocations mapped on every rank
+        over NVLink / NVSwitch; the records and the owners' reverse results are STORED straight into every rank's
+        buffers (bshot_push_cands_dev / bshot_reverse_owned_push_dev) and bshot_peer_barrier_dev replaces each
+        collective -- no NCCL call on the data path;
+      * "nccl": one all_gather_into_tensor of the records and one all_reduce(MAX) of the reverse result.
+    mode="auto" takes "peer" when symmetric memory can be set up on every rank, else "nccl"."""
+
+    def __init__(self, ctx, world, rank, nq, mode="auto", device=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.world, self.rank, self.nq = ctx, world, rank, nq
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.ExternalStream(ctx.stream)
+        self.cand = torch.empty((nq, 3), dtype=torch.int64, device=dev)
+        self.merged = torch.empty((nq, 3), dtype=torch.int64, device=dev)
+        self.peer = None
+        self.exchange = "none"
+        if world == 1:
+            return
+        import torch.distributed as dist
+        self.dist = dist
+        if mode in ("auto", "peer"):
+            err = None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                g = symm_mem.empty(world * nq * 3, dtype=torch.int64, device=dev)
+                r = symm_mem.empty(nq, dtype=torch.int32, device=dev)
+                f = symm_mem.empty(64, dtype=torch.int32, device=dev)
+                g.zero_(); r.fill_(-1); f.zero_()
+                torch.cuda.synchronize()
+                hs = [symm_mem.rendezvous(t, dist.group.WORLD) for t in (g, r, f)]
+                self.peer = dict(g=g, r=r, f=f, handles=hs, pg=int(hs[0].buffer_ptrs_dev), pr=int(hs[1].buffer_ptrs_dev),
+                                 pf=int(hs[2].buffer_ptrs_dev))
+            except Exception as e:  # noqa: BLE001 -- any failure means "no symmetric memory here"
+                err, self.peer = e, None
+            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same path; also the barrier
+            torch.cuda.synchronize()                           # that makes all flag arrays zero before first use
+            if int(ok.item()) == 0:
+                self.peer = None
+                if mode == "peer":
+                    raise RuntimeError(f"symmetric memory unavailable on some rank ({err})")
+        if self.peer is not None:
+            self.exchange = "peer"
+        else:
+            self.exchange = "nccl"
+            self.gathered = torch.empty((world, nq, 3), dtype=torch.int64, device=dev)
+            self.rq = torch.empty(nq, dtype=torch.int32, device=dev)
+
+    def describe(self):
+        return {"none": "none",
+                "peer": "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the "
+                        "owner) + 2 flag barriers over symmetric memory (no NCCL on the data path)",
+                "nccl": "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result"}[self.exchange]
+
+    def match(self, d_q_ptr, global_base):
+        """asynchronous; returns the device tensor (nq, 3) int64 = bshot_cand records with rq filled"""
+        c, nq, w, rk = self.ctx, self.nq, self.world, self.rank
+        if w == 1:
+            c.match_shard_dev(d_q_ptr, nq, global_base, True, self.cand.data_ptr())
+            c.merge_cands_dev(self.cand.data_ptr(), 1, nq, self.merged.data_ptr())
+            return self.merged
+        c.match_shard_dev(d_q_ptr, nq, global_base, False, self.cand.data_ptr())
+        if self.peer is not None:
+            p = self.peer
+            c.push_cands_dev(self.cand.data_ptr(), nq, p["pg"], w, rk)
+            c.peer_barrier_dev(p["pf"], w, rk)
+            c.merge_cands_dev(p["g"].data_ptr(), w, nq, self.merged.data_ptr())
+            c.reverse_owned_push_dev(d_q_ptr, nq, global_base, self.merged.data_ptr(), p["pr"], w, rk)
+            c.peer_barrier_dev(p["pf"], w, rk)
+            c.apply_rq_dev(self.merged.data_ptr(), p["r"].data_ptr(), nq)
+            return self.merged
+        torch, dist = self.torch, self.dist
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.cand.view(-1))
+        c.merge_cands_dev(self.gathered.data_ptr(), w, nq, self.merged.data_ptr())
+        c.reverse_owned_dev(d_q_ptr, nq, global_base, self.merged.data_ptr(), self.rq.data_ptr())
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.rq, op=dist.ReduceOp.MAX)     # one owner per query, the others hold -1
+        c.apply_rq_dev(self.merged.data_ptr(), self.rq.data_ptr(), nq)
+        return self.merged
+
+    def check(self):
+        """raises if a peer barrier gave up waiting for a rank"""
+        if self.peer is not None and self.ctx.peer_barrier_timeouts():
+            raise RuntimeError("a peer barrier timed out (a rank did not arrive)")

@@ -30,7 +30,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import load_bshot, load_oracle, load_synth  # noqa: E402  (loaders only, no pytest needed)
+from conftest import load_bshot, load_oracle, load_sharded, load_synth  # noqa: E402  (loaders only, no pytest needed)
 
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 N_FRAMES = 12               # distinct synthetic frames per rank, cycled
@@ -300,70 +300,17 @@ def main():
         q[:64] = tfull[planted]
         del tfull
         dq = torch.from_numpy(q.view(np.int64)).cuda()
-        cand = torch.empty((Q, 3), dtype=torch.int64, device="cuda")
-        merged = torch.empty((Q, 3), dtype=torch.int64, device="cuda")
-
-        # Per call at N > 1: shard search (no rq) -> all-gather of 24 B/query records -> merge -> reverse pass only
-        # for the winners this rank owns (Q*Q/ranks pairs) -> all-reduce of the 4 B/query reverse result -> records
-        # completed.  Everything is stream-ordered on the context stream.  (Overlapping the collectives with the next
-        # call's shard kernel was measured and is slower: the NCCL kernels wait for SM slots behind a full-GPU grid.)
-        gathered = torch.empty((world, Q, 3), dtype=torch.int64, device="cuda")
-        rq = torch.empty(Q, dtype=torch.int32, device="cuda")
-
-        # Preferred exchange at N > 1: symmetric buffers mapped on every rank (torch symmetric memory over NVLink /
-        # NVSwitch).  Every rank STORES its records into slot `rank` of every rank's gather buffer and the owner of a
-        # winner stores rq[query] into every rank's array (bshot_push_cands_dev / bshot_reverse_owned_push_dev); one
-        # cross-rank barrier after each replaces the all-gather and the all-reduce.  Falls back to NCCL collectives if
-        # symmetric memory cannot be set up (BSHOT_EXCHANGE=nccl forces the fallback).
-        peer = None
-        if world > 1 and os.environ.get("BSHOT_EXCHANGE", "peer") != "nccl":
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                g_sym = symm_mem.empty(world * Q * 3, dtype=torch.int64, device=torch.device("cuda", local_rank))
-                r_sym = symm_mem.empty(Q, dtype=torch.int32, device=torch.device("cuda", local_rank))
-                f_sym = symm_mem.empty(64, dtype=torch.int32, device=torch.device("cuda", local_rank))
-                g_sym.zero_(); r_sym.fill_(-1); f_sym.zero_()
-                torch.cuda.synchronize()
-                h_g = symm_mem.rendezvous(g_sym, dist.group.WORLD)
-                h_r = symm_mem.rendezvous(r_sym, dist.group.WORLD)
-                h_f = symm_mem.rendezvous(f_sym, dist.group.WORLD)
-                peer = {"g": g_sym, "r": r_sym, "f": f_sym, "h": (h_g, h_r, h_f), "pg": int(h_g.buffer_ptrs_dev),
-                        "pr": int(h_r.buffer_ptrs_dev), "pf": int(h_f.buffer_ptrs_dev)}
-                dist.barrier()                                     # every rank's flag array is zero before the first barrier
-                torch.cuda.synchronize()
-            except Exception as e:  # noqa: BLE001
-                if rank == 0:
-                    print(f"bench.py: symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL collectives", file=sys.stderr)
-                peer = None
-            # all ranks must take the same path
-            flag = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()) == 0:
-                peer = None
+        # the per-call protocol (shard search, record exchange, merge, sharded reverse pass) lives in the package:
+        # sharded.DeviceShardedMatcher; BSHOT_EXCHANGE=nccl forces the NCCL exchange, default = peer memory if possible
+        sharded = load_sharded()
+        matcher = sharded.DeviceShardedMatcher(ctx, world, rank, Q, mode="nccl" if os.environ.get("BSHOT_EXCHANGE") == "nccl" else "auto",
+                                               device=torch.device("cuda", local_rank))
 
         def map_calls(n):
+            out = None
             for _ in range(n):
-                if world == 1:
-                    ctx.match_shard_dev(dq.data_ptr(), Q, lo, True, cand.data_ptr())
-                    ctx.merge_cands_dev(cand.data_ptr(), 1, Q, merged.data_ptr())
-                    continue
-                ctx.match_shard_dev(dq.data_ptr(), Q, lo, False, cand.data_ptr())
-                if peer is not None:
-                    ctx.push_cands_dev(cand.data_ptr(), Q, peer["pg"], world, rank)
-                    ctx.peer_barrier_dev(peer["pf"], world, rank)
-                    ctx.merge_cands_dev(peer["g"].data_ptr(), world, Q, merged.data_ptr())
-                    ctx.reverse_owned_push_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), peer["pr"], world, rank)
-                    ctx.peer_barrier_dev(peer["pf"], world, rank)
-                    ctx.apply_rq_dev(merged.data_ptr(), peer["r"].data_ptr(), Q)
-                    continue
-                with torch.cuda.stream(st):
-                    dist.all_gather_into_tensor(gathered.view(-1), cand.view(-1))
-                ctx.merge_cands_dev(gathered.data_ptr(), world, Q, merged.data_ptr())
-                ctx.reverse_owned_dev(dq.data_ptr(), Q, lo, merged.data_ptr(), rq.data_ptr())
-                with torch.cuda.stream(st):
-                    dist.all_reduce(rq, op=dist.ReduceOp.MAX)      # one owner per query, the others hold -1
-                ctx.apply_rq_dev(merged.data_ptr(), rq.data_ptr(), Q)
-            return merged
+                out = matcher.match(dq.data_ptr(), lo)
+            return out
 
         last = map_calls(3)
         barrier()
@@ -378,8 +325,7 @@ def main():
         e1.record(st)
         barrier()
         mm_ms = max_over_ranks(e0.elapsed_time(e1)) / args.map_steps
-        if peer is not None and ctx.peer_barrier_timeouts():
-            raise SystemExit("bench.py: a peer barrier timed out (a rank did not arrive)")
+        matcher.check()
         popc_peak = ctx.popc_peak()
         pairs = float(Q) * float(T)
         map_match = {"workload": "C4", "Q": Q, "T": T, "shards": world, "ms_per_call": mm_ms,
@@ -388,10 +334,7 @@ def main():
                                   "peak": world * popc_peak / 1e12, "unit": "TPOPC32/s",
                                   "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
                                   "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
-                     "collective": ("none" if world == 1 else
-                                    "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the owner) + 2 flag barriers over symmetric memory (no NCCL on the data path)"
-                                    if peer is not None else
-                                    "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result"),
+                     "collective": matcher.describe(),
                      "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
 
 

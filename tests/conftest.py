@@ -28,6 +28,10 @@ def load_synth():
     return _load("bshot_b200_synth", os.path.join(PKG, "synth.py"))
 
 
+def load_sharded():
+    return _load("bshot_b200_sharded", os.path.join(PKG, "sharded.py"))
+
+
 def load_oracle():
     return _load("pyoracle", os.path.join(ROOT, "oracle", "pyoracle.py"))
 
