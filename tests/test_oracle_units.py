@@ -304,3 +304,96 @@ def test_planted_duplicate_descriptors_have_distance_zero(oracle, small_cloud):
     bits = oracle.bshot(shot)
     m = oracle.match(bits[:7], bits[7:])
     assert (m["left_dist"] == 0).all()
+
+
+def _bin_centre_cloud(R, placements):
+    """keypoint at the origin (identity LRF given explicitly) + one neighbour per (sector, upper, outer) placed at
+    the CENTRE of its spatial volume: azimuth -7pi/8 + sel*pi/4, inclination pi/4 (upper) or 3pi/4 (lower) from +z,
+    distance R/4 (inner husk) or 3R/4 (outer husk)."""
+    pts = [(0.0, 0.0, 0.0)]
+    for sel, upper, outer in placements:
+        phi = -7.0 * np.pi / 8.0 + sel * np.pi / 4.0
+        theta = np.pi / 4.0 if upper else 3.0 * np.pi / 4.0
+        d = 0.75 * R if outer else 0.25 * R
+        pts.append((d * np.sin(theta) * np.cos(phi), d * np.sin(theta) * np.sin(phi), d * np.cos(theta)))
+    return np.asarray(pts, np.float32)
+
+
+def test_shot_known_answer_at_bin_centres(oracle):
+    """Hand-computed SHOT352: a neighbour that sits at the centre of its volume in all four
+    interpolated dimensions (cosine bin, radial husk, inclination, azimuth sector) puts its whole weight
+    1 + 1 + 1 + 1 = 4 into ONE bin, index (sel*4 + outer*2 + upper)*11 + step with step = 10 for a normal parallel
+    to the z axis of the frame and step = 5 for a zero normal (the reference quirk).  N such neighbours in N
+    different volumes give a normalised histogram with exactly N entries 1/sqrt(N), and B-SHOT sets exactly those
+    bits (a lone non-zero value in its group of four exceeds 0.9 * sum)."""
+    R = 3000.0
+    placements = [(0, 1, 0), (1, 1, 0), (2, 0, 0), (3, 0, 1), (4, 1, 1), (5, 0, 0), (6, 1, 1), (7, 0, 1)]
+    pts = _bin_centre_cloud(R, placements)
+    oc = oracle.Cloud(pts)
+    rf_identity = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1]], np.float32)
+    for normal, step in (((0.0, 0.0, 1.0), 10), ((0.0, 0.0, 0.0), 5), ((0.0, 0.0, -1.0), 0)):
+        normals = np.zeros((len(pts), 4), np.float32)
+        normals[:, :3] = normal
+        shot, rf, nn, total = oc.shot(pts[:1], normals, R, rf_in=rf_identity)
+        assert nn[0] == len(pts) and total == len(pts)
+        expect = np.zeros(352, np.float32)
+        for sel, upper, outer in placements:
+            expect[(sel * 4 + outer * 2 + upper) * 11 + step] = 1.0 / np.sqrt(len(placements))
+        # float32 positions are not exactly on the centres: a leak of ~1e-7 into the neighbouring bins is expected
+        assert np.abs(shot[0] - expect).max() < 2e-6, np.abs(shot[0] - expect).max()
+        bits = oracle.bshot(shot)
+        from_bits = np.unpackbits(bits.view(np.uint8), bitorder="little")[:352].astype(bool)
+        assert from_bits[expect > 0.1].all()
+        # B-SHOT is scale free per group of four: a 1e-8 leak that is alone in its group sets its bit as well
+        # (include/bshot_bits.h:171-178), so extra bits may only sit on non-zero leak bins
+        extra = from_bits & ~(expect > 0.1)
+        assert (shot[0][extra] != 0).all() and (np.abs(shot[0][extra]) < 2e-6).all()
+
+
+def test_shot_known_answer_between_two_sectors(oracle):
+    """A neighbour exactly on the border of two azimuth sectors (angular offset 0.5) splits its azimuth share half
+    and half: own bin 1 (cosine) + 1 (radial) + 1 (inclination) + 0.5, the sector on the other side of the border
+    0.5; with a second, mirrored neighbour the two 3.5 / 0.5 pairs normalise to 3.5/5 and 0.5/5."""
+    R = 3000.0
+    pts = [(0.0, 0.0, 0.0)]
+    for sign in (+1.0, -1.0):                      # borders between sectors 3|4 (phi = 0) and 7|0 (phi = pi)
+        phi = 0.0 if sign > 0 else np.pi
+        theta, d = np.pi / 4.0, 0.25 * R
+        pts.append((d * np.sin(theta) * np.cos(phi), 0.0, d * np.cos(theta)))
+    for k in range(3):                             # filler so that the neighbourhood has >= 5 points; placed at centres
+        pts.append(tuple(_bin_centre_cloud(R, [(2 * k + 1, 0, 1)])[1]))
+    pts = np.asarray(pts, np.float32)
+    oc = oracle.Cloud(pts)
+    normals = np.zeros((len(pts), 4), np.float32)
+    normals[:, 2] = 1.0
+    shot, _, nn, _ = oc.shot(pts[:1], normals, R, rf_in=np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1]], np.float32))
+    h = shot[0]
+    raw = h / h.max() * 4.0                        # undo the normalisation: the filler bins hold exactly 4
+    nz = {int(i): float(raw[i]) for i in np.nonzero(np.abs(raw) > 1e-4)[0]}
+    fillers = {(s * 4 + 2 + 0) * 11 + 10 for s in (1, 3, 5)}
+    assert fillers <= set(nz) and all(abs(nz[i] - 4.0) < 1e-4 for i in fillers)
+    split = {i: v for i, v in nz.items() if i not in fillers}
+    # y == 0: PCL's sector rule puts x > 0 into sector 3 or 4 and x < 0 into 7 or 0; either way the pair of bins that
+    # share the border hold 3.5 and 0.5
+    assert len(split) == 4
+    vals = sorted(split.values())
+    assert np.allclose(vals, [0.5, 0.5, 3.5, 3.5], atol=1e-4)
+    for (a, b) in ((3, 4), (7, 0)):
+        ia, ib = (a * 4 + 1) * 11 + 10, (b * 4 + 1) * 11 + 10
+        assert {ia, ib} <= set(split) and abs(split[ia] + split[ib] - 4.0) < 1e-4
+
+
+def test_seg_ratio_known_answer_on_a_line(oracle):
+    """Hand-computed CV seg-ratio (src/lidar_odometry.cpp:76-97) for five collinear points 100 mm apart: the end
+    points see all neighbours on one side of the plane through themselves perpendicular to (p - centroid) ->
+    1 - 0/4 = 1; the second point has one neighbour on one side and three on the other -> 1 - 1/3; the middle point
+    coincides with the centroid, every dot product is 0 -> 0/0 = NaN (the reference skips it, :121)."""
+    x = 1000.0 + 100.0 * np.arange(5, dtype=np.float32)
+    pts = np.stack([x, np.full(5, 50.0, np.float32), np.full(5, -20.0, np.float32)], 1)
+    r = oracle.Cloud(pts).seg_ratio(1000.0, 300, oracle.SR_CV)
+    assert r[0] == 1.0 and r[4] == 1.0
+    assert r[1] == np.float32(1.0) - np.float32(1.0) / np.float32(3.0) and r[3] == r[1]
+    assert np.isnan(r[2])
+    # capped neighbourhood: max_nn = 3 keeps the 3 nearest (self + the two at 100 mm, for an end point self + 100 + 200)
+    r3 = oracle.Cloud(pts).seg_ratio(1000.0, 3, oracle.SR_CV)
+    assert r3[0] == 1.0 and np.isnan(r3[2]) and r3[4] == 1.0
