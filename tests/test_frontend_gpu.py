@@ -236,3 +236,38 @@ def test_process_frame_sequence(gpu_ctx, bshot, oracle, synth):
     assert np.array_equal(f0["pairs"], oracle.mutual(m0["left_idx"], m0["right_idx"]))
     m1 = oracle.match(f1["bits"], f0["bits"])
     assert np.array_equal(f1["pairs"], oracle.mutual(m1["left_idx"], m1["right_idx"]))
+
+
+def test_known_answers_without_the_oracle(gpu_ctx):
+    """hand-computed cases (the same ones that pin the oracle in tests/test_oracle_units.py), checked on the GPU
+    directly: LRF of neighbours on the coordinate axes incl. the sign rule, CV seg-ratio of five collinear points"""
+    def cloud(xs, ys, zs):
+        pts = [(0.0, 0.0, 0.0)] + [(x, 0.0, 0.0) for x in xs] + [(0.0, y, 0.0) for y in ys] + [(0.0, 0.0, z) for z in zs]
+        return np.asarray(pts, np.float32)
+
+    neg8 = lambda d: [-d * (1.0 - 0.03 * k) for k in range(8)]
+    cases = [
+        (cloud([2000, 1800, -2000], [1500, -1500], [1000, 900, -1000]), (1, 0, 0), (0, 0, 1)),
+        (cloud([2000] + neg8(2000), [1500, -1500], [1000, -1000]), (-1, 0, 0), (0, 0, 1)),
+        (cloud([2000, -2000], [1500, -1500], [500] + neg8(500)), (1, 0, 0), (0, 0, -1)),
+    ]
+    for pts, x_axis, z_axis in cases:
+        gpu_ctx.reset()
+        gpu_ctx.set_cloud(pts)
+        gpu_ctx.set_keypoints(pts[:1])
+        rf, valid = gpu_ctx.compute_lrf(R)
+        assert valid[0] == len(pts) - 1
+        y_axis = np.cross(np.asarray(z_axis, float), np.asarray(x_axis, float))
+        assert np.allclose(rf[0], np.concatenate([x_axis, y_axis, z_axis]), atol=1e-6), (rf[0], x_axis, z_axis)
+    few = cases[0][0][:5]                                    # 4 neighbours: NaN frame
+    gpu_ctx.set_cloud(few)
+    gpu_ctx.set_keypoints(few[:1])
+    rf, valid = gpu_ctx.compute_lrf(R)
+    assert valid[0] == 4 and np.isnan(rf[0]).all()
+    # five collinear points 100 mm apart: 1, 2/3, NaN, 2/3, 1 (src/lidar_odometry.cpp:76-97,121)
+    x = 1000.0 + 100.0 * np.arange(5, dtype=np.float32)
+    line = np.stack([x, np.full(5, 50.0, np.float32), np.full(5, -20.0, np.float32)], 1)
+    gpu_ctx.set_cloud(line)
+    r = gpu_ctx.seg_ratio(1000.0, 300, 0)
+    assert r[0] == 1.0 and r[4] == 1.0 and np.isnan(r[2])
+    assert r[1] == np.float32(1.0) - np.float32(1.0) / np.float32(3.0) and r[3] == r[1]

@@ -397,3 +397,34 @@ def test_seg_ratio_known_answer_on_a_line(oracle):
     # capped neighbourhood: max_nn = 3 keeps the 3 nearest (self + the two at 100 mm, for an end point self + 100 + 200)
     r3 = oracle.Cloud(pts).seg_ratio(1000.0, 3, oracle.SR_CV)
     assert r3[0] == 1.0 and np.isnan(r3[2]) and r3[4] == 1.0
+
+
+def test_lrf_known_answer_on_the_axes(oracle):
+    """Hand-computed SHOT LRF: neighbours on the coordinate axes give a diagonal weighted
+    covariance, so x^ = +-e_x (largest eigenvalue) and z^ = +-e_z (smallest) for the distances below.  The sign rule
+    counts v.axis >= 0 as '+', so the points on the OTHER axes (projection 0) vote '+' as well: an axis flips only
+    when the neighbours on its negative side outnumber its positive side plus all zero projections.  y^ = z^ x x^."""
+    R = 3000.0
+
+    def cloud(xs, ys, zs):
+        pts = [(0.0, 0.0, 0.0)] + [(x, 0.0, 0.0) for x in xs] + [(0.0, y, 0.0) for y in ys] + [(0.0, 0.0, z) for z in zs]
+        return np.asarray(pts, np.float32)
+
+    neg8 = lambda d: [-d * (1.0 - 0.03 * k) for k in range(8)]
+    cases = [
+        # no flip: xx > yy > zz, majorities on the positive sides
+        (cloud([2000, 1800, -2000], [1500, -1500], [1000, 900, -1000]), (1, 0, 0), (0, 0, 1)),
+        # eight neighbours on -x against 1 (+x) + 4 zero projections: x^ flips, z^ does not
+        (cloud([2000] + neg8(2000), [1500, -1500], [1000, -1000]), (-1, 0, 0), (0, 0, 1)),
+        # eight neighbours on -z (close, so zz stays the smallest) against 1 (+z) + 4 zeros: z^ flips, x^ does not
+        (cloud([2000, -2000], [1500, -1500], [500] + neg8(500)), (1, 0, 0), (0, 0, -1)),
+    ]
+    for pts, x_axis, z_axis in cases:
+        rf, valid = oracle.Cloud(pts).lrf(pts[:1], R)
+        assert valid[0] == len(pts) - 1                        # the keypoint itself is not a neighbour (A.4)
+        y_axis = np.cross(np.asarray(z_axis, float), np.asarray(x_axis, float))
+        assert np.allclose(rf[0], np.concatenate([x_axis, y_axis, z_axis]), atol=1e-6), (rf[0], x_axis, z_axis)
+    # fewer than 5 neighbours: NaN frame (A.4)
+    few = cases[0][0][:5]
+    rf, valid = oracle.Cloud(few).lrf(few[:1], R)
+    assert valid[0] == 4 and np.isnan(rf[0]).all()
