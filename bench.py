@@ -15,8 +15,11 @@ the previous frame.  One step = one frame.  metric = B-SHOT descriptors/s throug
  * N > 1 : frame extraction does not shard (replicas only) -> every rank processes a replica of
            the frame stream, no data-path collective, weak scaling.  The part of the path that
            DOES shard -- frame-to-map Hamming search against a map split over the ranks, per-rank
-           top-2 candidates merged after one NCCL all-gather -- is timed in the same run and
+           top-2 candidates exchanged by stores into symmetric peer memory + flag barriers (or one
+           NCCL all-gather + all-reduce, BSHOT_EXCHANGE=nccl) -- is timed in the same run and
            reported under "map_match" (C4: Q = 10 000 queries vs T = 1 048 576 map descriptors).
+ * extra objects at N = 1: "c3" (BASELINE.json configs[2]: HDL-64E 120 k-point frame, K = 10 000, and the
+           SHOT-radius sweep with FULL normals), "exact_mode" (the same C2 frames with BSHOT_EXACT_SUMS=1).
 """
 import argparse
 import json
