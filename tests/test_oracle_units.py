@@ -428,3 +428,15 @@ def test_lrf_known_answer_on_the_axes(oracle):
     few = cases[0][0][:5]
     rf, valid = oracle.Cloud(few).lrf(few[:1], R)
     assert valid[0] == 4 and np.isnan(rf[0]).all()
+
+
+def test_radius_search_boundary_is_strict(oracle):
+    """FLANN's RadiusResultSet keeps dist < radius^2 (strict): a point exactly on the sphere is not a
+    neighbour; equal distances come out in index order; max_nn keeps the nearest hits."""
+    pts = np.array([(10, 0, 0), (3010, 0, 0), (3009, 0, 0), (10, 500, 0), (10, -500, 0), (10, 0, 500)], np.float32)
+    oc = oracle.Cloud(pts)
+    idx, sqd = oc.radius_search(pts[0], 3000.0, 0)
+    assert list(idx) == [0, 3, 4, 5, 2]                       # index 1 sits exactly at 3000 mm: excluded
+    assert list(sqd) == [0.0, 250000.0, 250000.0, 250000.0, 2999.0 ** 2]
+    idx3, _ = oc.radius_search(pts[0], 3000.0, 3)
+    assert list(idx3) == [0, 3, 4]                             # the 3 nearest; ties broken by index
