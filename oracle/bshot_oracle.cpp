@@ -1,6 +1,7 @@
 // bshot_oracle.cpp -- CPU ORACLE (test infrastructure only; see bshot_oracle.h header comment).
 //
-// PARITY UNPINNED (no reference golden vectors exist; PCL is not installable here).
+// PARITY: reference-owned arithmetic is pinned to oracle/_ref (the reference header compiled unchanged); the
+// PCL-owned arithmetic is UNPINNED (no reference golden vectors exist; PCL is not installable here) -- see bshot_oracle.h.
 // Restates, function by function:
 //   reference-owned code  : include/bshot_bits.h, src/lidar_odometry.cpp of /root/reference
 //   PCL 1.8 algorithms     : SURVEY.md Appendix A (kd-tree radius search, centroid, normal,
@@ -283,27 +284,23 @@ void eigen33_smallest(const float mat[9], float& eigenvalue, float evec[3]) {
     for (int k = 0; k < 3; ++k) evec[k] = v[k] / inv;
 }
 
-// pcl::computePointNormal + flipNormalTowardsViewpoint(0,0,0)   (include/bshot_bits.h:66-87)
-void normal_point(const orc_cloud& c, const P3& q, float radius, int max_nn, float out4[4],
-                  std::vector<DistIdx>& nn) {
-    if (finite3(q)) c.search(q, radius, max_nn, nn); else nn.clear();
-    if (nn.empty()) {  // :67-74
-        out4[0] = out4[1] = out4[2] = out4[3] = kNaN;
-        return;
-    }
-    if (nn.size() < 3) {  // PCL >= 1.8 computePointNormal guard (version-sensitive)
+// pcl::computePointNormal(cloud, indices, plane_parameters, curvature) (Appendix A.3): normal + curvature
+// of the points `idx[0..n)` of `pts`, in index order; NaN when fewer than 3 indices.  get(i) -> P3.
+template <typename Get>
+void point_normal_from(Get&& get, int n, float out4[4]) {
+    if (n < 3) {  // PCL >= 1.8 computePointNormal guard (version-sensitive)
         out4[0] = out4[1] = out4[2] = out4[3] = kNaN;
         return;
     }
     // computeMeanAndCovarianceMatrix: single pass fp32, 9 accumulators, neighbour order
     float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t j = 0; j < nn.size(); ++j) {
-        const P3& p = c.pts[nn[j].second];
+    for (int j = 0; j < n; ++j) {
+        const P3 p = get(j);
         a[0] += p.x * p.x; a[1] += p.x * p.y; a[2] += p.x * p.z;
         a[3] += p.y * p.y; a[4] += p.y * p.z; a[5] += p.z * p.z;
         a[6] += p.x; a[7] += p.y; a[8] += p.z;
     }
-    const float fn = (float)nn.size();
+    const float fn = (float)n;
     for (int k = 0; k < 9; ++k) a[k] /= fn;
     float cov[9];
     cov[0] = a[0] - a[6] * a[6];
@@ -313,15 +310,28 @@ void normal_point(const orc_cloud& c, const P3& q, float radius, int max_nn, flo
     cov[5] = a[4] - a[7] * a[8];
     cov[8] = a[5] - a[8] * a[8];
     cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-    float ev, n[3];
-    eigen33_smallest(cov, ev, n);
+    float ev, nv[3];
+    eigen33_smallest(cov, ev, nv);
     const float eig_sum = cov[0] + cov[4] + cov[8];
     out4[3] = (eig_sum != 0) ? std::fabs(ev / eig_sum) : 0.0f;
+    out4[0] = nv[0]; out4[1] = nv[1]; out4[2] = nv[2];
+}
+
+// pcl::computePointNormal + flipNormalTowardsViewpoint(0,0,0)   (include/bshot_bits.h:66-87)
+void normal_point(const orc_cloud& c, const P3& q, float radius, int max_nn, float out4[4],
+                  std::vector<DistIdx>& nn) {
+    if (finite3(q)) c.search(q, radius, max_nn, nn); else nn.clear();
+    if (nn.empty()) {  // :67-74
+        out4[0] = out4[1] = out4[2] = out4[3] = kNaN;
+        return;
+    }
+    point_normal_from([&](int j) { return c.pts[nn[j].second]; }, (int)nn.size(), out4);
+    if (nn.size() < 3) return;
     // flipNormalTowardsViewpoint(point, 0,0,0, ...)
+    float* n = out4;
     const float vx = 0.0f - q.x, vy = 0.0f - q.y, vz = 0.0f - q.z;
     const float cos_theta = (vx * n[0] + vy * n[1] + vz * n[2]);
     if (cos_theta < 0) { n[0] *= -1; n[1] *= -1; n[2] *= -1; }
-    out4[0] = n[0]; out4[1] = n[1]; out4[2] = n[2];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -648,6 +658,15 @@ void orc_normals(const orc_cloud* c, const float* q_xyz, size_t nq, float radius
             normal_point(*c, q, radius, max_nn, normal4_out + 4 * i, nn);
         }
     }
+}
+
+void orc_point_normal_indices(const float* xyz, size_t n, size_t stride_floats, const int* idx, int n_idx, float out4[4]) {
+    (void)n;
+    point_normal_from([&](int j) {
+        const float* p = xyz + (size_t)idx[j] * stride_floats;
+        const P3 r = {p[0], p[1], p[2]};
+        return r;
+    }, n_idx, out4);
 }
 
 void orc_lrf(const orc_cloud* c, const float* kp_xyz, size_t nk, float radius, float* rf9_out,

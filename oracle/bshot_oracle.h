@@ -5,17 +5,21 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
  * (b-shot-slam_b200/csrc, include/bshot_b200.h) never links, loads or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference (TingKaiChen/B-SHOT-SLAM) ships no golden vectors, known-answer
- * tests or fixtures, and its arithmetic lives in PCL (>= 1.7.2, unvendored, not installable
- * here), so the reference itself cannot be executed in this environment.  The oracle restates
- *   - the reference's own code: include/bshot_bits.h:6-20,43-94,144-278 and
- *     src/lidar_odometry.cpp:61-153,186-242 (exactly), and
- *   - the published PCL 1.8 algorithms it calls (kd-tree radius search, computeCentroid,
- *     computePointNormal/eigen33, SHOTLocalReferenceFrameEstimation, SHOTEstimation) as
- *     recorded in SURVEY.md Appendix A.
- * It is pinned only by truth tables derived from the reference source, analytic cases,
- * numpy.linalg.eigh / scipy cKDTree cross-checks and an independent numpy restatement
- * (tests/test_oracle_*.py).
+ * PARITY PIN (what is and is not anchored to the reference):
+ *   - PINNED to reference-compiled code: the reference's own header include/bshot_bits.h is compiled
+ *     UNCHANGED into oracle/_ref/libbshot_ref.so (oracle/ref_shim.cpp + oracle/pcl_stub, recipe in
+ *     oracle/Makefile).  compute_bshot_from_SHOT (:144-278), minVect (:6-20), the 48-byte
+ *     std::bitset<352> record and the matching loops built on them are checked against it live and through
+ *     the committed vectors tests/golden/ref_pin.npz (tests/test_ref_pin.py); calculate_normals (:43-94)
+ *     and calculate_SHOT (:113-135) run from the reference header too, which pins their control flow,
+ *     NaN branches and the keypoint-ordinal / persistent-buffer placement quirk.
+ *   - UNPINNED: the PCL arithmetic behind those calls.  The reference ships no golden vectors, and PCL
+ *     (>= 1.7.2, unvendored) / Eigen / FLANN are not installable here, so kd-tree radius search,
+ *     computeCentroid, computePointNormal/eigen33, SHOTLocalReferenceFrameEstimation and SHOTEstimation
+ *     are restated from the published PCL 1.8 algorithms and pinned only by
+ *     truth tables, analytic known answers, numpy.linalg.eigh / scipy cKDTree cross-checks and an
+ *     independent numpy restatement (tests/test_oracle_*.py).  src/lidar_odometry.cpp (detector, top-K)
+ *     needs Sophus/g2o/OpenCV and cannot be compiled: restated exactly from :61-153,186-242.
  */
 #ifndef BSHOT_ORACLE_H
 #define BSHOT_ORACLE_H
@@ -55,6 +59,12 @@ int orc_select_keypoints(const float* ratio, size_t n, int top_k, int tie_mode, 
 /* include/bshot_bits.h:61-88 loop body: normal (nx,ny,nz,curvature) per query point. */
 void orc_normals(const orc_cloud* c, const float* q_xyz, size_t nq, float radius, int max_nn,
                  float* normal4_out, int threads);
+
+/* pcl::computePointNormal(cloud, indices, n, curvature) alone (Appendix A.3): normal + curvature of the
+ * points idx[0..n_idx) of xyz, accumulated in index order, NOT flipped; NaN when n_idx < 3.
+ * (what the PCL stand-ins of oracle/pcl_stub call when the reference header runs, oracle/ref_shim.cpp) */
+void orc_point_normal_indices(const float* xyz, size_t n, size_t stride_floats, const int* idx, int n_idx,
+                              float out4[4]);
 
 /* PCL SHOTLocalReferenceFrameEstimation::getLocalRF (Appendix A.4). rf = [x;y;z] rows. */
 void orc_lrf(const orc_cloud* c, const float* kp_xyz, size_t nk, float radius, float* rf9_out,

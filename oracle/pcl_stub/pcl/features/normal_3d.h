@@ -1,0 +1,3 @@
+// stand-in for <pcl/features/normal_3d.h> (PCL is not installed here): everything lives in stub_core.h
+#pragma once
+#include "../stub_core.h"

@@ -1,0 +1,3 @@
+// stand-in for <pcl/point_cloud.h> (PCL is not installed here): everything lives in stub_core.h
+#pragma once
+#include "stub_core.h"

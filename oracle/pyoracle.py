@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-PARITY UNPINNED -- see the header of oracle/bshot_oracle.h.
+Parity pin: see the header of oracle/bshot_oracle.h (reference-owned arithmetic pinned to oracle/_ref,
+PCL-owned arithmetic unpinned).
 """
 import ctypes as C
 import os
@@ -196,3 +197,80 @@ def eigen33_smallest(m):
     vec = np.empty(3, np.float32)
     lib().orc_eigen33_smallest(_f(m), _f(ev), _f(vec))
     return float(ev[0]), vec
+
+
+# ---- oracle/_ref: the reference's own header compiled unchanged (oracle/ref_shim.cpp, oracle/Makefile) ---------
+_REF = None
+
+
+def ref_lib():
+    """libbshot_ref.so (include/bshot_bits.h of the reference compiled against oracle/pcl_stub), or None when it
+    has not been built (it can only be built where /root/reference exists; the built .so travels to the GPU box)."""
+    global _REF
+    if _REF is None:
+        so = os.path.join(_HERE, "_ref", "libbshot_ref.so")
+        if os.path.isdir("/root/reference/include"):
+            subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        fp, ip, up = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint64)
+        L.ref_bshot_from_shot.argtypes = [fp, C.c_size_t, up]
+        L.ref_minvect_int.restype = C.c_int
+        L.ref_minvect_int.argtypes = [ip, C.c_int, ip]
+        L.ref_feature_matching.restype = C.c_int
+        L.ref_feature_matching.argtypes = [up, C.c_size_t, up, C.c_size_t, ip, ip, ip]
+        L.ref_cb_create.restype = C.c_void_p
+        L.ref_cb_destroy.argtypes = [C.c_void_p]
+        L.ref_cb_compute_descriptors.argtypes = [C.c_void_p, fp, C.c_size_t, fp, C.c_size_t, C.c_float, up, fp, fp, fp]
+        _REF = L
+    return _REF
+
+
+def ref_bshot(shot):
+    """bshot::compute_bshot_from_SHOT of the reference (include/bshot_bits.h:144-278), compiled unchanged"""
+    shot = np.ascontiguousarray(shot, dtype=np.float32).reshape(-1, 352)
+    bits = np.empty((shot.shape[0], 6), np.uint64)
+    ref_lib().ref_bshot_from_shot(_f(shot), shot.shape[0], _u(bits))
+    return bits
+
+
+def ref_minvect(v):
+    v = np.ascontiguousarray(v, dtype=np.int32)
+    ind = C.c_int(-1)
+    m = ref_lib().ref_minvect_int(_i(v), v.shape[0], C.byref(ind))
+    return int(m), int(ind.value)
+
+
+def ref_feature_matching(q, t):
+    """left_nn / right_nn / mutual pairs: the loops of src/lidar_odometry.cpp:212-242 around the reference's minVect"""
+    q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+    t = np.ascontiguousarray(t, dtype=np.uint64).reshape(-1, 6)
+    left = np.empty(q.shape[0], np.int32)
+    right = np.empty(t.shape[0], np.int32)
+    pairs = np.empty((q.shape[0], 2), np.int32)
+    n = ref_lib().ref_feature_matching(_u(q), q.shape[0], _u(t), t.shape[0], _i(left), _i(right), _i(pairs))
+    return dict(left_idx=left, right_idx=right, pairs=pairs[:n].copy())
+
+
+class RefCb:
+    """a `bshot cb` object of the reference living across frames (persistent cloud1_normals, include/bshot_bits.h:59)"""
+
+    def __init__(self):
+        self.h = ref_lib().ref_cb_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            ref_lib().ref_cb_destroy(self.h)
+            self.h = None
+
+    def compute_descriptors(self, xyz, kp, radius=3000.0):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(-1, 3)
+        k, n = kp.shape[0], xyz.shape[0]
+        bits = np.empty((k, 6), np.uint64)
+        shot = np.empty((k, 352), np.float32)
+        rf = np.empty((k, 9), np.float32)
+        normals = np.empty((n, 4), np.float32)
+        ref_lib().ref_cb_compute_descriptors(self.h, _f(xyz), n, _f(kp), k, radius, _u(bits), _f(shot), _f(rf), _f(normals))
+        return dict(bits=bits, shot=shot, rf=rf, normals=normals)
