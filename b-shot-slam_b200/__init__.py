@@ -31,7 +31,7 @@ EXPORTS = [
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
-    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak",
+    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters",
 ]
 
 
@@ -109,6 +109,7 @@ def lib():
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
         L.bshot_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        L.bshot_debug_counters.argtypes = [vp, C.POINTER(C.c_ulonglong * 8)]
         _LIB = L
     return _LIB
 
@@ -335,6 +336,13 @@ class Context:
         _chk(lib().bshot_frame_counters(self.h, C.byref(a)))
         return dict(detector_neighbours=int(a[0]), normals_neighbours=int(a[1]), shot_neighbours=int(a[2]),
                     keypoints=int(a[3]))
+
+    def debug_counters(self):
+        a = (C.c_ulonglong * 8)()
+        _chk(lib().bshot_debug_counters(self.h, C.byref(a)))
+        names = ["detector_neighbours", "normals_neighbours", "tiles_staged", "tile_points_swept", "query_attempts",
+                 "unresolved_attempts", "fallback_queries", "blocks"]
+        return {k: int(a[i]) for i, k in enumerate(names)}
 
     # sharded map
     def map_reset(self):

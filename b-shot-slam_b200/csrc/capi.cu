@@ -117,7 +117,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     }
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("BSHOT_EXACT_SUMS")) c->exact_sums = (atoi(e) != 0);
+    if (const char* e = getenv("BSHOT_WARP_PATH")) c->force_warp_path = (atoi(e) != 0);
     if (const char* e = getenv("BSHOT_YZ_MUL")) {  // tuning knob: row thickness relative to the cell length
         const float v = (float)atof(e);
         if (v >= 1.0f && v <= 8.0f) c->yz_mul = v;
@@ -141,14 +141,20 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_block_sums, 4096));
     A(dmalloc(&c->d_grid, 1));
     A(dmalloc(&c->d_bbox, 8));
+    A(dmalloc(&c->d_lvl, (size_t)kMaxCells + 16));
+    A(dmalloc(&c->d_sorted_pos, N));
+    A(dmalloc(&c->d_kp_flag, N));
+    A(dmalloc(&c->d_blocks, N));
+    A(dmalloc(&c->d_blk_area, N));
+    A(dmalloc(&c->d_nblocks, 8));
+    A(dmalloc(&c->d_ovf, N));
+    A(dmalloc(&c->d_fb_list, N));
     A(dmalloc(&c->d_ratio, N));
     A(dmalloc(&c->d_keys, N));
     A(dmalloc(&c->d_kp_idx, K));
     A(dmalloc(&c->d_kp_ratio, K));
     A(dmalloc(&c->d_kp, K));
     A(dmalloc(&c->d_kp_count, 4));
-    A(dmalloc(&c->d_sel_rho2, N));
-    A(dmalloc(&c->d_sel_thr, N));
     A(dmalloc(&c->d_tk_hist, 4096));
     A(dmalloc(&c->d_tk_state, 16));
     A(dmalloc(&c->d_tk_sure, K));
@@ -175,7 +181,8 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_pairs, K * 3));
     A(dmalloc(&c->d_pair_count, 4));
     A(dmalloc(&c->d_counters, 8));
-    if (r == BSHOT_OK && cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(int)) != cudaSuccess) {
+    if (r == BSHOT_OK && (cudaMallocHost((void**)&c->h_scratch, 64 * sizeof(int)) != cudaSuccess ||
+                          cudaMallocHost((void**)&c->h_pairs, 3 * K * sizeof(int)) != cudaSuccess)) {
         set_error("cudaMallocHost failed");
         r = BSHOT_E_CUDA;
     }
@@ -206,13 +213,14 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
-                    c->d_grid, c->d_bbox, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count, c->d_sel_rho2, c->d_sel_thr,
+                    c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    if (c->h_pairs) cudaFreeHost(c->h_pairs);
     for (int i = 0; i < 8; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -446,8 +454,8 @@ int bshot_match_mutual(bshot_ctx* ctx, const uint64_t* q, size_t nq, const uint6
     const int n = ctx->h_scratch[0];
     if (count_out) *count_out = n;
     if (n > 0 && (pairs_out || dist_out)) {
-        std::vector<int> tmp((size_t)n * 3);
-        BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_pairs, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        int* tmp = ctx->h_pairs;  // pinned, max_keypoints x 3
+        BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp, ctx->d_pairs, sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
         BSHOT_TRY(sync(ctx));
         for (int i = 0; i < n; ++i) {
             if (pairs_out) { pairs_out[2 * i] = tmp[3 * i]; pairs_out[2 * i + 1] = tmp[3 * i + 1]; }
@@ -478,19 +486,18 @@ int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits
                       int* n_pairs_out) {
     CHECK_CTX(ctx);
     if (top_k <= 0 || (size_t)top_k > ctx->max_kp) { set_error("bshot_fetch_frame: bad top_k"); return BSHOT_E_INVALID; }
-    const size_t kmax = (size_t)top_k;
+    if (ctx->last_top_k == 0) { set_error("bshot_fetch_frame: no frame has been processed"); return BSHOT_E_STATE; }
+    if ((size_t)top_k < ctx->last_top_k) { set_error("bshot_fetch_frame: top_k %d smaller than the %zu the frame was processed with", top_k, ctx->last_top_k); return BSHOT_E_INVALID; }
+    const size_t kmax = ctx->last_top_k;
     // counts + payload in one stream-ordered batch, a single synchronisation
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[1], ctx->d_pair_count, sizeof(int)));
     BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * kmax));
     BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * kmax));
-    std::vector<int> tmp;
-    if (pairs_out) {
-        tmp.resize(kmax * 3);
-        BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_pairs, sizeof(int) * 3 * kmax, cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    int* tmp = ctx->h_pairs;  // pinned, max_keypoints x 3: no per-frame host allocation, a true async copy
+    if (pairs_out) BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp, ctx->d_pairs, sizeof(int) * 3 * kmax, cudaMemcpyDeviceToHost, ctx->stream));
     BSHOT_TRY(sync(ctx));
-    const int k = ctx->h_scratch[0], np = ctx->h_scratch[1];
+    const int k = std::min(ctx->h_scratch[0], (int)kmax), np = std::min(ctx->h_scratch[1], k);
     ctx->n_kp = (size_t)k;
     if (n_kp_out) *n_kp_out = k;
     if (n_pairs_out) *n_pairs_out = np;
@@ -539,6 +546,13 @@ int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]) {
     BSHOT_TRY(sync(ctx));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = (unsigned long long)ctx->h_scratch[0];
     return BSHOT_OK;
+}
+
+int bshot_debug_counters(bshot_ctx* ctx, unsigned long long out[8]) {
+    CHECK_CTX(ctx);
+    if (!out) { set_error("bshot_debug_counters: null output"); return BSHOT_E_INVALID; }
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(out, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync(ctx);
 }
 
 // ---- sharded map --------------------------------------------------------------------------------

@@ -41,13 +41,23 @@ struct GridParams {
 };
 
 constexpr unsigned int kMaxCells = 1u << 23;       // cell_start capacity (32 MB of u32)
+
+// point counts of the 2^l-cell cubes (l = 1, 2, 3), three dense tables back to back (grid.cu, tile.cuh)
+__host__ __device__ __forceinline__ unsigned lvl_dim(int n, int l) { return (unsigned)((n + (1 << l) - 1) >> l); }
+__host__ __device__ __forceinline__ unsigned lvl_size(const GridParams& g, int l) { return lvl_dim(g.nx, l) * lvl_dim(g.ny, l) * lvl_dim(g.nz, l); }
+__host__ __device__ __forceinline__ unsigned lvl_total(const GridParams& g) { return lvl_size(g, 1) + lvl_size(g, 2) + lvl_size(g, 3); }
+__host__ __device__ __forceinline__ unsigned lvl_index(const GridParams& g, int l, int ix, int iy, int iz) {
+    unsigned off = 0;
+    for (int k = 1; k < l; ++k) off += lvl_size(g, k);
+    return off + ((unsigned)(iz >> l) * lvl_dim(g.ny, l) + (unsigned)(iy >> l)) * lvl_dim(g.nx, l) + (unsigned)(ix >> l);
+}
 constexpr int kDescWords = 12;                      // 48-byte record as u32 words (11 used)
 constexpr float kDefaultCell = 375.0f;              // R/8 for the reference radius 3000 mm
 
 struct Ctx {
     int device = 0;
     int sm_count = 148;
-    bool exact_sums = false;  // BSHOT_EXACT_SUMS=1: replay the reference's fp32 running sums in neighbour order (knn.cuh)
+    bool force_warp_path = false;  // BSHOT_WARP_PATH=1: skip the block-tiled kernels (tile.cuh), warp-per-query kernels everywhere (tests)
     float yz_mul = 1.0f;  // cell_yz / cell (tuning knob BSHOT_YZ_MUL; 2 helps SHOT by ~3 %, costs the detector ~6 %)
     cudaStream_t stream = nullptr;
     unsigned long long launches = 0;
@@ -65,6 +75,14 @@ struct Ctx {
     unsigned int* d_block_sums = nullptr;
     GridParams* d_grid = nullptr;
     float* d_bbox = nullptr;           // 6 floats as ordered ints
+    unsigned* d_lvl = nullptr;         // kMaxCells + 16: point counts of the 2^3 / 4^3 / 8^3-cell cubes (bit 31 = block emitted)
+    unsigned* d_sorted_pos = nullptr;  // N: original index -> position in d_sorted (0xFFFFFFFF = not binned)
+    int* d_kp_flag = nullptr;          // N: per sorted position, keypoint ordinal or -1 (reset by the grid build)
+    uint4* d_blocks = nullptr;         // N: query blocks {ix0, iy0, iz0, cells per edge | slice << 4} (tile.cuh)
+    float* d_blk_area = nullptr;       // N: surface area per point around the block (radius prediction)
+    unsigned* d_nblocks = nullptr;     // [0] heavy blocks, [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [5] light blocks
+    uint2* d_ovf = nullptr;            // N: queries whose block tile overflowed {position in d_sorted, radius bits} (tilek.cu)
+    unsigned* d_fb_list = nullptr;     // N: sorted positions of the queries the tiled kernels hand to the fallback
 
     // detector
     float* d_ratio = nullptr;                // N
@@ -73,11 +91,12 @@ struct Ctx {
     float* d_kp_ratio = nullptr;             // K
     float4* d_kp = nullptr;                  // K keypoint positions (w = index bits)
     int* d_kp_count = nullptr;               // device-side keypoint count
-    float* d_sel_rho2 = nullptr;             // N: detector neighbourhood of every point = {sqd < rho2, key <= thr} ...
-    unsigned long long* d_sel_thr = nullptr; // N: ... kept so that the keypoint normals re-collect it in one sweep
-    bool sel_valid = false;                  // d_sel_* describe the current cloud for (sel_radius, sel_max_nn)
+    bool sel_valid = false;                  // the detector ran on the current cloud with (sel_radius, sel_max_nn)
     float sel_radius = 0.0f;
     int sel_max_nn = 0;
+    bool fused_normals = false;              // d_normals already holds the FULL-mode normals for (fused_radius, fused_max_nn)
+    float fused_radius = 0.0f;
+    int fused_max_nn = 0;
     bool kp_from_detector = false;           // d_kp[i].w is the surface index of keypoint i
     unsigned* d_tk_hist = nullptr;           // top-K: 4096-bin ratio histogram (kept zeroed between frames)
     unsigned* d_tk_state = nullptr;          // top-K: 16 words of device-side state
@@ -99,8 +118,9 @@ struct Ctx {
     unsigned long long* d_sum_nn = nullptr;
     uint64_t* d_bits = nullptr;         // K x 6
     uint64_t* d_prev_bits = nullptr;    // K x 6 (previous frame)
-    size_t n_prev = 0;
+    size_t n_prev = 0;                  // host-side upper bound (top_k of the previous frame); d_prev_count is the real count
     int* d_prev_count = nullptr;
+    size_t last_top_k = 0;              // top_k of the last frame_run (what bshot_fetch_frame may copy out)
 
     // matching
     uint64_t* d_q = nullptr;            // max_kp x 6
@@ -120,6 +140,7 @@ struct Ctx {
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints
+    int* h_pairs = nullptr;             // 3 x max_kp ints: (query, match, distance) staging for the D2H copy
 
     // instrumentation
     unsigned long long* d_counters = nullptr;  // 8 work counters (see bshot_frame_counters)

@@ -1,9 +1,10 @@
 // detect.cu -- seg-ratio ("SR") keypoint detector and top-K selection.
 //
 // Replaces the per-point loop of LidarOdometry::extractKeypoints (src/lidar_odometry.cpp:61-126)
-// and the sort / keep-last-K that follows (:131-153).  One warp per point (taken in voxel order so
-// neighbouring warps share cache lines): nearest-<=max_nn-inside-R selection (knn.cuh), centroid,
-// then the CV / CVS / CVSN score.  Top-K is a multi-CTA histogram select over 64-bit keys
+// and the sort / keep-last-K that follows (:131-153).  The scores come from the block-tiled kernel (tilek.cu,
+// tile.cuh); the warp-per-point kernel below (nearest-<=max_nn-inside-R selection of knn.cuh, centroid, CV / CVS /
+// CVSN score) is its fallback for the queries whose tile does not fit and for max_nn beyond the tiled path.  Both
+// replay the reference's fp32 running sums in neighbour order.  Top-K is a multi-CTA histogram select over 64-bit keys
 // (ratio bits << 32 | ~index) followed by a rank-by-counting scatter, so keypoints come out
 // in ascending ratio order like the reference's `SegRatio.end()-600 .. end()` slice, with a
 // deterministic tie-break (lower point index wins) where std::sort's is unspecified.
@@ -26,8 +27,7 @@ template <int SR>
 __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsigned* __restrict__ cell_start,
                                                 const float4* __restrict__ sorted, const float4* __restrict__ pts,
                                                 const float4& q, float radius, int max_nn, KnnWarpSmem& sm,
-                                                unsigned long long* skeys, unsigned lane, float& seg, int& count,
-                                                float& sel_rho2, unsigned long long& sel_thr) {
+                                                unsigned long long* skeys, unsigned lane, float& seg, int& count) {
     const float nanf_ = __int_as_float(0x7FC00000);
     // centroid (pcl::computeCentroid, :76): sum in fp64, rounded once
     double sx = 0, sy = 0, sz = 0;
@@ -88,43 +88,34 @@ __device__ __forceinline__ void seg_ratio_point(const GridParams& g, const unsig
         seg = fabsf((float)sum) / fn;
     }
     count = res.count;
-    sel_rho2 = res.rho2;
-    sel_thr = res.thr;
 }
 
 // SR = score type (compile time: the CV kernel carries no CVS / CVSN code).  One warp per binned point, taken
-// in voxel order so that neighbouring warps share cache lines.
-template <int SR, bool EXACT>
-__global__ void __launch_bounds__(DT_THREADS, EXACT ? 4 : BSHOT_DT_MINBLOCKS)
+// in voxel order -- or, with `list`, per listed position of the cell-sorted array (tiled-path fallback).
+template <int SR>
+__global__ void __launch_bounds__(DT_THREADS, 4)
 seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start,
                  const float4* __restrict__ sorted, const float4* __restrict__ pts, unsigned n_total, float radius, int max_nn,
                  float* __restrict__ ratio, unsigned long long* __restrict__ keys,
-                 unsigned long long* __restrict__ counters, float* __restrict__ sel_rho2,
-                 unsigned long long* __restrict__ sel_thr) {
-    using Smem = typename std::conditional<EXACT, KnnExactSmem, KnnWarpSmem>::type;
-    __shared__ Smem smem[DT_WARPS];
+                 unsigned long long* __restrict__ counters, const unsigned* __restrict__ list, const unsigned* __restrict__ list_n) {
+    __shared__ KnnExactSmem smem[DT_WARPS];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const GridParams g = *gp;
-    KnnWarpSmem& sm = *reinterpret_cast<KnnWarpSmem*>(&smem[wid]);  // KnnExactSmem starts with its KnnWarpSmem
-    unsigned long long* skeys = nullptr;
-    if constexpr (EXACT) skeys = smem[wid].skeys;
-    const unsigned n_items = min(__ldg(cell_start + g.ncells), n_total);
+    KnnWarpSmem& sm = smem[wid].k;
+    unsigned long long* skeys = smem[wid].skeys;
+    const unsigned n_items = list ? *list_n : min(__ldg(cell_start + g.ncells), n_total);
     const float nanf_ = __int_as_float(0x7FC00000);
     for (unsigned j = blockIdx.x * DT_WARPS + wid; j < n_items; j += gridDim.x * DT_WARPS) {
-        const float4 q = __ldg(sorted + j);
+        const float4 q = __ldg(sorted + (list ? list[j] : j));
         const unsigned qi = __float_as_uint(q.w);
         if (q.x == 0.0f && q.y == 0.0f && q.z == 0.0f) {  // src/lidar_odometry.cpp:63
             if (lane == 0) { ratio[qi] = nanf_; keys[qi] = 0ull; }
             continue;
         }
-        float seg, rho2;
+        float seg;
         int count;
-        unsigned long long thr;
-        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, skeys, lane, seg, count, rho2, thr);
+        seg_ratio_point<SR>(g, cell_start, sorted, pts, q, radius, max_nn, sm, skeys, lane, seg, count);
         if (lane == 0) {
-            // the neighbourhood (sphere + threshold key) is kept: normals of the keypoints re-collect it in one sweep
-            sel_rho2[qi] = rho2;
-            sel_thr[qi] = thr;
             atomicAdd(&counters[0], (unsigned long long)count);
             ratio[qi] = seg;
             keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
@@ -132,10 +123,13 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
     }
 }
 
-__global__ void mark_unbinned_kernel(const unsigned* __restrict__ cell_of, unsigned n, float* __restrict__ ratio,
-                                     unsigned long long* __restrict__ keys) {
+// points without a score: not binned (non-finite) or at the origin (src/lidar_odometry.cpp:63)
+__global__ void mark_unscored_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ cell_of, unsigned n,
+                                     float* __restrict__ ratio, unsigned long long* __restrict__ keys) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && cell_of[i] == 0xFFFFFFFFu) { ratio[i] = __int_as_float(0x7FC00000); keys[i] = 0ull; }
+    if (i >= n) return;
+    const float4 p = pts[i];
+    if (cell_of[i] == 0xFFFFFFFFu || (p.x == 0.0f && p.y == 0.0f && p.z == 0.0f)) { ratio[i] = __int_as_float(0x7FC00000); keys[i] = 0ull; }
 }
 
 // ---- top-K (a3): multi-CTA histogram select + rank scatter ------------------------------------------
@@ -276,8 +270,8 @@ tk_compact_kernel(const unsigned long long* __restrict__ keys, unsigned n, unsig
 
 __global__ void __launch_bounds__(TK_THREADS)
 tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __restrict__ sure,
-               const unsigned long long* __restrict__ tie, const float4* __restrict__ pts, int* __restrict__ kp_idx,
-               float* __restrict__ kp_ratio, float4* __restrict__ kp) {
+               const unsigned long long* __restrict__ tie, const float4* __restrict__ pts, const unsigned* __restrict__ sorted_pos,
+               int* __restrict__ kp_flag, int* __restrict__ kp_idx, float* __restrict__ kp_ratio, float4* __restrict__ kp) {
     __shared__ unsigned long long s_keys[TK_TILE];
     __shared__ unsigned s_cnt[8][32];
     const unsigned tid = threadIdx.x, slot = tid & 31, part = tid >> 5;  // 32 items per CTA, every warp counts one eighth of a tile
@@ -317,39 +311,53 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
                 float4 p = pts[idx];
                 p.w = __uint_as_float(idx);
                 kp[pos] = p;
+                kp_flag[sorted_pos[idx]] = (int)pos;  // keypoint ordinal per cell-sorted position (tiled normals, tilek.cu)
             }
         }
         __syncthreads();
     }
 }
 
-int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type) {
+static int seg_ratio_warp_launch(Ctx* c, float radius, int max_nn, int sr_type, unsigned ctas, const unsigned* list, const unsigned* list_n) {
     const unsigned n = (unsigned)c->n_points;
-    if (n == 0) return BSHOT_OK;
-    if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
-    if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
-    mark_unbinned_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_cell_of, n, c->d_ratio, c->d_keys);
-    const unsigned ctas = (n + DT_WARPS - 1) / DT_WARPS;
-#define BSHOT_LAUNCH_SEG(SR)                                                                                              \
-    do {                                                                                                                  \
-        if (c->exact_sums)                                                                                                \
-            seg_ratio_kernel<SR, true><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, \
-                                                                           max_nn, c->d_ratio, c->d_keys, c->d_counters,  \
-                                                                           c->d_sel_rho2, c->d_sel_thr);                  \
-        else                                                                                                              \
-            seg_ratio_kernel<SR, false><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, \
-                                                                            max_nn, c->d_ratio, c->d_keys, c->d_counters, \
-                                                                            c->d_sel_rho2, c->d_sel_thr);                 \
-    } while (0)
+#define BSHOT_LAUNCH_SEG(SR)                                                                                                          \
+    seg_ratio_kernel<SR><<<ctas, DT_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_pts, n, radius, max_nn, c->d_ratio, \
+                                                             c->d_keys, c->d_counters, list, list_n)
     if (sr_type == BSHOT_SR_CV) BSHOT_LAUNCH_SEG(BSHOT_SR_CV);
     else if (sr_type == BSHOT_SR_CVS) BSHOT_LAUNCH_SEG(BSHOT_SR_CVS);
     else BSHOT_LAUNCH_SEG(BSHOT_SR_CVSN);
 #undef BSHOT_LAUNCH_SEG
-    count_launch(c, 2);
+    count_launch(c);
+    return check_launch("seg_ratio_kernel");
+}
+
+// fuse_normals: also compute the FULL-mode normal of every point from the same neighbourhoods (same radius / max_nn)
+int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_normals) {
+    const unsigned n = (unsigned)c->n_points;
+    c->fused_normals = false;
+    if (n == 0) return BSHOT_OK;
+    if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
+    if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
+    mark_unscored_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_pts, c->d_cell_of, n, c->d_ratio, c->d_keys);
+    count_launch(c);
+    if (tile_path_ok(c, max_nn)) {
+        fuse_normals = fuse_normals && !c->force_warp_path;
+        BSHOT_TRY(tile_neighbourhoods(c, sr_type, true, fuse_normals, radius, max_nn, nullptr, c->d_normals));
+        // queries whose tile did not fit (device-side list, usually empty)
+        BSHOT_TRY(seg_ratio_warp_launch(c, radius, max_nn, sr_type, (unsigned)c->sm_count * 4u, c->d_fb_list, c->d_nblocks + 1));
+        if (fuse_normals) {
+            BSHOT_TRY(normals_fallback_list(c, radius, max_nn, nullptr, c->d_normals));
+            c->fused_normals = true;
+            c->fused_radius = radius;
+            c->fused_max_nn = max_nn;
+        }
+    } else {
+        BSHOT_TRY(seg_ratio_warp_launch(c, radius, max_nn, sr_type, (n + DT_WARPS - 1) / DT_WARPS, nullptr, nullptr));
+    }
     c->sel_valid = true;
     c->sel_radius = radius;
     c->sel_max_nn = max_nn;
-    return check_launch("seg_ratio kernels");
+    return BSHOT_OK;
 }
 
 #ifdef BSHOT_KNN_STATS
@@ -365,11 +373,13 @@ void knn_stats_dump() {
 int detect_topk(Ctx* c, int top_k) {
     const unsigned n = (unsigned)c->n_points;
     if (top_k < 0 || (size_t)top_k > c->max_kp) { set_error("top_k %d exceeds max_keypoints %zu", top_k, c->max_kp); return BSHOT_E_CAPACITY; }
+    // keypoint ordinal per cell-sorted position, read by the tiled normals (REFERENCE mode): -1 = not a keypoint
+    if (n) BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_kp_flag, 0xFF, sizeof(int) * n, c->stream));
     const unsigned hist_ctas = std::max(1u, std::min((n + TK_THREADS * 16 - 1) / (TK_THREADS * 16), (unsigned)c->sm_count));
     tk_hist_kernel<<<hist_ctas, TK_THREADS, 0, c->stream>>>(c->d_keys, n, top_k, c->d_tk_hist, c->d_tk_state, c->d_kp_count);
     if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, (unsigned)c->max_kp);
-    tk_rank_kernel<<<(unsigned)c->sm_count * 4u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_kp_idx,
-                                                                             c->d_kp_ratio, c->d_kp);
+    tk_rank_kernel<<<(unsigned)c->sm_count * 4u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_sorted_pos,
+                                                                             c->d_kp_flag, c->d_kp_idx, c->d_kp_ratio, c->d_kp);
     count_launch(c, n ? 3 : 2);
 #ifdef BSHOT_KNN_STATS
     cudaStreamSynchronize(c->stream);

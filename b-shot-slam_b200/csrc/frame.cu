@@ -21,7 +21,9 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
     mark(0);
     BSHOT_TRY(grid_build(c, d_raw, n, stride_floats));
     mark(1);
-    BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type));
+    // FULL-mode normals use the detector's own neighbourhoods when the search parameters agree: one pass for both
+    const bool fuse = p->normals_mode == BSHOT_NORMALS_FULL && p->normal_radius == p->kp_radius && p->normal_max_nn == p->kp_max_nn;
+    BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type, fuse));
     mark(2);
     BSHOT_TRY(detect_topk(c, p->top_k));
     mark(3);
@@ -31,19 +33,24 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
     mark(5);
     // featureMatching: the initial frame is matched against itself (src/lidar_odometry.cpp:187-194),
     // later frames against the previous frame's descriptors.  Host-side counts are upper bounds
-    // (top_k); kernels read the device-side counts.
+    // (top_k); the kernels trim queries AND targets by the device-side keypoint counts, so a frame that
+    // yields fewer than top_k keypoints (the reference's `< 600` branch, :144-151) never matches stale records.
     const size_t k = (size_t)p->top_k;
     const bool initial = (c->n_prev == 0);
     const uint64_t* tgt = initial ? c->d_bits : c->d_prev_bits;
     const size_t nt = initial ? k : c->n_prev;
-    BSHOT_TRY(hamming_match_rq(c, c->d_bits, k, tgt, nt, 0, c->d_cand));
-    BSHOT_TRY(hamming_mutual_pairs(c, c->d_cand, k, c->d_pairs, c->d_pair_count));
+    const unsigned* d_nq = reinterpret_cast<const unsigned*>(c->d_kp_count);
+    const unsigned* d_nt = reinterpret_cast<const unsigned*>(initial ? c->d_kp_count : c->d_prev_count);
+    if (nt > 4 * k) { set_error("frame_run: previous frame holds %zu descriptors, more than 4 x top_k = %zu", nt, 4 * k); return BSHOT_E_INVALID; }
+    BSHOT_TRY(hamming_match_rq(c, c->d_bits, k, tgt, nt, 0, c->d_cand, d_nq, d_nt));
+    BSHOT_TRY(hamming_mutual_pairs(c, c->d_cand, k, c->d_pairs, c->d_pair_count, d_nq));
     copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp_count, (unsigned)k,
                                                                             c->d_prev_bits, c->d_prev_count);
     count_launch(c);
     mark(6);
     c->ev_valid = c->timing;
     c->n_prev = k;
+    c->last_top_k = k;
     return check_launch("copy_prev_kernel");
 }
 

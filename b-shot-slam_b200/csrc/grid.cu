@@ -7,9 +7,12 @@
 // the cells of one (iy,iz) row that a radius query needs are ONE contiguous range of the
 // cell-sorted point array (float4, w = original index) -> coalesced float4 row-segment gathers.
 // Everything is sized on the device (no host round trip): bbox reduce -> grid params -> count ->
-// 3-kernel exclusive scan -> scatter.
+// 3-kernel exclusive scan -> scatter.  The count pass also fills point counts of the 2^3 / 4^3 / 8^3-cell cubes
+// and the scatter pass cuts the grid into the query BLOCKS of the tiled neighbourhood kernels (tile.cuh): the
+// coarsest cube around a point that holds at most TL_QCAP points (denser single cells are sliced).
 #include "common.cuh"
 #include "nbr.cuh"
+#include "tile.cuh"
 
 namespace bshot {
 
@@ -104,27 +107,51 @@ __global__ void grid_params_kernel(const float* __restrict__ bbox, unsigned n, f
     *g = p;
 }
 
-__global__ void zero_cells_kernel(const GridParams* __restrict__ g, unsigned* __restrict__ cursor) {
+__global__ void zero_cells_kernel(const GridParams* __restrict__ g, unsigned* __restrict__ cursor, unsigned* __restrict__ lvl,
+                                  unsigned* __restrict__ nblocks) {
     const unsigned n = g->ncells;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cursor[i] = 0;
+    const unsigned nl = lvl_total(*g);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) lvl[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { nblocks[0] = 0; nblocks[5] = 0; }
+}
+
+// one atomicAdd per RUN of equal keys inside a warp: lidar points arrive in firing order, neighbouring lanes mostly
+// fall into the same cell / cube, and thousands of points share one 8^3-cell cube (a hot address otherwise)
+__device__ __forceinline__ void run_add(unsigned* __restrict__ table, unsigned key, bool valid, unsigned lane) {
+    const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = (lane == 0) || (key != prev);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (head && valid) {
+        const unsigned next = heads & ~((2u << lane) - 1u);  // heads above this lane (lane 31: 2u << 31 == 0 -> mask 0xFFFFFFFF -> none)
+        const unsigned end = (lane == 31 || next == 0u) ? 32u : (unsigned)(__ffs(next) - 1);
+        atomicAdd(&table[key], end - lane);
+    }
 }
 
 __global__ void __launch_bounds__(GB_THREADS)
 count_kernel(const float4* __restrict__ pts, unsigned n, const GridParams* __restrict__ gp,
-             unsigned* __restrict__ cell_of, unsigned* __restrict__ cursor) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+             unsigned* __restrict__ cell_of, unsigned* __restrict__ cursor, unsigned* __restrict__ lvl) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const GridParams g = *gp;
-    const float4 p = pts[i];
-    unsigned cid = 0xFFFFFFFFu;
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) p = pts[i];
+    const bool valid = i < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    unsigned cid = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+    if (valid) {
         const int ix = min(max(cell_coord(p.x, g.ox, g.inv_cell), 0), g.nx - 1);
         const int iy = min(max(cell_coord(p.y, g.oy, g.inv_cell_yz), 0), g.ny - 1);
         const int iz = min(max(cell_coord(p.z, g.oz, g.inv_cell_yz), 0), g.nz - 1);
         cid = ((unsigned)iz * g.ny + iy) * g.nx + ix;
-        atomicAdd(&cursor[cid], 1u);
+        k1 = lvl_index(g, 1, ix, iy, iz);
+        k2 = lvl_index(g, 2, ix, iy, iz);
+        k3 = lvl_index(g, 3, ix, iy, iz);
     }
-    cell_of[i] = cid;
+    run_add(cursor, cid, valid, lane);
+    run_add(lvl, k1, valid, lane);
+    run_add(lvl, k2, valid, lane);
+    run_add(lvl, k3, valid, lane);
+    if (i < n) cell_of[i] = cid;
 }
 
 // exclusive scan of cursor[0..ncells) -> cell_start[0..ncells], three kernels
@@ -229,17 +256,54 @@ scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ curs
     }
 }
 
+// Scatter into cell order + block emission.  Leaf level of a point = coarsest cube (8^3, 4^3, 2^3 cells, 1 cell) around
+// it with at most TL_QCAP points; all points of a cube take the same decision, one of them (claim bit 31 of the
+// cube's counter; the first point of a single cell) emits the block(s).  blk_area = surface area per point (mm^2) seen
+// one level up, from which the kernels predict the radius that holds max_nn neighbours.
 __global__ void __launch_bounds__(GB_THREADS)
-scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __restrict__ cell_of,
-               unsigned* __restrict__ cursor, float4* __restrict__ sorted) {
+scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __restrict__ cell_of, const GridParams* __restrict__ gp,
+               const unsigned* __restrict__ cell_start, unsigned* __restrict__ cursor, float4* __restrict__ sorted,
+               unsigned* __restrict__ sorted_pos, unsigned* __restrict__ lvl, uint4* __restrict__ blocks,
+               float* __restrict__ blk_area, unsigned* __restrict__ nblocks, unsigned block_cap) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned cid = cell_of[i];
-    if (cid == 0xFFFFFFFFu) return;
+    if (cid == 0xFFFFFFFFu) { sorted_pos[i] = 0xFFFFFFFFu; return; }
     const unsigned pos = atomicAdd(&cursor[cid], 1u);
     float4 p = pts[i];
     p.w = __uint_as_float(i);
     sorted[pos] = p;
+    sorted_pos[i] = pos;
+    const GridParams g = *gp;
+    const int ix = (int)(cid % (unsigned)g.nx), iy = (int)((cid / (unsigned)g.nx) % (unsigned)g.ny), iz = (int)(cid / ((unsigned)g.nx * (unsigned)g.ny));
+    const unsigned c0 = __ldg(cell_start + cid + 1) - __ldg(cell_start + cid);
+    unsigned cnt[4];
+    cnt[0] = c0;
+#pragma unroll
+    for (int l = 1; l <= 3; ++l) cnt[l] = lvl[lvl_index(g, l, ix, iy, iz)] & 0x7FFFFFFFu;
+    int leaf = 0;
+#pragma unroll
+    for (int l = 1; l <= 3; ++l)
+        if (cnt[l] <= (unsigned)TL_QCAP) leaf = l;
+    bool emit;
+    if (leaf == 0) emit = (pos == __ldg(cell_start + cid));
+    else emit = ((atomicOr(&lvl[lvl_index(g, leaf, ix, iy, iz)], 0x80000000u) >> 31) == 0u);
+    if (!emit) return;
+    const float side = fmaxf(g.cell, g.cell_yz);
+    float area;
+    if (leaf == 3) area = (8.0f * side) * (8.0f * side) / (float)max(cnt[3], 1u);
+    else if (leaf == 0 && c0 > (unsigned)TL_QCAP) area = side * side / (float)c0;
+    else { const float s2 = side * (float)(2 << leaf); area = s2 * s2 / (float)cnt[leaf + 1]; }
+    const unsigned nb = (leaf == 0) ? (c0 + TL_QCAP - 1) / TL_QCAP : 1u;
+    const int L = 1 << leaf;
+    // blocks with many queries are listed from the front, light ones from the back: the kernels walk the list front
+    // to back, so the expensive blocks start first (longest-processing-time-first keeps the tail short)
+    for (unsigned sidx = 0; sidx < nb; ++sidx) {
+        const unsigned weight = (leaf == 0) ? min(c0 - sidx * TL_QCAP, (unsigned)TL_QCAP) : cnt[leaf];
+        const unsigned slot = (weight >= (unsigned)(TL_QCAP / 2)) ? atomicAdd(nblocks, 1u) : block_cap - 1u - atomicAdd(nblocks + 5, 1u);
+        blocks[slot] = make_uint4((unsigned)(ix & ~(L - 1)), (unsigned)(iy & ~(L - 1)), (unsigned)(iz & ~(L - 1)), (unsigned)L | (sidx << 4));
+        blk_area[slot] = area;
+    }
 }
 
 int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
@@ -248,12 +312,13 @@ int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
     bbox_init_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox);
     if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
     grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->yz_mul, c->d_grid);
-    zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor);
-    if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor);
+    zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_lvl, c->d_nblocks);
+    if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor, c->d_lvl);
     scan_reduce_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums);
     scan_blocks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_block_sums, c->d_cell_start);
     scan_final_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums, c->d_cell_start);
-    if (pb) scatter_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_cell_of, c->d_cell_cursor, c->d_sorted);
+    if (pb) scatter_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_cell_of, c->d_grid, c->d_cell_start, c->d_cell_cursor, c->d_sorted,
+                                                             c->d_sorted_pos, c->d_lvl, c->d_blocks, c->d_blk_area, c->d_nblocks, (unsigned)c->max_points);
     count_launch(c, pb ? 9 : 6);
     BSHOT_TRY(check_launch("grid_build"));
     // vector::resize semantics of cloud1_normals (include/bshot_bits.h:59): entries beyond the new

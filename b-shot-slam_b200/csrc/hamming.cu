@@ -106,10 +106,12 @@ __device__ __forceinline__ uint32_t pair_update(const uint32_t (&qw)[QPT][11], c
 template <int QPT, bool COLMIN>
 __global__ void __launch_bounds__(HM_THREADS)
 hamming_top2_kernel(const uint4* __restrict__ q, unsigned nq_cap, const unsigned* __restrict__ nq_dev,
-                    const uint4* __restrict__ t, unsigned nt, unsigned chunk, unsigned long long global_base,
-                    unsigned long long* __restrict__ partial, unsigned* __restrict__ gcol) {
-    // nq_cap sizes the grid and the partial layout; an optional device-side count trims the work
+                    const uint4* __restrict__ t, unsigned nt_cap, const unsigned* __restrict__ nt_dev, unsigned chunk,
+                    unsigned long long global_base, unsigned long long* __restrict__ partial, unsigned* __restrict__ gcol) {
+    // nq_cap / nt_cap size the grid and the partial layout; optional device-side counts trim the work (a frame that
+    // yields fewer keypoints than top_k: records beyond the count are stale and must not take part)
     const unsigned nq = nq_dev ? min(nq_cap, *nq_dev) : nq_cap;
+    const unsigned nt = nt_dev ? min(nt_cap, *nt_dev) : nt_cap;
     if (blockIdx.x * (unsigned)(HM_THREADS * QPT) >= nq) return;
     __shared__ __align__(128) uint4 tile[HM_STAGES][HM_TILE * 3];
     __shared__ __align__(8) unsigned long long full[HM_STAGES];
@@ -218,12 +220,13 @@ __device__ __forceinline__ void top2_insert(unsigned long long key, unsigned lon
 constexpr int HM_MERGE_LANES = 8;
 
 __global__ void __launch_bounds__(256)
-merge_top2_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq,
+merge_top2_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq, const unsigned* __restrict__ nq_dev,
                   const unsigned* __restrict__ gcol, unsigned long long global_base, bshot_cand* __restrict__ out) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned qi = t / HM_MERGE_LANES, sub = t % HM_MERGE_LANES;
+    const unsigned nq_live = nq_dev ? min(nq, *nq_dev) : nq;  // rows beyond the device-side count were never written
     unsigned long long k1 = HM_NONE, k2 = HM_NONE;
-    if (qi < nq) {
+    if (qi < nq_live) {
         const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src);
 #pragma unroll 4
         for (unsigned sp = sub; sp < nsrc; sp += HM_MERGE_LANES) {
@@ -300,11 +303,12 @@ __global__ void unpack_cands_kernel(const bshot_cand* __restrict__ cand, unsigne
 }
 
 // mutual-NN filter (src/lidar_odometry.cpp:234-242): single CTA, ordered compaction
-__global__ void mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq, int* __restrict__ pairs,
-                                    int* __restrict__ count) {
+__global__ void mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq_cap, const unsigned* __restrict__ nq_dev,
+                                    int* __restrict__ pairs, int* __restrict__ count) {
     __shared__ unsigned warp_tot[32];
     __shared__ unsigned running;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned nq = nq_dev ? min(nq_cap, *nq_dev) : nq_cap;
     if (tid == 0) running = 0;
     __syncthreads();
     for (unsigned base = 0; base < nq; base += blockDim.x) {
@@ -363,7 +367,7 @@ static int pick_qpt(size_t nq, size_t nt, int sm_count) {
 
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out, unsigned* d_colmin, const unsigned* d_nq) {
+                 bshot_cand* d_out, unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt) {
     if (nq == 0) return BSHOT_OK;
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
         set_error("hamming_top2: sizes exceed 32-bit index range");
@@ -415,7 +419,7 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
         BSHOT_CUDA_TRY(cudaMemsetAsync(d_colmin, 0xFF, sizeof(unsigned) * nt, c->stream));
     }
 #define BSHOT_LAUNCH_TOP2(QPT, CM)                                                                                    \
-    hamming_top2_kernel<QPT, CM><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, d_nq, t4, (unsigned)nt, (unsigned)chunk, \
+    hamming_top2_kernel<QPT, CM><<<grid, HM_THREADS, 0, c->stream>>>(q4, (unsigned)nq, d_nq, t4, (unsigned)nt, d_nt, (unsigned)chunk, \
                                                                      global_base, c->d_partial, d_colmin)
     switch (qpt) {
         case 4: if (colmin) BSHOT_LAUNCH_TOP2(4, true); else BSHOT_LAUNCH_TOP2(4, false); break;
@@ -426,7 +430,7 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     count_launch(c);
     BSHOT_TRY(check_launch("hamming_top2_kernel"));
     merge_top2_kernel<<<(unsigned)((nq * HM_MERGE_LANES + 255) / 256), 256, 0, c->stream>>>(
-        c->d_partial, nsplit, (unsigned)nq, colmin ? d_colmin : nullptr, global_base, d_out);
+        c->d_partial, nsplit, (unsigned)nq, d_nq, colmin ? d_colmin : nullptr, global_base, d_out);
     count_launch(c);
     return check_launch("merge_top2_kernel");
 }
@@ -460,8 +464,8 @@ int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* 
     return check_launch("unpack_cands_kernel");
 }
 
-int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count) {
-    mutual_pairs_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (unsigned)nq, d_pairs3, d_count);
+int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count, const unsigned* d_nq) {
+    mutual_pairs_kernel<<<1, 1024, 0, c->stream>>>(d_cand, (unsigned)nq, d_nq, d_pairs3, d_count);
     count_launch(c);
     return check_launch("mutual_pairs_kernel");
 }
@@ -512,10 +516,11 @@ namespace bshot {
 // query set the column minima are tracked inside the single distance-matrix pass (Q x T pairs instead
 // of Q x T + Q x Q); for map-sized target sets the Q x Q reverse pass is negligible and kept separate.
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                     bshot_cand* d_out) {
+                     bshot_cand* d_out, const unsigned* d_nq, const unsigned* d_nt) {
     if (nq == 0) return BSHOT_OK;
     if (nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
-        return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right));
+        return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right), d_nq, d_nt);
+    if (d_nq || d_nt) { set_error("hamming_match_rq: device-side counts need the fused reverse pass (nt <= 4 nq)"); return BSHOT_E_INVALID; }
     BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr));
     return hamming_reverse(c, d_q, nq, d_t, global_base, d_out);
 }

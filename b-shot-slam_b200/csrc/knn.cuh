@@ -334,11 +334,13 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
             bbelow = __shfl_sync(0xffffffffu, found_below, src);
             const unsigned bcnt = __shfl_sync(0xffffffffu, found_cnt, src);
             if (bcnt <= KN_LIST || iter == 7) break;
-            // narrow to the crossing bin and histogram again
+            // narrow to the crossing bin and histogram again -- unless the bin is already only a few ulps wide (a pile
+            // of equal distances cannot be split by distance: the bisection over the full key below takes over)
             const float w = (hi - lo) / (float)KN_BINS;
-            const float nlo = lo + w * (float)bin, nhi = lo + w * (float)(bin + 1);
-            lo = fmaxf(lo, nlo - w * 1e-3f);
-            hi = fminf(hi, nhi + w * 1e-3f);
+            const float nlo = fmaxf(lo, lo + w * (float)bin - w * 1e-3f), nhi = fminf(hi, lo + w * (float)(bin + 1) + w * 1e-3f);
+            if (!(nhi - nlo > 64.0f * 1.1920929e-07f * nhi)) break;
+            lo = nlo;
+            hi = nhi;
         }
     }
     // ---- 3. accumulate below the bin, collect the bin, rank, accumulate the rest -----------------------
@@ -364,10 +366,36 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
         res.count = n;
         return res;
     }
-    const unsigned ln = min(sm.list_n, (unsigned)KN_LIST);
     const unsigned need = (unsigned)max_nn - bbelow;  // 1..bcnt
-    // fallback threshold (only reachable for > KN_LIST exact distance duplicates)
-    if (lane == 0) sm.thr = (unsigned long long)__float_as_uint(hi) << 32;
+    if (sm.list_n > (unsigned)KN_LIST) {
+        // More equal (or nearly equal) distances around the max_nn-th neighbour than the list holds, e.g. a pile of
+        // (0,0,0) invalid returns that are all equidistant from the query: exact threshold key by bisection over the
+        // crossing bin, then one sweep accumulates the `need` smallest keys of the bin.
+        const float tlo = lo, thi = hi, tscale = scale;
+        const int tbin = bin;
+        auto in_bin = [&](float sqd) { return sqd < thi && sqd >= tlo && min(KN_BINS - 1, (int)((sqd - tlo) * tscale)) == tbin; };
+        unsigned long long klo = 0ull, khi = ((unsigned long long)__float_as_uint(thi) << 32);
+        while (klo < khi) {
+            const unsigned long long mid = klo + ((khi - klo) >> 1);
+            int cb = 0;
+            knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
+                const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (in_bin(sqd) && knn_key(sqd, p.w) <= mid) ++cb;
+            });
+            cb = warp_sum(cb);
+            if ((unsigned)cb >= need) khi = mid; else klo = mid + 1ull;
+        }
+        const unsigned long long thr = klo;
+        knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
+            const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (in_bin(sqd) && knn_key(sqd, p.w) <= thr) acc(p);
+        });
+        res.thr = thr;
+        res.count = max_nn;
+        return res;
+    }
+    const unsigned ln = sm.list_n;
+    if (lane == 0) sm.thr = 0ull;
     __syncwarp();
     for (unsigned e = lane; e < ln; e += 32) {
         const unsigned long long ke = sm.v.list[e];
@@ -384,37 +412,13 @@ __device__ __forceinline__ KnnResult knn_select(const GridParams& g, const unsig
     return res;
 }
 
-// Re-collect a neighbourhood that an earlier knn_select() of the SAME query point already determined
-// (rho2 and the threshold key were kept): one enumeration and one sweep instead of the whole sizing /
-// crossing-bin procedure.  Calls acc(p) for exactly the same selected set; returns its size.
-template <typename Acc>
-__device__ __forceinline__ int knn_collect_cached(const GridParams& g, const unsigned* __restrict__ cell_start,
-                                                  const float4* __restrict__ sorted, const float4& q, float rho2,
-                                                  unsigned long long thr, KnnWarpSmem& sm, unsigned lane, Acc&& acc) {
-    KnnIter it;
-    it.rho = sqrtf(rho2) * 1.0001f;  // covers every point with sqd < rho2
-    it.rr = row_range(g, q.y, q.z, it.rho);
-    bool filled;
-    it.total = knn_expand(g, cell_start, q, it.rho, it.rr, 0u, (unsigned)KN_CAP, sm, lane, filled);
-    it.list = filled;
-    it.cached = false;
-    int cnt = 0;
-    knn_for_each(g, cell_start, sorted, q, it, sm, lane, [&](const float4 p) {
-        const float sqd = sqdist_rn(q.x, q.y, q.z, p.x, p.y, p.z);
-        if (sqd < rho2 && knn_key(sqd, p.w) <= thr) {
-            acc(p);
-            ++cnt;
-        }
-    });
-    return warp_sum(cnt);
-}
-
-// ---- exact-order sums (opt-in, BSHOT_EXACT_SUMS=1) --------------------------------------------------------
+// ---- exact-order sums ------------------------------------------------------------------------------------------
 // pcl::computeCentroid and pcl::computeMeanAndCovarianceMatrix add their fp32 accumulators in NEIGHBOUR ORDER
-// (ascending distance).  The default kernels sum in fp64 in candidate order -- more accurate than the reference,
-// but not bit-identical to it: a vote next to the dividing plane may flip.  The exact mode materialises the selected
-// set as sorted keys and replays the reference's sequential fp32 additions, so seg-ratios, keypoints and normals
-// come out bit-identical to the oracle.  Sets larger than KN_EXACT_CAP (uncapped searches) keep the default sums.
+// (ascending distance).  knn_select() hands the selected points to `acc` in candidate order (the callers sum them in
+// fp64: more accurate than the reference, but not bit-identical to it -- a vote next to the dividing plane may flip).
+// The callers therefore materialise the selected set as sorted keys and replay the reference's sequential fp32
+// additions, so seg-ratios, keypoints and normals come out bit-identical to the oracle.  Sets larger than
+// KN_EXACT_CAP (max_nn > 512 or uncapped searches) keep the fp64 sums.
 constexpr int KN_EXACT_CAP = 512;
 
 struct KnnExactSmem {
@@ -469,7 +473,7 @@ __device__ __forceinline__ void knn_replay_in_order(const float4* __restrict__ p
     for (int base = 0; base < count; base += 32) {
         const int j = base + (int)lane;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < count) p = __ldg(pts + (unsigned)(skeys[j] & 0xFFFFFFFFull));
+        if (j < count && skeys[j] != ~0ull) p = __ldg(pts + (unsigned)(skeys[j] & 0xFFFFFFFFull));
         const int m = min(32, count - base);
 #pragma unroll 1
         for (int l = 0; l < m; ++l)

@@ -8,8 +8,15 @@ namespace bshot {
 int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats);
 
 // a2/a3: seg-ratio for every point -> d_ratio, d_keys ; top-K -> d_kp_idx/d_kp_ratio/d_kp/d_kp_count (detect.cu)
-int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type);
+int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_normals = false);
 int detect_topk(Ctx* c, int top_k);
+
+// block-tiled exact neighbourhoods of cloud points (tilek.cu): seg-ratio scores and / or normals; d_flags = nullptr: every
+// point, else per cell-sorted position the output slot (>= 0) of the points that want a normal
+int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out);
+bool tile_path_ok(const Ctx* c, int max_nn);
+// normals of the queries the tiled kernel put on the fallback list (normals.cu)
+int normals_fallback_list(Ctx* c, float radius, int max_nn, const int* d_flags, float4* d_out);
 
 // a4: normals (normals.cu). normals_query: q (float4 xyz_) -> out (nx,ny,nz,curvature); in-place allowed
 int normals_query(Ctx* c, const float4* d_q, size_t nq, float radius, int max_nn, float4* d_out);
@@ -21,7 +28,7 @@ int binarize(Ctx* c, const float* d_shot, size_t k, uint64_t* d_bits);
 
 // a10/a11 (hamming.cu)
 int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out, unsigned* d_colmin = nullptr, const unsigned* d_nq = nullptr);
+                 bshot_cand* d_out, unsigned* d_colmin = nullptr, const unsigned* d_nq = nullptr, const unsigned* d_nt = nullptr);
 int hamming_reverse_owned(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                           const bshot_cand* d_merged, unsigned* d_rq_out, const void* d_peer_rq = nullptr, unsigned nranks = 1,
                           unsigned rank = 0);
@@ -29,12 +36,12 @@ int hamming_peer_barrier(Ctx* c, const void* d_peer_flags, unsigned nranks, unsi
 int hamming_push_cands(Ctx* c, const bshot_cand* d_cands, size_t nq, const void* d_peer_ptrs, unsigned nranks, unsigned rank);
 int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq);
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                     bshot_cand* d_out);
+                     bshot_cand* d_out, const unsigned* d_nq = nullptr, const unsigned* d_nt = nullptr);
 int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
                     bshot_cand* d_cand);
 int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, void* d_out);
 int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* d1, int* idx2, int* d2);
-int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count);
+int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count, const unsigned* d_nq = nullptr);
 int popc_peak(Ctx* c, double* out);
 
 // whole frame on the resident cloud (frame.cu)

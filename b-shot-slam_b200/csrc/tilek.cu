@@ -1,0 +1,384 @@
+// tilek.cu -- the block-tiled neighbourhood kernel (tile.cuh): seg-ratio keypoint scores (SURVEY 8a row a2,
+// src/lidar_odometry.cpp:61-126) and / or point normals (row a4, include/bshot_bits.h:43-94) for queries that are
+// cloud points, with the reference's own arithmetic: fp32 running sums in neighbour order (pcl::computeCentroid :76,
+// pcl::computeMeanAndCovarianceMatrix), so scores, keypoint indices and normals are bit-identical to the oracle.
+#include "normal_math.cuh"
+#include "stages.h"
+#include "tile.cuh"
+
+namespace bshot {
+
+#ifndef BSHOT_TL_MINBLOCKS
+#define BSHOT_TL_MINBLOCKS 5
+#endif
+
+// Everything that follows the selection of one query's neighbourhood (w.order[0..count) = tile slots in neighbour
+// order): coordinates into SoA, the reference's fp32 running sums replayed in that order, the score.  nsum (shared
+// memory, 10 floats) receives the nine accumulators of pcl::computeMeanAndCovarianceMatrix + the count when NRM.
+template <int SR, bool SEG, bool NRM>
+__device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ tile, const float4& q, int count, TileWarp& w, unsigned lane,
+                                                   float* __restrict__ ratio, unsigned long long* __restrict__ keys, float* nsum) {
+    const float nanf_ = __int_as_float(0x7FC00000);
+    const unsigned qi = __float_as_uint(q.w);
+    tile_gather(tile, count, w, lane);
+    const float fn = (float)count;
+    float sx, sy, sz;
+    if (NRM) {
+        // the nine accumulators, one lane each (6..8 = plain sums = the centroid sums of pcl::computeCentroid)
+        const int c = (int)(lane % 9u);
+        const int rowa = (c < 3) ? 0 : (c < 5 ? 1 : (c == 5 ? 2 : c - 6));
+        const int rowb = (c < 3) ? c : (c < 5 ? c - 2 : (c == 5 ? 2 : -1));
+        const float acc = tile_seq_sum_prod(w, rowa, rowb, count);
+        if (lane < 9) nsum[lane] = acc;
+        if (lane == 9) nsum[9] = fn;
+        sx = __shfl_sync(0xffffffffu, acc, 6);
+        sy = __shfl_sync(0xffffffffu, acc, 7);
+        sz = __shfl_sync(0xffffffffu, acc, 8);
+    } else {
+        const float acc = tile_seq_sum(w, (int)(lane % 3u), count);  // pcl::computeCentroid (:76)
+        sx = __shfl_sync(0xffffffffu, acc, 0);
+        sy = __shfl_sync(0xffffffffu, acc, 1);
+        sz = __shfl_sync(0xffffffffu, acc, 2);
+    }
+    if (SEG && !(NRM && q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) {  // :63 the detector skips the origin
+        const float vx = __fsub_rn(q.x, sx / fn), vy = __fsub_rn(q.y, sy / fn), vz = __fsub_rn(q.z, sz / fn);  // :79
+        float seg;
+        if (SR == BSHOT_SR_CV) {  // :83-97
+            int pos = 0, neg = 0;
+            for (int r = (int)lane; r < count; r += 32) {
+                const float d = dot3_rn(vx, vy, vz, __fsub_rn(w.u.soa[0][r], q.x), __fsub_rn(w.u.soa[1][r], q.y), __fsub_rn(w.u.soa[2][r], q.z));
+                if (d > 0.0f) ++pos;
+                else if (d < 0.0f) ++neg;
+            }
+            pos = warp_sum(pos);
+            neg = warp_sum(neg);
+            const float fp = (float)pos, fq = (float)neg;
+            seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);
+            if (pos == 0 && neg == 0) seg = nanf_;  // 0/0 like the reference
+        } else {  // CVS :98-108 / CVSN :109-119: per-neighbour terms in parallel, fp32 running sum in neighbour order
+            const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
+            __syncwarp();
+            for (int r = (int)lane; r < count; r += 32) {
+                const float dx = __fsub_rn(w.u.soa[0][r], q.x), dy = __fsub_rn(w.u.soa[1][r], q.y), dz = __fsub_rn(w.u.soa[2][r], q.z);
+                const float dn = sqrtf(dot3_rn(dx, dy, dz, dx, dy, dz));
+                float term = 0.0f;  // the reference skips the neighbour (:103,:114); adding +0 is the same sum
+                if (ctn != 0.0f && dn != 0.0f) {
+                    const float d = dot3_rn(vx, vy, vz, dx, dy, dz);
+                    term = (SR == BSHOT_SR_CVS) ? d : d / __fmul_rn(ctn, dn);
+                }
+                w.u.soa[0][r] = term;
+            }
+            __syncwarp();
+            seg = fabsf(tile_seq_sum(w, 0, count)) / fn;
+        }
+        if (lane == 0) {
+            ratio[qi] = seg;
+            keys[qi] = isnan(seg) ? 0ull : (((unsigned long long)__float_as_uint(seg) << 32) | (unsigned)(~qi));
+        }
+    }
+}
+
+// ctl = {[0] heavy blocks (front of the list), [1] fallback-list length, [2] work counter (blocks), [3] work counter
+//        (overflow queries), [4] overflow queries, [5] light blocks (back of the list)}
+// counters: [0] / [1] selected neighbours (detector / normals), [2] tiles staged, [3] tile points swept, [4] query
+// attempts, [5] attempts that found fewer than max_nn points, [6] queries handed to the fallback, [7] blocks.
+
+// SR: score type.  SEG: write ratio / keys for every (non-origin) point of the block.  NRM: write normals --
+// for every query (flags == nullptr, out index = surface index) or for the flagged ones (flags[sorted position] =
+// keypoint ordinal >= 0, out index = ordinal: the reference's placement, include/bshot_bits.h:79-81).
+// One CTA per block of the grid's block list, one shared 1024-point tile, one warp per query.  Queries whose block tile
+// does not fit (very dense spots, density jumps) go to the overflow list {position, radius} for tile_single_kernel.
+template <int SR, bool SEG, bool NRM>
+__global__ void __launch_bounds__(TL_WARPS * 32, NRM ? BSHOT_TL_MINBLOCKS : BSHOT_TL_MINBLOCKS + 1)
+tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
+            const uint4* __restrict__ blocks, const float* __restrict__ blk_area, unsigned* __restrict__ ctl, float radius, int max_nn,
+            float* __restrict__ ratio, unsigned long long* __restrict__ keys, const int* __restrict__ flags, float4* __restrict__ nrm_out,
+            unsigned long long* __restrict__ counters, uint2* __restrict__ ovf, unsigned block_cap) {
+    using SM = TileShared<NRM, TL_CAP, TL_WARPS>;
+    __shared__ SM sm;
+    unsigned& s_block = sm.cur_block;
+    unsigned& s_slot = sm.ovf_slot;
+    unsigned* const work = ctl + 2;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const GridParams g = *gp;
+    const float R = radius;
+    const float R2 = (float)((double)R * (double)R);
+    const unsigned n_heavy = ctl[0], nb = n_heavy + ctl[5];  // heavy blocks from the front of the list, light ones from its back
+    unsigned long long st_staged = 0, st_swept = 0, st_attempts = 0, st_blocks = 0;  // thread 0 only
+    for (;;) {
+        __syncthreads();  // previous block's epilogue is done with the shared state
+        if (tid == 0) s_block = atomicAdd(work, 1u);  // blocks differ widely in cost: dynamic assignment, heavy blocks first
+        __syncthreads();
+        if (s_block >= nb) break;
+        const unsigned b = s_block < n_heavy ? s_block : block_cap - 1u - (s_block - n_heavy);
+        const uint4 desc = __ldg(blocks + b);
+        tile_block_queries(g, cell_start, sorted, desc, SEG ? nullptr : flags, SEG && !NRM, sm, tid);
+        const unsigned nq = sm.nq;
+        if (nq == 0) continue;
+        ++st_blocks;
+        // first radius: max_nn points on a surface of `area` mm^2 per point
+        float rho = BSHOT_TL_SAFETY * sqrtf((float)max_nn * __ldg(blk_area + b) * 0.31830989f);
+        // sub-blocks still to do (bit g = group g)
+        unsigned long long todo = 1ull;
+        unsigned ngrp = 1;
+        while (todo) {
+            const unsigned grp = (unsigned)__ffsll((long long)todo) - 1u;
+            todo &= todo - 1ull;
+            tile_block_bbox(sm, grp, tid);
+            if (sm.pending == 0) continue;
+            // a box much wider than the search radius makes every query sweep far more candidates than its own
+            // neighbourhood: halve it first (the tile of each half is smaller; staging is cheap next to the sweeps)
+            if (sm.pending > 8u && ngrp < 64u) {
+                const float edge = fmaxf(fmaxf(sm.bbox[3] - sm.bbox[0], sm.bbox[4] - sm.bbox[1]), sm.bbox[5] - sm.bbox[2]);
+                if (edge > fminf(rho, R) && tile_block_split(sm, grp, ngrp, tid)) {
+                    todo |= (1ull << grp) | (1ull << ngrp);
+                    ++ngrp;
+                    continue;
+                }
+            }
+            bool shrunk = false;
+            for (;;) {
+                __syncthreads();  // everyone is done with the previous attempt's shared state
+                const bool at_R = !(rho < R);
+                const float rr = at_R ? R : rho;
+                const float rs = rr * 1.0001f + 0.1f;           // staging radius: covers fp32 rounding of the distances
+                const float rho2 = at_R ? R2 : __fmul_rn(rr, rr);
+                const bool ok = tile_enumerate(g, cell_start, rs, sm, tid);
+                if (ok && !at_R && (float)sm.seg_total < 1.2f * (float)max_nn) {  // cannot hold max_nn points: grow before touching a point
+                    rho = rr * fminf(fmaxf(sqrtf(1.6f * (float)max_nn / (float)max(sm.seg_total, 1u)), 1.2f), 3.0f);
+                    continue;
+                }
+                // more than 2.2 x the tile before the box filter never fits: skip the copy
+                const bool hopeless = !ok || sm.seg_total > (unsigned)(2.2f * (float)SM::kCap);
+                if (!hopeless) tile_stage(sorted, rs, sm, tid);
+                const unsigned S = hopeless ? sm.seg_total : sm.tile_n;
+                if (hopeless || S > (unsigned)SM::kCap) {
+                    if (!shrunk && ok && rr > 0.25f * g.cell) {  // the prediction may simply be too generous: one smaller try
+                        shrunk = true;
+                        rho = rr * fminf(fmaxf(sqrtf(0.6f * (float)SM::kCap / (float)S), 0.4f), 0.9f);
+                        continue;
+                    }
+                    // does not fit a shared tile: every pending query gets its own tile (tile_single_kernel)
+                    __syncthreads();
+                    if (tid == 0) { s_slot = atomicAdd(ctl + 4, sm.pending); sm.next_q = 0; }
+                    __syncthreads();
+                    for (unsigned k = tid; k < nq; k += SM::kThreads)
+                        if (sm.q_nin[k] >= 0 && sm.q_grp[k] == grp) {
+                            ovf[s_slot + atomicAdd(&sm.next_q, 1u)] = make_uint2(sm.q_pos[k], __float_as_uint(fminf(rr, R)));
+                            sm.q_nin[k] = -2;
+                        }
+                    break;
+                }
+                if (!at_R && S < (unsigned)max_nn) {
+                    rho = rr * fminf(fmaxf(sqrtf(1.5f * (float)max_nn / (float)max(S, 8u)), 1.2f), 3.0f);
+                    continue;
+                }
+                const unsigned S_pad = (S + 127u) & ~127u;
+                if (tid == 0) { sm.min_nin = 0x7FFFFFFF; sm.next_q = 0; }
+                ++st_staged; st_swept += (unsigned long long)S * sm.pending; st_attempts += sm.pending;
+                __syncthreads();
+                shrunk = true;  // from here on the radius only grows
+                TileWarp& w = sm.u.w[wid];
+                for (;;) {
+                    unsigned k = 0;
+                    if (lane == 0) k = atomicAdd(&sm.next_q, 1u);  // queries differ in cost too
+                    k = __shfl_sync(0xffffffffu, k, 0);
+                    if (k >= nq) break;
+                    if (sm.q_nin[k] < 0 || sm.q_grp[k] != grp) continue;
+                    const float4 q = sm.q_pt[k];
+                    const TileQuery tq = tile_select(sm.tile, S_pad, q, rho2, at_R, max_nn, w, lane);
+                    if (tq.count == 0) {
+                        if (lane == 0) { sm.q_nin[k] = max(tq.n_in, 1); atomicMin(&sm.min_nin, tq.n_in); atomicAdd(&counters[5], 1ull); }
+                        continue;
+                    }
+                    tile_query_outputs<SR, SEG, NRM>(sm.tile, q, tq.count, w, lane, ratio, keys, NRM ? sm.nsum[k] : nullptr);
+                    if (lane == 0) {
+                        sm.q_nin[k] = -1;
+                        atomicSub(&sm.pending, 1u);
+                        atomicAdd(&sm.nbr_total, (unsigned long long)tq.count);
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+                if (sm.pending == 0) break;
+                // some spheres held fewer than max_nn points: grow by the density they saw (count ~ r^2 on surfaces)
+                rho = rr * fminf(fmaxf(sqrtf(1.35f * (float)max_nn / (float)max(sm.min_nin, 1)), 1.15f), 3.0f);
+            }
+        }
+        __syncthreads();
+        if (NRM) {  // eigen-solves of the block's queries in parallel
+            for (unsigned k = tid; k < nq; k += SM::kThreads) {
+                if (sm.q_nin[k] != -1) continue;
+                const float4 q = sm.q_pt[k];
+                float a[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) a[i] = sm.nsum[k][i];
+                const float4 o = normal_from_sums(a, (int)sm.nsum[k][9], q.x, q.y, q.z);
+                const unsigned oi = flags ? (unsigned)__ldg(flags + sm.q_pos[k]) : __float_as_uint(q.w);
+                nrm_out[oi] = o;
+            }
+        }
+        if (tid == 0 && sm.nbr_total) atomicAdd(&counters[SEG ? 0 : 1], sm.nbr_total);
+    }
+    if (tid == 0) {
+        atomicAdd(&counters[2], st_staged); atomicAdd(&counters[3], st_swept); atomicAdd(&counters[4], st_attempts);
+        atomicAdd(&counters[7], st_blocks);
+    }
+}
+
+// ---- one private tile per query ------------------------------------------------------------------------------------
+// The overflow queries of tile_kernel: each warp takes ONE query at a time, stages the ball around it into its own
+// TS_CAP-point tile (row segments read by the warp, no CTA-wide step) and brackets the radius until the ball holds at
+// least max_nn and at most TS_CAP points -- always possible unless more than TS_CAP points coincide in distance, which
+// goes to the warp-per-query fallback list (knn.cuh).
+constexpr int TS_WARPS = 4;
+constexpr int TS_CAP = 640;
+
+struct SingleWarp {
+    float4 tile[TS_CAP];
+    TileWarp w;
+    float nsum[12];
+};
+
+// stages every point with distance <= rs of q into st.tile; returns the number found (may exceed TS_CAP: tile unusable)
+__device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
+                                                 const float4& q, float rs, SingleWarp& st, unsigned lane) {
+    const RowRange rr = row_range(g, q.y, q.z, rs);
+    const float rs2 = rs * rs;
+    unsigned n = 0;
+    for (int r0 = 0; r0 < rr.nrows; r0 += 32) {
+        const int r = r0 + (int)lane;
+        unsigned s = 0, len = 0;
+        if (r < rr.nrows) {
+            int iy, iz;
+            row_coords(rr, r, iy, iz);
+            unsigned e;
+            if (row_segment(g, cell_start, q.x, q.y, q.z, rs, iy, iz, s, e)) len = e - s;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, len > 0);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1u;
+            const unsigned ss = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src);
+            for (unsigned j0 = 0; j0 < ll; j0 += 32) {
+                const unsigned j = j0 + lane;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool keep = false;
+                if (j < ll) {
+                    p = __ldg(sorted + ss + j);
+                    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+                    keep = dx * dx + dy * dy + dz * dz <= rs2;
+                }
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
+                if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
+                n += __popc(km);
+            }
+        }
+    }
+    if (n <= (unsigned)TS_CAP) {
+        const unsigned pad = (n + 127u) & ~127u;
+        for (unsigned j = n + lane; j < pad; j += 32) st.tile[j] = make_float4(1e30f, 1e30f, 1e30f, __uint_as_float(0xFFFFFFFFu));
+    }
+    __syncwarp();
+    return n;
+}
+
+template <int SR, bool SEG, bool NRM>
+__global__ void __launch_bounds__(TS_WARPS * 32, 3)
+tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
+                   unsigned* __restrict__ ctl, float radius, int max_nn, float* __restrict__ ratio, unsigned long long* __restrict__ keys,
+                   const int* __restrict__ flags, float4* __restrict__ nrm_out, unsigned long long* __restrict__ counters,
+                   const uint2* __restrict__ ovf, unsigned* __restrict__ fb_list) {
+    extern __shared__ __align__(16) unsigned char single_smem_raw[];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    SingleWarp& st = reinterpret_cast<SingleWarp*>(single_smem_raw)[wid];
+    const GridParams g = *gp;
+    const float R = radius;
+    const float R2 = (float)((double)R * (double)R);
+    const unsigned n_items = ctl[4];
+    unsigned long long nbr = 0;
+    for (;;) {
+        unsigned i = 0;
+        if (lane == 0) i = atomicAdd(ctl + 3, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_items) break;
+        const uint2 item = ovf[i];
+        const float4 q = __ldg(sorted + item.x);
+        float rho = __uint_as_float(item.y), rho_lo = 0.0f, rho_hi = 3.0e38f;
+        bool done = false;
+        for (int it = 0; it < 48 && !done; ++it) {
+            const bool at_R = !(rho < R);
+            const float rr = at_R ? R : rho;
+            const float rs = rr * 1.0001f + 0.1f;
+            const float rho2 = at_R ? R2 : __fmul_rn(rr, rr);
+            const unsigned S = single_stage(g, cell_start, sorted, q, rs, st, lane);
+            if (S > (unsigned)TS_CAP) {  // too many: shrink (between the brackets when a smaller radius already failed)
+                rho_hi = fminf(rho_hi, rr);
+                if (rho_lo > 0.0f) { if (!(rho_hi > 1.0005f * rho_lo)) break; rho = sqrtf(rho_lo * rho_hi); }
+                else rho = rr * fminf(fmaxf(sqrtf(0.6f * (float)TS_CAP / (float)S), 0.3f), 0.9f);
+                continue;
+            }
+            int n_in = (int)S;
+            if (at_R || S >= (unsigned)max_nn) {
+                const TileQuery tq = tile_select(st.tile, (S + 127u) & ~127u, q, rho2, at_R, max_nn, st.w, lane);
+                if (tq.count > 0) {
+                    tile_query_outputs<SR, SEG, NRM>(st.tile, q, tq.count, st.w, lane, ratio, keys, st.nsum);
+                    if (NRM) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            float a[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) a[k] = st.nsum[k];
+                            const float4 o = normal_from_sums(a, (int)st.nsum[9], q.x, q.y, q.z);
+                            nrm_out[flags ? (unsigned)__ldg(flags + item.x) : __float_as_uint(q.w)] = o;
+                        }
+                    }
+                    nbr += (unsigned long long)tq.count;
+                    done = true;
+                    continue;
+                }
+                n_in = tq.n_in;
+            }
+            // fewer than max_nn points inside: grow by the density seen (count ~ r^2 on surfaces), below the overflowing radius
+            rho_lo = fmaxf(rho_lo, rr);
+            rho = rr * fminf(fmaxf(sqrtf(1.35f * (float)max_nn / (float)max(n_in, 1)), 1.1f), 3.0f);
+            if (rho >= rho_hi) { if (!(rho_hi > 1.0005f * rho_lo)) break; rho = sqrtf(rho_lo * rho_hi); }
+        }
+        if (!done && lane == 0) { fb_list[atomicAdd(ctl + 1, 1u)] = item.x; atomicAdd(&counters[6], 1ull); }
+        __syncwarp();
+    }
+    if (lane == 0 && nbr) atomicAdd(&counters[SEG ? 0 : 1], nbr);
+}
+
+bool tile_path_ok(const Ctx* c, int max_nn) { return !c->force_warp_path && max_nn > 0 && max_nn <= TL_MAXNN; }
+
+int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out) {
+    if (max_nn <= 0 || max_nn > TL_MAXNN) { set_error("tile_neighbourhoods: max_nn %d outside (0, %d]", max_nn, TL_MAXNN); return BSHOT_E_INVALID; }
+    // persistent CTAs pulling blocks / queries from work counters; d_nblocks[1..4]: fallback-list length, work counters, overflow count
+    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, 4 * sizeof(unsigned), c->stream));
+    const size_t single_smem = sizeof(SingleWarp) * TS_WARPS;
+#define BSHOT_TILE(SR, SEG, NRM)                                                                                                           \
+    do {                                                                                                                                   \
+        static bool attr_set = false;                                                                                                      \
+        if (!attr_set) {                                                                                                                   \
+            BSHOT_CUDA_TRY(cudaFuncSetAttribute(tile_single_kernel<SR, SEG, NRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)single_smem)); \
+            attr_set = true;                                                                                                               \
+        }                                                                                                                                  \
+        tile_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * (BSHOT_TL_MINBLOCKS + 1), TL_WARPS * 32, 0, c->stream>>>(                       \
+            c->d_grid, c->d_cell_start, c->d_sorted, c->d_blocks, c->d_blk_area, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, \
+            d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points);                                                                  \
+        tile_single_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(                            \
+            c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, d_nrm_out, c->d_counters,   \
+            c->d_ovf, c->d_fb_list);                                                                                                       \
+    } while (0)
+    if (!seg) BSHOT_TILE(BSHOT_SR_CV, false, true);
+    else if (sr_type == BSHOT_SR_CV) { if (nrm) BSHOT_TILE(BSHOT_SR_CV, true, true); else BSHOT_TILE(BSHOT_SR_CV, true, false); }
+    else if (sr_type == BSHOT_SR_CVS) { if (nrm) BSHOT_TILE(BSHOT_SR_CVS, true, true); else BSHOT_TILE(BSHOT_SR_CVS, true, false); }
+    else { if (nrm) BSHOT_TILE(BSHOT_SR_CVSN, true, true); else BSHOT_TILE(BSHOT_SR_CVSN, true, false); }
+#undef BSHOT_TILE
+    count_launch(c, 2);
+    return check_launch("tile_kernel");
+}
+
+}  // namespace bshot

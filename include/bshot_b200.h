@@ -222,6 +222,11 @@ int bshot_stage_times(bshot_ctx* ctx, float ms_out[8]);
 /* work counters of the last frame: [0] sum over points of min(#neighbours, max_nn) in the detector,
  * [1] same for the normals queries, [2] sum of SHOT neighbour counts, [3] keypoints */
 int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]);
+/* raw device counters of the last frame, for tuning the block-tiled neighbourhood kernel: [0],[1] as above,
+ * [2] tiles staged, [3] tile points swept (sum over query attempts of the tile size), [4] query attempts,
+ * [5] attempts whose sphere held fewer than max_nn points (retried with a larger tile), [6] queries handed to the
+ * warp-per-query fallback, [7] query blocks processed (all tiled launches of the frame together) */
+int bshot_debug_counters(bshot_ctx* ctx, unsigned long long out[8]);
 /* POPC-pipe microbenchmark: returns measured POPC32 instructions/s over the whole GPU */
 int bshot_popc_peak(bshot_ctx* ctx, double* popc_per_s_out);
 

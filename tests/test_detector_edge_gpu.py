@@ -1,6 +1,7 @@
 """a2/a3/a4 edge cases: top-K selection (ties, K larger than the cloud, K = 1), neighbourhoods that do not fit
-the fast candidate list (very dense clouds, uncapped searches -> segment-list path of knn.cuh), and the
-row-thickness tuning knob of the voxel grid (results must not depend on it)."""
+the shared-memory tile (very dense clouds -> warp-per-query fallback list; uncapped searches -> segment-list path of
+knn.cuh), piles of equidistant points, frames with fewer keypoints than top_k, the row-thickness tuning knob of the
+voxel grid (results must not depend on it), and index equality with the oracle on full HDL-32E / HDL-64E scans."""
 import os
 
 import numpy as np
@@ -66,10 +67,14 @@ def test_dense_cloud_takes_the_segment_list_path(gpu_ctx, oracle, max_nn, n):
     assert np.array_equal(np.isnan(rg), np.isnan(ro))
     ok = ~np.isnan(ro)
     diff = np.abs(rg[ok] - ro[ok])
-    # votes are integers; the centroid of an isotropic blob sits close to the query, so the fp64 (GPU) vs fp32
-    # running-sum (PCL) centroid flips a vote or two near the dividing plane
-    assert (diff == 0).mean() > 0.3, (diff == 0).mean()
-    assert (diff <= 0.03).mean() > 0.99 and diff.max() < 0.15, (diff.max(), (diff <= 0.03).mean())
+    if max_nn > 0:
+        # capped search: the tile of every block overflows -> fallback list -> still the reference's summation order
+        assert np.array_equal(rg[ok], ro[ok]), diff.max()
+    else:
+        # uncapped (5000 neighbours each, beyond the exact-order replay): fp64 sums; votes are integers and the
+        # centroid of an isotropic blob sits close to the query, so a vote or two flips near the dividing plane
+        assert (diff == 0).mean() > 0.3, (diff == 0).mean()
+        assert (diff <= 0.03).mean() > 0.99 and diff.max() < 0.15, (diff.max(), (diff <= 0.03).mean())
     # normals through the same neighbourhood code
     q = pts[:256]
     ng = gpu_ctx.query_normals(q, 3000.0, max_nn)
@@ -96,34 +101,27 @@ def test_row_thickness_knob_does_not_change_results(bshot, synth):
             os.environ.pop("BSHOT_YZ_MUL", None)
     r0, k0, b0 = outs[0]
     for r, k, b in outs[1:]:
-        same = (r == r0) | (np.isnan(r) & np.isnan(r0))
-        assert same.mean() > 0.999, same.mean()             # fp64 centroid sums may differ in the last bit
-        assert len(np.intersect1d(k, k0)) >= 0.99 * len(k0)
-        if np.array_equal(k, k0):
-            assert (synth.unpack_bits(b) == synth.unpack_bits(b0)).mean() >= 0.999
+        assert np.array_equal(r, r0, equal_nan=True)        # exact-order sums: independent of the candidate order
+        assert np.array_equal(k, k0)
+        assert (synth.unpack_bits(b) == synth.unpack_bits(b0)).mean() >= 0.999
 
 
-def test_keypoint_normals_reuse_detector_neighbourhoods(gpu_ctx, synth):
-    """REFERENCE-mode normals of detector keypoints re-collect the neighbourhood the detector kept (sphere +
-    threshold key) instead of selecting it again: same selected set, so the same normals as a fresh search"""
+def test_keypoint_normals_tiled_vs_external_queries(gpu_ctx, synth):
+    """REFERENCE-mode normals of detector keypoints come from the block-tiled kernel (keypoints flagged per cell-sorted
+    position); the same points given as EXTERNAL queries go through the warp-per-query kernel.  Both replay the nine
+    fp32 accumulators in neighbour order: identical results"""
     scan = synth.make_scan("hdl32e", 4)
     gpu_ctx.reset()
     gpu_ctx.set_cloud(scan)
     idx, _, xyz = gpu_ctx.detect_keypoints(3000.0, 300, 0, 512)
-    cached = gpu_ctx.compute_normals(0, 3000.0, 300)[: len(idx)]       # keypoint ordinal i -> index i (reference quirk)
+    tiled = gpu_ctx.compute_normals(0, 3000.0, 300)[: len(idx)]        # keypoint ordinal i -> index i (reference quirk)
     fresh = gpu_ctx.query_normals(xyz, 3000.0, 300)
-    assert np.array_equal(np.isnan(cached), np.isnan(fresh))
-    ok = ~np.isnan(fresh[:, 0])
-    # identical selected sets; only the fp64 summation order differs (then rounded to fp32)
-    assert (cached[ok] == fresh[ok]).all(1).mean() > 0.95
-    assert np.abs(cached[ok] - fresh[ok]).max() < 1e-3
-    # different search parameters must not use the kept neighbourhoods
+    assert np.array_equal(tiled, fresh, equal_nan=True)
     other = gpu_ctx.compute_normals(0, 2000.0, 100)[: len(idx)]
     fresh2 = gpu_ctx.query_normals(xyz, 2000.0, 100)
-    assert np.array_equal(np.isnan(other), np.isnan(fresh2))
-    ok2 = ~np.isnan(fresh2[:, 0])
-    assert np.abs(other[ok2] - fresh2[ok2]).max() < 1e-3
-    assert not np.array_equal(other[ok & ok2], cached[ok & ok2])       # a smaller neighbourhood gives other normals
+    assert np.array_equal(other, fresh2, equal_nan=True)
+    ok = ~np.isnan(fresh[:, 0]) & ~np.isnan(fresh2[:, 0])
+    assert not np.array_equal(other[ok], tiled[ok])                     # a smaller neighbourhood gives other normals
 
 
 @pytest.mark.parametrize("sr_type", [1, 2])
@@ -143,41 +141,108 @@ def test_topk_on_unbounded_scores(gpu_ctx, oracle, sr_type):
         assert np.array_equal(idx, idx_d) and np.array_equal(rat, rat_d)
 
 
-def test_exact_sums_mode_is_bit_identical_to_the_oracle(bshot, oracle, synth):
-    """BSHOT_EXACT_SUMS=1 replays the reference's fp32 running sums in neighbour (ascending distance) order:
-    seg-ratios of all three score types and the keypoint set then match the oracle bit for bit, the keypoint normals
-    to the last ulp of the device / host trigonometric functions, and the whole REFERENCE-mode descriptor chain to
-    >= 99.95 % of the bits (the default mode sums in fp64, which flips a vote next to the dividing plane for ~3 % of
-    the points)."""
-    scan = synth.make_scan("hdl32e", 5)[::2].copy()
+def check_scan_against_oracle(bshot, oracle, synth, scan, top_k, max_points):
+    """scores bit-identical, keypoint INDICES identical, keypoint normals to the last ulp of atan2f / cosf / sinf, and
+    the whole REFERENCE chain (detector -> normals placement -> SHOT -> B-SHOT) >= 99.9 % of the bits"""
     oc = oracle.Cloud(scan)
-    os.environ["BSHOT_EXACT_SUMS"] = "1"
-    try:
-        with bshot.Context(0, 65536, 2048, 4096) as ctx:
-            ctx.set_cloud(scan)
-            for sr in (0, 1, 2):
-                rg = ctx.seg_ratio(3000.0, 300, sr)
-                ro = oc.seg_ratio(3000.0, 300, sr)
-                nan = np.isnan(ro)
-                assert np.array_equal(np.isnan(rg), nan)
-                assert np.array_equal(rg[~nan], ro[~nan]), (sr, np.abs(rg[~nan] - ro[~nan]).max())
-            ro = oc.seg_ratio(3000.0, 300, 0)
-            idx_o, rat_o = oracle.select_keypoints(ro, 400, oracle.TIE_DETERMINISTIC)
-            idx_g, rat_g, xyz = ctx.detect_keypoints(3000.0, 300, 0, 400)
-            assert np.array_equal(idx_g, idx_o) and np.array_equal(rat_g, rat_o)
-            ng = ctx.compute_normals(0, 3000.0, 300)[:400]
-            no = oc.normals(scan[idx_o], 3000.0, 300)
-            assert np.array_equal(np.isnan(ng), np.isnan(no))
-            ok = ~np.isnan(no[:, 0])
-            # same sums, same covariance; the closed-form eigen-solver calls atan2f / cosf / sinf, whose device and
-            # host implementations may differ in the last bit
-            assert np.abs(ng[ok] - no[ok]).max() <= 1e-6, np.abs(ng[ok] - no[ok]).max()
-            # whole chain: detector -> normals (reference placement) -> SHOT -> B-SHOT
-            ctx.reset()
-            f = ctx.process_frame(scan, bshot.default_params(top_k=400))
-            od = oc.compute_descriptors(scan[idx_o], 3000.0, 300, oracle.MODE_REFERENCE)
-            assert np.array_equal(f["kp_idx"], idx_o)
-            same = synth.unpack_bits(f["bits"]) == synth.unpack_bits(od["bits"])
-            assert same.mean() >= 0.9995, same.mean()
-    finally:
-        os.environ.pop("BSHOT_EXACT_SUMS", None)
+    with bshot.Context(0, max_points, top_k, top_k) as ctx:
+        ctx.set_cloud(scan)
+        ro = oc.seg_ratio(3000.0, 300, 0)
+        rg = ctx.seg_ratio(3000.0, 300, 0)
+        nan = np.isnan(ro)
+        assert np.array_equal(np.isnan(rg), nan)
+        assert np.array_equal(rg[~nan], ro[~nan]), np.abs(rg[~nan] - ro[~nan]).max()
+        idx_o, rat_o = oracle.select_keypoints(ro, top_k, oracle.TIE_DETERMINISTIC)
+        idx_g, rat_g, _ = ctx.detect_keypoints(3000.0, 300, 0, top_k)
+        assert np.array_equal(idx_g, idx_o) and np.array_equal(rat_g, rat_o)
+        ng = ctx.compute_normals(0, 3000.0, 300)[:top_k]
+        no = oc.normals(scan[idx_o], 3000.0, 300)
+        assert np.array_equal(np.isnan(ng), np.isnan(no))
+        ok = ~np.isnan(no[:, 0])
+        assert np.abs(ng[ok] - no[ok]).max() <= 1e-6, np.abs(ng[ok] - no[ok]).max()
+        ctx.reset()
+        f = ctx.process_frame(scan, bshot.default_params(top_k=top_k))
+        od = oc.compute_descriptors(scan[idx_o], 3000.0, 300, oracle.MODE_REFERENCE)
+        assert np.array_equal(f["kp_idx"], idx_o)
+        same = synth.unpack_bits(f["bits"]) == synth.unpack_bits(od["bits"])
+        assert same.mean() >= 0.999, same.mean()
+        return ctx.frame_counters()
+
+
+def test_hdl32e_full_scan_index_equality(bshot, oracle, synth):
+    """C1/C2 workload in the benchmarked (default) mode: a full HDL-32E scan, K = 2048"""
+    check_scan_against_oracle(bshot, oracle, synth, synth.make_scan("hdl32e", 5), 2048, 65536)
+
+
+def test_hdl64e_full_scan_index_equality(bshot, oracle, synth):
+    """C3 workload (the north_star frame) in the benchmarked mode: HDL-64E, 120 k points, K = 10 000"""
+    check_scan_against_oracle(bshot, oracle, synth, synth.make_scan("hdl64e", 1), 10000, 131072)
+
+
+@pytest.mark.parametrize("sr_type", [0, 1, 2])
+def test_all_score_types_bit_identical(gpu_ctx, oracle, synth, sr_type):
+    scan = synth.make_scan("hdl32e", 5)[::2].copy()
+    gpu_ctx.set_cloud(scan)
+    rg = gpu_ctx.seg_ratio(3000.0, 300, sr_type)
+    ro = oracle.Cloud(scan).seg_ratio(3000.0, 300, sr_type)
+    assert np.array_equal(rg, ro, equal_nan=True)
+
+
+def test_tiled_and_warp_paths_agree(bshot, synth):
+    """BSHOT_WARP_PATH=1 forces the warp-per-query kernels (the fallback of the tiled path) for every point: two
+    independent implementations of the same neighbourhood + summation order"""
+    scan = synth.make_scan("hdl64e", 2)[::3].copy()
+    outs = []
+    for env in (None, "1"):
+        if env:
+            os.environ["BSHOT_WARP_PATH"] = env
+        try:
+            with bshot.Context(0, 65536, 1024, 1024) as ctx:
+                ctx.set_cloud(scan)
+                outs.append((ctx.seg_ratio(3000.0, 300, 0), ctx.seg_ratio(700.0, 40, 2), ctx.compute_normals(1, 3000.0, 300)))
+        finally:
+            os.environ.pop("BSHOT_WARP_PATH", None)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_pile_of_equidistant_points(gpu_ctx, oracle):
+    """400 invalid returns at (0,0,0) -- the reason for the reference's `skip the origin` test (:63) -- are all
+    equidistant from any query: the max_nn-th neighbour falls inside the pile and must be cut by POINT INDEX"""
+    rng = np.random.default_rng(5)
+    real = rng.uniform(-1500, 1500, (700, 3)).astype(np.float32)
+    real[:, 2] = real[:, 2] * 0.1 + 200.0
+    pts = np.concatenate([real[:350], np.zeros((400, 3), np.float32), real[350:]]).astype(np.float32)
+    oc = oracle.Cloud(pts)
+    gpu_ctx.set_cloud(pts)
+    for max_nn in (300, 120):
+        rg = gpu_ctx.seg_ratio(3000.0, max_nn, 0)
+        ro = oc.seg_ratio(3000.0, max_nn, 0)
+        assert np.isnan(rg[350:750]).all()
+        assert np.array_equal(rg, ro, equal_nan=True), np.nanmax(np.abs(rg - ro))
+    q = real[:64]
+    ng, no = gpu_ctx.query_normals(q, 3000.0, 300), oc.normals(q, 3000.0, 300)
+    assert np.array_equal(np.isnan(ng), np.isnan(no)) and np.nanmax(np.abs(ng - no)) <= 1e-6
+
+
+def test_fewer_keypoints_than_top_k(bshot, oracle, synth):
+    """the reference's `< 600` branch (src/lidar_odometry.cpp:144-151): a frame that yields fewer valid points than
+    top_k, followed by a smaller one.  Only the real keypoints may take part in the matching (no stale records)."""
+    rng = np.random.default_rng(9)
+    f0 = synth.make_scan("hdl32e", 0)[::200].copy()                      # ~300 points
+    f1 = synth.make_scan("hdl32e", 1)[::350].copy()                      # fewer
+    f0[::7] = 0.0                                                        # origin points never become keypoints
+    p = bshot.default_params(top_k=600)
+    with bshot.Context(0, 4096, 600, 600) as ctx:
+        r0 = ctx.process_frame(f0, p)
+        r1 = ctx.process_frame(f1, p)
+        r2 = ctx.process_frame(f0, p)
+    for f, r in ((f0, r0), (f1, r1), (f0, r2)):
+        ro = oracle.Cloud(f).seg_ratio(3000.0, 300, 0)
+        idx_o, _ = oracle.select_keypoints(ro, 600, oracle.TIE_DETERMINISTIC)
+        assert len(idx_o) < 600 and np.array_equal(r["kp_idx"], idx_o)
+        assert len(r["bits"]) == len(idx_o)
+    for q, t in ((r0, r0), (r1, r0), (r2, r1)):
+        m = oracle.match(q["bits"], t["bits"])
+        assert np.array_equal(q["pairs"], oracle.mutual(m["left_idx"], m["right_idx"]))
+        assert (q["pairs"][:, 0] < len(q["bits"])).all() and (q["pairs"][:, 1] < len(t["bits"])).all()

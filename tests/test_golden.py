@@ -30,7 +30,9 @@ def test_gpu_matches_golden(bshot, synth):
         ratio = ctx.seg_ratio(R, NN, 0)
         ok = ~np.isnan(G["ratio"])
         assert np.array_equal(np.isnan(ratio), ~ok)
-        assert (ratio[ok] == G["ratio"][ok]).mean() > 0.97
+        assert np.array_equal(ratio[ok], G["ratio"][ok])          # bit-exact scores
+        idx, _, _ = ctx.detect_keypoints(R, NN, 0, K)
+        assert np.array_equal(idx, G["kp_idx"])                    # keypoint index equality
         ctx.set_keypoints(G["pts"][G["kp_idx"]])
         bits = ctx.compute_descriptors(bshot.default_params(top_k=K, kp_radius=R, kp_max_nn=NN, normal_radius=R,
                                                             normal_max_nn=NN, shot_radius=R))
