@@ -31,7 +31,7 @@ EXPORTS = [
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
-    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters",
+    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
         L.bshot_map_reset.argtypes = [vp]
         L.bshot_map_append.argtypes = [vp, vp, sz]
         L.bshot_map_size.argtypes = [vp, C.POINTER(sz)]
+        L.bshot_map_append_dev.argtypes = [vp, vp, sz]
         L.bshot_match_shard_dev.argtypes = [vp, vp, sz, C.c_uint64, ci, vp]
         L.bshot_match_dev.argtypes = [vp, vp, sz, vp, sz, C.c_uint64, ci, vp]
         L.bshot_merge_cands_dev.argtypes = [vp, vp, sz, sz, vp]
@@ -351,6 +352,9 @@ class Context:
     def map_append(self, desc):
         desc = np.ascontiguousarray(desc, dtype=np.uint64).reshape(-1, 6)
         _chk(lib().bshot_map_append(self.h, _p(desc), desc.shape[0]))
+
+    def map_append_dev(self, d_desc_ptr, n):
+        _chk(lib().bshot_map_append_dev(self.h, d_desc_ptr, n))
 
     def map_size(self):
         n = C.c_size_t()

@@ -148,6 +148,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_blk_area, N));
     A(dmalloc(&c->d_nblocks, 8));
     A(dmalloc(&c->d_ovf, N));
+    A(dmalloc(&c->d_rho_hint, N));
     A(dmalloc(&c->d_fb_list, N));
     A(dmalloc(&c->d_ratio, N));
     A(dmalloc(&c->d_keys, N));
@@ -213,7 +214,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
-                    c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
+                    c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
@@ -567,6 +568,15 @@ int bshot_map_append(bshot_ctx* ctx, const uint64_t* desc, size_t n) {
     if (!desc && n) { set_error("bshot_map_append: null descriptors"); return BSHOT_E_INVALID; }
     if (ctx->n_map + n > ctx->max_targets) { set_error("bshot_map_append: shard would hold %zu > capacity %zu", ctx->n_map + n, ctx->max_targets); return BSHOT_E_CAPACITY; }
     BSHOT_TRY(h2d(ctx, ctx->d_map + ctx->n_map * 6, desc, n * 48));
+    ctx->n_map += n;
+    return sync(ctx);
+}
+
+int bshot_map_append_dev(bshot_ctx* ctx, const void* d_desc, size_t n) {
+    CHECK_CTX(ctx);
+    if (!d_desc && n) { set_error("bshot_map_append_dev: null descriptors"); return BSHOT_E_INVALID; }
+    if (ctx->n_map + n > ctx->max_targets) { set_error("bshot_map_append_dev: shard would hold %zu > capacity %zu", ctx->n_map + n, ctx->max_targets); return BSHOT_E_CAPACITY; }
+    if (n) BSHOT_CUDA_TRY(cudaMemcpyAsync(ctx->d_map + ctx->n_map * 6, d_desc, n * 48, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->n_map += n;
     return sync(ctx);
 }

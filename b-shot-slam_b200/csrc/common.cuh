@@ -81,6 +81,7 @@ struct Ctx {
     uint4* d_blocks = nullptr;         // N: query blocks {ix0, iy0, iz0, cells per edge | slice << 4} (tile.cuh)
     float* d_blk_area = nullptr;       // N: surface area per point around the block (radius prediction)
     unsigned* d_nblocks = nullptr;     // [0] heavy blocks, [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [5] light blocks
+    float* d_rho_hint = nullptr;       // N: radius of the detector's neighbourhood of every point (distance of its last member)
     uint2* d_ovf = nullptr;            // N: queries whose block tile overflowed {position in d_sorted, radius bits} (tilek.cu)
     unsigned* d_fb_list = nullptr;     // N: sorted positions of the queries the tiled kernels hand to the fallback
 

@@ -125,9 +125,11 @@ seg_ratio_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__
 
 // points without a score: not binned (non-finite) or at the origin (src/lidar_odometry.cpp:63)
 __global__ void mark_unscored_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ cell_of, unsigned n,
-                                     float* __restrict__ ratio, unsigned long long* __restrict__ keys) {
+                                     float* __restrict__ ratio, unsigned long long* __restrict__ keys, float* __restrict__ rho_hint,
+                                     float radius) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    rho_hint[i] = radius;  // the tiled kernel overwrites it with the radius of the point's neighbourhood
     const float4 p = pts[i];
     if (cell_of[i] == 0xFFFFFFFFu || (p.x == 0.0f && p.y == 0.0f && p.z == 0.0f)) { ratio[i] = __int_as_float(0x7FC00000); keys[i] = 0ull; }
 }
@@ -338,7 +340,7 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_no
     if (n == 0) return BSHOT_OK;
     if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
-    mark_unscored_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_pts, c->d_cell_of, n, c->d_ratio, c->d_keys);
+    mark_unscored_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_pts, c->d_cell_of, n, c->d_ratio, c->d_keys, c->d_rho_hint, radius);
     count_launch(c);
     if (tile_path_ok(c, max_nn)) {
         fuse_normals = fuse_normals && !c->force_warp_path;

@@ -135,9 +135,14 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
         c->fused_normals = false;  // keypoint normals overwrite the prefix of d_normals
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
-            if (tiled && c->kp_from_detector) {
-                // keypoints are cloud points flagged by the top-K pass: straight into d_normals[ordinal] (include/bshot_bits.h:79-81)
-                        BSHOT_TRY(tile_neighbourhoods(c, 0, false, true, radius, max_nn, c->d_kp_flag, c->d_normals));
+            if (tiled && c->kp_from_detector && c->sel_valid && c->sel_radius == radius && c->sel_max_nn == max_nn) {
+                // keypoints are cloud points the detector just searched with the same parameters: one private tile per
+                // keypoint with the radius kept for it, straight into d_normals[ordinal] (include/bshot_bits.h:79-81)
+                BSHOT_TRY(tile_keypoint_normals(c, radius, max_nn, c->d_normals));
+                BSHOT_TRY(normals_fallback_list(c, radius, max_nn, c->d_kp_flag, c->d_normals));
+            } else if (tiled && c->kp_from_detector) {
+                // other search parameters: keypoints flagged per cell-sorted position, shared tiles
+                BSHOT_TRY(tile_neighbourhoods(c, 0, false, true, radius, max_nn, c->d_kp_flag, c->d_normals));
                 BSHOT_TRY(normals_fallback_list(c, radius, max_nn, c->d_kp_flag, c->d_normals));
             } else {
                 BSHOT_TRY(normals_launch(c, c->d_kp, c->d_kp_count, k, radius, max_nn, c->d_qnormals));

@@ -15,6 +15,8 @@ int detect_topk(Ctx* c, int top_k);
 // point, else per cell-sorted position the output slot (>= 0) of the points that want a normal
 int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out);
 bool tile_path_ok(const Ctx* c, int max_nn);
+// normals of the detector's keypoints at their ordinals, from the radii the detector kept (tilek.cu)
+int tile_keypoint_normals(Ctx* c, float radius, int max_nn, float4* d_nrm_out);
 // normals of the queries the tiled kernel put on the fallback list (normals.cu)
 int normals_fallback_list(Ctx* c, float radius, int max_nn, const int* d_flags, float4* d_out);
 

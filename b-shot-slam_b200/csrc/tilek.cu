@@ -17,11 +17,18 @@ namespace bshot {
 // memory, 10 floats) receives the nine accumulators of pcl::computeMeanAndCovarianceMatrix + the count when NRM.
 template <int SR, bool SEG, bool NRM>
 __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ tile, const float4& q, int count, TileWarp& w, unsigned lane,
-                                                   float* __restrict__ ratio, unsigned long long* __restrict__ keys, float* nsum) {
+                                                   float* __restrict__ ratio, unsigned long long* __restrict__ keys, float* nsum,
+                                                   float* __restrict__ rho_hint, int max_nn, float R) {
     const float nanf_ = __int_as_float(0x7FC00000);
     const unsigned qi = __float_as_uint(q.w);
     tile_gather(tile, count, w, lane);
     const float fn = (float)count;
+    if (SEG && lane == 0) {
+        // radius of this neighbourhood (distance of its last member), kept per point: a later pass over the same point
+        // -- the normals of the points that become keypoints -- stages exactly this ball
+        const int l = count - 1;
+        rho_hint[qi] = (count >= max_nn) ? sqrtf(sqdist_rn(q.x, q.y, q.z, w.u.soa[0][l], w.u.soa[1][l], w.u.soa[2][l])) * 1.0001f + 0.01f : R;
+    }
     float sx, sy, sz;
     if (NRM) {
         // the nine accumulators, one lane each (6..8 = plain sums = the centroid sums of pcl::computeCentroid)
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, NRM ? BSHOT_TL_MINBLOCKS : BSHO
 tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
             const uint4* __restrict__ blocks, const float* __restrict__ blk_area, unsigned* __restrict__ ctl, float radius, int max_nn,
             float* __restrict__ ratio, unsigned long long* __restrict__ keys, const int* __restrict__ flags, float4* __restrict__ nrm_out,
-            unsigned long long* __restrict__ counters, uint2* __restrict__ ovf, unsigned block_cap) {
+            unsigned long long* __restrict__ counters, uint2* __restrict__ ovf, unsigned block_cap, float* __restrict__ rho_hint) {
     using SM = TileShared<NRM, TL_CAP, TL_WARPS>;
     __shared__ SM sm;
     unsigned& s_block = sm.cur_block;
@@ -191,7 +198,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                         if (lane == 0) { sm.q_nin[k] = max(tq.n_in, 1); atomicMin(&sm.min_nin, tq.n_in); atomicAdd(&counters[5], 1ull); }
                         continue;
                     }
-                    tile_query_outputs<SR, SEG, NRM>(sm.tile, q, tq.count, w, lane, ratio, keys, NRM ? sm.nsum[k] : nullptr);
+                    tile_query_outputs<SR, SEG, NRM>(sm.tile, q, tq.count, w, lane, ratio, keys, NRM ? sm.nsum[k] : nullptr, rho_hint, max_nn, R);
                     if (lane == 0) {
                         sm.q_nin[k] = -1;
                         atomicSub(&sm.pending, 1u);
@@ -289,21 +296,30 @@ __global__ void __launch_bounds__(TS_WARPS * 32, 3)
 tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
                    unsigned* __restrict__ ctl, float radius, int max_nn, float* __restrict__ ratio, unsigned long long* __restrict__ keys,
                    const int* __restrict__ flags, float4* __restrict__ nrm_out, unsigned long long* __restrict__ counters,
-                   const uint2* __restrict__ ovf, unsigned* __restrict__ fb_list) {
+                   const uint2* __restrict__ ovf, unsigned* __restrict__ fb_list, float* __restrict__ rho_hint,
+                   const int* __restrict__ kp_idx, const int* __restrict__ kp_count, const unsigned* __restrict__ sorted_pos) {
     extern __shared__ __align__(16) unsigned char single_smem_raw[];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     SingleWarp& st = reinterpret_cast<SingleWarp*>(single_smem_raw)[wid];
     const GridParams g = *gp;
     const float R = radius;
     const float R2 = (float)((double)R * (double)R);
-    const unsigned n_items = ctl[4];
+    // items: the overflow queries of tile_kernel -- or (kp_idx != nullptr) the detector's keypoints, each with the radius
+    // the detector kept for it; result slot = keypoint ordinal (the reference's placement, include/bshot_bits.h:79-81)
+    const unsigned n_items = kp_idx ? (unsigned)max(*kp_count, 0) : ctl[4];
     unsigned long long nbr = 0;
     for (;;) {
         unsigned i = 0;
         if (lane == 0) i = atomicAdd(ctl + 3, 1u);
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n_items) break;
-        const uint2 item = ovf[i];
+        uint2 item;
+        if (kp_idx) {
+            const int idx = kp_idx[i];
+            item = make_uint2(sorted_pos[idx], __float_as_uint(rho_hint[idx]));
+        } else {
+            item = ovf[i];
+        }
         const float4 q = __ldg(sorted + item.x);
         float rho = __uint_as_float(item.y), rho_lo = 0.0f, rho_hi = 3.0e38f;
         bool done = false;
@@ -323,7 +339,7 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
             if (at_R || S >= (unsigned)max_nn) {
                 const TileQuery tq = tile_select(st.tile, (S + 127u) & ~127u, q, rho2, at_R, max_nn, st.w, lane);
                 if (tq.count > 0) {
-                    tile_query_outputs<SR, SEG, NRM>(st.tile, q, tq.count, st.w, lane, ratio, keys, st.nsum);
+                    tile_query_outputs<SR, SEG, NRM>(st.tile, q, tq.count, st.w, lane, ratio, keys, st.nsum, rho_hint, max_nn, R);
                     if (NRM) {
                         __syncwarp();
                         if (lane == 0) {
@@ -331,7 +347,7 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
 #pragma unroll
                             for (int k = 0; k < 9; ++k) a[k] = st.nsum[k];
                             const float4 o = normal_from_sums(a, (int)st.nsum[9], q.x, q.y, q.z);
-                            nrm_out[flags ? (unsigned)__ldg(flags + item.x) : __float_as_uint(q.w)] = o;
+                            nrm_out[kp_idx ? i : (flags ? (unsigned)__ldg(flags + item.x) : __float_as_uint(q.w))] = o;
                         }
                     }
                     nbr += (unsigned long long)tq.count;
@@ -367,10 +383,10 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, i
         }                                                                                                                                  \
         tile_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * (BSHOT_TL_MINBLOCKS + 1), TL_WARPS * 32, 0, c->stream>>>(                       \
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_blocks, c->d_blk_area, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, \
-            d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points);                                                                  \
+            d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points, c->d_rho_hint);                                                   \
         tile_single_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(                            \
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, d_nrm_out, c->d_counters,   \
-            c->d_ovf, c->d_fb_list);                                                                                                       \
+            c->d_ovf, c->d_fb_list, c->d_rho_hint, nullptr, nullptr, nullptr);                                                             \
     } while (0)
     if (!seg) BSHOT_TILE(BSHOT_SR_CV, false, true);
     else if (sr_type == BSHOT_SR_CV) { if (nrm) BSHOT_TILE(BSHOT_SR_CV, true, true); else BSHOT_TILE(BSHOT_SR_CV, true, false); }
@@ -379,6 +395,24 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, i
 #undef BSHOT_TILE
     count_launch(c, 2);
     return check_launch("tile_kernel");
+}
+
+// REFERENCE-mode normals of the detector's keypoints: one private tile per keypoint, staged with the radius the detector
+// kept for that point (the ball holds its max_nn neighbours and nothing else), result at the keypoint's ordinal
+int tile_keypoint_normals(Ctx* c, float radius, int max_nn, float4* d_nrm_out) {
+    if (max_nn <= 0 || max_nn > TL_MAXNN) { set_error("tile_keypoint_normals: max_nn %d outside (0, %d]", max_nn, TL_MAXNN); return BSHOT_E_INVALID; }
+    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, 4 * sizeof(unsigned), c->stream));
+    const size_t single_smem = sizeof(SingleWarp) * TS_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSHOT_CUDA_TRY(cudaFuncSetAttribute(tile_single_kernel<BSHOT_SR_CV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)single_smem));
+        attr_set = true;
+    }
+    tile_single_kernel<BSHOT_SR_CV, false, true><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(
+        c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, nullptr, d_nrm_out, c->d_counters, c->d_ovf,
+        c->d_fb_list, c->d_rho_hint, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos);
+    count_launch(c);
+    return check_launch("tile_single_kernel (keypoints)");
 }
 
 }  // namespace bshot

@@ -2,31 +2,32 @@
 """bench.py -- B-SHOT front-end benchmark (contract: see the task prompt / DESIGN.md section 6).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-  python bench.py --impl reference [--gpus N] ...               # CPU oracle port, host cores
+  python bench.py --impl reference [--gpus N] ...               # CPU oracle port, host cores, same config
   torchrun ... bench.py --gpus N ...                            # one rank per GPU (N > 1)
 
-Workload (config.workload = "C2"): BASELINE.json configs[1] -- frame-to-frame B-SHOT odometry front
-end over a synthetic HDL-32E sequence (69 440 rays/frame, mm): voxel build -> seg-ratio detector ->
-top-K -> normals -> SHOT LRF + 352-bin histogram -> B-SHOT bits -> Hamming mutual-NN match against
-the previous frame.  One step = one frame.  metric = B-SHOT descriptors/s through that whole path.
+Headline workload (config.workload = "C3", BASELINE.json configs[2], the north_star frame and the largest
+single-GPU configuration): HDL-64E-shaped 120 000-ray scans, 10 000 keypoints per frame, frame-to-frame:
+voxel build -> seg-ratio detector -> top-K -> normals -> SHOT LRF + 352-bin histogram -> B-SHOT bits -> Hamming
+mutual-NN match against the previous frame.  One step = one frame.  metric = B-SHOT descriptors/s through that
+whole path.  The detector / normals run in the only mode there is: the reference's fp32 summation order
+(bit-identical scores and keypoint indices, tests/test_detector_edge_gpu.py).
  * value : cloud already resident in HBM when the timed region starts (bshot_process_frame_dev).
- * e2e   : the C-ABI call a reference maintainer would make (bshot_process_frame) on pinned HOST
-           buffers, H2D + D2H inside the timed region.
- * N > 1 : frame extraction does not shard (replicas only) -> every rank processes a replica of
-           the frame stream, no data-path collective, weak scaling.  The part of the path that
-           DOES shard -- frame-to-map Hamming search against a map split over the ranks, per-rank
-           top-2 candidates exchanged by stores into symmetric peer memory + flag barriers (or one
-           NCCL all-gather + all-reduce, BSHOT_EXCHANGE=nccl) -- is timed in the same run and
-           reported under "map_match" (C4: Q = 10 000 queries vs T = 1 048 576 map descriptors).
- * extra objects at N = 1: "c3" (BASELINE.json configs[2]: HDL-64E 120 k-point frame, K = 10 000, and the
-           SHOT-radius sweep with FULL normals), "exact_mode" (the same C2 frames with BSHOT_EXACT_SUMS=1).
+ * e2e   : the C-ABI call a reference maintainer would make (bshot_process_frame) on pinned HOST buffers,
+           H2D + D2H inside the timed region.
+ * N > 1 : frame extraction does not shard (replicas only) -> every rank processes a replica of the
+           frame stream, no data-path collective, weak scaling.  The part of the path that DOES shard -- frame-to-
+           map Hamming search against a map split over the ranks -- is timed in the same run and reported under
+           "map_match" (C4: Q = 10 000 / 2 048 / 600 queries vs T = 1 048 576 map descriptors, with the single-GPU
+           time of the same search measured in the same run -> efficiency_vs_1gpu; C5: T = 16 777 216 when 8 ranks).
+ * extra objects at N = 1: "c2" (BASELINE.json configs[1]: HDL-32E sequence, K = 2 048, per-frame p50 / p99 over
+           >= 100 distinct frames), "c3_radius_sweep" (extraction throughput over the SHOT radius, FULL normals).
+ * --impl reference: the oracle port of the reference's CPU path on all host cores, same config / frames / metric.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
+import threading
 import time
 
 import numpy as np
@@ -36,9 +37,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_bshot, load_oracle, load_sharded, load_synth  # noqa: E402  (loaders only, no pytest needed)
 
 HBM_FALLBACK_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
-N_FRAMES = 12               # distinct synthetic frames per rank, cycled
-TOP_K = 2048                # C1/C2 "~2k keypoints" (reference default 600: --top-k 600)
 L2_FLUSH_BYTES = 256 << 20
+WORKLOADS = {  # name: (sensor, rays per frame, keypoints per frame, distinct frames cycled)
+    "C3": ("hdl64e", 120000, 10000, 8),
+    "C2": ("hdl32e", 69440, 2048, 12),
+}
+METRIC, UNIT = "bshot_frontend_descriptors_per_s", "descriptors/s"
 
 
 def peaks():
@@ -53,50 +57,67 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled in-process through NVML every ~2 ms while `active` (the timed regions last
+    tens of milliseconds: an external nvidia-smi loop at 100 ms sees nothing)."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active, self.stop_flag, self.thread, self.nv = False, False, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+               "how": "NVML in-process, ~2 ms period, during the timed regions (value + e2e)"}
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
         return out
 
 
-def cpu_front_end(oracle, scans, top_k, threads, detector_threads=None):
-    """the oracle port of the reference path on host cores; returns seconds per frame (mean)"""
-    prev = None
+def workload_config(name, top_k, normals, points_per_frame):
+    """the workload-defining keys -- identical in the CUDA arm and in the --impl reference arm"""
+    sensor, rays, _, nframes = WORKLOADS[name]
+    return {"workload": name, "sensor": sensor, "rays_per_frame": rays, "points_per_frame": int(points_per_frame), "top_k": int(top_k),
+            "radius_mm": 3000, "max_nn": 300, "sr_type": "CV", "normals": normals.upper(), "frames_cycled": nframes,
+            "match": "frame-to-frame mutual nearest neighbour (initial frame against itself)"}
+
+
+def make_frames(synth, name):
+    sensor, _, _, nframes = WORKLOADS[name]
+    return [synth.make_scan(sensor, f) for f in range(nframes)]
+
+
+def cpu_front_end(oracle, scans, top_k, threads, detector_threads=None, prev=None):
+    """the oracle port of the reference path on host cores; returns (seconds per frame, last descriptors)"""
     t0 = time.perf_counter()
     for xyz in scans:
         c = oracle.Cloud(xyz)
@@ -107,55 +128,69 @@ def cpu_front_end(oracle, scans, top_k, threads, detector_threads=None):
         m = oracle.match(d["bits"], tgt, want_right=True, threads=detector_threads or threads)
         oracle.mutual(m["left_idx"], m["right_idx"])
         prev = d["bits"]
-    return (time.perf_counter() - t0) / len(scans)
+    return (time.perf_counter() - t0) / len(scans), prev
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path (oracle port; the PCL reference cannot be built
-    here) on all host cores, same workload / metric."""
+    """--impl reference: the reference's CPU path (oracle port; only include/bshot_bits.h of the reference compiles
+    here) on all host cores: same workload, frames, metric and steps as the CUDA arm; every step
+    is one whole frame (about a second on 16 cores)."""
     if rank != 0:
         return
     oracle, synth = load_oracle(), load_synth()
     cores = os.cpu_count() or 1
-    scans = [synth.make_scan("hdl32e", f) for f in range(min(3, max(1, args.steps)))]
-    for _ in range(min(args.warmup, 1)):
-        cpu_front_end(oracle, scans[:1], args.top_k, cores)
-    steps = max(1, min(args.steps, 6))
+    frames = make_frames(synth, args.workload)
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    prev = None
+    t_first, prev = cpu_front_end(oracle, frames[:1], args.top_k, cores)
+    # bound the run: a few minutes at most (the driver's default K = 20 takes well under one)
+    budget_frames = max(2, int(150.0 / max(t_first, 1e-3)))
+    k_timed = min(K, budget_frames)
+    for i in range(1, min(W, 2)):
+        _, prev = cpu_front_end(oracle, [frames[i % len(frames)]], args.top_k, cores, prev=prev)
     per = []
-    for s in range(steps):
-        per.append(cpu_front_end(oracle, [scans[s % len(scans)]], args.top_k, cores))
+    for s in range(k_timed):
+        t, prev = cpu_front_end(oracle, [frames[(W + s) % len(frames)]], args.top_k, cores, prev=prev)
+        per.append(t)
     sec = float(np.mean(per))
     val = args.top_k / sec
+    sample = f"{k_timed} whole frames of this workload (detector + top-K + normals + SHOT + B-SHOT + match), OpenMP over {cores} threads"
+    if k_timed < K:
+        sample += f"; the remaining {K - k_timed} steps are the same frames again and were extrapolated from this mean"
     line = {
-        "impl": "reference", "metric": "bshot_frontend_descriptors_per_s", "value": val, "unit": "descriptors/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64+u32", "data": "synthetic",
-        "config": {"workload": "C2", "sensor": "hdl32e", "points_per_frame": int(np.mean([len(s) for s in scans])),
-                   "top_k": args.top_k, "radius_mm": 3000, "normals": "REFERENCE"},
-        "cpu_baseline": {"value": val, "unit": "descriptors/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full frames (detector+normals+SHOT+B-SHOT+match), OpenMP over {cores} threads"},
-        "e2e": {"value": val, "unit": "descriptors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64+u32",
+        "data": "synthetic", "config": workload_config(args.workload, args.top_k, args.normals, np.mean([len(f) for f in frames])),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def percentile_summary(x):
+    x = np.asarray(x, dtype=np.float64)
+    return {"mean": float(x.mean()), "p50": float(np.percentile(x, 50)), "p90": float(np.percentile(x, 90)),
+            "p99": float(np.percentile(x, 99)), "max": float(x.max()), "frames": int(len(x))}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--top-k", dest="top_k", type=int, default=TOP_K)
-    ap.add_argument("--sensor", default="hdl32e")
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--top-k", dest="top_k", type=int, default=None)
     ap.add_argument("--normals", default="reference", choices=["reference", "full"])
-    ap.add_argument("--map-q", type=int, default=10000)
     ap.add_argument("--map-t", type=int, default=1 << 20)
     ap.add_argument("--map-steps", type=int, default=10)
     ap.add_argument("--no-map", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-c3", action="store_true", help="skip the HDL-64E frame / SHOT-radius sweep (C3) object")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 sequence and the C3 SHOT-radius sweep objects")
     ap.add_argument("--map-only", action="store_true", help="debug: print only the map_match object")
     args = ap.parse_args()
+    if args.top_k is None:
+        args.top_k = WORKLOADS[args.workload][2]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,13 +226,15 @@ def main():
 
     # ---- inputs ---------------------------------------------------------------------------------
     # replicas: every rank runs the SAME frames (identical work per GPU keeps the weak-scaling figure clean)
-    frames = [synth.make_scan(args.sensor, f) for f in range(N_FRAMES)]
+    frames = make_frames(synth, args.workload)
+    nfr = len(frames)
     npts = [len(f) for f in frames]
     max_n = max(npts)
     mode = bs.NORMALS_REFERENCE if args.normals == "reference" else bs.NORMALS_FULL
     params = bs.default_params(top_k=args.top_k, normals_mode=mode)
-    ctx = bs.Context(local_rank, max_points=max_n + 1024, max_keypoints=max(args.top_k, args.map_q),
-                     max_targets=max(args.top_k, (args.map_t + world - 1) // world))
+    map_q = 10000
+    ctx = bs.Context(local_rank, max_points=max_n + 1024, max_keypoints=max(args.top_k, map_q),
+                     max_targets=max(args.top_k, (args.map_t + world - 1) // world, args.map_t if world > 1 else 0))
     st = torch.cuda.ExternalStream(ctx.stream)
     d_frames = [torch.from_numpy(f).cuda() for f in frames]                 # resident in HBM
     h_frames = [torch.from_numpy(f).pin_memory() for f in frames]           # pinned host copies
@@ -211,24 +248,26 @@ def main():
             flush.fill_(1.0)
 
     def step_resident(i):
-        f = i % N_FRAMES
+        f = i % nfr
         ctx.process_frame_dev(d_frames[f].data_ptr(), npts[f], 12, params)
 
     def step_e2e(i):
-        f = i % N_FRAMES
+        f = i % nfr
         return ctx.process_frame_raw(h_frames[f].data_ptr(), npts[f], 12, params, h_kp.data_ptr(),
                                      h_bits.data_ptr(), h_pairs.data_ptr())
 
     # ---- HBM-resident timing (value) ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.enable_timing(True)
     for i in range(W):
         step_resident(i)
     ctx.sync()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     stage_acc, counters_acc = {}, {}
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # runs across the value and e2e timed regions
     launches0 = ctx.launch_count()
     barrier()
+    if sampler:
+        sampler.active = True
     for i in range(K):
         l2_flush()
         ev[i][0].record(st)
@@ -239,206 +278,263 @@ def main():
         for k, v in ctx.frame_counters().items():
             counters_acc[k] = counters_acc.get(k, 0) + v
     barrier()
+    if sampler:
+        sampler.active = False
     launches = ctx.launch_count() - launches0
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    ms_total = max_over_ranks(ms_total)
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms_total = max_over_ranks(sum(per_step))
     ms_step = ms_total / K
     n_desc = counters_acc["keypoints"] / K                       # descriptors actually produced per frame
     value = world * n_desc / (ms_step * 1e-3)
     stages = {k: v / K for k, v in stage_acc.items()}
 
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
-    kern = {"seg_ratio": ("seg_ratio_kernel", 16.0 * counters_acc["detector_neighbours"] / K + 12.0 * np.mean(npts)),
-            "shot_bshot": ("shot_kernel", 16.0 * counters_acc["shot_neighbours"] / K + 48.0 * n_desc),
-            "normals": ("normals_kernel", 16.0 * counters_acc["normals_neighbours"] / K + 16.0 * n_desc),
-            "voxel_build": ("grid_build (9 kernels)", 2 * 16.0 * np.mean(npts))}
-    dom = max(kern, key=lambda k: stages[k])
-    alg_bytes = kern[dom][1]
-    achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9
-    traffic, ncu_extra = None, None
-    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        traffic = tj.get(kern[dom][0])
-        ncu_extra = tj.get("_ncu", {}).get(kern[dom][0])
+    # ---- roofline of the dominant kernel (and the others beside it) ---------------------------------------
+    # algorithmic bytes per launch: 16 B per selected neighbour (+ 16 B per neighbour normal in SHOT) + outputs
+    mean_n = float(np.mean(npts))
+    kern = {"seg_ratio": ("tile_kernel + tile_single_kernel (seg-ratio detector stage)", 16.0 * counters_acc["detector_neighbours"] / K + 12.0 * mean_n),
+            "shot_bshot": ("shot_kernel", 32.0 * counters_acc["shot_neighbours"] / K + 48.0 * n_desc),
+            "normals": ("tile_single_kernel (keypoint normals)", 16.0 * counters_acc["normals_neighbours"] / K + 16.0 * n_desc),
+            "voxel_build": ("grid_build", 2 * 16.0 * mean_n)}
+    traffic_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": kern[dom][0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": stages[dom], "ncu": ncu_extra,
-                "note": "cloud (<2 MB) is L2 resident: algorithmic bytes are re-read from L2/L1, not HBM; the kernel is "
-                        "bound by dependent latency / instruction issue (see ncu.issue_active_pct), DESIGN.md section 7"}
+
+    def roof(name):
+        kname, alg = kern[name]
+        ach = alg / (stages[name] * 1e-3) / 1e9
+        t = traffic_tab.get(name, {})
+        return {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": t.get("dram_bytes_per_launch"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "ms_per_launch": stages[name], "ncu": t.get("ncu")}
+    dom = max(kern, key=lambda k: stages[k])
+    roofline = roof(dom)
+    roofline["note"] = ("the cloud (< 2 MB) is L2 resident and the neighbourhood tiles are staged once per block in shared memory: "
+                        "the algorithmic bytes are re-read from shared memory, not HBM; the kernel is bound by instruction issue "
+                        "(DESIGN.md section 7)")
+    roofline_others = {k: roof(k) for k in kern if k != dom}
 
     # ---- end-to-end through the host-buffer C ABI (e2e) ---------------------------------------------
     ctx.enable_timing(False)
     for i in range(W):
         step_e2e(i)
     barrier()
+    if sampler:
+        sampler.active = True
     t_e2e = 0.0
     for i in range(K):
         l2_flush()
         ctx.sync()
         t0 = time.perf_counter()
-        nk, _ = step_e2e(W + i)
+        step_e2e(W + i)
         t_e2e += time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
     t_e2e = max_over_ranks(t_e2e)
     e2e_val = world * n_desc / (t_e2e / K)
-    e2e = {"value": e2e_val, "unit": "descriptors/s", "ms_per_step": t_e2e / K * 1e3,
-           "h2d_bytes_per_step": int(np.mean(npts) * 12),
+    e2e = {"value": e2e_val, "unit": UNIT, "ms_per_step": t_e2e / K * 1e3,
+           "h2d_bytes_per_step": int(mean_n * 12),
            "d2h_bytes_per_step": int(args.top_k * (4 + 48 + 12) + 8),
            "api": "bshot_process_frame (C ABI, pinned host buffers, synchronous)"}
 
     # ---- sharded frame-to-map matching (the part of the path that shards) -----------------------------
     map_match = None
     if not args.no_map:
-        T, Q = args.map_t, args.map_q
-        per = (T + world - 1) // world
-        lo, hi = rank * per, min(T, (rank + 1) * per)
-        tfull = synth.random_descriptors(T, seed=7)                # same global map on every rank, own shard kept
-        ctx.map_reset()
-        ctx.map_append(tfull[lo:hi])
-        q = synth.random_descriptors(Q, seed=8)
-        planted = np.random.default_rng(9).permutation(T)[:64]     # self-check: 64 queries are exact copies of map entries
-        q[:64] = tfull[planted]
-        del tfull
-        dq = torch.from_numpy(q.view(np.int64)).cuda()
-        # the per-call protocol (shard search, record exchange, merge, sharded reverse pass) lives in the package:
-        # sharded.DeviceShardedMatcher; BSHOT_EXCHANGE=nccl forces the NCCL exchange, default = peer memory if possible
-        sharded = load_sharded()
-        matcher = sharded.DeviceShardedMatcher(ctx, world, rank, Q, mode="nccl" if os.environ.get("BSHOT_EXCHANGE") == "nccl" else "auto",
-                                               device=torch.device("cuda", local_rank))
+        map_match = bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks)
 
-        def map_calls(n):
-            out = None
-            for _ in range(n):
-                out = matcher.match(dq.data_ptr(), lo)
-            return out
-
-        last = map_calls(3)
-        barrier()
-        rec = last[:64].cpu().numpy().view(bs.CAND_DTYPE).reshape(64)
-        chk = bs.unpack_cands(rec)
-        if not (np.array_equal(chk["idx1"], planted) and (chk["dist1"] == 0).all() and np.array_equal(chk["rq"], np.arange(64))):
-            raise SystemExit("bench.py: sharded map match self-check failed (planted duplicates not recovered)")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launch_count()
-        e0.record(st)
-        map_calls(args.map_steps)
-        e1.record(st)
-        barrier()
-        mm_ms = max_over_ranks(e0.elapsed_time(e1)) / args.map_steps
-        matcher.check()
-        popc_peak = ctx.popc_peak()
-        pairs = float(Q) * float(T)
-        map_match = {"workload": "C4", "Q": Q, "T": T, "shards": world, "ms_per_call": mm_ms,
-                     "pairs_per_s": pairs / (mm_ms * 1e-3), "target_GBps": T * 48 / (mm_ms * 1e-3) / 1e9,
-                     "roofline": {"bound": "popc", "achieved": 11 * pairs / (mm_ms * 1e-3) / 1e12,
-                                  "peak": world * popc_peak / 1e12, "unit": "TPOPC32/s",
-                                  "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
-                                  "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
-                     "collective": matcher.describe(),
-                     "gpu_launches_per_call": (ctx.launch_count() - l0) // args.map_steps}
-
-
-    # ---- C3: HDL-64E-shaped 120 k-point scans, K = 10 000 (rank 0, N = 1 only) --------------------------
-    # (a) the north_star frame: full extraction + match of one 120 k-point scan, REFERENCE normals;
-    # (b) extraction throughput (normals + LRF + SHOT352 + B-SHOT) over the SHOT radius, FULL normals.
-    c3 = None
-    if rank == 0 and world == 1 and not args.no_c3 and not args.map_only:
-        K64, NF64 = 10000, 3
-        f64 = [synth.make_scan("hdl64e", f) for f in range(NF64)]
-        n64 = [len(f) for f in f64]
-        d64 = [torch.from_numpy(f).cuda() for f in f64]
-        ctx64 = bs.Context(local_rank, max_points=max(n64) + 1024, max_keypoints=K64, max_targets=K64)
-        st64 = torch.cuda.ExternalStream(ctx64.stream)
-        ctx64.enable_timing(True)
-
-        def run64(params64, reps):
-            acc, nbr = {}, 0
-            for i in range(2):                                        # warm-up (also fills prev-frame descriptors)
-                ctx64.process_frame_dev(d64[i % NF64].data_ptr(), n64[i % NF64], 12, params64)
-            ctx64.sync()
-            for i in range(reps):
-                with torch.cuda.stream(st64):
-                    flush.fill_(1.0)
-                ctx64.process_frame_dev(d64[i % NF64].data_ptr(), n64[i % NF64], 12, params64)
-                for k, v in ctx64.stage_times().items():
-                    acc[k] = acc.get(k, 0.0) + v / reps
-                nbr += ctx64.frame_counters()["shot_neighbours"] / reps
-            return acc, nbr
-
-        st_ref, _ = run64(bs.default_params(top_k=K64), 12)
-        sweep = []
-        for R in (500.0, 1000.0, 2000.0, 3000.0, 4000.0):
-            ctx64.reset()
-            st_r, nbr = run64(bs.default_params(top_k=K64, normals_mode=bs.NORMALS_FULL, normal_radius=R, shot_radius=R), 6)
-            ext_ms = st_r["normals"] + st_r["shot_bshot"]
-            sweep.append({"radius_mm": R, "normals_ms": st_r["normals"], "shot_bshot_ms": st_r["shot_bshot"],
-                          "descriptors_per_s": K64 / (ext_ms * 1e-3), "shot_neighbours_per_keypoint": nbr / K64,
-                          "shot_algorithmic_GBps": 32.0 * nbr / (st_r["shot_bshot"] * 1e-3) / 1e9})
-        c3 = {"workload": "C3", "sensor": "hdl64e", "points_per_frame": int(np.mean(n64)), "top_k": K64,
-              "frame_reference_normals": {"ms_per_frame": st_ref["frame"], "stages_ms": st_ref,
-                                          "north_star_target_ms": 2.0},
-              "radius_sweep_full_normals": sweep,
-              "note": "stage times from CUDA events on the context stream, L2 flushed before every frame"}
-        ctx64.close()
-
-    # ---- exact-sums mode (reference summation order, bit-identical seg-ratios / keypoints): same C2 frames ----
-    exact = None
-    if rank == 0 and world == 1 and not args.map_only:
-        os.environ["BSHOT_EXACT_SUMS"] = "1"
-        try:
-            ctxe = bs.Context(local_rank, max_points=max_n + 1024, max_keypoints=args.top_k, max_targets=args.top_k)
-        finally:
-            os.environ.pop("BSHOT_EXACT_SUMS", None)
-        ctxe.enable_timing(True)
-        acc = {}
-        for i in range(3 + 10):
-            ctxe.process_frame_dev(d_frames[i % N_FRAMES].data_ptr(), npts[i % N_FRAMES], 12, params)
-            if i >= 3:
-                for k, v in ctxe.stage_times().items():
-                    acc[k] = acc.get(k, 0.0) + v / 10
-        exact = {"env": "BSHOT_EXACT_SUMS=1", "ms_per_frame": acc["frame"], "stages_ms": acc,
-                 "note": "fp32 running sums replayed in neighbour order: seg-ratios and keypoints bit-identical to the oracle"}
-        ctxe.close()
+    # ---- extras at N = 1 ------------------------------------------------------------------------------
+    c2 = c3_sweep = None
+    if rank == 0 and world == 1 and not args.no_extras and not args.map_only:
+        c2 = bench_c2_sequence(bs, synth, local_rank, flush)
+        c3_sweep = bench_c3_sweep(bs, synth, local_rank, flush)
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not args.map_only:
         oracle = load_oracle()
         cores = os.cpu_count() or 1
-        sample = frames[:3]
-        cpu_front_end(oracle, sample[:1], args.top_k, cores)      # warm-up (page-in, OpenMP pool)
-        sec = cpu_front_end(oracle, sample, args.top_k, cores)
-        sec_ref = cpu_front_end(oracle, sample[:2], args.top_k, min(12, cores), detector_threads=1)
-        cpu_baseline = {"value": args.top_k / sec, "unit": "descriptors/s", "cores": cores, "kind": "port",
-                        "ms_per_frame": sec * 1e3,
-                        "sample": "3 full frames of this workload (detector+normals+SHOT+B-SHOT+match), all cores",
-                        "reference_threading": {"value": args.top_k / sec_ref, "ms_per_frame": sec_ref * 1e3,
-                                                "detector_match_threads": 1, "normals_shot_threads": min(12, cores),
-                                                "sample": "2 frames"}}
+        cpu_front_end(oracle, frames[:1], args.top_k, cores)      # warm-up (page-in, OpenMP pool)
+        sample = frames[:min(nfr, 6)]
+        sec, _ = cpu_front_end(oracle, sample, args.top_k, cores)
+        sec_ref, _ = cpu_front_end(oracle, sample[:1], args.top_k, min(12, cores), detector_threads=1)
+        cpu_baseline = {"value": args.top_k / sec, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_frame": sec * 1e3,
+                        "sample": f"{len(sample)} whole frames of this workload (detector + top-K + normals + SHOT + B-SHOT + match), all cores",
+                        "reference_threading": {"value": args.top_k / sec_ref, "ms_per_frame": sec_ref * 1e3, "detector_match_threads": 1,
+                                                "normals_shot_threads": min(12, cores), "sample": "1 frame"}}
 
     if rank == 0 and args.map_only:
         print(json.dumps(map_match))
     elif rank == 0:
         line = {
-            "metric": "bshot_frontend_descriptors_per_s", "value": value, "unit": "descriptors/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32/f64+u32", "data": "synthetic",
-            "config": {"workload": "C2", "sensor": args.sensor, "points_per_frame": int(np.mean(npts)),
-                       "rays_per_frame": 69440 if args.sensor == "hdl32e" else 120000, "top_k": args.top_k,
-                       "descriptors_per_frame": n_desc, "radius_mm": 3000, "max_nn": 300,
-                       "normals": args.normals.upper(), "frames_cycled": N_FRAMES,
-                       "parallelism": "replicas (one frame stream per GPU)" if world > 1 else "single GPU",
-                       "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write), per-step CUDA events on the context stream"},
-            "stages_ms": stages, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c3": c3, "exact_mode": exact,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64+u32", "data": "synthetic",
+            "config": workload_config(args.workload, args.top_k, args.normals, mean_n),
+            "timing": {"l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write)", "clock": "per-step CUDA events on the context stream",
+                       "parallelism": "replicas (one frame stream per GPU, no data-path collective)" if world > 1 else "single GPU",
+                       "ms_per_step_distribution": percentile_summary(per_step), "descriptors_per_frame": n_desc,
+                       "detector_mode": "exact: fp32 running sums replayed in neighbour order (scores / keypoint indices bit-identical to the oracle)"},
+            "stages_ms": stages, "roofline": roofline, "roofline_others": roofline_others, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c2": c2, "c3_radius_sweep": c3_sweep,
         }
         print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks):
+    """C4 / C5: Q queries vs a T-descriptor map split over the ranks; per-call device time (max over ranks), the single-GPU
+    time of the SAME search in the same run (-> efficiency_vs_1gpu) and the POPC roofline."""
+    import torch
+    sharded = load_sharded()
+    dev = torch.device("cuda", local_rank)
+    popc_peak = ctx.popc_peak()
+    rows = []
+
+    def timed(fn, reps):
+        fn(); fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(st)
+        for _ in range(reps):
+            fn()
+        e1.record(st)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps, (ctx.launch_count() - l0) // reps
+
+    def device_map(T, seed):
+        """map descriptors generated on the device (i.i.d. 352-bit words; word 5 keeps only its low 32 bits)"""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        m = torch.randint(-2 ** 63, 2 ** 63 - 1, (T, 6), dtype=torch.int64, device=dev, generator=g)
+        m[:, 5] &= 0xFFFFFFFF
+        return m
+
+    configs = [("C4", args.map_t, q) for q in (10000, 2048, 600)]
+    if world == 8:
+        configs.append(("C5", 1 << 24, 10000))
+    for name, T, Q in configs:
+        per = (T + world - 1) // world
+        lo, hi = rank * per, min(T, (rank + 1) * per)
+        if name == "C4":
+            tfull = synth.random_descriptors(T, seed=7)            # same global map on every rank
+            q = synth.random_descriptors(Q, seed=8)
+            planted = np.random.default_rng(9).permutation(T)[:64]  # self-check: 64 queries are exact copies of map entries
+            q[:64] = tfull[planted]
+            dq = torch.from_numpy(q.view(np.int64)).to(dev)
+            # single-GPU time of the same search, measured in this run (world > 1 only; at world 1 it IS the measurement)
+            t1 = None
+            if world > 1:
+                ctx.map_reset()
+                ctx.map_append(tfull)
+                single = sharded.DeviceShardedMatcher(ctx, 1, 0, Q, device=dev)
+                t1, _ = timed(lambda: single.match(dq.data_ptr(), 0), max(3, args.map_steps // 2))
+            ctx.map_reset()
+            ctx.map_append(tfull[lo:hi])
+            del tfull
+        else:
+            full = device_map(per, 1000 + rank)                     # C5: every rank generates its own shard on the device
+            ctx.map_reset()
+            ctx.map_append_dev(full.data_ptr(), per)
+            hi = lo + per
+            q = synth.random_descriptors(Q, seed=8)
+            dq = torch.from_numpy(q.view(np.int64)).to(dev)
+            planted, t1 = None, None
+            del full
+        matcher = sharded.DeviceShardedMatcher(ctx, world, rank, Q, mode="nccl" if os.environ.get("BSHOT_EXCHANGE") == "nccl" else "auto", device=dev)
+        last = matcher.match(dq.data_ptr(), lo)
+        barrier()
+        if planted is not None:
+            rec = last[:64].cpu().numpy().view(bs.CAND_DTYPE).reshape(64)
+            chk = bs.unpack_cands(rec)
+            if not (np.array_equal(chk["idx1"], planted) and (chk["dist1"] == 0).all() and np.array_equal(chk["rq"], np.arange(64))):
+                raise SystemExit("bench.py: sharded map match self-check failed (planted duplicates not recovered)")
+        mm_ms, per_call = timed(lambda: matcher.match(dq.data_ptr(), lo), args.map_steps)
+        matcher.check()
+        pairs = float(Q) * float(T)
+        row = {"workload": name, "Q": Q, "T": T, "shards": world, "ms_per_call": mm_ms, "pairs_per_s": pairs / (mm_ms * 1e-3),
+               "target_GBps": T * 48 / (mm_ms * 1e-3) / 1e9,
+               "roofline": {"bound": "popc", "achieved": 11 * pairs / (mm_ms * 1e-3) / 1e12, "peak": world * popc_peak / 1e12,
+                            "unit": "TPOPC32/s", "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
+                            "issued_popc_per_pair": 6, "frac_of_issued": 6 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
+                            "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
+               "collective": matcher.describe(), "gpu_launches_per_call": per_call}
+        if world == 1:
+            row["ms_per_call_1gpu"], row["efficiency_vs_1gpu"] = mm_ms, 1.0
+        elif t1 is not None:
+            row["ms_per_call_1gpu"], row["efficiency_vs_1gpu"] = t1, t1 / (world * mm_ms)
+        rows.append(row)
+        del matcher
+    out = dict(rows[0])
+    out["others"] = rows[1:]
+    return out
+
+
+def bench_c2_sequence(bs, synth, device, flush, n_frames=120, top_k=2048):
+    """C2 (BASELINE.json configs[1]): frame-to-frame odometry front end over a synthetic HDL-32E sequence -- per-frame device
+    times over >= 100 DISTINCT frames (pose k = 500 mm * k along x, yaw 0.5 deg * k), L2 flushed before every frame"""
+    import torch
+    frames = [synth.make_scan("hdl32e", f) for f in range(n_frames)]
+    ctx = bs.Context(device, max_points=max(len(f) for f in frames) + 1024, max_keypoints=top_k, max_targets=top_k)
+    st = torch.cuda.ExternalStream(ctx.stream)
+    p = bs.default_params(top_k=top_k)
+    d = [torch.from_numpy(f).cuda() for f in frames]
+    for i in range(3):
+        ctx.process_frame_dev(d[i].data_ptr(), len(frames[i]), 12, p)
+    ctx.reset()
+    ctx.sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in frames]
+    for i, f in enumerate(frames):
+        with torch.cuda.stream(st):
+            flush.fill_(1.0)
+        ev[i][0].record(st)
+        ctx.process_frame_dev(d[i].data_ptr(), len(f), 12, p)
+        ev[i][1].record(st)
+    ctx.sync()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    ctx.enable_timing(True)
+    acc = {}
+    for i in range(8):
+        ctx.process_frame_dev(d[i].data_ptr(), len(frames[i]), 12, p)
+        for k, v in ctx.stage_times().items():
+            acc[k] = acc.get(k, 0.0) + v / 8
+    ctx.close()
+    return {"workload": "C2", "sensor": "hdl32e", "top_k": top_k, "points_per_frame": int(np.mean([len(f) for f in frames])),
+            "ms_per_frame": percentile_summary(ms), "descriptors_per_s": top_k / (float(np.mean(ms)) * 1e-3), "stages_ms": acc}
+
+
+def bench_c3_sweep(bs, synth, device, flush, top_k=10000):
+    """C3 (BASELINE.json configs[2]): extraction throughput (normals + LRF + SHOT352 + B-SHOT) over the SHOT radius, FULL normals"""
+    import torch
+    frames = [synth.make_scan("hdl64e", f) for f in range(3)]
+    d = [torch.from_numpy(f).cuda() for f in frames]
+    ctx = bs.Context(device, max_points=max(len(f) for f in frames) + 1024, max_keypoints=top_k, max_targets=top_k)
+    st = torch.cuda.ExternalStream(ctx.stream)
+    ctx.enable_timing(True)
+    sweep = []
+    for R in (500.0, 1000.0, 2000.0, 3000.0, 4000.0):
+        ctx.reset()
+        p = bs.default_params(top_k=top_k, normals_mode=bs.NORMALS_FULL, normal_radius=R, shot_radius=R)
+        for i in range(2):
+            ctx.process_frame_dev(d[i % 3].data_ptr(), len(frames[i % 3]), 12, p)
+        ctx.sync()
+        acc, nbr, reps = {}, 0, 6
+        for i in range(reps):
+            with torch.cuda.stream(st):
+                flush.fill_(1.0)
+            ctx.process_frame_dev(d[i % 3].data_ptr(), len(frames[i % 3]), 12, p)
+            for k, v in ctx.stage_times().items():
+                acc[k] = acc.get(k, 0.0) + v / reps
+            nbr += ctx.frame_counters()["shot_neighbours"] / reps
+        ext_ms = acc["normals"] + acc["shot_bshot"]
+        sweep.append({"radius_mm": R, "normals_ms": acc["normals"], "shot_bshot_ms": acc["shot_bshot"], "frame_ms": acc["frame"],
+                      "descriptors_per_s": top_k / (ext_ms * 1e-3), "shot_neighbours_per_keypoint": nbr / top_k,
+                      "shot_algorithmic_GBps": 32.0 * nbr / (acc["shot_bshot"] * 1e-3) / 1e9})
+    ctx.close()
+    return {"workload": "C3", "sensor": "hdl64e", "top_k": top_k, "normals": "FULL (normal radius = SHOT radius)", "sweep": sweep,
+            "note": "stage times from CUDA events on the context stream, L2 flushed before every frame; the detector keeps R = 3000"}
 
 
 if __name__ == "__main__":

@@ -166,6 +166,8 @@ int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits
  * record in the global target array. */
 int bshot_map_reset(bshot_ctx* ctx);
 int bshot_map_append(bshot_ctx* ctx, const uint64_t* desc, size_t n);
+/* same with descriptors that already live on the device (48-byte records) */
+int bshot_map_append_dev(bshot_ctx* ctx, const void* d_desc, size_t n);
 int bshot_map_size(bshot_ctx* ctx, size_t* n_out);
 /* candidate record per query produced by one shard: packed keys (distance << 32 | global index),
  * 0xFFFFFFFFFFFFFFFF = none; rq = best query for target k1 among this call's queries. */
