@@ -128,6 +128,35 @@ __device__ __forceinline__ void pack_bits_block(const float* hist, unsigned* wor
     __syncthreads();
 }
 
+// acos(x), x in [-1, 1]: sqrt(1 - |x|) * P7(|x|) (Abramowitz & Stegun 4.4.46), |error| < 2.5e-7 rad in fp32 -- the
+// elevation angle only enters the descriptor linearly, as an interpolation weight on a ~4e-6 fixed-point grid
+__device__ __forceinline__ float acos_poly(float x) {
+    const float a = fabsf(x);
+    float p = -0.0012624911f;
+    p = fmaf(p, a, 0.0066700901f);
+    p = fmaf(p, a, -0.0170881256f);
+    p = fmaf(p, a, 0.0308918810f);
+    p = fmaf(p, a, -0.0501743046f);
+    p = fmaf(p, a, 0.0889789874f);
+    p = fmaf(p, a, -0.2145988016f);
+    p = fmaf(p, a, 1.5707963050f);
+    const float r = __fsqrt_rn(1.0f - a) * p;
+    return x < 0.0f ? 3.14159265358979f - r : r;
+}
+
+// atan(t) for |t| <= 0.47 (an angle inside one 45-degree azimuth sector, measured from the sector centre):
+// odd polynomial, |error| < 4e-8 rad in fp32
+__device__ __forceinline__ float atan_sector(float t) {
+    const float u = t * t;
+    float p = -0.05407935f;
+    p = fmaf(p, u, 0.10297535f);
+    p = fmaf(p, u, -0.1419787f);
+    p = fmaf(p, u, 0.19995609f);
+    p = fmaf(p, u, -0.33333252f);
+    p = fmaf(p, u, 1.0f);
+    return p * t;
+}
+
 #ifndef BSHOT_SHOT_FP64_INTERP
 #define BSHOT_SHOT_FP64_INTERP 0  // 1: PCL's double-precision interpolation arithmetic (slower; same bits to >= 99.9 %)
 #endif
@@ -525,7 +554,7 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             }
             {   // elevation interpolation (z <= 0 is PCL's `inclination > 90 deg` test, see above)
                 const float inc_cos = fminf(1.0f, fmaxf(-1.0f, zr / dist));
-                const float inc = acosf(inc_cos);
+                const float inc = acos_poly(inc_cos);
                 const bool lower = !(zr > 0.0f);
                 const float id = (inc - (lower ? F_135 : F_45)) * INV_90;
                 w += 1.0f - fabsf(id);
@@ -534,9 +563,18 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                 if (to_nb && fv != 0.0f) vote((desc_index + (lower ? 1 : -1)) * 11 + step_index, fv);
             }
             if (yr != 0.0f || xr != 0.0f) {  // azimuth interpolation
-                const float azimuth = atan2f(yr, xr);
+                // angle from the centre of the point's 45-degree sector: rotate (xr, yr) by minus the sector's reference
+                // angle and take the arctangent of a ratio that stays below tan(22.5 deg) -- no full-range atan2
                 const int sel = desc_index >> 2;
-                float ad = (azimuth - (F_45 * (float)sel - F_78)) * INV_45;
+                const float cr = ((sel + 2) & 4) ? 0.92387953f : -0.92387953f, cq = ((sel + 2) & 4) ? 0.38268343f : -0.38268343f;
+                const bool steep = ((sel + 1) & 2) != 0;  // sectors 1, 2, 5, 6: |sin| = 0.9239
+                const float cs = steep ? cq : cr;                                          // cos(ref)
+                const float sn = (sel < 4 ? -1.0f : 1.0f) * (steep ? 0.92387953f : 0.38268343f);  // sin(ref)
+                const float xq = fmaf(xr, cs, yr * sn), yq = fmaf(yr, cs, -(xr * sn));
+                float delta;
+                if (xq > 0.0f && fabsf(yq) <= 0.47f * xq) delta = atan_sector(yq / xq);
+                else delta = atan2f(yr, xr) - (F_45 * (float)sel - F_78);                // (never on consistent sector bits)
+                float ad = delta * INV_45;
                 ad = fmaxf(-0.5f, fminf(ad, 0.5f));
                 w += 1.0f - fabsf(ad);
                 const int nbv = (ad > 0.0f) ? ((desc_index + 4) & 31) : ((desc_index + 28) & 31);

@@ -111,23 +111,54 @@ public:
                                  sizeof(pcl::SHOT352) / sizeof(float), reinterpret_cast<uint64_t*>(bshot_descriptors.data()));
     }
 
+    // B200 addition: tells the shim that the context already holds exactly cloud1 / cloud1_keypoints (LidarOdometry's
+    // extractKeypoints uploaded the cloud and left the detector's keypoints on the device): the next calculate_normals
+    // / calculate_SHOT then skip the upload and the keypoint normals reuse the detector's neighbourhoods.
+    void device_holds_current_inputs() {
+        cloud_fp_ = fingerprint(cloud1.points.empty() ? nullptr : cloud1.points[0].data, cloud1.size());
+        kp_fp_ = fingerprint(cloud1_keypoints.points.empty() ? nullptr : cloud1_keypoints.points[0].data, cloud1_keypoints.size());
+        have_cloud_ = have_kp_ = true;
+        normals_uploaded_ = false; bits_valid_ = false;
+    }
+
 private:
+    // Content fingerprint of a point array (never its address: `cb.cloud1 = next_cloud` reuses the vector's buffer, and
+    // allocators hand back the same address for a same-size cloud).  Every point is hashed up to 32 k points; above
+    // that every k-th one (a new scan differs everywhere), plus the size.
+    static uint64_t fingerprint(const float* xyzw, size_t n) {
+        uint64_t h = 0xCBF29CE484222325ull ^ (uint64_t)n;
+        if (!xyzw || n == 0) return h;
+        const size_t step = n <= 32768 ? 1 : (n + 32767) / 32768;
+        auto mix = [&](size_t i) {
+            uint64_t a, b;
+            std::memcpy(&a, xyzw + 4 * i, 8);
+            std::memcpy(&b, xyzw + 4 * i + 2, 4);
+            b &= 0xFFFFFFFFull;
+            h = (h ^ a) * 0x100000001B3ull;
+            h = (h ^ b ^ (uint64_t)i) * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+        };
+        for (size_t i = 0; i < n; i += step) mix(i);
+        mix(n - 1);
+        return h;
+    }
+
     bool upload() {
         if (!ctx_) { status_ = BSHOT_E_CUDA; return false; }
-        // re-upload when the caller replaced the clouds (`cb.cloud1 = src_pcl_`, src/lidar_odometry.cpp:159-162)
-        const void* key = cloud1.points.empty() ? nullptr : (const void*)cloud1.points.data();
-        if (key != cloud_key_ || cloud1.size() != cloud_n_) {
+        // re-upload whenever the CONTENT of the clouds changed (`cb.cloud1 = src_pcl_`, src/lidar_odometry.cpp:159-162)
+        const uint64_t cfp = fingerprint(cloud1.points.empty() ? nullptr : cloud1.points[0].data, cloud1.size());
+        if (!have_cloud_ || cfp != cloud_fp_) {
             status_ = bshot_set_cloud(ctx_, cloud1.points.empty() ? nullptr : cloud1.points[0].data, cloud1.size(), sizeof(pcl::PointXYZ));
             if (status_ != BSHOT_OK) return false;
-            cloud_key_ = key; cloud_n_ = cloud1.size();
-            normals_uploaded_ = false; bits_valid_ = false; kp_key_ = nullptr;
+            cloud_fp_ = cfp; have_cloud_ = true;
+            normals_uploaded_ = false; bits_valid_ = false; have_kp_ = false;
         }
-        const void* kkey = cloud1_keypoints.points.empty() ? nullptr : (const void*)cloud1_keypoints.points.data();
-        if (kkey != kp_key_ || cloud1_keypoints.size() != kp_n_) {
+        const uint64_t kfp = fingerprint(cloud1_keypoints.points.empty() ? nullptr : cloud1_keypoints.points[0].data, cloud1_keypoints.size());
+        if (!have_kp_ || kfp != kp_fp_) {
             status_ = bshot_set_keypoints(ctx_, cloud1_keypoints.points.empty() ? nullptr : cloud1_keypoints.points[0].data,
                                           cloud1_keypoints.size(), sizeof(pcl::PointXYZ));
             if (status_ != BSHOT_OK) return false;
-            kp_key_ = kkey; kp_n_ = cloud1_keypoints.size();
+            kp_fp_ = kfp; have_kp_ = true;
             bits_valid_ = false;
         }
         return true;
@@ -135,9 +166,8 @@ private:
 
     bshot_ctx* ctx_;
     int status_;
-    const void* cloud_key_ = nullptr;
-    const void* kp_key_ = nullptr;
-    size_t cloud_n_ = 0, kp_n_ = 0;
+    uint64_t cloud_fp_ = 0, kp_fp_ = 0;
+    bool have_cloud_ = false, have_kp_ = false;
     bool normals_uploaded_ = false, bits_valid_ = false;
     std::vector<bshot_descriptor> pending_bits_;
 };

@@ -48,6 +48,9 @@ public:
         cb.cloud2 = ref_pcl_;
         cb.cloud1_keypoints = eigen2pcl(src_->getKeypoints());
         cb.cloud2_keypoints = eigen2pcl(ref_->getKeypoints());
+        // the context already holds this cloud (voxel grid built once) and the detector's keypoints: computeDescriptors
+        // does not upload them again and the keypoint normals reuse the detector's neighbourhoods
+        if (last_status_ == BSHOT_OK) cb.device_holds_current_inputs();
     }
 
     void computeDescriptors() {  // :173-184

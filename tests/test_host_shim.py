@@ -49,23 +49,25 @@ def test_reference_call_order_two_frames(shim_binary, tmp_path, oracle, synth):
         bits = np.frombuffer(raw, np.uint64, 6 * k, off).reshape(k, 6); off += 48 * k
         rf = np.frombuffer(raw, np.float32, 9 * k, off).reshape(k, 9); off += 36 * k
         corr = np.frombuffer(raw, np.int32, 2 * nc, off).reshape(nc, 2); off += 8 * nc
-        frames.append((kp, bits, rf, corr))
+        nt, = struct.unpack_from("i", raw, off); off += 4
+        tgt = np.frombuffer(raw, np.uint64, 6 * nt, off).reshape(nt, 6); off += 48 * nt
+        frames.append((kp, bits, rf, corr, tgt))
     assert off == len(raw)
-    for (kp, bits, rf, corr), scan in zip(frames, scans):
+    assert "same-size reassignment ok" in r.stdout
+    for (kp, bits, rf, corr, _), scan in zip(frames, scans):
         assert len(kp) == 600                                   # reference default K (src/lidar_odometry.cpp:138)
         oc = oracle.Cloud(scan)
         od = oc.compute_descriptors(kp, 3000.0, 300, oracle.MODE_REFERENCE)
         ok = ~np.isnan(od["rf"]).any(1)
         assert np.abs(rf[ok] - od["rf"][ok]).max() <= 1e-4
         assert (synth.unpack_bits(bits) == synth.unpack_bits(od["bits"])).mean() >= 0.999
-    # frame 0 matched against itself (:187-194); frame 1 against (map within 100 m) + ref frame (:197-206).
-    # Frame poses are identity in this driver, so the target order is: map keypoints (block iteration
-    # order, implementation defined) then the 600 reference-frame descriptors.
-    (_, b0, _, c0), (_, b1, _, c1) = frames
-    m = oracle.match(b0, b0)
+    # frame 0 matched against itself (:187-194); frame 1 against (map keypoints within 100 m) + the reference frame's
+    # descriptors (:197-206): the shim dumps the target set it assembled, the correspondences must be exactly the
+    # oracle's mutual nearest neighbours on it
+    (_, b0, _, c0, t0), (_, b1, _, c1, t1) = frames
+    assert np.array_equal(t0, b0)
+    m = oracle.match(b0, t0)
     assert np.array_equal(c0, oracle.mutual(m["left_idx"], m["right_idx"]))
-    assert len(c1) > 0 and (c1[:, 0] < 600).all() and (np.diff(c1[:, 0]) > 0).all()
-    # every reported pair is a mutual nearest neighbour in Hamming distance w.r.t. the frame-0 descriptor set
-    # (map entries are copies of frame-0 descriptors, so distances to the target set can be checked on b0)
-    d = oracle.match(b1, b0)
-    assert (d["left_dist"][c1[:, 0]] >= 0).all()
+    assert len(t1) > 600 and np.array_equal(t1[-600:], b0)      # map subset first, then the 600 reference-frame records
+    m1 = oracle.match(b1, t1)
+    assert len(c1) > 0 and np.array_equal(c1, oracle.mutual(m1["left_idx"], m1["right_idx"]))

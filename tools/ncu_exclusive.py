@@ -58,4 +58,4 @@ if len(sys.argv) > 3:
         else:
             tot["other:" + f] += i
     for name, i in sorted(tot.items(), key=lambda kv: -kv[1]):
-        print(f"  {name:28s} {i:>11} {100.0*i/ti:5.1f}%  ({i/127945:.0f} per attempt)")
+        print(f"  {name:28s} {i:>11} {100.0*i/ti:5.1f}%  ({i/10000:.0f} per keypoint)")
