@@ -118,6 +118,10 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("BSHOT_WARP_PATH")) c->force_warp_path = (atoi(e) != 0);
+    if (const char* e = getenv("BSHOT_MAX_CELLS_LOG2")) {  // tuning knob: voxel table size (default 2^22 cells)
+        const int v = atoi(e);
+        if (v >= 10 && v <= 23) c->max_cells = 1u << v;
+    }
     if (const char* e = getenv("BSHOT_YZ_MUL")) {  // tuning knob: row thickness relative to the cell length
         const float v = (float)atof(e);
         if (v >= 1.0f && v <= 8.0f) c->yz_mul = v;
@@ -191,6 +195,11 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
         // pcl::Normal default-constructs to (0,0,0): the persistent normals array starts zeroed
         cudaError_t e = cudaMemsetAsync(c->d_normals, 0, sizeof(float4) * N, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_prev_count, 0, 4 * sizeof(int), c->stream);
+        if (e == cudaSuccess) {  // bounding box armed (+inf / -inf), ticket zero: the grid build re-arms it after every frame
+            const float inf = __builtin_inff();
+            const float box[8] = {inf, inf, inf, -inf, -inf, -inf, 0.0f, 0.0f};
+            e = cudaMemcpyAsync(c->d_bbox, box, sizeof(box), cudaMemcpyHostToDevice, c->stream);
+        }
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_kp_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_pair_count, 0, 4 * sizeof(int), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_tk_hist, 0, 4096 * sizeof(unsigned), c->stream);

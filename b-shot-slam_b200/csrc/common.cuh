@@ -58,6 +58,7 @@ struct Ctx {
     int device = 0;
     int sm_count = 148;
     bool force_warp_path = false;  // BSHOT_WARP_PATH=1: skip the block-tiled kernels (tile.cuh), warp-per-query kernels everywhere (tests)
+    unsigned max_cells = 1u << 22;  // voxel table size actually used (<= kMaxCells; BSHOT_MAX_CELLS_LOG2): zeroed and scanned every frame
     float yz_mul = 1.0f;  // cell_yz / cell (tuning knob BSHOT_YZ_MUL; 2 helps SHOT by ~3 %, costs the detector ~6 %)
     cudaStream_t stream = nullptr;
     unsigned long long launches = 0;

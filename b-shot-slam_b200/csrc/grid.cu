@@ -6,8 +6,9 @@
 // hash: cell (ix,iy,iz) of edge `cell` over the cloud's bounding box, linearised x-fastest, so that
 // the cells of one (iy,iz) row that a radius query needs are ONE contiguous range of the
 // cell-sorted point array (float4, w = original index) -> coalesced float4 row-segment gathers.
-// Everything is sized on the device (no host round trip): bbox reduce -> grid params -> count ->
-// 3-kernel exclusive scan -> scatter.  The count pass also fills point counts of the 2^3 / 4^3 / 8^3-cell cubes
+// Everything is sized on the device (no host round trip), six launches: convert + bbox (the last CTA to finish turns
+// the box into the grid parameters and re-arms the box for the next frame) -> zero tables -> count -> tile sums ->
+// exclusive scan (every tile adds up the sums of the tiles before it) -> scatter.  The count pass also fills point counts of the 2^3 / 4^3 / 8^3-cell cubes
 // and the scatter pass cuts the grid into the query BLOCKS of the tiled neighbourhood kernels (tile.cuh): the
 // coarsest cube around a point that holds at most TL_QCAP points (denser single cells are sliced).
 #include "common.cuh"
@@ -20,12 +21,6 @@ constexpr int GB_THREADS = 256;
 constexpr int SCAN_THREADS = 1024;
 constexpr int SCAN_ITEMS = 8;                        // cells per thread
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS; // 8192 cells per block
-constexpr int SCAN_BLOCKS = kMaxCells / SCAN_TILE;   // 1024
-
-__global__ void bbox_init_kernel(float* bbox) {
-    if (threadIdx.x < 3) bbox[threadIdx.x] = __int_as_float(0x7F800000);       // +inf
-    else if (threadIdx.x < 6) bbox[threadIdx.x] = __int_as_float(0xFF800000);  // -inf
-}
 
 __device__ __forceinline__ void atomic_min_float(float* a, float v) {
     if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
@@ -36,10 +31,43 @@ __device__ __forceinline__ void atomic_max_float(float* a, float v) {
     else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
 }
 
-// raw caller layout -> float4 (x,y,z,1) + bounding box of the finite points
+__device__ void grid_params_from_bbox(float* bbox, unsigned n, float cell0, float yz_mul, unsigned max_cells, GridParams* g) {
+    GridParams p;
+    float mn[3] = {bbox[0], bbox[1], bbox[2]}, mx[3] = {bbox[3], bbox[4], bbox[5]};
+    if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.0f; mx[0] = mx[1] = mx[2] = 0.0f; }  // empty cloud
+    float cell = cell0;
+    for (;;) {
+        const double cyz = (double)cell * (double)yz_mul;
+        const double cells = (floor((double)(mx[0] - mn[0]) / cell) + 1.0) * (floor((double)(mx[1] - mn[1]) / cyz) + 1.0) *
+                             (floor((double)(mx[2] - mn[2]) / cyz) + 1.0);
+        if (cells <= (double)max_cells) break;
+        cell *= 1.125f;
+    }
+    p.ox = mn[0]; p.oy = mn[1]; p.oz = mn[2];
+    p.cell = cell;
+    p.inv_cell = 1.0f / cell;
+    p.cell_yz = cell * yz_mul;
+    p.inv_cell_yz = 1.0f / p.cell_yz;
+    p.nx = cell_coord(mx[0], p.ox, p.inv_cell) + 1;
+    p.ny = cell_coord(mx[1], p.oy, p.inv_cell_yz) + 1;
+    p.nz = cell_coord(mx[2], p.oz, p.inv_cell_yz) + 1;
+    // cell_coord rounds in fp32; shrink until the table fits (never triggers in practice)
+    while ((double)p.nx * p.ny * p.nz > (double)max_cells) {
+        if (p.nx >= p.ny && p.nx >= p.nz) p.nx--; else if (p.ny >= p.nz) p.ny--; else p.nz--;
+    }
+    p.ncells = (unsigned)p.nx * (unsigned)p.ny * (unsigned)p.nz;
+    p.npoints = n;
+    *g = p;
+    // re-arm the box for the next frame (it starts armed: bshot_ctx_create)
+    bbox[0] = bbox[1] = bbox[2] = __int_as_float(0x7F800000);
+    bbox[3] = bbox[4] = bbox[5] = __int_as_float(0xFF800000);
+}
+
+// raw caller layout -> float4 (x,y,z,1) + bounding box of the finite points; the last CTA to finish (ticket) derives the
+// grid parameters from the box.  bbox[6] is the ticket counter (as unsigned), kept at zero between frames.
 __global__ void __launch_bounds__(GB_THREADS)
 convert_bbox_kernel(const float* __restrict__ raw, unsigned n, int stride, float4* __restrict__ pts,
-                    float* __restrict__ bbox) {
+                    float* __restrict__ bbox, float cell0, float yz_mul, unsigned max_cells, GridParams* __restrict__ g) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const float inf = __int_as_float(0x7F800000);
     float mn[3] = {inf, inf, inf}, mx[3] = {-inf, -inf, -inf};
@@ -65,6 +93,7 @@ convert_bbox_kernel(const float* __restrict__ raw, unsigned n, int stride, float
         }
     }
     __shared__ float smn[GB_THREADS / 32][3], smx[GB_THREADS / 32][3];
+    __shared__ unsigned s_last;
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0)
         for (int k = 0; k < 3; ++k) { smn[wid][k] = mn[k]; smx[wid][k] = mx[k]; }
@@ -75,36 +104,28 @@ convert_bbox_kernel(const float* __restrict__ raw, unsigned n, int stride, float
         for (int w = 0; w < GB_THREADS / 32; ++w) { a = fminf(a, smn[w][k]); b = fmaxf(b, smx[w][k]); }
         if (a <= b) { atomic_min_float(&bbox[k], a); atomic_max_float(&bbox[3 + k], b); }
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned*>(bbox) + 6, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        volatile float* vb = bbox;
+        float box[6] = {vb[0], vb[1], vb[2], vb[3], vb[4], vb[5]};
+        grid_params_from_bbox(box, n, cell0, yz_mul, max_cells, g);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) vb[k] = box[k];
+        reinterpret_cast<unsigned*>(bbox)[6] = 0u;
+    }
 }
 
-__global__ void grid_params_kernel(const float* __restrict__ bbox, unsigned n, float cell0, float yz_mul, GridParams* g) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    GridParams p;
-    float mn[3] = {bbox[0], bbox[1], bbox[2]}, mx[3] = {bbox[3], bbox[4], bbox[5]};
-    if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.0f; mx[0] = mx[1] = mx[2] = 0.0f; }  // empty cloud
-    float cell = cell0;
-    for (;;) {
-        const double cyz = (double)cell * (double)yz_mul;
-        const double cells = (floor((double)(mx[0] - mn[0]) / cell) + 1.0) * (floor((double)(mx[1] - mn[1]) / cyz) + 1.0) *
-                             (floor((double)(mx[2] - mn[2]) / cyz) + 1.0);
-        if (cells <= (double)kMaxCells) break;
-        cell *= 1.25f;
+// empty cloud: no convert launch, the parameters of an empty grid
+__global__ void grid_params_empty_kernel(float* bbox, float cell0, float yz_mul, unsigned max_cells, GridParams* g) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float box[6] = {__int_as_float(0x7F800000), __int_as_float(0x7F800000), __int_as_float(0x7F800000),
+                        __int_as_float(0xFF800000), __int_as_float(0xFF800000), __int_as_float(0xFF800000)};
+        grid_params_from_bbox(box, 0u, cell0, yz_mul, max_cells, g);
     }
-    p.ox = mn[0]; p.oy = mn[1]; p.oz = mn[2];
-    p.cell = cell;
-    p.inv_cell = 1.0f / cell;
-    p.cell_yz = cell * yz_mul;
-    p.inv_cell_yz = 1.0f / p.cell_yz;
-    p.nx = cell_coord(mx[0], p.ox, p.inv_cell) + 1;
-    p.ny = cell_coord(mx[1], p.oy, p.inv_cell_yz) + 1;
-    p.nz = cell_coord(mx[2], p.oz, p.inv_cell_yz) + 1;
-    // cell_coord rounds in fp32; shrink until the table fits (never triggers in practice)
-    while ((double)p.nx * p.ny * p.nz > (double)kMaxCells) {
-        if (p.nx >= p.ny && p.nx >= p.nz) p.nx--; else if (p.ny >= p.nz) p.ny--; else p.nz--;
-    }
-    p.ncells = (unsigned)p.nx * (unsigned)p.ny * (unsigned)p.nz;
-    p.npoints = n;
-    *g = p;
 }
 
 __global__ void zero_cells_kernel(const GridParams* __restrict__ g, unsigned* __restrict__ cursor, unsigned* __restrict__ lvl,
@@ -182,25 +203,6 @@ scan_reduce_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_blocks_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ block_sums, unsigned* __restrict__ cell_start) {
-    const unsigned n = gp->ncells;
-    const unsigned nb = (n + SCAN_TILE - 1) / SCAN_TILE;  // <= 1024
-    __shared__ unsigned sh[SCAN_THREADS];
-    const unsigned t = threadIdx.x;
-    const unsigned v = (t < nb) ? block_sums[t] : 0u;
-    sh[t] = v;
-    __syncthreads();
-    for (unsigned o = 1; o < SCAN_THREADS; o <<= 1) {
-        const unsigned add = (t >= o) ? sh[t - o] : 0u;
-        __syncthreads();
-        sh[t] += add;
-        __syncthreads();
-    }
-    if (t < nb) block_sums[t] = sh[t] - v;  // exclusive
-    if (t == SCAN_THREADS - 1) cell_start[n] = sh[t];
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
 scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ cursor, const unsigned* __restrict__ block_sums,
                   unsigned* __restrict__ cell_start) {
     const unsigned n = gp->ncells;
@@ -241,7 +243,24 @@ scan_final_kernel(const GridParams* __restrict__ gp, unsigned* __restrict__ curs
         ws[lane] = winc - w;
     }
     __syncthreads();
-    unsigned run = block_sums[blockIdx.x] + ws[wid] + (inc - s);
+    // exclusive prefix of this tile = sum of the sums of the tiles before it (at most 1024 values: one pass of the CTA)
+    __shared__ unsigned tile_base;
+    {
+        unsigned part = 0;
+        for (unsigned t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) part += block_sums[t];
+        part = (unsigned)warp_sum((int)part);
+        __shared__ unsigned wb[32];
+        if (lane == 0) wb[wid] = part;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned v2 = wb[lane];
+            v2 = (unsigned)warp_sum((int)v2);
+            if (lane == 0) tile_base = v2;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == SCAN_THREADS - 1 && base + SCAN_TILE >= n) cell_start[n] = tile_base + ws[wid] + inc;  // grand total (last tile)
+    unsigned run = tile_base + ws[wid] + (inc - s);
     unsigned o[SCAN_ITEMS];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { o[k] = run; run += v[k]; }
@@ -309,17 +328,16 @@ scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __res
 int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
     const unsigned nn = (unsigned)n;
     const unsigned pb = (nn + GB_THREADS - 1) / GB_THREADS;
-    bbox_init_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox);
-    if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(d_raw, nn, stride_floats, c->d_pts, c->d_bbox);
-    grid_params_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, nn, kDefaultCell, c->yz_mul, c->d_grid);
+    const unsigned scan_blocks = (c->max_cells + SCAN_TILE - 1) / SCAN_TILE;
+    if (pb) convert_bbox_kernel<<<pb, GB_THREADS, 0, c->stream>>>(d_raw, nn, stride_floats, c->d_pts, c->d_bbox, kDefaultCell, c->yz_mul, c->max_cells, c->d_grid);
+    else grid_params_empty_kernel<<<1, 32, 0, c->stream>>>(c->d_bbox, kDefaultCell, c->yz_mul, c->max_cells, c->d_grid);
     zero_cells_kernel<<<c->sm_count * 4, 1024, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_lvl, c->d_nblocks);
     if (pb) count_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_grid, c->d_cell_of, c->d_cell_cursor, c->d_lvl);
-    scan_reduce_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums);
-    scan_blocks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_block_sums, c->d_cell_start);
-    scan_final_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums, c->d_cell_start);
+    scan_reduce_kernel<<<scan_blocks, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums);
+    scan_final_kernel<<<scan_blocks, SCAN_THREADS, 0, c->stream>>>(c->d_grid, c->d_cell_cursor, c->d_block_sums, c->d_cell_start);
     if (pb) scatter_kernel<<<pb, GB_THREADS, 0, c->stream>>>(c->d_pts, nn, c->d_cell_of, c->d_grid, c->d_cell_start, c->d_cell_cursor, c->d_sorted,
                                                              c->d_sorted_pos, c->d_lvl, c->d_blocks, c->d_blk_area, c->d_nblocks, (unsigned)c->max_points);
-    count_launch(c, pb ? 9 : 6);
+    count_launch(c, pb ? 6 : 4);
     BSHOT_TRY(check_launch("grid_build"));
     // vector::resize semantics of cloud1_normals (include/bshot_bits.h:59): entries beyond the new
     // size are dropped, so stale keypoint normals above n must not survive a smaller cloud

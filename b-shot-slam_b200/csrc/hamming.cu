@@ -302,43 +302,51 @@ __global__ void unpack_cands_kernel(const bshot_cand* __restrict__ cand, unsigne
     if (d2) d2[qi] = h2 ? (int)(c.k2 >> 32) : -1;
 }
 
-// mutual-NN filter (src/lidar_odometry.cpp:234-242): single CTA, ordered compaction
-__global__ void mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq_cap, const unsigned* __restrict__ nq_dev,
-                                    int* __restrict__ pairs, int* __restrict__ count) {
+// mutual-NN filter (src/lidar_odometry.cpp:234-242): ordered compaction by one CTA -- every thread owns a contiguous
+// run of queries, one block-wide exclusive scan of the per-thread counts gives each run its output offset
+__global__ void __launch_bounds__(1024)
+mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq_cap, const unsigned* __restrict__ nq_dev,
+                    int* __restrict__ pairs, int* __restrict__ count) {
     __shared__ unsigned warp_tot[32];
-    __shared__ unsigned running;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned nq = nq_dev ? min(nq_cap, *nq_dev) : nq_cap;
-    if (tid == 0) running = 0;
+    const unsigned per = (nq + blockDim.x - 1) / blockDim.x;
+    const unsigned q0 = tid * per, q1 = min(nq, q0 + per);
+    unsigned mine = 0;
+    for (unsigned qi = q0; qi < q1; ++qi) {
+        const bshot_cand c = cand[qi];
+        mine += ((c.k1 != HM_NONE) && (c.rq == qi)) ? 1u : 0u;
+    }
+    unsigned inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += up;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    for (unsigned base = 0; base < nq; base += blockDim.x) {
-        const unsigned qi = base + tid;
-        bool keep = false;
-        bshot_cand c;
-        if (qi < nq) {
-            c = cand[qi];
-            keep = (c.k1 != HM_NONE) && (c.rq == qi);
+    if (wid == 0) {
+        const unsigned w = warp_tot[lane];
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o) winc += up;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[wid] = __popc(m);
-        __syncthreads();
-        unsigned off = running;
-        for (unsigned w = 0; w < wid; ++w) off += warp_tot[w];
-        if (keep) {
-            const unsigned pos = off + __popc(m & ((1u << lane) - 1));
+        warp_tot[lane] = winc - w;
+        if (lane == 31) *count = (int)winc;
+    }
+    __syncthreads();
+    unsigned pos = warp_tot[wid] + inc - mine;
+    for (unsigned qi = q0; qi < q1; ++qi) {
+        const bshot_cand c = cand[qi];
+        if ((c.k1 != HM_NONE) && (c.rq == qi)) {
             pairs[3 * pos] = (int)qi;
             pairs[3 * pos + 1] = (int)(c.k1 & 0xFFFFFFFFull);
             pairs[3 * pos + 2] = (int)(c.k1 >> 32);
+            ++pos;
         }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned tot = 0;
-            for (unsigned w = 0; w < (blockDim.x >> 5); ++w) tot += warp_tot[w];
-            running += tot;
-        }
-        __syncthreads();
     }
-    if (tid == 0) *count = (int)running;
 }
 
 // ---- host side ----------------------------------------------------------------------------
