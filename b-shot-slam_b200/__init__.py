@@ -31,7 +31,9 @@ EXPORTS = [
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
-    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev",
+    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev", "bshot_comm_create", "bshot_comm_export", "bshot_comm_import",
+    "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
+    "bshot_match_map_sharded",
 ]
 
 
@@ -97,6 +99,15 @@ def lib():
         L.bshot_map_append.argtypes = [vp, vp, sz]
         L.bshot_map_size.argtypes = [vp, C.POINTER(sz)]
         L.bshot_map_append_dev.argtypes = [vp, vp, sz]
+        L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
+        L.bshot_comm_export.argtypes = [vp, vp]
+        L.bshot_comm_import.argtypes = [vp, vp]
+        L.bshot_comm_region.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+        L.bshot_comm_import_ptrs.argtypes = [vp, C.POINTER(vp)]
+        L.bshot_comm_destroy.argtypes = [vp]
+        L.bshot_comm_check.argtypes = [vp]
+        L.bshot_match_map_sharded_dev.argtypes = [vp, vp, sz, C.c_uint64, vp]
+        L.bshot_match_map_sharded.argtypes = [vp, vp, sz, C.c_uint64, vp]
         L.bshot_match_shard_dev.argtypes = [vp, vp, sz, C.c_uint64, ci, vp]
         L.bshot_match_dev.argtypes = [vp, vp, sz, vp, sz, C.c_uint64, ci, vp]
         L.bshot_merge_cands_dev.argtypes = [vp, vp, sz, sz, vp]
@@ -355,6 +366,43 @@ class Context:
 
     def map_append_dev(self, d_desc_ptr, n):
         _chk(lib().bshot_map_append_dev(self.h, d_desc_ptr, n))
+
+    # multi-rank exchange behind the C ABI (CUDA IPC peer memory)
+    def comm_create(self, rank, nranks, max_queries):
+        _chk(lib().bshot_comm_create(self.h, rank, nranks, max_queries))
+
+    def comm_export(self):
+        h = np.zeros(64, np.uint8)
+        _chk(lib().bshot_comm_export(self.h, _p(h)))
+        return h
+
+    def comm_import(self, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1, 64)
+        _chk(lib().bshot_comm_import(self.h, _p(handles)))
+
+    def comm_region(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _chk(lib().bshot_comm_region(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def comm_import_ptrs(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) for p in ptrs])
+        _chk(lib().bshot_comm_import_ptrs(self.h, arr))
+
+    def comm_destroy(self):
+        _chk(lib().bshot_comm_destroy(self.h))
+
+    def comm_check(self):
+        _chk(lib().bshot_comm_check(self.h))
+
+    def match_map_sharded_dev(self, d_q_ptr, nq, global_base, d_cand_ptr):
+        _chk(lib().bshot_match_map_sharded_dev(self.h, d_q_ptr, nq, global_base, d_cand_ptr))
+
+    def match_map_sharded(self, q, global_base=0):
+        q = np.ascontiguousarray(q, dtype=np.uint64).reshape(-1, 6)
+        cand = np.empty(q.shape[0], CAND_DTYPE)
+        _chk(lib().bshot_match_map_sharded(self.h, _p(q), q.shape[0], global_base, _p(cand)))
+        return cand
 
     def map_size(self):
         n = C.c_size_t()

@@ -218,10 +218,13 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     return BSHOT_OK;
 }
 
+static void comm_free(bshot_ctx* c);
+
 void bshot_ctx_destroy(bshot_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    comm_free(c);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
                     c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
@@ -665,6 +668,118 @@ int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t n
     CHECK_CTX(ctx);
     if (!d_cands || !d_rq) { set_error("bshot_apply_rq_dev: null device pointer"); return BSHOT_E_INVALID; }
     return hamming_apply_rq(ctx, reinterpret_cast<bshot_cand*>(d_cands), reinterpret_cast<const unsigned*>(d_rq), nq);
+}
+
+// ---- multi-rank exchange behind the C ABI (no Python / torch needed) -------------------------------------------
+static void comm_free(bshot_ctx* c) {
+    Comm& m = c->comm;
+    for (int p = 0; p < 32; ++p)
+        if (m.opened[p]) { cudaIpcCloseMemHandle(m.opened[p]); m.opened[p] = nullptr; }
+    if (m.d_region) cudaFree(m.d_region);
+    if (m.d_peer_gather) cudaFree(m.d_peer_gather);
+    if (m.d_peer_rq) cudaFree(m.d_peer_rq);
+    if (m.d_peer_flags) cudaFree(m.d_peer_flags);
+    if (m.d_ticket) cudaFree(m.d_ticket);
+    m = Comm();
+}
+
+int bshot_comm_create(bshot_ctx* ctx, int rank, int nranks, size_t max_queries) {
+    CHECK_CTX(ctx);
+    if (nranks < 1 || nranks > 32 || rank < 0 || rank >= nranks || max_queries == 0) { set_error("bshot_comm_create: bad arguments"); return BSHOT_E_INVALID; }
+    if (max_queries > ctx->max_kp) { set_error("bshot_comm_create: max_queries %zu > max_keypoints %zu", max_queries, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(sync(ctx));
+    comm_free(ctx);
+    Comm& m = ctx->comm;
+    m.rank = rank; m.nranks = nranks; m.max_q = max_queries;
+    const size_t bytes = comm_region_bytes(m);
+    BSHOT_CUDA_TRY(cudaMalloc((void**)&m.d_region, bytes));
+    BSHOT_CUDA_TRY(cudaMalloc((void**)&m.d_peer_gather, sizeof(void*) * 32));
+    BSHOT_CUDA_TRY(cudaMalloc((void**)&m.d_peer_rq, sizeof(void*) * 32));
+    BSHOT_CUDA_TRY(cudaMalloc((void**)&m.d_peer_flags, sizeof(void*) * 32));
+    BSHOT_CUDA_TRY(cudaMalloc((void**)&m.d_ticket, sizeof(unsigned) * 4));
+    BSHOT_CUDA_TRY(cudaMemsetAsync(m.d_region, 0, bytes, ctx->stream));          // flags start at epoch 0
+    BSHOT_CUDA_TRY(cudaMemsetAsync(m.d_ticket, 0, sizeof(unsigned) * 4, ctx->stream));
+    BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_pair_count + 3, 0, sizeof(int), ctx->stream));
+    BSHOT_TRY(sync(ctx));
+    if (nranks == 1) {
+        void* none[1] = {nullptr};
+        return comm_set_peers(ctx, none);
+    }
+    return BSHOT_OK;
+}
+
+int bshot_comm_destroy(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(sync(ctx));
+    comm_free(ctx);
+    return BSHOT_OK;
+}
+
+int bshot_comm_region(bshot_ctx* ctx, void** d_region_out, size_t* bytes_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->comm.d_region) { set_error("bshot_comm_region: no communicator"); return BSHOT_E_STATE; }
+    if (d_region_out) *d_region_out = ctx->comm.d_region;
+    if (bytes_out) *bytes_out = comm_region_bytes(ctx->comm);
+    return BSHOT_OK;
+}
+
+int bshot_comm_export(bshot_ctx* ctx, bshot_ipc_handle* handle_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->comm.d_region || !handle_out) { set_error("bshot_comm_export: no communicator / null output"); return BSHOT_E_STATE; }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(bshot_ipc_handle), "handle size");
+    cudaIpcMemHandle_t h;
+    BSHOT_CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->comm.d_region));
+    memset(handle_out, 0, sizeof(*handle_out));
+    memcpy(handle_out, &h, sizeof(h));
+    return BSHOT_OK;
+}
+
+int bshot_comm_import(bshot_ctx* ctx, const bshot_ipc_handle* handles) {
+    CHECK_CTX(ctx);
+    Comm& m = ctx->comm;
+    if (!m.d_region || !handles) { set_error("bshot_comm_import: no communicator / null handles"); return BSHOT_E_STATE; }
+    void* ptrs[32] = {nullptr};
+    for (int p = 0; p < m.nranks; ++p) {
+        if (p == m.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &handles[p], sizeof(h));
+        BSHOT_CUDA_TRY(cudaIpcOpenMemHandle(&m.opened[p], h, cudaIpcMemLazyEnablePeerAccess));
+        ptrs[p] = m.opened[p];
+    }
+    return comm_set_peers(ctx, ptrs);
+}
+
+int bshot_comm_import_ptrs(bshot_ctx* ctx, void* const* d_regions) {
+    CHECK_CTX(ctx);
+    if (!ctx->comm.d_region || !d_regions) { set_error("bshot_comm_import_ptrs: no communicator / null pointers"); return BSHOT_E_STATE; }
+    return comm_set_peers(ctx, d_regions);
+}
+
+int bshot_comm_check(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[16], ctx->d_pair_count + 3, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    if (ctx->h_scratch[16] != 0) {
+        set_error("sharded match: a rank did not arrive within the time limit (call #%u); the records of that call are incomplete", (unsigned)ctx->h_scratch[16]);
+        return BSHOT_E_STATE;
+    }
+    return BSHOT_OK;
+}
+
+int bshot_match_map_sharded_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, void* d_cand_out) {
+    CHECK_CTX(ctx);
+    if (!d_q || !d_cand_out) { set_error("bshot_match_map_sharded_dev: null device pointer"); return BSHOT_E_INVALID; }
+    return hamming_match_sharded(ctx, d_q, nq, global_base, reinterpret_cast<bshot_cand*>(d_cand_out));
+}
+
+int bshot_match_map_sharded(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base, bshot_cand* cand_out) {
+    CHECK_CTX(ctx);
+    if ((!q || !cand_out) && nq) { set_error("bshot_match_map_sharded: null buffer"); return BSHOT_E_INVALID; }
+    if (nq > ctx->max_kp) { set_error("bshot_match_map_sharded: %zu queries > capacity %zu", nq, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(h2d(ctx, ctx->d_q, q, nq * 48));
+    BSHOT_TRY(hamming_match_sharded(ctx, ctx->d_q, nq, global_base, ctx->d_cand2));
+    BSHOT_TRY(d2h(ctx, cand_out, ctx->d_cand2, sizeof(bshot_cand) * nq));
+    return bshot_comm_check(ctx);
 }
 
 int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base, bshot_cand* cand_out) {

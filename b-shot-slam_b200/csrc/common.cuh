@@ -54,6 +54,20 @@ __host__ __device__ __forceinline__ unsigned lvl_index(const GridParams& g, int 
 constexpr int kDescWords = 12;                      // 48-byte record as u32 words (11 used)
 constexpr float kDefaultCell = 375.0f;              // R/8 for the reference radius 3000 mm
 
+// peer-memory exchange of the sharded map match (hamming.cu, capi.cu): one region per rank, mapped on every rank
+struct Comm {
+    int rank = -1, nranks = 0;
+    size_t max_q = 0;
+    unsigned char* d_region = nullptr;        // own region: [gather nranks x max_q records][rq max_q u32][flags 64 u32]
+    void* opened[32] = {nullptr};             // regions of the other ranks opened through CUDA IPC (closed on destroy)
+    bshot_cand** d_peer_gather = nullptr;     // device arrays of nranks pointers into every rank's region
+    unsigned** d_peer_rq = nullptr;
+    unsigned** d_peer_flags = nullptr;
+    unsigned* d_ticket = nullptr;             // 2 "last CTA" tickets
+    unsigned epoch = 0;                       // calls issued so far (the flags carry it)
+    bool connected = false;
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
@@ -139,6 +153,8 @@ struct Ctx {
     int* d_pairs = nullptr;             // 3 x max_kp (q, m, dist)
     int* d_pair_count = nullptr;        // [0] mutual pairs, [1] owned winners, [3] peer-barrier timeout flag
     unsigned peer_epoch = 0;            // barriers issued on the symmetric flag array so far
+
+    Comm comm;
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints

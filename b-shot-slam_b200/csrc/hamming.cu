@@ -9,6 +9,7 @@
 // tie-break.  Target ranges are split over blockIdx.y; a small merge kernel combines the
 // per-split candidates (and, across GPUs, the all-gathered per-rank candidates).
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "stages.h"
@@ -374,9 +375,9 @@ static int pick_qpt(size_t nq, size_t nt, int sm_count) {
 }
 
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
-int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                 bshot_cand* d_out, unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt) {
-    if (nq == 0) return BSHOT_OK;
+// the distance-matrix pass alone: per-split top-2 candidates in c->d_partial ([nsplit][nq][2]); *nsplit_out splits
+static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                                 unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt, unsigned* nsplit_out) {
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
         set_error("hamming_top2: sizes exceed 32-bit index range");
         return BSHOT_E_INVALID;
@@ -436,9 +437,17 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
     }
 #undef BSHOT_LAUNCH_TOP2
     count_launch(c);
-    BSHOT_TRY(check_launch("hamming_top2_kernel"));
+    *nsplit_out = nsplit;
+    return check_launch("hamming_top2_kernel");
+}
+
+int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
+                 bshot_cand* d_out, unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt) {
+    if (nq == 0) return BSHOT_OK;
+    unsigned nsplit = 1;
+    BSHOT_TRY(hamming_top2_partials(c, d_q, nq, d_t, nt, global_base, d_colmin, d_nq, d_nt, &nsplit));
     merge_top2_kernel<<<(unsigned)((nq * HM_MERGE_LANES + 255) / 256), 256, 0, c->stream>>>(
-        c->d_partial, nsplit, (unsigned)nq, d_nq, colmin ? d_colmin : nullptr, global_base, d_out);
+        c->d_partial, nsplit, (unsigned)nq, d_nq, d_colmin, global_base, d_out);
     count_launch(c);
     return check_launch("merge_top2_kernel");
 }
@@ -677,6 +686,227 @@ int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq
     apply_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, d_rq, (unsigned)nq);
     count_launch(c);
     return check_launch("apply_rq_kernel");
+}
+
+
+// ---- fused exchange over peer memory: the sharded call in six launches --------------------------------------------
+//   1 hamming_top2_kernel        shard search (per-split candidates)
+//   2 merge_push_kernel          merge the splits; STORE every record into slot `rank` of every rank's gather buffer;
+//                                the last CTA to finish releases flag[rank] = epoch on every rank
+//   3 wait_merge_select_kernel   acquire all flags; merge the ranks' records by (distance, global index); winners that
+//                                live in this rank's shard are appended to the owned list and their records gathered
+//   4 hamming_top2_kernel        owned winners against all queries (grid trimmed by the device-side count)
+//   5 merge_push_rq_kernel       best query of every owned winner -> rq[query] on every rank; second flag set released
+//   6 wait_apply_rq_kernel       acquire the second flags; records completed
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// every CTA fences its peer stores and takes a ticket; the last one tells every rank "rank `rank` is done with epoch"
+__device__ __forceinline__ void signal_when_grid_done(unsigned* ticket, unsigned* const* peer_flags, unsigned flag_off, unsigned nranks,
+                                                      unsigned rank, unsigned epoch) {
+    __shared__ unsigned s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x < nranks) st_release_sys(peer_flags[threadIdx.x] + flag_off + rank, epoch);
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// thread 0 of the CTA waits until every rank has released `epoch` into flags[flag_off + r]; bounded (~2 s)
+__device__ __forceinline__ void wait_all_ranks(const unsigned* flags, unsigned flag_off, unsigned nranks, unsigned epoch, unsigned* timeout_flag) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (unsigned r = 0; r < nranks; ++r) {
+            for (;;) {
+                if ((int)(ld_acquire_sys(flags + flag_off + r) - epoch) >= 0) break;
+                if (clock64() - t0 > 4000000000ll) { *timeout_flag = epoch; break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+merge_push_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq, bshot_cand* __restrict__ local_out,
+                  bshot_cand* const* __restrict__ peer_gather, unsigned* const* __restrict__ peer_flags, unsigned nranks, unsigned rank,
+                  unsigned epoch, unsigned* __restrict__ ticket, unsigned* __restrict__ owned_count) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned qi = t / HM_MERGE_LANES, sub = t % HM_MERGE_LANES;
+    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+    if (qi < nq) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src);
+#pragma unroll 4
+        for (unsigned sp = sub; sp < nsrc; sp += HM_MERGE_LANES) {
+            const ulonglong2 v = p[(size_t)sp * nq + qi];
+            top2_insert(v.x, k1, k2);
+            top2_insert(v.y, k1, k2);
+        }
+    }
+#pragma unroll
+    for (int o = HM_MERGE_LANES / 2; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        top2_insert(o1, k1, k2);
+        top2_insert(o2, k1, k2);
+    }
+    if (qi < nq && sub == 0) {
+        bshot_cand c;
+        c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
+        local_out[qi] = c;
+        for (unsigned p = 0; p < nranks; ++p) peer_gather[(p + rank) % nranks][(size_t)rank * nq + qi] = c;  // own buffer first, links spread
+    }
+    if (t == 0) *owned_count = 0u;  // for step 3 of this call
+    signal_when_grid_done(ticket, peer_flags, 0u, nranks, rank, epoch);
+}
+
+__global__ void __launch_bounds__(256)
+wait_merge_select_kernel(const bshot_cand* __restrict__ gather, const unsigned* __restrict__ flags, unsigned nranks, unsigned nq, unsigned epoch,
+                         unsigned long long lo, unsigned long long hi, const uint4* __restrict__ t, bshot_cand* __restrict__ merged,
+                         uint4* __restrict__ gathered, unsigned* __restrict__ owner_q, unsigned* __restrict__ count,
+                         unsigned* __restrict__ timeout_flag) {
+    wait_all_ranks(flags, 0u, nranks, epoch, timeout_flag);
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    bool mine = false;
+    unsigned long long idx = 0;
+    if (qi < nq) {
+        unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+        for (unsigned r = 0; r < nranks; ++r) {
+            const bshot_cand c = gather[(size_t)r * nq + qi];  // written by rank r's stores, ordered by the flag acquire above
+            top2_insert(c.k1, k1, k2);
+            top2_insert(c.k2, k1, k2);
+        }
+        bshot_cand c;
+        c.k1 = k1; c.k2 = k2; c.rq = 0xFFFFFFFFu; c.pad = 0;
+        merged[qi] = c;
+        idx = k1 & 0xFFFFFFFFull;
+        mine = (k1 != HM_NONE) && idx >= lo && idx < hi;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, mine);
+    if (m == 0) return;
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (mine) {
+        const unsigned slot = base + __popc(m & ((1u << lane) - 1));
+        owner_q[slot] = qi;
+        const uint4* src = t + (size_t)(idx - lo) * 3;
+        gathered[(size_t)slot * 3] = __ldg(src);
+        gathered[(size_t)slot * 3 + 1] = __ldg(src + 1);
+        gathered[(size_t)slot * 3 + 2] = __ldg(src + 2);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+merge_push_rq_kernel(const unsigned long long* __restrict__ src, unsigned nsrc, unsigned nq_cap, const unsigned* __restrict__ count,
+                     const unsigned* __restrict__ owner_q, unsigned* const* __restrict__ peer_rq, unsigned* const* __restrict__ peer_flags,
+                     unsigned nranks, unsigned rank, unsigned epoch, unsigned* __restrict__ ticket) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = t / HM_MERGE_LANES, sub = t % HM_MERGE_LANES;
+    const unsigned n = min(*count, nq_cap);
+    unsigned long long k1 = HM_NONE, k2 = HM_NONE;
+    if (i < n) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(src);
+        for (unsigned sp = sub; sp < nsrc; sp += HM_MERGE_LANES) {
+            const ulonglong2 v = p[(size_t)sp * nq_cap + i];
+            top2_insert(v.x, k1, k2);
+            top2_insert(v.y, k1, k2);
+        }
+    }
+#pragma unroll
+    for (int o = HM_MERGE_LANES / 2; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        top2_insert(o1, k1, k2);
+        top2_insert(o2, k1, k2);
+    }
+    if (i < n && sub == 0) {
+        const unsigned v = (k1 != HM_NONE) ? (unsigned)(k1 & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+        const unsigned q = owner_q[i];
+        for (unsigned p = 0; p < nranks; ++p) peer_rq[(p + rank) % nranks][q] = v;  // exactly one owner per query
+    }
+    signal_when_grid_done(ticket, peer_flags, 32u, nranks, rank, epoch);
+}
+
+__global__ void __launch_bounds__(256)
+wait_apply_rq_kernel(bshot_cand* __restrict__ merged, const unsigned* __restrict__ rq, unsigned nq, const unsigned* __restrict__ flags,
+                     unsigned nranks, unsigned epoch, unsigned* __restrict__ timeout_flag) {
+    wait_all_ranks(flags, 32u, nranks, epoch, timeout_flag);
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) merged[qi].rq = (merged[qi].k1 != HM_NONE) ? __ldcg(rq + qi) : 0xFFFFFFFFu;
+}
+
+// region of one rank: [gather: nranks x max_q records][rq: max_q u32][flags: 64 u32]
+static size_t comm_gather_bytes(const Comm& m) { return sizeof(bshot_cand) * (size_t)m.nranks * m.max_q; }
+size_t comm_region_bytes(const Comm& m) { return comm_gather_bytes(m) + sizeof(unsigned) * m.max_q + sizeof(unsigned) * 64; }
+
+int comm_set_peers(Ctx* c, void* const* region_ptrs) {
+    Comm& m = c->comm;
+    std::vector<void*> g(m.nranks), r(m.nranks), f(m.nranks);
+    for (int p = 0; p < m.nranks; ++p) {
+        unsigned char* base = reinterpret_cast<unsigned char*>(p == m.rank ? (void*)m.d_region : region_ptrs[p]);
+        if (!base) { set_error("bshot_comm: null region for rank %d", p); return BSHOT_E_INVALID; }
+        g[p] = base;
+        r[p] = base + comm_gather_bytes(m);
+        f[p] = base + comm_gather_bytes(m) + sizeof(unsigned) * m.max_q;
+    }
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(m.d_peer_gather, g.data(), sizeof(void*) * m.nranks, cudaMemcpyHostToDevice, c->stream));
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(m.d_peer_rq, r.data(), sizeof(void*) * m.nranks, cudaMemcpyHostToDevice, c->stream));
+    BSHOT_CUDA_TRY(cudaMemcpyAsync(m.d_peer_flags, f.data(), sizeof(void*) * m.nranks, cudaMemcpyHostToDevice, c->stream));
+    BSHOT_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    m.connected = true;
+    return BSHOT_OK;
+}
+
+// the whole sharded call, asynchronous on the context stream; d_out: nq complete records (every rank gets all of them)
+int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long global_base, bshot_cand* d_out) {
+    Comm& m = c->comm;
+    if (!m.connected) { set_error("sharded match: bshot_comm_create / bshot_comm_import first"); return BSHOT_E_STATE; }
+    if (nq == 0) return BSHOT_OK;
+    if (nq > m.max_q || nq > c->max_kp) { set_error("sharded match: %zu queries > capacity %zu", nq, std::min(m.max_q, c->max_kp)); return BSHOT_E_CAPACITY; }
+    const unsigned nranks = (unsigned)m.nranks, rank = (unsigned)m.rank;
+    const unsigned epoch = ++m.epoch;
+    unsigned char* base = m.d_region;
+    bshot_cand* gather = reinterpret_cast<bshot_cand*>(base);
+    unsigned* rq = reinterpret_cast<unsigned*>(base + comm_gather_bytes(m));
+    unsigned* flags = rq + m.max_q;
+    unsigned* owner_q = reinterpret_cast<unsigned*>(c->d_left);
+    unsigned* count = reinterpret_cast<unsigned*>(c->d_pair_count) + 1;
+    unsigned* timeout_flag = reinterpret_cast<unsigned*>(c->d_pair_count) + 3;
+    const unsigned qb = (unsigned)((nq + 255) / 256), mb = (unsigned)((nq * HM_MERGE_LANES + 255) / 256);
+    unsigned nsplit = 1;
+    // 1 + 2: shard search, merged records pushed to every rank
+    if (c->n_map) {
+        BSHOT_TRY(hamming_top2_partials(c, d_q, nq, c->d_map, c->n_map, global_base, nullptr, nullptr, nullptr, &nsplit));
+    } else {  // empty shard: one "split" of none-candidates
+        BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_partial, 0xFF, sizeof(unsigned long long) * 2 * nq, c->stream));
+    }
+    merge_push_kernel<<<mb, 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, c->d_cand, m.d_peer_gather, m.d_peer_flags, nranks, rank, epoch,
+                                                m.d_ticket, count);
+    // 3: all ranks' records merged, own winners selected and gathered
+    wait_merge_select_kernel<<<qb, 256, 0, c->stream>>>(gather, flags, nranks, (unsigned)nq, epoch, global_base, global_base + c->n_map,
+                                                       reinterpret_cast<const uint4*>(c->d_map), d_out, reinterpret_cast<uint4*>(c->d_gather), owner_q, count,
+                                                       timeout_flag);
+    count_launch(c, 2);
+    BSHOT_TRY(check_launch("sharded exchange kernels"));
+    // 4 + 5: best query of every owned winner, pushed to every rank
+    BSHOT_TRY(hamming_top2_partials(c, c->d_gather, nq, d_q, nq, 0, nullptr, count, nullptr, &nsplit));
+    merge_push_rq_kernel<<<mb, 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, count, owner_q, m.d_peer_rq, m.d_peer_flags, nranks, rank, epoch,
+                                                   m.d_ticket + 1);
+    // 6
+    wait_apply_rq_kernel<<<qb, 256, 0, c->stream>>>(d_out, rq, (unsigned)nq, flags, nranks, epoch, timeout_flag);
+    count_launch(c, 2);
+    return check_launch("sharded exchange kernels");
 }
 
 }  // namespace bshot

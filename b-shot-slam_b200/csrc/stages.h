@@ -45,6 +45,10 @@ int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, v
 int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* d1, int* idx2, int* d2);
 int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count, const unsigned* d_nq = nullptr);
 int popc_peak(Ctx* c, double* out);
+// sharded map match over peer memory (six launches, hamming.cu)
+size_t comm_region_bytes(const Comm& m);
+int comm_set_peers(Ctx* c, void* const* region_ptrs);
+int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long global_base, bshot_cand* d_out);
 
 // whole frame on the resident cloud (frame.cu)
 int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);

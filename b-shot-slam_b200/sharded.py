@@ -131,7 +131,10 @@ class DeviceShardedMatcher:
 
     Per call at world > 1: shard search (no rq) -> exchange of the 24 B/query records -> merge by (distance, global
     index) -> reverse pass only for the winners this rank owns (Q * Q / ranks pairs) -> exchange of the 4 B/query
-    reverse result -> records completed.  Two interchangeable exchanges:
+    reverse result -> records completed.  Three interchangeable exchanges:
+      * "ipc" (default): the communicator of the C ABI (bshot_comm_*, include/bshot_b200.h): CUDA-IPC peer memory, the
+        whole call is bshot_match_map_sharded_dev -- six kernel launches with the stores and the flag barriers fused into
+        the merge kernels.  torch.distributed only carries the 64-byte handles once at set-up;
       * "peer": gather buffer, rq array and a flag array are torch symmetric-memory allocations mapped on every rank
         over NVLink / NVSwitch; the records and the owners' reverse results are STORED straight into every rank's
         buffers (bshot_push_cands_dev / bshot_reverse_owned_push_dev) and bshot_peer_barrier_dev replaces each
@@ -149,10 +152,30 @@ class DeviceShardedMatcher:
         self.merged = torch.empty((nq, 3), dtype=torch.int64, device=dev)
         self.peer = None
         self.exchange = "none"
+        self.ipc = False
         if world == 1:
             return
         import torch.distributed as dist
         self.dist = dist
+        if mode in ("auto", "ipc"):
+            ok = 1
+            try:
+                ctx.comm_create(rank, world, nq)
+                mine = torch.from_numpy(ctx.comm_export()).to(dev)
+                allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(allh.view(-1), mine)
+                ctx.comm_import(allh.cpu().numpy())
+            except Exception as e:  # noqa: BLE001 -- e.g. no peer access between the GPUs
+                ok, self.ipc_error = 0, e
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)           # every rank takes the same path
+            torch.cuda.synchronize()
+            if int(t.item()) == 1:
+                self.ipc = True
+                self.exchange = "ipc"
+                return
+            if mode == "ipc":
+                raise RuntimeError(f"CUDA IPC communicator unavailable on some rank ({getattr(self, 'ipc_error', None)})")
         if mode in ("auto", "peer"):
             err = None
             try:
@@ -183,6 +206,8 @@ class DeviceShardedMatcher:
 
     def describe(self):
         return {"none": "none",
+                "ipc": "per call: bshot_match_map_sharded_dev (C ABI): 6 launches; records and reverse results STORED into every rank's "
+                       "CUDA-IPC peer buffers by the merge kernels, flag release / acquire fused into them (no NCCL on the data path)",
                 "peer": "per call: peer-memory stores (24 B/query records to every rank, 4 B/query reverse result from the "
                         "owner) + 2 flag barriers over symmetric memory (no NCCL on the data path)",
                 "nccl": "per call: nccl all_gather of 24 B/query records + all_reduce of 4 B/query reverse result"}[self.exchange]
@@ -193,6 +218,9 @@ class DeviceShardedMatcher:
         if w == 1:
             c.match_shard_dev(d_q_ptr, nq, global_base, True, self.cand.data_ptr())
             c.merge_cands_dev(self.cand.data_ptr(), 1, nq, self.merged.data_ptr())
+            return self.merged
+        if self.ipc:
+            c.match_map_sharded_dev(d_q_ptr, nq, global_base, self.merged.data_ptr())
             return self.merged
         c.match_shard_dev(d_q_ptr, nq, global_base, False, self.cand.data_ptr())
         if self.peer is not None:
@@ -216,5 +244,7 @@ class DeviceShardedMatcher:
 
     def check(self):
         """raises if a peer barrier gave up waiting for a rank"""
+        if self.ipc:
+            self.ctx.comm_check()
         if self.peer is not None and self.ctx.peer_barrier_timeouts():
             raise RuntimeError("a peer barrier timed out (a rank did not arrive)")

@@ -443,7 +443,7 @@ def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_ov
             dq = torch.from_numpy(q.view(np.int64)).to(dev)
             planted, t1 = None, None
             del full
-        matcher = sharded.DeviceShardedMatcher(ctx, world, rank, Q, mode="nccl" if os.environ.get("BSHOT_EXCHANGE") == "nccl" else "auto", device=dev)
+        matcher = sharded.DeviceShardedMatcher(ctx, world, rank, Q, mode=os.environ.get("BSHOT_EXCHANGE", "auto"), device=dev)
         last = matcher.match(dq.data_ptr(), lo)
         barrier()
         if planted is not None:

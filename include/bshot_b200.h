@@ -208,6 +208,32 @@ int bshot_peer_barrier_dev(bshot_ctx* ctx, const void* d_peer_flag_ptrs, int nra
 int bshot_peer_barrier_timeouts(bshot_ctx* ctx, unsigned* epoch_out);
 int bshot_reverse_owned_push_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
                                  const void* d_merged, const void* d_peer_rq_ptrs, int nranks, int rank);
+/* ---- multi-rank exchange behind the C ABI (one process per GPU on one node; no Python / torch / NCCL needed) ------
+ * Replaces what featureMatching (src/lidar_odometry.cpp:197-232) does against Map::getKeypoints' output when the
+ * map is sharded over GPUs: every rank owns a contiguous range of the global target array (bshot_map_append) and
+ * calls bshot_match_map_sharded[_dev] with the same queries; every rank receives all nq complete records (top-2 over
+ * the WHOLE map with the reference's first-minimum tie-break, rq = best query of the winner).
+ * Set-up, once:  bshot_comm_create on every rank -> bshot_comm_export -> exchange the 64-byte handles by any means
+ * (pipe, file, MPI, torch.distributed) -> bshot_comm_import.  Ranks that live in ONE process pass device pointers
+ * instead (bshot_comm_region / bshot_comm_import_ptrs; the caller enables peer access between the devices).
+ * Per call (six kernel launches, stream-ordered, no host synchronisation): shard search; the merged top-2 records are
+ * STORED into every rank's gather buffer over NVLink and a flag is released by the last CTA; the consumer kernel
+ * acquires the flags, merges the ranks' records and selects the winners that live in its own shard; their best query
+ * (Q x Q / ranks pairs) is stored into every rank's rq array behind a second flag set.  A rank that never arrives
+ * makes the others give up after ~2 s: the next bshot_comm_check / bshot_match_map_sharded returns BSHOT_E_STATE. */
+typedef struct bshot_ipc_handle { unsigned char bytes[64]; } bshot_ipc_handle;
+int bshot_comm_create(bshot_ctx* ctx, int rank, int nranks, size_t max_queries);
+int bshot_comm_export(bshot_ctx* ctx, bshot_ipc_handle* handle_out);
+int bshot_comm_import(bshot_ctx* ctx, const bshot_ipc_handle* handles /* nranks entries, own entry ignored */);
+int bshot_comm_region(bshot_ctx* ctx, void** d_region_out, size_t* bytes_out);
+int bshot_comm_import_ptrs(bshot_ctx* ctx, void* const* d_regions /* nranks device pointers, own entry ignored */);
+int bshot_comm_destroy(bshot_ctx* ctx);
+int bshot_comm_check(bshot_ctx* ctx);
+/* device pointers, asynchronous on the context stream: d_q (nq x 48 B) -> d_cand_out (nq bshot_cand records) */
+int bshot_match_map_sharded_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base, void* d_cand_out);
+/* host buffers, synchronous; checks the arrival of every rank */
+int bshot_match_map_sharded(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base, bshot_cand* cand_out);
+
 /* host-buffer convenience over the three calls above for a single rank */
 int bshot_match_map(bshot_ctx* ctx, const uint64_t* q, size_t nq, uint64_t global_base,
                     bshot_cand* cand_out);
