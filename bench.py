@@ -234,7 +234,8 @@ def main():
     params = bs.default_params(top_k=args.top_k, normals_mode=mode)
     map_q = 10000
     ctx = bs.Context(local_rank, max_points=max_n + 1024, max_keypoints=max(args.top_k, map_q),
-                     max_targets=max(args.top_k, (args.map_t + world - 1) // world, args.map_t if world > 1 else 0))
+                     max_targets=max(args.top_k, (args.map_t + world - 1) // world, args.map_t if world > 1 else 0,
+                                     (1 << 24) // world if world == 8 else 0))
     st = torch.cuda.ExternalStream(ctx.stream)
     d_frames = [torch.from_numpy(f).cuda() for f in frames]                 # resident in HBM
     h_frames = [torch.from_numpy(f).pin_memory() for f in frames]           # pinned host copies
