@@ -33,7 +33,8 @@ EXPORTS = [
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
     "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev", "bshot_comm_create", "bshot_comm_export", "bshot_comm_import",
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
-    "bshot_match_map_sharded",
+    "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
+    "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit",
 ]
 
 
@@ -99,6 +100,15 @@ def lib():
         L.bshot_map_append.argtypes = [vp, vp, sz]
         L.bshot_map_size.argtypes = [vp, C.POINTER(sz)]
         L.bshot_map_append_dev.argtypes = [vp, vp, sz]
+        L.bshot_gmap_create.argtypes = [vp, sz, sz]
+        L.bshot_gmap_reset.argtypes = [vp]
+        L.bshot_gmap_size.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+        L.bshot_gmap_add.argtypes = [vp, vp, vp, vp, sz, vp]
+        L.bshot_gmap_update_from_frame.argtypes = [vp, vp]
+        L.bshot_gmap_get_keypoints.argtypes = [vp, vp, cf, vp, vp, sz, C.POINTER(sz)]
+        L.bshot_extract_frame.argtypes = [vp, C.POINTER(Params), vp, sz, sz, vp, vp, vp, vp, vp]
+        L.bshot_match_frame_to_map.argtypes = [vp, vp, cf, vp, vp, vp, C.POINTER(sz), vp, sz]
+        L.bshot_frame_commit.argtypes = [vp]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
         L.bshot_comm_import.argtypes = [vp, vp]
@@ -366,6 +376,61 @@ class Context:
 
     def map_append_dev(self, d_desc_ptr, n):
         _chk(lib().bshot_map_append_dev(self.h, d_desc_ptr, n))
+
+    # GPU-resident global map + frame-to-map flow
+    def gmap_create(self, max_entries, max_blocks=4096):
+        _chk(lib().bshot_gmap_create(self.h, max_entries, max_blocks))
+
+    def gmap_reset(self):
+        _chk(lib().bshot_gmap_reset(self.h))
+
+    def gmap_size(self):
+        n, d = C.c_size_t(), C.c_size_t()
+        _chk(lib().bshot_gmap_size(self.h, C.byref(n), C.byref(d)))
+        return n.value, d.value
+
+    def gmap_add(self, xyz, ratio, desc, pose=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        ratio = np.ascontiguousarray(ratio, dtype=np.float32).reshape(-1)
+        desc = np.ascontiguousarray(desc, dtype=np.uint64).reshape(-1, 6)
+        pose = None if pose is None else np.ascontiguousarray(pose, dtype=np.float32).reshape(12)
+        _chk(lib().bshot_gmap_add(self.h, _p(xyz), _p(ratio), _p(desc), xyz.shape[0], _p(pose)))
+
+    def gmap_update_from_frame(self, pose=None):
+        pose = None if pose is None else np.ascontiguousarray(pose, dtype=np.float32).reshape(12)
+        _chk(lib().bshot_gmap_update_from_frame(self.h, _p(pose)))
+
+    def gmap_get_keypoints(self, pos, rng, cap=1 << 20):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(3)
+        n = C.c_size_t()
+        _chk(lib().bshot_gmap_get_keypoints(self.h, _p(pos), rng, None, None, 0, C.byref(n)))
+        xyz = np.empty((n.value, 3), np.float32)
+        desc = np.empty((n.value, 6), np.uint64)
+        _chk(lib().bshot_gmap_get_keypoints(self.h, _p(pos), rng, _p(xyz), _p(desc), n.value, C.byref(n)))
+        return xyz, desc
+
+    def extract_frame(self, xyz, params):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        k = params.top_k
+        idx, kp, ratio, bits = np.empty(k, np.int32), np.empty((k, 3), np.float32), np.empty(k, np.float32), np.empty((k, 6), np.uint64)
+        nk = C.c_int()
+        _chk(lib().bshot_extract_frame(self.h, C.byref(params), _p(xyz), xyz.shape[0], xyz.shape[1] * 4, _p(idx), _p(kp), _p(ratio),
+                                       _p(bits), C.byref(nk)))
+        n = nk.value
+        self.n_points, self.n_kp = xyz.shape[0], n
+        return dict(kp_idx=idx[:n].copy(), kp_xyz=kp[:n].copy(), seg_ratio=ratio[:n].copy(), bits=bits[:n].copy())
+
+    def match_frame_to_map(self, ref_pos, rng=100000.0, ref_pose=None, target_cap=1 << 20):
+        ref_pos = np.ascontiguousarray(ref_pos, dtype=np.float32).reshape(3)
+        ref_pose = None if ref_pose is None else np.ascontiguousarray(ref_pose, dtype=np.float32).reshape(12)
+        pairs = np.empty((max(self.max_keypoints, 1), 2), np.int32)
+        npairs, nt = C.c_int(), C.c_size_t()
+        txyz = np.empty((target_cap, 3), np.float32)
+        _chk(lib().bshot_match_frame_to_map(self.h, _p(ref_pos), rng, _p(ref_pose), _p(pairs), C.byref(npairs), C.byref(nt), _p(txyz), target_cap))
+        return dict(pairs=pairs[:npairs.value].copy(), n_targets=nt.value, target_xyz=txyz[:nt.value].copy())
+
+    def frame_commit(self):
+        _chk(lib().bshot_frame_commit(self.h))
 
     # multi-rank exchange behind the C ABI (CUDA IPC peer memory)
     def comm_create(self, rank, nranks, max_queries):

@@ -172,6 +172,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_sum_nn, 2));
     A(dmalloc(&c->d_bits, K * 6));
     A(dmalloc(&c->d_prev_bits, K * 6));
+    A(dmalloc(&c->d_prev_kp, K));
     A(dmalloc(&c->d_prev_count, 4));
     A(dmalloc(&c->d_q, K * 6));
     A(dmalloc(&c->d_t, T * 6));
@@ -225,9 +226,10 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     comm_free(c);
+    gmap_free(c);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
                     c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
-                    c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits,
+                    c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits, c->d_prev_kp,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
     for (void* p : ptrs)
@@ -670,6 +672,131 @@ int bshot_apply_rq_dev(bshot_ctx* ctx, void* d_cands, const void* d_rq, size_t n
     return hamming_apply_rq(ctx, reinterpret_cast<bshot_cand*>(d_cands), reinterpret_cast<const unsigned*>(d_rq), nq);
 }
 
+// ---- GPU-resident global map + frame-to-map flow --------------------------------------------
+int bshot_gmap_create(bshot_ctx* ctx, size_t max_entries, size_t max_blocks) {
+    CHECK_CTX(ctx);
+    if (max_entries == 0 || max_blocks == 0 || max_entries > 0x7FFFFFFFull) { set_error("bshot_gmap_create: bad capacities"); return BSHOT_E_INVALID; }
+    if (ctx->gmap.d_tab) { set_error("bshot_gmap_create: the context already has a map"); return BSHOT_E_STATE; }
+    BSHOT_TRY(gmap_create(ctx, max_entries, max_blocks));
+    return sync(ctx);
+}
+
+int bshot_gmap_reset(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(gmap_reset(ctx));
+    ctx->gmap.entries_upper = 0;
+    return sync(ctx);
+}
+
+int bshot_gmap_size(bshot_ctx* ctx, size_t* entries_out, size_t* dropped_out) {
+    CHECK_CTX(ctx);
+    if (!ctx->gmap.d_tab) { set_error("bshot_gmap_size: no map"); return BSHOT_E_STATE; }
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[40], ctx->gmap.d_ctl, 8 * sizeof(unsigned)));
+    BSHOT_TRY(sync(ctx));
+    if (entries_out) *entries_out = (size_t)(unsigned)ctx->h_scratch[40];
+    if (dropped_out) *dropped_out = (size_t)(unsigned)ctx->h_scratch[43];
+    return BSHOT_OK;
+}
+
+int bshot_gmap_add(bshot_ctx* ctx, const float* xyz, const float* seg_ratio, const uint64_t* desc, size_t n, const float* pose3x4) {
+    CHECK_CTX(ctx);
+    if (n == 0) return BSHOT_OK;
+    if (!xyz || !seg_ratio || !desc) { set_error("bshot_gmap_add: null input"); return BSHOT_E_INVALID; }
+    if (n > ctx->max_kp) { set_error("bshot_gmap_add: %zu keypoints > max_keypoints %zu per call", n, ctx->max_kp); return BSHOT_E_CAPACITY; }
+    // staged in the scratch buffers of the matcher (d_gather as float4 positions, d_left as ratios, d_q as descriptors)
+    float4* d_pos = reinterpret_cast<float4*>(ctx->d_gather);
+    float* d_ratio = reinterpret_cast<float*>(ctx->d_left);
+    BSHOT_CUDA_TRY(cudaMemsetAsync(d_pos, 0, sizeof(float4) * n, ctx->stream));
+    BSHOT_CUDA_TRY(cudaMemcpy2DAsync(d_pos, 16, xyz, 12, 12, n, cudaMemcpyHostToDevice, ctx->stream));
+    BSHOT_TRY(h2d(ctx, d_ratio, seg_ratio, sizeof(float) * n));
+    BSHOT_TRY(h2d(ctx, ctx->d_q, desc, 48 * n));
+    BSHOT_TRY(gmap_update(ctx, d_pos, d_ratio, ctx->d_q, nullptr, n, pose3x4));
+    ctx->gmap.entries_upper += n;
+    return sync(ctx);
+}
+
+int bshot_gmap_update_from_frame(bshot_ctx* ctx, const float* pose3x4) {
+    CHECK_CTX(ctx);
+    if (!ctx->have_kp || ctx->last_top_k == 0) { set_error("bshot_gmap_update_from_frame: no extracted frame"); return BSHOT_E_STATE; }
+    BSHOT_TRY(gmap_update(ctx, ctx->d_kp, ctx->d_kp_ratio, ctx->d_bits, ctx->d_kp_count, ctx->last_top_k, pose3x4));
+    ctx->gmap.entries_upper += ctx->last_top_k;
+    return BSHOT_OK;  // asynchronous
+}
+
+int bshot_gmap_get_keypoints(bshot_ctx* ctx, const float pos[3], float range, float* xyz_out, uint64_t* desc_out, size_t cap, size_t* n_out) {
+    CHECK_CTX(ctx);
+    if (!pos) { set_error("bshot_gmap_get_keypoints: null position"); return BSHOT_E_INVALID; }
+    unsigned* d_total = ctx->gmap.d_ctl ? ctx->gmap.d_ctl + 6 : nullptr;
+    BSHOT_TRY(gmap_gather(ctx, pos, range, nullptr, nullptr, nullptr, 0, nullptr, ctx->d_t, ctx->max_targets, d_total));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[40], ctx->gmap.d_ctl, 8 * sizeof(unsigned)));
+    BSHOT_TRY(sync(ctx));
+    const size_t n = (size_t)(unsigned)ctx->h_scratch[44];
+    if (n_out) *n_out = n;
+    if (n > ctx->max_targets) { set_error("bshot_gmap_get_keypoints: %zu keypoints in range > max_targets %zu", n, ctx->max_targets); return BSHOT_E_CAPACITY; }
+    const size_t m = std::min(n, cap);
+    if (xyz_out && m) BSHOT_CUDA_TRY(cudaMemcpy2DAsync(xyz_out, 12, ctx->gmap.d_tpos, 16, 12, m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc_out && m) BSHOT_TRY(d2h(ctx, desc_out, ctx->d_t, 48 * m));
+    return sync(ctx);
+}
+
+int bshot_extract_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n, size_t stride_bytes, int* kp_idx_out, float* kp_xyz_out,
+                        float* seg_ratio_out, uint64_t* bits_out, int* n_kp_out) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (!xyz && n) { set_error("bshot_extract_frame: null cloud"); return BSHOT_E_INVALID; }
+    BSHOT_TRY(frame_args_ok(ctx, p, n, stride_bytes, "bshot_extract_frame"));
+    BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
+    BSHOT_TRY(frame_extract(ctx, p, ctx->d_raw, n, (int)(stride_bytes / 4)));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    const int k = std::min(ctx->h_scratch[0], p->top_k);
+    ctx->n_kp = (size_t)k;
+    if (n_kp_out) *n_kp_out = k;
+    BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * k));
+    BSHOT_TRY(d2h(ctx, seg_ratio_out, ctx->d_kp_ratio, sizeof(float) * k));
+    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, 48 * (size_t)k));
+    if (kp_xyz_out && k) BSHOT_CUDA_TRY(cudaMemcpy2DAsync(kp_xyz_out, 12, ctx->d_kp, 16, 12, k, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync(ctx);
+}
+
+int bshot_frame_commit(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    if (ctx->last_top_k == 0) { set_error("bshot_frame_commit: no extracted frame"); return BSHOT_E_STATE; }
+    return frame_commit(ctx, ctx->last_top_k);
+}
+
+int bshot_match_frame_to_map(bshot_ctx* ctx, const float ref_pos[3], float range, const float* ref_pose3x4, int* pairs_out, int* n_pairs_out,
+                             size_t* n_targets_out, float* target_xyz_out, size_t target_cap) {
+    CHECK_CTX(ctx);
+    if (!ref_pos) { set_error("bshot_match_frame_to_map: null position"); return BSHOT_E_INVALID; }
+    if (!ctx->gmap.d_tab || ctx->last_top_k == 0) { set_error("bshot_match_frame_to_map: needs a map and an extracted frame"); return BSHOT_E_STATE; }
+    const size_t k = ctx->last_top_k;
+    unsigned* d_total = ctx->gmap.d_ctl + 6;
+    // target set = map keypoints in range ++ reference (previous) frame, assembled on the device (src/lidar_odometry.cpp:197-206)
+    BSHOT_TRY(gmap_gather(ctx, ref_pos, range, ctx->d_prev_kp, ctx->d_prev_bits, ctx->d_prev_count, ctx->n_prev, ref_pose3x4, ctx->d_t, ctx->max_targets, d_total));
+    const size_t nt_cap = std::min(ctx->max_targets, ctx->gmap.entries_upper + ctx->n_prev);
+    if (nt_cap == 0) { if (n_pairs_out) *n_pairs_out = 0; if (n_targets_out) *n_targets_out = 0; return sync(ctx); }
+    const unsigned* d_nq = reinterpret_cast<const unsigned*>(ctx->d_kp_count);
+    BSHOT_TRY(hamming_match_rq(ctx, ctx->d_bits, k, ctx->d_t, nt_cap, 0, ctx->d_cand, d_nq, d_total));
+    BSHOT_TRY(hamming_mutual_pairs(ctx, ctx->d_cand, k, ctx->d_pairs, ctx->d_pair_count, d_nq));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[1], ctx->d_pair_count, sizeof(int)));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[40], ctx->gmap.d_ctl, 8 * sizeof(unsigned)));
+    if (pairs_out) BSHOT_CUDA_TRY(cudaMemcpyAsync(ctx->h_pairs, ctx->d_pairs, sizeof(int) * 3 * k, cudaMemcpyDeviceToHost, ctx->stream));
+    BSHOT_TRY(sync(ctx));
+    const size_t gathered = (size_t)(unsigned)ctx->h_scratch[44] + 0, total = (size_t)(unsigned)ctx->h_scratch[46];
+    if (gathered + ctx->n_prev > ctx->max_targets && total == ctx->max_targets) { set_error("bshot_match_frame_to_map: target set exceeds max_targets %zu", ctx->max_targets); return BSHOT_E_CAPACITY; }
+    const int np = std::min(ctx->h_scratch[1], (int)k);
+    if (n_pairs_out) *n_pairs_out = np;
+    if (n_targets_out) *n_targets_out = total;
+    if (pairs_out) for (int i = 0; i < np; ++i) { pairs_out[2 * i] = ctx->h_pairs[3 * i]; pairs_out[2 * i + 1] = ctx->h_pairs[3 * i + 1]; }
+    if (target_xyz_out && total) {
+        BSHOT_CUDA_TRY(cudaMemcpy2DAsync(target_xyz_out, 12, ctx->gmap.d_tpos, 16, 12, std::min(total, target_cap), cudaMemcpyDeviceToHost, ctx->stream));
+        BSHOT_TRY(sync(ctx));
+    }
+    return BSHOT_OK;
+}
+
 // ---- multi-rank exchange behind the C ABI (no Python / torch needed) -------------------------------------------
 static void comm_free(bshot_ctx* c) {
     Comm& m = c->comm;
@@ -689,6 +816,7 @@ int bshot_comm_create(bshot_ctx* ctx, int rank, int nranks, size_t max_queries) 
     if (max_queries > ctx->max_kp) { set_error("bshot_comm_create: max_queries %zu > max_keypoints %zu", max_queries, ctx->max_kp); return BSHOT_E_CAPACITY; }
     BSHOT_TRY(sync(ctx));
     comm_free(ctx);
+    BSHOT_TRY(hamming_preload_sharded());
     Comm& m = ctx->comm;
     m.rank = rank; m.nranks = nranks; m.max_q = max_queries;
     const size_t bytes = comm_region_bytes(m);

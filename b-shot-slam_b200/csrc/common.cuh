@@ -68,6 +68,25 @@ struct Comm {
     bool connected = false;
 };
 
+// GPU-resident global keypoint map (gmap.cu)
+struct Gmap {
+    void* d_tab = nullptr;              // block hash table (GmapBlock[tab_cap])
+    float4* d_epos = nullptr;           // entries: snapped position + seg-ratio
+    uint64_t* d_edesc = nullptr;        // entries: 48-byte descriptors
+    unsigned* d_chunks = nullptr;       // 33-word chunks: 32 entry indices + next chunk
+    float4* d_world = nullptr;          // per update: snapped world positions of the frame's keypoints
+    unsigned* d_blk_of = nullptr;       // per update: block slot of every keypoint
+    unsigned* d_touched = nullptr;      // per update: distinct blocks
+    unsigned* d_probe_slot = nullptr;   // per gather: slot / offset of every probed block
+    unsigned* d_probe_off = nullptr;
+    unsigned* d_ctl = nullptr;          // [0] entries [1] touched [2] chunks [3] dropped [4] gathered [5] probes [6] total targets
+    float* d_pose = nullptr;            // 2 x 12 floats
+    float4* d_tpos = nullptr;           // positions of the assembled target set (max_targets)
+    unsigned tab_cap = 0, max_entries = 0, max_chunks = 0, max_probe = 0, epoch = 0;
+    size_t n_gathered = 0;
+    size_t entries_upper = 0;           // host-side upper bound of the number of entries (sizes the match grid without a sync)
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
@@ -155,6 +174,8 @@ struct Ctx {
     unsigned peer_epoch = 0;            // barriers issued on the symmetric flag array so far
 
     Comm comm;
+    Gmap gmap;
+    float4* d_prev_kp = nullptr;        // K: keypoint positions of the previous frame (reference frame of the map match)
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints

@@ -5,15 +5,26 @@
 
 namespace bshot {
 
-__global__ void copy_prev_kernel(const uint64_t* __restrict__ bits, const int* __restrict__ count, unsigned cap,
-                                 uint64_t* __restrict__ prev, int* __restrict__ prev_count) {
+__global__ void copy_prev_kernel(const uint64_t* __restrict__ bits, const float4* __restrict__ kp, const int* __restrict__ count, unsigned cap,
+                                 uint64_t* __restrict__ prev, float4* __restrict__ prev_kp, int* __restrict__ prev_count) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = *count;
     if (i < cap * 6 && (int)(i / 6) < k) prev[i] = bits[i];
+    if (i < cap && (int)i < k) prev_kp[i] = kp[i];
     if (i == 0) *prev_count = k;
 }
 
-int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats) {
+// the current frame becomes the reference frame (descriptors + keypoint positions + count stay on the device)
+int frame_commit(Ctx* c, size_t k) {
+    copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp, c->d_kp_count, (unsigned)k, c->d_prev_bits, c->d_prev_kp,
+                                                                            c->d_prev_count);
+    count_launch(c);
+    c->n_prev = k;
+    return check_launch("copy_prev_kernel");
+}
+
+// extractKeypoints + computeDescriptors (src/lidar_odometry.cpp:51-184) on a cloud in device memory, asynchronous
+int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats) {
     auto mark = [&](int i) {
         if (c->timing) cudaEventRecord(c->ev[i], c->stream);
     };
@@ -31,6 +42,15 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
     mark(4);
     BSHOT_TRY(shot_compute(c, p->shot_radius, false, false));
     mark(5);
+    c->last_top_k = (size_t)p->top_k;
+    return BSHOT_OK;
+}
+
+int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats) {
+    auto mark = [&](int i) {
+        if (c->timing) cudaEventRecord(c->ev[i], c->stream);
+    };
+    BSHOT_TRY(frame_extract(c, p, d_raw, n, stride_floats));
     // featureMatching: the initial frame is matched against itself (src/lidar_odometry.cpp:187-194),
     // later frames against the previous frame's descriptors.  Host-side counts are upper bounds
     // (top_k); the kernels trim queries AND targets by the device-side keypoint counts, so a frame that
@@ -41,17 +61,12 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
     const size_t nt = initial ? k : c->n_prev;
     const unsigned* d_nq = reinterpret_cast<const unsigned*>(c->d_kp_count);
     const unsigned* d_nt = reinterpret_cast<const unsigned*>(initial ? c->d_kp_count : c->d_prev_count);
-    if (nt > 4 * k) { set_error("frame_run: previous frame holds %zu descriptors, more than 4 x top_k = %zu", nt, 4 * k); return BSHOT_E_INVALID; }
     BSHOT_TRY(hamming_match_rq(c, c->d_bits, k, tgt, nt, 0, c->d_cand, d_nq, d_nt));
     BSHOT_TRY(hamming_mutual_pairs(c, c->d_cand, k, c->d_pairs, c->d_pair_count, d_nq));
-    copy_prev_kernel<<<(unsigned)((k * 6 + 255) / 256), 256, 0, c->stream>>>(c->d_bits, c->d_kp_count, (unsigned)k,
-                                                                            c->d_prev_bits, c->d_prev_count);
-    count_launch(c);
+    BSHOT_TRY(frame_commit(c, k));
     mark(6);
     c->ev_valid = c->timing;
-    c->n_prev = k;
-    c->last_top_k = k;
-    return check_launch("copy_prev_kernel");
+    return BSHOT_OK;
 }
 
 }  // namespace bshot

@@ -454,13 +454,13 @@ int hamming_top2(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt,
 
 // fills d_cand[i].rq = best query (index into d_q) for the target d_cand[i].k1
 int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
-                    bshot_cand* d_cand) {
+                    bshot_cand* d_cand, const unsigned* d_nq) {
     if (nq == 0) return BSHOT_OK;
     gather_best_kernel<<<(unsigned)((nq * 3 + 255) / 256), 256, 0, c->stream>>>(
         d_cand, (unsigned)nq, reinterpret_cast<const uint4*>(d_t), global_base, reinterpret_cast<uint4*>(c->d_gather));
     count_launch(c);
     BSHOT_TRY(check_launch("gather_best_kernel"));
-    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2, nullptr));
+    BSHOT_TRY(hamming_top2(c, c->d_gather, nq, d_q, nq, 0, c->d_cand2, nullptr, d_nq, d_nq));  // only the live queries search / are searched
     set_rq_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(d_cand, c->d_cand2, (unsigned)nq);
     count_launch(c);
     return check_launch("set_rq_kernel");
@@ -537,9 +537,8 @@ int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t
     if (nq == 0) return BSHOT_OK;
     if (nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
         return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right), d_nq, d_nt);
-    if (d_nq || d_nt) { set_error("hamming_match_rq: device-side counts need the fused reverse pass (nt <= 4 nq)"); return BSHOT_E_INVALID; }
-    BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr));
-    return hamming_reverse(c, d_q, nq, d_t, global_base, d_out);
+    BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr, d_nq, d_nt));
+    return hamming_reverse(c, d_q, nq, d_t, global_base, d_out, d_nq);
 }
 }  // namespace bshot
 
@@ -844,6 +843,21 @@ wait_apply_rq_kernel(bshot_cand* __restrict__ merged, const unsigned* __restrict
     wait_all_ranks(flags, 32u, nranks, epoch, timeout_flag);
     const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi < nq) merged[qi].rq = (merged[qi].k1 != HM_NONE) ? __ldcg(rq + qi) : 0xFFFFFFFFu;
+}
+
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel may have to wait for running kernels; a
+// consumer kernel spinning on a flag that a not-yet-loaded producer kernel of ANOTHER rank in the same process must release
+// would then never see it.  Loading every kernel of the sharded call up front removes that dependency.
+int hamming_preload_sharded() {
+    cudaFuncAttributes a;
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_top2_kernel<4, false>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_top2_kernel<2, false>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_top2_kernel<1, false>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, merge_push_kernel));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, wait_merge_select_kernel));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, merge_push_rq_kernel));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, wait_apply_rq_kernel));
+    return BSHOT_OK;
 }
 
 // region of one rank: [gather: nranks x max_q records][rq: max_q u32][flags: 64 u32]

@@ -40,7 +40,7 @@ int hamming_apply_rq(Ctx* c, bshot_cand* d_cand, const unsigned* d_rq, size_t nq
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                      bshot_cand* d_out, const unsigned* d_nq = nullptr, const unsigned* d_nt = nullptr);
 int hamming_reverse(Ctx* c, const void* d_q, size_t nq, const void* d_t, unsigned long long global_base,
-                    bshot_cand* d_cand);
+                    bshot_cand* d_cand, const unsigned* d_nq = nullptr);
 int hamming_merge_cands(Ctx* c, const void* d_cands, size_t nranks, size_t nq, void* d_out);
 int hamming_unpack(Ctx* c, const bshot_cand* d_cand, size_t nq, int* idx1, int* d1, int* idx2, int* d2);
 int hamming_mutual_pairs(Ctx* c, const bshot_cand* d_cand, size_t nq, int* d_pairs3, int* d_count, const unsigned* d_nq = nullptr);
@@ -48,9 +48,20 @@ int popc_peak(Ctx* c, double* out);
 // sharded map match over peer memory (six launches, hamming.cu)
 size_t comm_region_bytes(const Comm& m);
 int comm_set_peers(Ctx* c, void* const* region_ptrs);
+int hamming_preload_sharded();
 int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long global_base, bshot_cand* d_out);
 
+// GPU-resident global map (gmap.cu)
+int gmap_create(Ctx* c, size_t max_entries, size_t max_blocks);
+void gmap_free(Ctx* c);
+int gmap_reset(Ctx* c);
+int gmap_update(Ctx* c, const float4* d_kp, const float* d_ratio, const uint64_t* d_bits, const int* d_count, size_t n_cap, const float* pose12);
+int gmap_gather(Ctx* c, const float pos[3], float range, const float4* d_ref_kp, const uint64_t* d_ref_bits, const int* d_ref_count,
+                size_t ref_cap, const float* ref_pose12, uint64_t* d_t_out, size_t out_cap, unsigned* d_total);
+
 // whole frame on the resident cloud (frame.cu)
+int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);
+int frame_commit(Ctx* c, size_t k);
 int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);
 
 }  // namespace bshot

@@ -160,6 +160,37 @@ int bshot_process_frame_dev(bshot_ctx* ctx, const bshot_params* p, const void* d
 int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out,
                       int* pairs_out, int* n_pairs_out);
 
+/* ---- GPU-resident global map + frame-to-map flow (RUN status of featureMatching) ------------------------------------
+ * Replaces, on the device: Keypoint::createKeypoint's 10 mm snap (src/keypoint.cpp:23-32), Map::addKeypoint
+ * (src/mymap.cpp:4-26: 10 m blocks, reject when a stored keypoint of the block within 800 mm is at least as salient, else
+ * insert / overwrite at the same position), LidarOdometry::updateMap (src/lidar_odometry.cpp:343-358: every keypoint of the
+ * frame in order, transformed by the pose), Map::getKeypoints (src/mymap.cpp:28-74: blocks of the +-range cube, x outermost,
+ * z innermost) and the target assembly of featureMatching (src/lidar_odometry.cpp:197-206: map subset, then the reference
+ * frame's keypoints transformed by its pose).  Inside a block keypoints come out in insertion order (the reference's
+ * unordered_map order is implementation defined).  pose3x4 = row-major [R|T], NULL = identity.
+ * Per-frame call order of a host that keeps RANSAC / ICP (src/lidar_odometry.cpp:251-301) on the CPU:
+ *   bshot_extract_frame -> bshot_match_frame_to_map -> (host: pose) -> bshot_gmap_update_from_frame(pose) -> bshot_frame_commit */
+int bshot_gmap_create(bshot_ctx* ctx, size_t max_entries, size_t max_blocks);
+int bshot_gmap_reset(bshot_ctx* ctx);
+/* entries stored so far; dropped = keypoints lost to a full table / pool (0 unless the capacities are too small) */
+int bshot_gmap_size(bshot_ctx* ctx, size_t* entries_out, size_t* dropped_out);
+/* Map::addKeypoint for n keypoints given on the host (xyz n x 3 floats, in keypoint order), n <= max_keypoints per call */
+int bshot_gmap_add(bshot_ctx* ctx, const float* xyz, const float* seg_ratio, const uint64_t* desc, size_t n, const float* pose3x4);
+/* updateMap for the frame extracted last (keypoints, seg-ratios and descriptors are still on the device); asynchronous */
+int bshot_gmap_update_from_frame(bshot_ctx* ctx, const float* pose3x4);
+/* Map::getKeypoints to host buffers (cap records); *n_out = keypoints in range */
+int bshot_gmap_get_keypoints(bshot_ctx* ctx, const float pos[3], float range, float* xyz_out, uint64_t* desc_out, size_t cap, size_t* n_out);
+/* extractKeypoints + computeDescriptors of one scan (no matching); outputs hold up to p->top_k records, any may be NULL */
+int bshot_extract_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz, size_t n, size_t stride_bytes, int* kp_idx_out,
+                        float* kp_xyz_out, float* seg_ratio_out, uint64_t* bits_out, int* n_kp_out);
+/* featureMatching in RUN status for the frame extracted last: targets = map keypoints within `range` of ref_pos, then the
+ * committed (previous) frame transformed by ref_pose3x4; mutual nearest neighbours -> pairs_out (index_query, index_match
+ * into that target set).  target_xyz_out (optional, target_cap x 3 floats) = positions of the targets for the host's RANSAC. */
+int bshot_match_frame_to_map(bshot_ctx* ctx, const float ref_pos[3], float range, const float* ref_pose3x4, int* pairs_out,
+                             int* n_pairs_out, size_t* n_targets_out, float* target_xyz_out, size_t target_cap);
+/* the frame extracted last becomes the reference frame (passSrc2Ref, src/lidar_odometry.cpp:43-47); asynchronous */
+int bshot_frame_commit(bshot_ctx* ctx);
+
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
  * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first

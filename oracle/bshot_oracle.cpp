@@ -798,6 +798,95 @@ long long orc_compute_descriptors(const orc_cloud* c, const float* kp_xyz, size_
     return total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// global keypoint map: src/keypoint.cpp:23-32 (10 mm snap), src/mymap.cpp:4-26 (addKeypoint), :28-74 (getKeypoints),
+// :103-112 (getBlockID), src/lidar_odometry.cpp:343-358 (updateMap: every keypoint of the frame in order, R * p + T).
+// Order inside a block: insertion order (the reference iterates an unordered_map: implementation defined).
+struct orc_map_entry { float x, y, z, ratio; uint64_t d[6]; };
+struct orc_map {
+    std::vector<std::pair<uint64_t, std::vector<orc_map_entry>>> blocks;  // creation order; lookups are linear (test sizes)
+    std::vector<orc_map_entry>* find(uint64_t id) {
+        for (auto& b : blocks) if (b.first == id) return &b.second;
+        return nullptr;
+    }
+};
+static uint64_t map_block_id(float x, float y, float z) {
+    const int prec = 10000;
+    const float v[3] = {x, y, z};
+    uint64_t key = 0;
+    for (int a = 0; a < 3; ++a) {
+        const int g = int(std::round(v[a] / prec)) * prec;
+        key = (key << 21) | ((uint64_t)(int64_t)g & 0x1FFFFFull);
+    }
+    return key;
+}
+
+orc_map* orc_map_create() { return new orc_map(); }
+void orc_map_destroy(orc_map* m) { delete m; }
+size_t orc_map_size(const orc_map* m) {
+    size_t n = 0;
+    for (auto& b : m->blocks) n += b.second.size();
+    return n;
+}
+
+void orc_map_add(orc_map* m, const float* xyz, const float* ratio, const uint64_t* desc, size_t n, const float* pose12) {
+    for (size_t i = 0; i < n; ++i) {
+        float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (pose12) {  // kp_pos = R * kp_pos + T (src/lidar_odometry.cpp:351)
+            const float px = x, py = y, pz = z;
+            x = ((pose12[0] * px + pose12[1] * py) + pose12[2] * pz) + pose12[3];
+            y = ((pose12[4] * px + pose12[5] * py) + pose12[6] * pz) + pose12[7];
+            z = ((pose12[8] * px + pose12[9] * py) + pose12[10] * pz) + pose12[11];
+        }
+        orc_map_entry e;  // Keypoint::createKeypoint: int(trunc(pos / prec)) * prec, prec = 10
+        e.x = (float)(int(std::trunc(x / 10)) * 10);
+        e.y = (float)(int(std::trunc(y / 10)) * 10);
+        e.z = (float)(int(std::trunc(z / 10)) * 10);
+        e.ratio = ratio[i];
+        std::memcpy(e.d, desc + 6 * i, 48);
+        const uint64_t id = map_block_id(e.x, e.y, e.z);
+        std::vector<orc_map_entry>* blk = m->find(id);
+        if (!blk) {  // :7-11 new block
+            m->blocks.push_back(std::make_pair(id, std::vector<orc_map_entry>(1, e)));
+            continue;
+        }
+        bool candidate = true;  // :15-21
+        for (auto& k : *blk) {
+            const float dx = e.x - k.x, dy = e.y - k.y, dz = e.z - k.z;
+            if (std::sqrt(dot3f(dx, dy, dz, dx, dy, dz)) < 800 && e.ratio <= k.ratio) candidate = false;
+        }
+        if (!candidate) continue;
+        bool over = false;      // :23 keypoints_[block][position] = keypoint
+        for (auto& k : *blk)
+            if (k.x == e.x && k.y == e.y && k.z == e.z) { k = e; over = true; break; }
+        if (!over) blk->push_back(e);
+    }
+}
+
+size_t orc_map_get(orc_map* m, const float pos[3], float range, float* xyz_out, uint64_t* desc_out, size_t cap) {
+    const int prec = 10000;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = int(std::round((pos[a] - range) / prec)) * prec;
+        hi[a] = int(std::round((pos[a] + range) / prec)) * prec;
+    }
+    size_t n = 0;
+    for (int x = lo[0]; x <= hi[0]; x += prec)
+        for (int y = lo[1]; y <= hi[1]; y += prec)
+            for (int z = lo[2]; z <= hi[2]; z += prec) {
+                std::vector<orc_map_entry>* blk = m->find(map_block_id((float)x, (float)y, (float)z));
+                if (!blk) continue;
+                for (auto& k : *blk) {
+                    if (n < cap) {
+                        if (xyz_out) { xyz_out[3 * n] = k.x; xyz_out[3 * n + 1] = k.y; xyz_out[3 * n + 2] = k.z; }
+                        if (desc_out) std::memcpy(desc_out + 6 * n, k.d, 48);
+                    }
+                    ++n;
+                }
+            }
+    return n;
+}
+
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]) { eigh3(m, evals, evecs_cols); }
 void orc_eigen33_smallest(const float m[9], float* eval, float evec[3]) { eigen33_smallest(m, *eval, evec); }
 

@@ -96,6 +96,16 @@ long long orc_compute_descriptors(const orc_cloud* c, const float* kp_xyz, size_
                                   float* shot352_out, float* rf9_out, float* normals4_out,
                                   int threads);
 
+/* global keypoint map: Keypoint::createKeypoint (src/keypoint.cpp:23-32), Map::addKeypoint / getKeypoints / getBlockID
+ * (src/mymap.cpp:4-26, 28-74, 103-112), updateMap's pose (src/lidar_odometry.cpp:351; pose12 = row-major [R|T] or NULL).
+ * Keypoints of one block come out in insertion order (the reference's unordered_map order is implementation defined). */
+typedef struct orc_map orc_map;
+orc_map* orc_map_create(void);
+void orc_map_destroy(orc_map* m);
+size_t orc_map_size(const orc_map* m);
+void orc_map_add(orc_map* m, const float* xyz, const float* ratio, const uint64_t* desc, size_t n, const float* pose12);
+size_t orc_map_get(orc_map* m, const float pos[3], float range, float* xyz_out, uint64_t* desc_out, size_t cap);
+
 /* symmetric 3x3 eigen decomposition used by orc_lrf (double, ascending), exposed for tests */
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]);
 /* pcl::eigen33 smallest-eigenpair (fp32), exposed for tests */

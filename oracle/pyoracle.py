@@ -59,6 +59,13 @@ def lib():
         L.orc_compute_descriptors.restype = C.c_longlong
         L.orc_compute_descriptors.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_float, C.c_int,
                                               C.c_int, up, fp, fp, fp, C.c_int]
+        L.orc_map_create.restype = C.c_void_p
+        L.orc_map_destroy.argtypes = [C.c_void_p]
+        L.orc_map_size.restype = C.c_size_t
+        L.orc_map_size.argtypes = [C.c_void_p]
+        L.orc_map_add.argtypes = [C.c_void_p, fp, fp, up, C.c_size_t, fp]
+        L.orc_map_get.restype = C.c_size_t
+        L.orc_map_get.argtypes = [C.c_void_p, fp, C.c_float, fp, up, C.c_size_t]
         L.orc_eigh3.argtypes = [C.POINTER(C.c_double)] * 3
         L.orc_eigen33_smallest.argtypes = [fp, fp, fp]
         _LIB = L
@@ -144,6 +151,36 @@ class Cloud:
             self.h, _f(kp), k, radius, max_nn, mode, _u(bits), _f(shot), _f(rf),
             _f(normals) if want_normals else None, threads)
         return dict(bits=bits, shot=shot, rf=rf, normals=normals, sum_neighbours=total)
+
+
+class Map:
+    """the reference's global keypoint map (src/mymap.cpp, src/keypoint.cpp:23-32); insertion order inside a block"""
+
+    def __init__(self):
+        self.h = lib().orc_map_create()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_map_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return lib().orc_map_size(self.h)
+
+    def add(self, xyz, ratio, desc, pose=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        ratio = np.ascontiguousarray(ratio, dtype=np.float32).reshape(-1)
+        desc = np.ascontiguousarray(desc, dtype=np.uint64).reshape(-1, 6)
+        pose = None if pose is None else np.ascontiguousarray(pose, dtype=np.float32).reshape(12)
+        lib().orc_map_add(self.h, _f(xyz), _f(ratio), _u(desc), xyz.shape[0], None if pose is None else _f(pose))
+
+    def get(self, pos, rng):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(3)
+        n = lib().orc_map_get(self.h, _f(pos), rng, None, None, 0)
+        xyz = np.empty((n, 3), np.float32)
+        desc = np.empty((n, 6), np.uint64)
+        lib().orc_map_get(self.h, _f(pos), rng, _f(xyz), _u(desc), n)
+        return xyz, desc
 
 
 def select_keypoints(ratio, top_k=600, tie_mode=TIE_DETERMINISTIC):

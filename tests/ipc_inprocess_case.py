@@ -38,4 +38,6 @@ for o in outs:
     got = o.cpu().numpy().view(bshot.CAND_DTYPE).reshape(Q)
     assert np.array_equal(got["k1"], want["k1"]) and np.array_equal(got["k2"], want["k2"])
     assert np.array_equal(got["rq"], want["rq"])
+for c in ctxs + [whole]:
+    c.close()
 print("in-process ranks ok")

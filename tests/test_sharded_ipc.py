@@ -43,7 +43,8 @@ def test_multi_process_sharded_match(ipc_binary, nranks, T, Q):
 def test_in_process_ranks_with_device_pointers():
     """ranks that live in ONE process (several contexts, device pointers instead of IPC handles).  The consumer kernels
     spin on flags that the other ranks' kernels release, so the streams must not share a hardware queue: the case runs in
-    a fresh interpreter with CUDA_DEVICE_MAX_CONNECTIONS=32 (tests/ipc_inprocess_case.py)"""
+    a fresh interpreter with CUDA_DEVICE_MAX_CONNECTIONS=32 (tests/ipc_inprocess_case.py); bshot_comm_create loads the
+    kernels of the call up front, so lazy module loading cannot stall a producer behind a spinning consumer"""
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
     r = subprocess.run([os.sys.executable, os.path.join(ROOT, "tests", "ipc_inprocess_case.py")], capture_output=True, text=True,
                        timeout=300, env=env)
