@@ -26,7 +26,10 @@ namespace bshot {
 
 constexpr int TL_WARPS = 4;      // shared tiles: 4 warps, 1024 points (6 CTAs per SM)
 constexpr int TL_CAP = 1024;
-constexpr int TL_QCAP = 64;      // queries per block
+#ifndef BSHOT_TL_QCAP
+#define BSHOT_TL_QCAP 64
+#endif
+constexpr int TL_QCAP = BSHOT_TL_QCAP;  // queries per block
 constexpr int TL_BINS = 1024;    // sqd histogram bins (u16 counters, two per word)
 constexpr int TL_ENT = 352;      // entries the counting sort can hold (max_nn + crossing-bin overshoot)
 constexpr int TL_MAXNN = 304;    // largest max_nn the tiled path handles
