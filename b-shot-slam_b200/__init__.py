@@ -34,7 +34,7 @@ EXPORTS = [
     "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev", "bshot_comm_create", "bshot_comm_export", "bshot_comm_import",
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
-    "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit",
+    "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
 ]
 
 
@@ -109,6 +109,7 @@ def lib():
         L.bshot_extract_frame.argtypes = [vp, C.POINTER(Params), vp, sz, sz, vp, vp, vp, vp, vp]
         L.bshot_match_frame_to_map.argtypes = [vp, vp, cf, vp, vp, vp, C.POINTER(sz), vp, sz]
         L.bshot_frame_commit.argtypes = [vp]
+        L.bshot_ransac.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, cf, vp, vp, vp, vp]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
         L.bshot_comm_import.argtypes = [vp, vp]
@@ -428,6 +429,17 @@ class Context:
         txyz = np.empty((target_cap, 3), np.float32)
         _chk(lib().bshot_match_frame_to_map(self.h, _p(ref_pos), rng, _p(ref_pose), _p(pairs), C.byref(npairs), C.byref(nt), _p(txyz), target_cap))
         return dict(pairs=pairs[:npairs.value].copy(), n_targets=nt.value, target_xyz=txyz[:nt.value].copy())
+
+    def ransac(self, src_xyz, tgt_xyz, pairs, max_iterations=2000, threshold=1500.0):
+        src_xyz = np.ascontiguousarray(src_xyz, dtype=np.float32).reshape(-1, 3)
+        tgt_xyz = np.ascontiguousarray(tgt_xyz, dtype=np.float32).reshape(-1, 3)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.empty((max(len(pairs), 1), 2), np.int32)
+        T = np.empty((4, 4), np.float32)
+        n, it = C.c_int(), C.c_int()
+        _chk(lib().bshot_ransac(self.h, _p(src_xyz), src_xyz.shape[0], _p(tgt_xyz), tgt_xyz.shape[0], _p(pairs), pairs.shape[0],
+                                max_iterations, threshold, _p(out), C.byref(n), _p(T), C.byref(it)))
+        return dict(pairs=out[:n.value].copy(), transform=T, iterations=it.value)
 
     def frame_commit(self):
         _chk(lib().bshot_frame_commit(self.h))

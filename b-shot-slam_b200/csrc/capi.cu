@@ -797,6 +797,20 @@ int bshot_match_frame_to_map(bshot_ctx* ctx, const float ref_pos[3], float range
     return BSHOT_OK;
 }
 
+// ---- RANSAC correspondence rejection -----------------------------------------------------------------------
+int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const int* pairs, size_t n_pairs,
+                 int max_iterations, float inlier_threshold, int* inlier_pairs_out, int* n_inliers_out, float* transform4x4_out, int* iterations_out) {
+    CHECK_CTX(ctx);
+    if ((!src_xyz || !tgt_xyz || !pairs) && n_pairs) { set_error("bshot_ransac: null input"); return BSHOT_E_INVALID; }
+    for (size_t i = 0; i < n_pairs; ++i)
+        if (pairs[2 * i] < 0 || (size_t)pairs[2 * i] >= n_src || pairs[2 * i + 1] < 0 || (size_t)pairs[2 * i + 1] >= n_tgt) {
+            set_error("bshot_ransac: correspondence %zu out of range", i);
+            return BSHOT_E_INVALID;
+        }
+    return ransac_run(ctx, src_xyz, tgt_xyz, pairs, n_pairs, max_iterations, (double)inlier_threshold, inlier_pairs_out, n_inliers_out, transform4x4_out,
+                      iterations_out);
+}
+
 // ---- multi-rank exchange behind the C ABI (no Python / torch needed) -------------------------------------------
 static void comm_free(bshot_ctx* c) {
     Comm& m = c->comm;

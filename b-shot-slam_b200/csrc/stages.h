@@ -59,6 +59,10 @@ int gmap_update(Ctx* c, const float4* d_kp, const float* d_ratio, const uint64_t
 int gmap_gather(Ctx* c, const float pos[3], float range, const float4* d_ref_kp, const uint64_t* d_ref_bits, const int* d_ref_count,
                 size_t ref_cap, const float* ref_pose12, uint64_t* d_t_out, size_t out_cap, unsigned* d_total);
 
+// RANSAC correspondence rejection (ransac.cu)
+int ransac_run(Ctx* c, const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations, double threshold,
+               int* inlier_pairs_out, int* n_inliers_out, float* transform_out, int* iterations_out);
+
 // whole frame on the resident cloud (frame.cu)
 int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);
 int frame_commit(Ctx* c, size_t k);

@@ -191,6 +191,19 @@ int bshot_match_frame_to_map(bshot_ctx* ctx, const float ref_pos[3], float range
 /* the frame extracted last becomes the reference frame (passSrc2Ref, src/lidar_odometry.cpp:43-47); asynchronous */
 int bshot_frame_commit(bshot_ctx* ctx);
 
+/* ---- RANSAC correspondence rejection (the consumer of the path's output) ----------------------------------------------------
+ * Replaces Ransac_based_Rejection.setMaximumIterations(2000) / setInputSource / setInputTarget / setInlierThreshold(1500) /
+ * setInputCorrespondences / getCorrespondences (src/lidar_odometry.cpp:251-261), i.e. PCL 1.8's
+ * CorrespondenceRejectorSampleConsensus: RandomSampleConsensus over SampleConsensusModelRegistration with PCL's deterministic
+ * sample sequence (mt19937 seeded 12345), Umeyama on three pairs, adaptive stop, first best wins.  All max_iterations + 1
+ * hypotheses are scored in parallel on the device; the adaptive loop is replayed over the scores.
+ * pairs: n_pairs x (index_query into src, index_match into tgt).  Outputs: the surviving correspondences in their original
+ * order (capacity n_pairs), their number, the best transformation (row-major 4x4, float) and the iterations PCL would have run.
+ * Fewer than 3 correspondences / inliers: everything is kept and the transformation is the identity (PCL's behaviour). */
+int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const int* pairs,
+                 size_t n_pairs, int max_iterations, float inlier_threshold, int* inlier_pairs_out, int* n_inliers_out,
+                 float* transform4x4_out, int* iterations_out);
+
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
  * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first

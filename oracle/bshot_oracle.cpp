@@ -887,6 +887,184 @@ size_t orc_map_get(orc_map* m, const float pos[3], float range, float* xyz_out, 
     return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// RANSAC correspondence rejection: src/lidar_odometry.cpp:251-261 -> PCL 1.8 CorrespondenceRejectorSampleConsensus =
+// RandomSampleConsensus::computeModel over SampleConsensusModelRegistration (restated from the published PCL 1.8 sources;
+// PCL is not installable here: UNPINNED like the rest of the PCL arithmetic).  Sequential, exactly as PCL runs it.
+namespace {
+struct OrcMt19937 {
+    uint32_t s[624]; int idx;
+    explicit OrcMt19937(uint32_t seed) { s[0] = seed; for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i; idx = 624; }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7FFFFFFFu);
+                s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = s[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9D2C5680u; y ^= (y << 15) & 0xEFC60000u; y ^= y >> 18;
+        return y;
+    }
+};
+
+// Eigen::JacobiSVD stand-in: one-sided Jacobi (Hestenes) in double, singular values descending
+void orc_svd3(const double a_in[9], double U[9], double sv[3], double V[9]) {
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = a_in[3 * r + c];
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int r = 0; r < 3; ++r) { alpha += a[r][p] * a[r][p]; beta += a[r][q] * a[r][q]; gamma += a[r][p] * a[r][q]; }
+                if (gamma == 0.0) continue;
+                if (gamma * gamma <= 1e-30 * (alpha * beta)) continue;
+                off += gamma * gamma;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+                for (int r = 0; r < 3; ++r) {
+                    const double x = a[r][p], y = a[r][q];
+                    a[r][p] = c * x - sn * y; a[r][q] = sn * x + c * y;
+                    const double vx = v[r][p], vy = v[r][q];
+                    v[r][p] = c * vx - sn * vy; v[r][q] = sn * vx + c * vy;
+                }
+            }
+        if (off == 0.0) break;
+    }
+    double n[3]; int o[3] = {0, 1, 2};
+    for (int c = 0; c < 3; ++c) n[c] = std::sqrt(a[0][c] * a[0][c] + a[1][c] * a[1][c] + a[2][c] * a[2][c]);
+    if (n[o[0]] < n[o[1]]) std::swap(o[0], o[1]);
+    if (n[o[1]] < n[o[2]]) std::swap(o[1], o[2]);
+    if (n[o[0]] < n[o[1]]) std::swap(o[0], o[1]);
+    for (int k = 0; k < 3; ++k) {
+        sv[k] = n[o[k]];
+        for (int r = 0; r < 3; ++r) { V[3 * r + k] = v[r][o[k]]; U[3 * r + k] = (sv[k] > 0.0) ? a[r][o[k]] / sv[k] : 0.0; }
+    }
+}
+
+// pcl::umeyama (with_scaling = false) on three pairs; float row-major 4x4 (estimateRigidTransformationSVD's cast)
+void orc_umeyama3(const double src[3][3], const double dst[3][3], float T[16]) {
+    double sm[3], dm[3];
+    for (int c = 0; c < 3; ++c) { sm[c] = (src[0][c] + src[1][c] + src[2][c]) / 3.0; dm[c] = (dst[0][c] + dst[1][c] + dst[2][c]) / 3.0; }
+    double sigma[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            for (int i = 0; i < 3; ++i) acc += (dst[i][r] - dm[r]) * (src[i][c] - sm[c]);
+            sigma[3 * r + c] = acc / 3.0;
+        }
+    double U[9], sv[3], V[9];
+    orc_svd3(sigma, U, sv, V);
+    // rank 2: right-handed completion of both bases -> R = U V^T is the proper rotation of Eq. (40)-(43)
+    U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+    V[2] = V[3] * V[7] - V[6] * V[4]; V[5] = V[6] * V[1] - V[0] * V[7]; V[8] = V[0] * V[4] - V[3] * V[1];
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[3 * r + c] = (U[3 * r] * V[3 * c] + U[3 * r + 1] * V[3 * c + 1]) + U[3 * r + 2] * V[3 * c + 2];
+    for (int r = 0; r < 3; ++r) {
+        const double t = dm[r] - ((R[3 * r] * sm[0] + R[3 * r + 1] * sm[1]) + R[3 * r + 2] * sm[2]);
+        T[4 * r] = (float)R[3 * r]; T[4 * r + 1] = (float)R[3 * r + 1]; T[4 * r + 2] = (float)R[3 * r + 2]; T[4 * r + 3] = (float)t;
+    }
+    T[12] = T[13] = T[14] = 0.0f; T[15] = 1.0f;
+}
+
+inline float orc_transfer_sqd(const float T[16], const float* s, const float* t) {
+    const float px = ((T[0] * s[0] + T[1] * s[1]) + T[2] * s[2]) + T[3];
+    const float py = ((T[4] * s[0] + T[5] * s[1]) + T[6] * s[2]) + T[7];
+    const float pz = ((T[8] * s[0] + T[9] * s[1]) + T[10] * s[2]) + T[11];
+    const float dx = px - t[0], dy = py - t[1], dz = pz - t[2];
+    return (dx * dx + dy * dy) + dz * dz;
+}
+}  // namespace
+
+int orc_ransac(const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations, double threshold,
+               int* inlier_pairs_out, float transform_out[16], int* iterations_out) {
+    const size_t n = n_pairs;
+    auto keep_all = [&]() {
+        if (inlier_pairs_out) std::memcpy(inlier_pairs_out, pairs, sizeof(int) * 2 * n);
+        if (transform_out) for (int k = 0; k < 16; ++k) transform_out[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+        if (iterations_out) *iterations_out = 0;
+        return (int)n;
+    };
+    if (n < 3) return keep_all();
+    std::vector<float> s(3 * n), t(3 * n);
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) { s[3 * i + k] = src_xyz[3 * (size_t)pairs[2 * i] + k]; t[3 * i + k] = tgt_xyz[3 * (size_t)pairs[2 * i + 1] + k]; }
+    // computeSampleDistanceThreshold: covariance of the sources (single pass, float), eigenvalues, (mean of sqrt)^2
+    double sdt;
+    {
+        float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i < n; ++i) {
+            const float x = s[3 * i], y = s[3 * i + 1], z = s[3 * i + 2];
+            a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z; a[6] += x; a[7] += y; a[8] += z;
+        }
+        const float fn = (float)n;
+        for (int k = 0; k < 9; ++k) a[k] /= fn;
+        const double cov[9] = {(double)(a[0] - a[6] * a[6]), (double)(a[1] - a[6] * a[7]), (double)(a[2] - a[6] * a[8]),
+                               (double)(a[1] - a[6] * a[7]), (double)(a[3] - a[7] * a[7]), (double)(a[4] - a[7] * a[8]),
+                               (double)(a[2] - a[6] * a[8]), (double)(a[4] - a[7] * a[8]), (double)(a[5] - a[8] * a[8])};
+        double U[9], w[3], V[9];
+        orc_svd3(cov, U, w, V);
+        const float e0 = (float)w[0], e1 = (float)w[1], e2 = (float)w[2];
+        const double m = (double)((std::sqrt(std::max(e0, 0.0f)) + std::sqrt(std::max(e1, 0.0f))) + std::sqrt(std::max(e2, 0.0f))) / 3.0;
+        sdt = m * m;
+    }
+    std::vector<int> shuffled(n);
+    for (size_t i = 0; i < n; ++i) shuffled[i] = (int)i;
+    OrcMt19937 rng(12345u);
+    const double thresh2 = threshold * threshold;
+    int iterations = 0, n_best = -2147483647;
+    double k = 1.0;
+    const double log_probability = std::log(1.0 - 0.99), one_over_indices = 1.0 / (double)n;
+    float best_T[16];
+    bool have = false;
+    while ((double)iterations < k) {
+        bool good = false;  // getSamples: drawIndexSample until isSampleGood, at most 1000 tries
+        for (int tries = 0; tries < 1000 && !good; ++tries) {
+            for (size_t i = 0; i < 3; ++i) std::swap(shuffled[i], shuffled[i + ((rng.next() >> 1) % (n - i))]);
+            auto d2 = [&](int a, int b) {
+                const float dx = s[3 * b] - s[3 * a], dy = s[3 * b + 1] - s[3 * a + 1], dz = s[3 * b + 2] - s[3 * a + 2];
+                return (double)(dx * dx + dy * dy + dz * dz);
+            };
+            good = d2(shuffled[0], shuffled[1]) > sdt && d2(shuffled[0], shuffled[2]) > sdt && d2(shuffled[1], shuffled[2]) > sdt;
+        }
+        if (!good) break;
+        double sp[3][3], dp[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) { sp[i][c] = s[3 * (size_t)shuffled[i] + c]; dp[i][c] = t[3 * (size_t)shuffled[i] + c]; }
+        float T[16];
+        orc_umeyama3(sp, dp, T);
+        int cnt = 0;  // countWithinDistance
+        for (size_t i = 0; i < n; ++i)
+            if ((double)orc_transfer_sqd(T, &s[3 * i], &t[3 * i]) < thresh2) ++cnt;
+        if (cnt > n_best) {
+            n_best = cnt;
+            std::memcpy(best_T, T, sizeof(T));
+            have = true;
+            const double w = (double)n_best * one_over_indices;
+            double p_no_outliers = 1.0 - std::pow(w, 3.0);
+            p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+            p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+            k = log_probability / std::log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+    }
+    if (!have) return keep_all();
+    std::vector<int> keep;  // selectWithinDistance, original order
+    for (size_t i = 0; i < n; ++i)
+        if ((double)orc_transfer_sqd(best_T, &s[3 * i], &t[3 * i]) < thresh2) keep.push_back((int)i);
+    if (keep.size() < 3) return keep_all();
+    for (size_t j = 0; j < keep.size(); ++j)
+        if (inlier_pairs_out) { inlier_pairs_out[2 * j] = pairs[2 * keep[j]]; inlier_pairs_out[2 * j + 1] = pairs[2 * keep[j] + 1]; }
+    if (transform_out) std::memcpy(transform_out, best_T, sizeof(best_T));
+    if (iterations_out) *iterations_out = iterations;
+    return (int)keep.size();
+}
+
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]) { eigh3(m, evals, evecs_cols); }
 void orc_eigen33_smallest(const float m[9], float* eval, float evec[3]) { eigen33_smallest(m, *eval, evec); }
 

@@ -106,6 +106,13 @@ size_t orc_map_size(const orc_map* m);
 void orc_map_add(orc_map* m, const float* xyz, const float* ratio, const uint64_t* desc, size_t n, const float* pose12);
 size_t orc_map_get(orc_map* m, const float pos[3], float range, float* xyz_out, uint64_t* desc_out, size_t cap);
 
+/* RANSAC correspondence rejection, src/lidar_odometry.cpp:251-261 = PCL 1.8 CorrespondenceRejectorSampleConsensus
+ * (RandomSampleConsensus + SampleConsensusModelRegistration; mt19937(12345) sample sequence, Umeyama on three pairs,
+ * adaptive stop).  pairs: n_pairs x (index_query, index_match).  Returns the number of surviving correspondences
+ * (written to inlier_pairs_out in original order); UNPINNED restatement of PCL (not installable here). */
+int orc_ransac(const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations,
+               double threshold, int* inlier_pairs_out, float transform_out[16], int* iterations_out);
+
 /* symmetric 3x3 eigen decomposition used by orc_lrf (double, ascending), exposed for tests */
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]);
 /* pcl::eigen33 smallest-eigenpair (fp32), exposed for tests */

@@ -66,6 +66,8 @@ def lib():
         L.orc_map_add.argtypes = [C.c_void_p, fp, fp, up, C.c_size_t, fp]
         L.orc_map_get.restype = C.c_size_t
         L.orc_map_get.argtypes = [C.c_void_p, fp, C.c_float, fp, up, C.c_size_t]
+        L.orc_ransac.restype = C.c_int
+        L.orc_ransac.argtypes = [fp, fp, ip, C.c_size_t, C.c_int, C.c_double, ip, fp, ip]
         L.orc_eigh3.argtypes = [C.POINTER(C.c_double)] * 3
         L.orc_eigen33_smallest.argtypes = [fp, fp, fp]
         _LIB = L
@@ -181,6 +183,18 @@ class Map:
         desc = np.empty((n, 6), np.uint64)
         lib().orc_map_get(self.h, _f(pos), rng, _f(xyz), _u(desc), n)
         return xyz, desc
+
+
+def ransac(src_xyz, tgt_xyz, pairs, max_iterations=2000, threshold=1500.0):
+    """PCL 1.8 CorrespondenceRejectorSampleConsensus as the reference calls it (src/lidar_odometry.cpp:251-261)"""
+    src_xyz = np.ascontiguousarray(src_xyz, dtype=np.float32).reshape(-1, 3)
+    tgt_xyz = np.ascontiguousarray(tgt_xyz, dtype=np.float32).reshape(-1, 3)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+    out = np.empty((max(len(pairs), 1), 2), np.int32)
+    T = np.empty((4, 4), np.float32)
+    it = C.c_int()
+    n = lib().orc_ransac(_f(src_xyz), _f(tgt_xyz), _i(pairs), pairs.shape[0], max_iterations, threshold, _i(out), _f(T), C.byref(it))
+    return dict(pairs=out[:n].copy(), transform=T, iterations=it.value)
 
 
 def select_keypoints(ratio, top_k=600, tie_mode=TIE_DETERMINISTIC):
