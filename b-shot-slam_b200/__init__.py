@@ -35,6 +35,7 @@ EXPORTS = [
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
+    "bshot_preprocess",
 ]
 
 
@@ -110,6 +111,7 @@ def lib():
         L.bshot_match_frame_to_map.argtypes = [vp, vp, cf, vp, vp, vp, C.POINTER(sz), vp, sz]
         L.bshot_frame_commit.argtypes = [vp]
         L.bshot_ransac.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, cf, vp, vp, vp, vp]
+        L.bshot_preprocess.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, C.POINTER(sz)]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
         L.bshot_comm_import.argtypes = [vp, vp]
@@ -440,6 +442,18 @@ class Context:
         _chk(lib().bshot_ransac(self.h, _p(src_xyz), src_xyz.shape[0], _p(tgt_xyz), tgt_xyz.shape[0], _p(pairs), pairs.shape[0],
                                 max_iterations, threshold, _p(out), C.byref(n), _p(T), C.byref(it)))
         return dict(pairs=out[:n.value].copy(), transform=T, iterations=it.value)
+
+    def preprocess(self, azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0):
+        """Preprocessor::run (src/preprocess.cpp:213-223) on one rotation of returns sorted by azimuth -> (m, 3) float32 mm."""
+        az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
+        ve = np.ascontiguousarray(vertical_deg, dtype=np.float64)
+        di = np.ascontiguousarray(distance, dtype=np.uint16)
+        ring = np.ascontiguousarray(ring_deg, dtype=np.float64)
+        assert az.shape == ve.shape == di.shape
+        out = np.empty((max(az.size, 1), 3), np.float32)
+        n = C.c_size_t()
+        _chk(lib().bshot_preprocess(self.h, _p(az), _p(ve), _p(di), az.size, _p(ring), ring.size, vert_init, lowpt_th, _p(out), out.shape[0], C.byref(n)))
+        return out[:n.value].copy()
 
     def frame_commit(self):
         _chk(lib().bshot_frame_commit(self.h))

@@ -231,7 +231,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
                     c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits, c->d_prev_kp,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
-                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters};
+                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters, c->d_pre[0], c->d_pre[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -809,6 +809,19 @@ int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float
         }
     return ransac_run(ctx, src_xyz, tgt_xyz, pairs, n_pairs, max_iterations, (double)inlier_threshold, inlier_pairs_out, n_inliers_out, transform4x4_out,
                       iterations_out);
+}
+
+int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n, const double* ring_deg,
+                     size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out) {
+    CHECK_CTX(ctx);
+    if (n && (!azimuth_deg || !vertical_deg || !distance)) { set_error("bshot_preprocess: null input"); return BSHOT_E_INVALID; }
+    if (nv && !ring_deg) { set_error("bshot_preprocess: null ring table"); return BSHOT_E_INVALID; }
+    if (n > 0xFFFFFFFFull) { set_error("bshot_preprocess: too many returns"); return BSHOT_E_CAPACITY; }
+    size_t kept = 0;
+    BSHOT_TRY(preprocess_run(ctx, azimuth_deg, vertical_deg, distance, n, ring_deg, nv, vert_init_rad, lowpt_th, xyz_out, cap, &kept));
+    if (n_out) *n_out = kept;
+    if (kept > cap && xyz_out) { set_error("bshot_preprocess: %zu points kept > capacity %zu", kept, cap); return BSHOT_E_CAPACITY; }
+    return BSHOT_OK;
 }
 
 // ---- multi-rank exchange behind the C ABI (no Python / torch needed) -------------------------------------------

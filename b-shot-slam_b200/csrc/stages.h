@@ -63,6 +63,10 @@ int gmap_gather(Ctx* c, const float pos[3], float range, const float4* d_ref_kp,
 int ransac_run(Ctx* c, const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations, double threshold,
                int* inlier_pairs_out, int* n_inliers_out, float* transform_out, int* iterations_out);
 
+// scan preprocessor (preprocess.cu)
+int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const unsigned short* dist, size_t n, const double* ring_deg, size_t nv,
+                   double vert_init, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out);
+
 // whole frame on the resident cloud (frame.cu)
 int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);
 int frame_commit(Ctx* c, size_t k);

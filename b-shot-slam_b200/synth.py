@@ -105,6 +105,36 @@ def make_scan(sensor="hdl32e", frame=0, noise_mm=20.0, scene_seed=SCENE_SEED, ma
     return np.ascontiguousarray(pts)
 
 
+def make_lasers(sensor="hdl32e", frame=0, start_deg=123.45, dropout=0.02, noise_mm=20.0, scene_seed=SCENE_SEED, firings=None):
+    """One rotation of raw returns as the reference's capture class hands them to the preprocessor (velodyne::Laser,
+    include/VelodyneCapture.h:43-51): azimuth / vertical in degrees, distance in 2 mm units (0 = no return), in FIRING order
+    -- the rotation starts at start_deg and wraps through 0.  The scene of make_scan plus what the preprocessor is there to
+    remove: a ground plane 2450 mm under the sensor (src/preprocess.cpp:80-82), the roof of the own car, random dropouts.
+    Azimuth convention of src/preprocess.cpp:50-52: x = d cos(v) sin(az), y = d cos(v) cos(az)."""
+    vert, steps, max_range = SENSORS[sensor]
+    native = 360.0 / steps   # firings < a rotation: a partial sweep at the sensor's own azimuth step
+    steps = firings or steps
+    boxes, cyls = _scene(scene_seed)
+    ground = -1900.0
+    height = 2450.0
+    o = np.array([500.0 * frame, 0.0, ground + height])
+    roof = np.array([[o[0] - 800.0, o[0] + 800.0, -1700.0, 1200.0, o[2] - 900.0, o[2] - 550.0]])
+    boxes = np.concatenate([boxes, roof])
+    az_deg = np.round((start_deg + np.arange(steps) * native) % 360.0, 2) % 360.0   # centi-degrees, like the device
+    A, E = np.meshgrid(np.deg2rad(az_deg), np.deg2rad(vert), indexing="ij")
+    d = np.stack([np.cos(E) * np.sin(A), np.cos(E) * np.cos(A), np.sin(E)], axis=-1).reshape(-1, 3)
+    t = _raycast(o, d, boxes, cyls)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = (ground - o[2]) / d[:, 2]
+    t = np.where((tg > 0) & (tg < t), tg, t)
+    rng = np.random.default_rng(20260118 + 977 * frame)
+    t = t + rng.normal(0.0, noise_mm, t.shape)
+    ok = np.isfinite(t) & (t > 400.0) & (t <= min(max_range, 131000.0)) & (rng.random(t.shape) >= dropout)
+    dist = np.where(ok, np.round(np.where(ok, t, 0.0) / 2.0), 0).astype(np.uint16)
+    return dict(azimuth=np.repeat(az_deg, len(vert)).astype(np.float64), vertical=np.tile(np.asarray(vert, np.float64), steps),
+                distance=dist, ring_deg=np.sort(np.asarray(vert, np.float64)))
+
+
 def random_descriptors(n, seed=7, density=None):
     """(n,6) uint64 B-SHOT records: 352 random bits (i.i.d. p=0.5, or `density` bits set), pad 0."""
     rng = np.random.default_rng(seed)

@@ -204,6 +204,19 @@ int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float
                  size_t n_pairs, int max_iterations, float inlier_threshold, int* inlier_pairs_out, int* n_inliers_out,
                  float* transform4x4_out, int* iterations_out);
 
+/* ---- scan preprocessor ---------------------------------------------------- */
+/* Replaces myslam::Preprocessor::setLasers + setVerticalAngles + run + getPointCloud (include/preprocess.h:26-33,
+ * src/preprocess.cpp:213-223): one rotation of raw returns -> ground, self-car and occluded returns removed -> the cloud
+ * the front end consumes, in the reference's order (azimuth-major, vertical angle ascending).
+ * azimuth_deg / vertical_deg / distance: the n returns' velodyne::Laser fields (VelodyneCapture.h: azimuth and vertical in
+ * degrees as double, distance in 2 mm units), sorted by azimuth as `capture.retrieve(lasers, true)` delivers them.
+ * ring_deg: the sensor's nv vertical angles (setVerticalAngles).  vert_init_rad / lowpt_th: the constructor arguments
+ * (the SLAM driver uses -0.6 rad and -1950 mm, test/odometry_test.cpp:32-33).  xyz_out: cap x 3 floats (mm); *n_out = number of kept points (if it
+ * exceeds cap only the first cap are written and BSHOT_E_CAPACITY is returned). */
+int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance,
+                     size_t n, const double* ring_deg, size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out,
+                     size_t cap, size_t* n_out);
+
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
  * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first

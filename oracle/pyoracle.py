@@ -274,6 +274,9 @@ def ref_lib():
         L.ref_cb_create.restype = C.c_void_p
         L.ref_cb_destroy.argtypes = [C.c_void_p]
         L.ref_cb_compute_descriptors.argtypes = [C.c_void_p, fp, C.c_size_t, fp, C.c_size_t, C.c_float, up, fp, fp, fp]
+        dp = C.POINTER(C.c_double)
+        L.ref_preprocess.restype = C.c_size_t
+        L.ref_preprocess.argtypes = [dp, dp, C.POINTER(C.c_ushort), C.c_size_t, dp, C.c_size_t, C.c_double, C.c_double, fp, C.c_size_t]
         _REF = L
     return _REF
 
@@ -302,6 +305,20 @@ def ref_feature_matching(q, t):
     pairs = np.empty((q.shape[0], 2), np.int32)
     n = ref_lib().ref_feature_matching(_u(q), q.shape[0], _u(t), t.shape[0], _i(left), _i(right), _i(pairs))
     return dict(left_idx=left, right_idx=right, pairs=pairs[:n].copy())
+
+
+def ref_preprocess(azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0):
+    """myslam::Preprocessor::run of the reference (src/preprocess.cpp:213-223, compiled unchanged) on one rotation of
+    returns; vert_init / lowpt_th as the SLAM driver sets them (test/odometry_test.cpp:118-119)"""
+    az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
+    ve = np.ascontiguousarray(vertical_deg, dtype=np.float64)
+    di = np.ascontiguousarray(distance, dtype=np.uint16)
+    ring = np.ascontiguousarray(ring_deg, dtype=np.float64)
+    out = np.empty((max(az.size, 1), 3), np.float32)
+    dp = C.POINTER(C.c_double)
+    n = ref_lib().ref_preprocess(az.ctypes.data_as(dp), ve.ctypes.data_as(dp), di.ctypes.data_as(C.POINTER(C.c_ushort)), az.size,
+                                 ring.ctypes.data_as(dp), ring.size, vert_init, lowpt_th, _f(out), out.shape[0])
+    return out[:n].copy()
 
 
 class RefCb:

@@ -92,3 +92,37 @@ void ref_cb_compute_descriptors(void* h, const float* xyz, size_t n, const float
 }
 
 }  // extern "C"
+
+// ---- the reference's preprocessor (src/preprocess.cpp), compiled unchanged into this library by oracle/Makefile -----------
+// (its translation unit is built with the include guards of common_include.h / VelodyneCapture.h pre-defined and
+// oracle/pre_stub/pre_stub.h force-included; here only the class declaration is needed, through the same route)
+#include "ref_preprocess_decl.h"
+
+extern "C" {
+// Preprocessor::run() on one rotation: lasers (azimuth / vertical in degrees, distance in 2 mm units) -> kept points.
+// returns the number of points (written up to cap)
+size_t ref_preprocess(const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
+                      const double* vert_angles_deg, size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap) {
+    std::vector<velodyne::Laser> lasers(n);
+    for (size_t i = 0; i < n; ++i) {
+        lasers[i].azimuth = azimuth_deg[i];
+        lasers[i].vertical = vertical_deg[i];
+        lasers[i].distance = distance[i];
+        lasers[i].intensity = 0;
+        lasers[i].id = (unsigned char)(i % 256);
+        lasers[i].time = 0;
+    }
+    std::vector<double> va(vert_angles_deg, vert_angles_deg + nv);
+    std::sort(va.begin(), va.end());                       // test/odometry_test.cpp:111-112
+    auto pc = std::make_shared<std::vector<Vector3f>>();
+    myslam::Preprocessor pre;
+    pre.setVerticalAngles(va);                              // :115-117
+    pre.setVerticalInitial(vert_init_rad);
+    pre.setLowPtThreshold(lowpt_th);
+    pre.setPointCloud(pc);                                  // :125
+    pre.setLasers(lasers);                                  // :143
+    pre.run();
+    for (size_t i = 0; i < pc->size() && i < cap; ++i) { xyz_out[3 * i] = (*pc)[i][0]; xyz_out[3 * i + 1] = (*pc)[i][1]; xyz_out[3 * i + 2] = (*pc)[i][2]; }
+    return pc->size();
+}
+}
