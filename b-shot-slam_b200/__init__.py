@@ -35,7 +35,7 @@ EXPORTS = [
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
-    "bshot_preprocess",
+    "bshot_preprocess", "bshot_icp", "bshot_evaluate_estimation",
 ]
 
 
@@ -111,6 +111,8 @@ def lib():
         L.bshot_match_frame_to_map.argtypes = [vp, vp, cf, vp, vp, vp, C.POINTER(sz), vp, sz]
         L.bshot_frame_commit.argtypes = [vp]
         L.bshot_ransac.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, cf, vp, vp, vp, vp]
+        L.bshot_icp.argtypes = [vp, vp, sz, vp, sz, vp, ci, vp, vp, vp, vp]
+        L.bshot_evaluate_estimation.argtypes = [vp, vp, vp, ci, vp, sz, vp, sz, ci, vp, vp, vp, vp, vp]
         L.bshot_preprocess.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, C.POINTER(sz)]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
@@ -442,6 +444,29 @@ class Context:
         _chk(lib().bshot_ransac(self.h, _p(src_xyz), src_xyz.shape[0], _p(tgt_xyz), tgt_xyz.shape[0], _p(pairs), pairs.shape[0],
                                 max_iterations, threshold, _p(out), C.byref(n), _p(T), C.byref(it)))
         return dict(pairs=out[:n.value].copy(), transform=T, iterations=it.value)
+
+    def icp(self, src_xyz, tgt_xyz, pre=None, max_iterations=10):
+        """pcl::IterativeClosestPoint with PCL's defaults (src/lidar_odometry.cpp:283-291) on src moved by `pre`"""
+        src_xyz = np.ascontiguousarray(src_xyz, dtype=np.float32).reshape(-1, 3)
+        tgt_xyz = np.ascontiguousarray(tgt_xyz, dtype=np.float32).reshape(-1, 3)
+        pre = None if pre is None else np.ascontiguousarray(pre, dtype=np.float32).reshape(16)
+        T = np.empty((4, 4), np.float32)
+        it, st, mse = C.c_int(), C.c_int(), C.c_double()
+        _chk(lib().bshot_icp(self.h, _p(src_xyz), src_xyz.shape[0], _p(tgt_xyz), tgt_xyz.shape[0], _p(pre), max_iterations, _p(T), C.byref(it),
+                             C.byref(st), C.byref(mse)))
+        return dict(transform=T, iterations=it.value, state=st.value, mse=mse.value)
+
+    def evaluate_estimation(self, T_ransac, T_ref, n_corr, src_kp, tgt_kp, run_icp=True):
+        """LidarOdometry::evaluateEstimation (src/lidar_odometry.cpp:267-296)"""
+        T_ransac = np.ascontiguousarray(T_ransac, dtype=np.float32).reshape(16)
+        T_ref = np.ascontiguousarray(T_ref, dtype=np.float32).reshape(16)
+        src_kp = np.ascontiguousarray(src_kp, dtype=np.float32).reshape(-1, 3)
+        tgt_kp = np.ascontiguousarray(tgt_kp, dtype=np.float32).reshape(-1, 3)
+        T = np.empty((4, 4), np.float32)
+        upd, it, h, t = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+        _chk(lib().bshot_evaluate_estimation(self.h, _p(T_ransac), _p(T_ref), n_corr, _p(src_kp), src_kp.shape[0], _p(tgt_kp), tgt_kp.shape[0],
+                                             1 if run_icp else 0, _p(T), C.byref(upd), C.byref(h), C.byref(t), C.byref(it)))
+        return dict(T_best=T, should_update_map=bool(upd.value), h_diff=h.value, t_diff=t.value, icp_iterations=it.value)
 
     def preprocess(self, azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0):
         """Preprocessor::run (src/preprocess.cpp:213-223) on one rotation of returns sorted by azimuth -> (m, 3) float32 mm."""

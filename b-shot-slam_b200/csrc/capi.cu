@@ -231,7 +231,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
                     c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits, c->d_prev_kp,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
-                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters, c->d_pre[0], c->d_pre[1]};
+                    c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters, c->d_pre[0], c->d_pre[1], c->d_pre[2]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -809,6 +809,72 @@ int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float
         }
     return ransac_run(ctx, src_xyz, tgt_xyz, pairs, n_pairs, max_iterations, (double)inlier_threshold, inlier_pairs_out, n_inliers_out, transform4x4_out,
                       iterations_out);
+}
+
+int bshot_icp(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const float* pre4x4, int max_iterations,
+              float* final4x4_out, int* iterations_out, int* state_out, double* mse_out) {
+    CHECK_CTX(ctx);
+    if ((n_src && !src_xyz) || (n_tgt && !tgt_xyz)) { set_error("bshot_icp: null input"); return BSHOT_E_INVALID; }
+    if (max_iterations < 0 || max_iterations > 1000) { set_error("bshot_icp: max_iterations out of range"); return BSHOT_E_INVALID; }
+    if (n_src > 0x7FFFFFFFull || n_tgt > 0x7FFFFFFFull) { set_error("bshot_icp: too many points"); return BSHOT_E_CAPACITY; }
+    return icp_run(ctx, src_xyz, n_src, tgt_xyz, n_tgt, pre4x4, max_iterations, final4x4_out, iterations_out, state_out, mse_out);
+}
+
+// general 4x4 inverse by cofactors in float (Matrix4f::inverse(), src/lidar_odometry.cpp:269)
+static void inverse4x4(const float* m, float* o) {
+    float inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    const float id = 1.0f / det;
+    for (int e = 0; e < 16; ++e) o[e] = inv[e] * id;
+}
+
+static void mul4x4(const float* a, const float* b, float* o) {
+    float r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r[4 * i + j] = ((a[4 * i] * b[j] + a[4 * i + 1] * b[4 + j]) + a[4 * i + 2] * b[8 + j]) + a[4 * i + 3] * b[12 + j];
+    for (int e = 0; e < 16; ++e) o[e] = r[e];
+}
+
+int bshot_evaluate_estimation(bshot_ctx* ctx, const float* T_ransac, const float* T_ref, int n_correspondences, const float* src_kp, size_t n_src,
+                              const float* tgt_kp, size_t n_tgt, int run_icp, float* T_best_out, int* should_update_map_out, float* h_diff_out,
+                              float* t_diff_out, int* icp_iterations_out) {
+    CHECK_CTX(ctx);
+    if (!T_ransac || !T_ref || !T_best_out) { set_error("bshot_evaluate_estimation: null matrix"); return BSHOT_E_INVALID; }
+    float Ti_inv[16], Tij[16];
+    inverse4x4(T_ref, Ti_inv);
+    mul4x4(Ti_inv, T_ransac, Tij);                                   // T_ij = T_i.inverse() * T_j (:269)
+    const float h_diff = acosf(Tij[5]);                              // heading (0,1,0): heading^T R heading = R(1,1) (:271-272)
+    const float t_diff = sqrtf((Tij[3] * Tij[3] + Tij[7] * Tij[7]) + Tij[11] * Tij[11]);
+    const bool reject = (double)(h_diff * 180) / M_PI > 10 || t_diff > 1200 || n_correspondences < 15;   // :281
+    const float* T_est = reject ? T_ref : T_ransac;
+    if (should_update_map_out) *should_update_map_out = reject ? 0 : 1;
+    if (h_diff_out) *h_diff_out = h_diff;
+    if (t_diff_out) *t_diff_out = t_diff;
+    if (icp_iterations_out) *icp_iterations_out = 0;
+    if (run_icp) {
+        float F[16];
+        BSHOT_TRY(bshot_icp(ctx, src_kp, n_src, tgt_kp, n_tgt, T_est, 10, F, icp_iterations_out, nullptr, nullptr));
+        mul4x4(F, T_est, T_best_out);                                // T_best_ = icp.getFinalTransformation() * T_est (:293)
+    } else {
+        for (int e = 0; e < 16; ++e) T_best_out[e] = T_ransac[e];    // :295
+    }
+    return BSHOT_OK;
 }
 
 int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n, const double* ring_deg,

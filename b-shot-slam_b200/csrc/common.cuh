@@ -176,8 +176,8 @@ struct Ctx {
     Comm comm;
     Gmap gmap;
     float4* d_prev_kp = nullptr;        // K: keypoint positions of the previous frame (reference frame of the map match)
-    void* d_pre[2] = {nullptr, nullptr};  // preprocessor scratch (per-return / per-column), grown on demand
-    size_t pre_bytes[2] = {0, 0};
+    void* d_pre[3] = {nullptr, nullptr, nullptr};  // scratch grown on demand: preprocessor per-return / per-column, ICP
+    size_t pre_bytes[3] = {0, 0, 0};
 
     // pinned host scratch
     int* h_scratch = nullptr;           // 64 ints

@@ -344,7 +344,7 @@ __global__ void pre_write_kernel(const double* __restrict__ c_vert, const double
     }
 }
 
-static int pre_reserve(Ctx* c, int which, size_t bytes) {
+int scratch_reserve(Ctx* c, int which, size_t bytes) {
     if (c->pre_bytes[which] >= bytes) return BSHOT_OK;
     if (c->d_pre[which]) { cudaFree(c->d_pre[which]); c->d_pre[which] = nullptr; c->pre_bytes[which] = 0; }
     bytes += bytes / 4;
@@ -376,7 +376,7 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     for (size_t i = 0; i < nv; ++i) ring[i] = ring_deg[i] * PRE_PI / 180.0;   // removeOccluded :171
     const unsigned nn = (unsigned)n;
     const size_t pad = 256 * 16;
-    BSHOT_TRY(pre_reserve(c, 0, n * (8 + 8 + 2 + 8 + 4 + 4 + 4 + 8 + 4 + 8 + 4 + 4 + 4 + 4) + 8 * 256 + 12 * cap + pad));
+    BSHOT_TRY(scratch_reserve(c, 0, n * (8 + 8 + 2 + 8 + 4 + 4 + 4 + 8 + 4 + 8 + 4 + 4 + 4 + 4) + 8 * 256 + 12 * cap + pad));
     Carver A{(char*)c->d_pre[0]};
     double* d_az = A.take<double>(n); double* d_vert = A.take<double>(n); unsigned short* d_dist = A.take<unsigned short>(n);
     double* d_azr = A.take<double>(n);
@@ -412,7 +412,7 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     BSHOT_CUDA_TRY(cudaStreamSynchronize(c->stream));
     const unsigned ncol = h_ctl[3];
     const size_t cw = (size_t)ncol * (PRE_LMAX + 1), rw = std::max<size_t>(nv, 1) * ncol;
-    BSHOT_TRY(pre_reserve(c, 1, cw * (8 + 8 + 1) + (size_t)ncol * (4 + 8 + 4 + 4) + rw * (8 + 4) + pad));
+    BSHOT_TRY(scratch_reserve(c, 1, cw * (8 + 8 + 1) + (size_t)ncol * (4 + 8 + 4 + 4) + rw * (8 + 4) + pad));
     Carver B{(char*)c->d_pre[1]};
     double* c_vert = B.take<double>(cw); double* c_dist = B.take<double>(cw); unsigned char* c_rm = B.take<unsigned char>(cw);
     unsigned* c_cnt = B.take<unsigned>(ncol); double* c_az = B.take<double>(ncol);

@@ -63,7 +63,12 @@ int gmap_gather(Ctx* c, const float pos[3], float range, const float4* d_ref_kp,
 int ransac_run(Ctx* c, const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations, double threshold,
                int* inlier_pairs_out, int* n_inliers_out, float* transform_out, int* iterations_out);
 
-// scan preprocessor (preprocess.cu)
+// ICP refinement (icp.cu)
+int icp_run(Ctx* c, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const float* pre4x4, int max_iterations,
+            float* final4x4_out, int* iterations_out, int* state_out, double* mse_out);
+
+// scan preprocessor (preprocess.cu); scratch_reserve grows one of the context's on-demand scratch buffers
+int scratch_reserve(Ctx* c, int which, size_t bytes);
 int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const unsigned short* dist, size_t n, const double* ring_deg, size_t nv,
                    double vert_init, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out);
 

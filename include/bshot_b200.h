@@ -204,6 +204,25 @@ int bshot_ransac(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float
                  size_t n_pairs, int max_iterations, float inlier_threshold, int* inlier_pairs_out, int* n_inliers_out,
                  float* transform4x4_out, int* iterations_out);
 
+/* ---- ICP refinement and the estimation gate ------------------------------- */
+/* Replaces pcl::IterativeClosestPoint<PointXYZ, PointXYZ> with PCL's defaults as LidarOdometry::evaluateEstimation uses it
+ * (src/lidar_odometry.cpp:283-291): the n_src source points are first moved by pre4x4 (row-major 4x4, NULL = identity; the
+ * reference's transformPointCloud with T_est), then aligned to the n_tgt target points: nearest neighbour correspondences,
+ * Umeyama without scaling, at most max_iterations (PCL default 10) rounds.  final4x4_out = icp.getFinalTransformation();
+ * state_out: 0 not converged, 1 iteration limit, 2 transformation epsilon, 3 absolute MSE, 5 fewer than 3 correspondences
+ * (pcl::registration::DefaultConvergenceCriteria::ConvergenceState); mse_out = mean squared correspondence distance of the
+ * last round.  Any output pointer may be NULL. */
+int bshot_icp(bshot_ctx* ctx, const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const float* pre4x4,
+              int max_iterations, float* final4x4_out, int* iterations_out, int* state_out, double* mse_out);
+/* LidarOdometry::evaluateEstimation (src/lidar_odometry.cpp:267-296) without its printing: T_ij = T_ref^-1 * T_ransac, heading
+ * change acos(T_ij(1,1)) and translation |t_ij|; the estimate is rejected (T_est = T_ref, *should_update_map_out = 0) when the
+ * heading moved more than 10 degrees, the translation more than 1200 mm or fewer than 15 correspondences survived RANSAC;
+ * otherwise T_est = T_ransac.  run_icp != 0: T_best = ICP(src_kp moved by T_est -> tgt_kp) * T_est; else T_best = T_ransac. */
+int bshot_evaluate_estimation(bshot_ctx* ctx, const float* T_ransac4x4, const float* T_ref4x4, int n_correspondences,
+                              const float* src_kp_xyz, size_t n_src, const float* tgt_kp_xyz, size_t n_tgt, int run_icp,
+                              float* T_best4x4_out, int* should_update_map_out, float* h_diff_rad_out, float* t_diff_out,
+                              int* icp_iterations_out);
+
 /* ---- scan preprocessor ---------------------------------------------------- */
 /* Replaces myslam::Preprocessor::setLasers + setVerticalAngles + run + getPointCloud (include/preprocess.h:26-33,
  * src/preprocess.cpp:213-223): one rotation of raw returns -> ground, self-car and occluded returns removed -> the cloud

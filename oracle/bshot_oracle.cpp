@@ -1065,6 +1065,149 @@ int orc_ransac(const float* src_xyz, const float* tgt_xyz, const int* pairs, siz
     return (int)keep.size();
 }
 
+// ---- ICP (src/lidar_odometry.cpp:283-291: pcl::IterativeClosestPoint with PCL's defaults) ----------------------------
+// PCL 1.8 restated (UNPINNED: PCL is not installable here): IterativeClosestPoint::computeTransformation,
+// CorrespondenceEstimation::determineCorrespondences (nearest target, squared float distance, no cap),
+// TransformationEstimationSVD<.., float> -> pcl::umeyama without scaling, DefaultConvergenceCriteria::hasConverged with
+// ICP's settings (10 iterations, rotation threshold 1 - 0 and translation threshold 0, absolute mse 1e-12, relative mse
+// -DBL_MAX).  Eigen's vectorised float sums have no defined order: they are taken as 256 strided partial sums and a
+// halving tree -- the order the device uses; the 3x3 SVD runs in double (orc_svd3) on the float cross-covariance.
+}  // extern "C"
+namespace {
+template <typename T, typename F>
+T orc_strided_sum(size_t n, F term) {
+    T part[256];
+    for (int t = 0; t < 256; ++t) {
+        T a = 0;
+        for (size_t i = (size_t)t; i < n; i += 256) a += term(i);
+        part[t] = a;
+    }
+    for (int s = 128; s > 0; s >>= 1)
+        for (int t = 0; t < s; ++t) part[t] = part[t] + part[t + s];
+    return part[0];
+}
+inline void orc_apply(const float T[16], const float* p, float* o) {
+    const float x = p[0], y = p[1], z = p[2];
+    o[0] = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+    o[1] = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+    o[2] = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+}
+inline void orc_mul4(const float* a, const float* b, float* o) {
+    float r[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) r[4 * i + j] = ((a[4 * i] * b[j] + a[4 * i + 1] * b[4 + j]) + a[4 * i + 2] * b[8 + j]) + a[4 * i + 3] * b[12 + j];
+    std::memcpy(o, r, sizeof(r));
+}
+}  // namespace
+extern "C" {
+
+int orc_icp(const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const float* pre4x4, int max_iterations, float final_out[16],
+            int* iterations_out, double* mse_out) {
+    const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    float F[16];
+    std::memcpy(F, ident, sizeof(F));
+    int iterations = 0, state = 0;
+    double prev_mse = std::numeric_limits<double>::max(), mse = 0.0;
+    std::vector<float> cur(3 * n_src);
+    for (size_t i = 0; i < n_src; ++i) orc_apply(pre4x4 ? pre4x4 : ident, &src_xyz[3 * i], &cur[3 * i]);   // transformPointCloud(.., T_est)
+    std::vector<long long> nn(n_src);
+    std::vector<float> nd(n_src);
+    if (n_src == 0 || n_tgt == 0 || max_iterations <= 0) state = 5;
+    while (state == 0) {
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n_src; ++i) {   // nearestKSearch(.., 1, ..): first minimum = lowest index
+            float best = 0.f; long long bi = -1;
+            for (size_t k = 0; k < n_tgt; ++k) {
+                const float dx = cur[3 * i] - tgt_xyz[3 * k], dy = cur[3 * i + 1] - tgt_xyz[3 * k + 1], dz = cur[3 * i + 2] - tgt_xyz[3 * k + 2];
+                const float d = (dx * dx + dy * dy) + dz * dz;
+                if (d == d && (bi < 0 || d < best)) { best = d; bi = (long long)k; }
+            }
+            nn[i] = bi; nd[i] = best;
+        }
+        const float cnt = orc_strided_sum<float>(n_src, [&](size_t i) { return nn[i] >= 0 ? 1.f : 0.f; });
+        const unsigned n = (unsigned)cnt;
+        if (n < 3) { state = 5; break; }
+        const float one_over_n = 1.0f / (float)n;
+        float sm[3], dm[3];
+        for (int c = 0; c < 3; ++c) {
+            sm[c] = orc_strided_sum<float>(n_src, [&](size_t i) { return nn[i] >= 0 ? cur[3 * i + c] : 0.f; }) * one_over_n;
+            dm[c] = orc_strided_sum<float>(n_src, [&](size_t i) { return nn[i] >= 0 ? tgt_xyz[3 * nn[i] + c] : 0.f; }) * one_over_n;
+        }
+        double sg[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                sg[3 * r + c] = (double)(one_over_n * orc_strided_sum<float>(n_src, [&](size_t i) {
+                                             return nn[i] >= 0 ? (tgt_xyz[3 * nn[i] + r] - dm[r]) * (cur[3 * i + c] - sm[c]) : 0.f; }));
+        const double mse_sum = orc_strided_sum<double>(n_src, [&](size_t i) { return nn[i] >= 0 ? (double)nd[i] : 0.0; });
+        double U[9], sv[3], V[9];
+        orc_svd3(sg, U, sv, V);
+        const double det = sg[0] * (sg[4] * sg[8] - sg[5] * sg[7]) - sg[1] * (sg[3] * sg[8] - sg[5] * sg[6]) + sg[2] * (sg[3] * sg[7] - sg[4] * sg[6]);
+        double sgn = 1.0;
+        if (sv[2] <= sv[0] * 1e-5) {
+            U[2] = U[3] * U[7] - U[6] * U[4]; U[5] = U[6] * U[1] - U[0] * U[7]; U[8] = U[0] * U[4] - U[3] * U[1];
+            V[2] = V[3] * V[7] - V[6] * V[4]; V[5] = V[6] * V[1] - V[0] * V[7]; V[8] = V[0] * V[4] - V[3] * V[1];
+        } else if (det < 0) sgn = -1.0;
+        float Rt[16];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) Rt[4 * r + c] = (float)((U[3 * r] * V[3 * c] + U[3 * r + 1] * V[3 * c + 1]) + sgn * (U[3 * r + 2] * V[3 * c + 2]));
+            Rt[4 * r + 3] = dm[r] - ((Rt[4 * r] * sm[0] + Rt[4 * r + 1] * sm[1]) + Rt[4 * r + 2] * sm[2]);
+        }
+        Rt[12] = Rt[13] = Rt[14] = 0.f; Rt[15] = 1.f;
+        for (size_t i = 0; i < n_src; ++i) { float o[3]; orc_apply(Rt, &cur[3 * i], o); cur[3 * i] = o[0]; cur[3 * i + 1] = o[1]; cur[3 * i + 2] = o[2]; }
+        orc_mul4(Rt, F, F);
+        ++iterations;
+        mse = mse_sum / (double)n;
+        if (iterations >= max_iterations) state = 1;
+        else {
+            const double cos_angle = 0.5 * (double)(((Rt[0] + Rt[5]) + Rt[10]) - 1.0f);
+            const double translation_sqr = (double)((Rt[3] * Rt[3] + Rt[7] * Rt[7]) + Rt[11] * Rt[11]);
+            if (cos_angle >= 1.0 && translation_sqr <= 0.0) state = 2;
+            else if (std::fabs(mse - prev_mse) < 1e-12) state = 3;
+            else prev_mse = mse;
+        }
+    }
+    if (final_out) std::memcpy(final_out, F, sizeof(F));
+    if (iterations_out) *iterations_out = iterations;
+    if (mse_out) *mse_out = mse;
+    return state;
+}
+
+// LidarOdometry::evaluateEstimation (src/lidar_odometry.cpp:267-296)
+int orc_evaluate_estimation(const float* T_j, const float* T_i, int n_corr, const float* src_kp, size_t n_src, const float* tgt_kp, size_t n_tgt,
+                            int run_icp, float T_best[16], float* h_diff_out, float* t_diff_out) {
+    // rigid T_i: inverse = [R^T | -R^T t] would do; the reference inverts the general 4x4 (Matrix4f::inverse) -- by cofactors here
+    double m[16], inv[16];
+    for (int e = 0; e < 16; ++e) m[e] = T_i[e];
+    // Gauss-Jordan in double, cast to float: an independent route to the same inverse (agreement with the device's float
+    // cofactor expansion is to rounding, which is what the gate needs)
+    double a[4][8];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = m[4 * r + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+    for (int col = 0; col < 4; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 4; ++r) if (std::fabs(a[r][col]) > std::fabs(a[piv][col])) piv = r;
+        for (int c = 0; c < 8; ++c) std::swap(a[col][c], a[piv][c]);
+        const double d = a[col][col];
+        for (int c = 0; c < 8; ++c) a[col][c] /= d;
+        for (int r = 0; r < 4; ++r) if (r != col) { const double f = a[r][col]; for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c]; }
+    }
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) inv[4 * r + c] = a[r][4 + c];
+    float Ti_inv[16], Tij[16];
+    for (int e = 0; e < 16; ++e) Ti_inv[e] = (float)inv[e];
+    orc_mul4(Ti_inv, T_j, Tij);
+    const float h_diff = std::acos(Tij[5]);
+    const float t_diff = std::sqrt((Tij[3] * Tij[3] + Tij[7] * Tij[7]) + Tij[11] * Tij[11]);
+    const bool reject = (double)(h_diff * 180) / M_PI > 10 || t_diff > 1200 || n_corr < 15;
+    const float* T_est = reject ? T_i : T_j;
+    if (h_diff_out) *h_diff_out = h_diff;
+    if (t_diff_out) *t_diff_out = t_diff;
+    if (run_icp) {
+        float F[16];
+        orc_icp(src_kp, n_src, tgt_kp, n_tgt, T_est, 10, F, nullptr, nullptr);
+        orc_mul4(F, T_est, T_best);
+    } else std::memcpy(T_best, T_j, 16 * sizeof(float));
+    return reject ? 0 : 1;
+}
+
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]) { eigh3(m, evals, evecs_cols); }
 void orc_eigen33_smallest(const float m[9], float* eval, float evec[3]) { eigen33_smallest(m, *eval, evec); }
 

@@ -113,6 +113,15 @@ size_t orc_map_get(orc_map* m, const float pos[3], float range, float* xyz_out, 
 int orc_ransac(const float* src_xyz, const float* tgt_xyz, const int* pairs, size_t n_pairs, int max_iterations,
                double threshold, int* inlier_pairs_out, float transform_out[16], int* iterations_out);
 
+/* src/lidar_odometry.cpp:283-291: pcl::IterativeClosestPoint (PCL 1.8 defaults) on src moved by pre4x4 (NULL = identity);
+ * returns the convergence state (1 iteration limit, 2 transformation, 3 absolute mse, 5 no correspondences).
+ * UNPINNED restatement of PCL. */
+int orc_icp(const float* src_xyz, size_t n_src, const float* tgt_xyz, size_t n_tgt, const float* pre4x4, int max_iterations,
+            float final_out[16], int* iterations_out, double* mse_out);
+/* LidarOdometry::evaluateEstimation (src/lidar_odometry.cpp:267-296); returns shouldUpdateMap */
+int orc_evaluate_estimation(const float* T_j, const float* T_i, int n_corr, const float* src_kp, size_t n_src, const float* tgt_kp,
+                            size_t n_tgt, int run_icp, float T_best[16], float* h_diff_out, float* t_diff_out);
+
 /* symmetric 3x3 eigen decomposition used by orc_lrf (double, ascending), exposed for tests */
 void orc_eigh3(const double m[9], double evals[3], double evecs_cols[9]);
 /* pcl::eigen33 smallest-eigenpair (fp32), exposed for tests */

@@ -197,6 +197,36 @@ def ransac(src_xyz, tgt_xyz, pairs, max_iterations=2000, threshold=1500.0):
     return dict(pairs=out[:n].copy(), transform=T, iterations=it.value)
 
 
+def icp(src_xyz, tgt_xyz, pre=None, max_iterations=10):
+    """pcl::IterativeClosestPoint with PCL's defaults as src/lidar_odometry.cpp:283-291 uses it"""
+    src_xyz = np.ascontiguousarray(src_xyz, dtype=np.float32).reshape(-1, 3)
+    tgt_xyz = np.ascontiguousarray(tgt_xyz, dtype=np.float32).reshape(-1, 3)
+    pre = None if pre is None else np.ascontiguousarray(pre, dtype=np.float32).reshape(16)
+    T = np.empty((4, 4), np.float32)
+    it, mse = C.c_int(), C.c_double()
+    L = lib()
+    L.orc_icp.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    st = L.orc_icp(src_xyz.ctypes.data, src_xyz.shape[0], tgt_xyz.ctypes.data, tgt_xyz.shape[0], None if pre is None else pre.ctypes.data,
+                   max_iterations, T.ctypes.data, C.addressof(it), C.addressof(mse))
+    return dict(transform=T, iterations=it.value, state=st, mse=mse.value)
+
+
+def evaluate_estimation(T_ransac, T_ref, n_corr, src_kp, tgt_kp, run_icp=True):
+    """LidarOdometry::evaluateEstimation (src/lidar_odometry.cpp:267-296)"""
+    T_ransac = np.ascontiguousarray(T_ransac, dtype=np.float32).reshape(16)
+    T_ref = np.ascontiguousarray(T_ref, dtype=np.float32).reshape(16)
+    src_kp = np.ascontiguousarray(src_kp, dtype=np.float32).reshape(-1, 3)
+    tgt_kp = np.ascontiguousarray(tgt_kp, dtype=np.float32).reshape(-1, 3)
+    T = np.empty((4, 4), np.float32)
+    h, t = C.c_float(), C.c_float()
+    L = lib()
+    L.orc_evaluate_estimation.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]
+    upd = L.orc_evaluate_estimation(T_ransac.ctypes.data, T_ref.ctypes.data, n_corr, src_kp.ctypes.data, src_kp.shape[0], tgt_kp.ctypes.data,
+                                    tgt_kp.shape[0], 1 if run_icp else 0, T.ctypes.data, C.addressof(h), C.addressof(t))
+    return dict(T_best=T, should_update_map=bool(upd), h_diff=h.value, t_diff=t.value)
+
+
 def select_keypoints(ratio, top_k=600, tie_mode=TIE_DETERMINISTIC):
     ratio = np.ascontiguousarray(ratio, dtype=np.float32)
     idx = np.empty(max(top_k, 1), np.int32)
