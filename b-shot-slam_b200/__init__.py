@@ -35,7 +35,7 @@ EXPORTS = [
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
-    "bshot_preprocess", "bshot_icp", "bshot_evaluate_estimation",
+    "bshot_preprocess", "bshot_preprocess_select", "bshot_icp", "bshot_evaluate_estimation",
 ]
 
 
@@ -113,6 +113,7 @@ def lib():
         L.bshot_ransac.argtypes = [vp, vp, sz, vp, sz, vp, sz, ci, cf, vp, vp, vp, vp]
         L.bshot_icp.argtypes = [vp, vp, sz, vp, sz, vp, ci, vp, vp, vp, vp]
         L.bshot_evaluate_estimation.argtypes = [vp, vp, vp, ci, vp, sz, vp, sz, ci, vp, vp, vp, vp, vp]
+        L.bshot_preprocess_select.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, ci, ci, vp, sz, C.POINTER(sz)]
         L.bshot_preprocess.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, C.POINTER(sz)]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
@@ -468,7 +469,7 @@ class Context:
                                              1 if run_icp else 0, _p(T), C.byref(upd), C.byref(h), C.byref(t), C.byref(it)))
         return dict(T_best=T, should_update_map=bool(upd.value), h_diff=h.value, t_diff=t.value, icp_iterations=it.value)
 
-    def preprocess(self, azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0):
+    def preprocess(self, azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0, select=None, save_selected=True):
         """Preprocessor::run (src/preprocess.cpp:213-223) on one rotation of returns sorted by azimuth -> (m, 3) float32 mm."""
         az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
         ve = np.ascontiguousarray(vertical_deg, dtype=np.float64)
@@ -477,7 +478,9 @@ class Context:
         assert az.shape == ve.shape == di.shape
         out = np.empty((max(az.size, 1), 3), np.float32)
         n = C.c_size_t()
-        _chk(lib().bshot_preprocess(self.h, _p(az), _p(ve), _p(di), az.size, _p(ring), ring.size, vert_init, lowpt_th, _p(out), out.shape[0], C.byref(n)))
+        sel = None if select is None else np.ascontiguousarray(select, dtype=np.int32)
+        _chk(lib().bshot_preprocess_select(self.h, _p(az), _p(ve), _p(di), az.size, _p(ring), ring.size, vert_init, lowpt_th, _p(sel),
+                                           0 if sel is None else sel.size, 0 if sel is None else 1, 1 if save_selected else 0, _p(out), out.shape[0], C.byref(n)))
         return out[:n.value].copy()
 
     def frame_commit(self):

@@ -877,17 +877,36 @@ int bshot_evaluate_estimation(bshot_ctx* ctx, const float* T_ransac, const float
     return BSHOT_OK;
 }
 
-int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n, const double* ring_deg,
-                     size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out) {
+int bshot_preprocess_select(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
+                            const double* ring_deg, size_t nv, double vert_init_rad, double lowpt_th, const int* select_list, size_t n_select,
+                            int have_select_list, int save_selected, float* xyz_out, size_t cap, size_t* n_out) {
     CHECK_CTX(ctx);
     if (n && (!azimuth_deg || !vertical_deg || !distance)) { set_error("bshot_preprocess: null input"); return BSHOT_E_INVALID; }
     if (nv && !ring_deg) { set_error("bshot_preprocess: null ring table"); return BSHOT_E_INVALID; }
+    if (n_select && !select_list) { set_error("bshot_preprocess: null select list"); return BSHOT_E_INVALID; }
     if (n > 0xFFFFFFFFull) { set_error("bshot_preprocess: too many returns"); return BSHOT_E_CAPACITY; }
+    // selmap of readFrame (src/preprocess.cpp:58-67): the sorted list (setSelectedPoints sorts it, :25-28) is walked with one
+    // cursor that only advances on a hit -- restated as is, including what a duplicated entry does to the rest of the list
+    std::vector<unsigned char> sel;
+    if (have_select_list) {
+        std::vector<int> list(select_list, select_list + n_select);
+        std::sort(list.begin(), list.end());
+        sel.assign(n, 0);
+        size_t cursor = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (cursor < list.size() && list[cursor] == (int)i) { sel[i] = 1; ++cursor; }
+    }
     size_t kept = 0;
-    BSHOT_TRY(preprocess_run(ctx, azimuth_deg, vertical_deg, distance, n, ring_deg, nv, vert_init_rad, lowpt_th, xyz_out, cap, &kept));
+    BSHOT_TRY(preprocess_run(ctx, azimuth_deg, vertical_deg, distance, n, ring_deg, nv, vert_init_rad, lowpt_th, have_select_list ? sel.data() : nullptr,
+                             save_selected, xyz_out, cap, &kept));
     if (n_out) *n_out = kept;
     if (kept > cap && xyz_out) { set_error("bshot_preprocess: %zu points kept > capacity %zu", kept, cap); return BSHOT_E_CAPACITY; }
     return BSHOT_OK;
+}
+
+int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n, const double* ring_deg,
+                     size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out) {
+    return bshot_preprocess_select(ctx, azimuth_deg, vertical_deg, distance, n, ring_deg, nv, vert_init_rad, lowpt_th, nullptr, 0, 0, 1, xyz_out, cap, n_out);
 }
 
 // ---- multi-rank exchange behind the C ABI (no Python / torch needed) -------------------------------------------

@@ -185,17 +185,18 @@ __device__ __forceinline__ float norm3(float x, float y, float z) {
 
 // per column: sorted (vertical, distance) entries incl. the synthetic start entry, ground / self-car flags, ring table
 __global__ void __launch_bounds__(64)
-pre_columns_kernel(const double* __restrict__ azr, const double* __restrict__ vert_deg, const unsigned short* __restrict__ dist_u16, unsigned n,
+pre_columns_kernel(const double* __restrict__ azr, const double* __restrict__ vert_deg, const unsigned short* __restrict__ dist_u16,
+                   const unsigned char* __restrict__ sel_in, unsigned n,
                    const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_idx, const unsigned* __restrict__ nrun_dev,
                    const unsigned* __restrict__ col_first, const unsigned* __restrict__ ncol_dev, const double* __restrict__ ring_rad, unsigned nv,
-                   PreParams P, double* __restrict__ c_vert, double* __restrict__ c_dist, unsigned char* __restrict__ c_rm, unsigned* __restrict__ c_cnt,
-                   double* __restrict__ c_az, double* __restrict__ ring_dist, int* __restrict__ ring_ent, unsigned* __restrict__ err) {
+                   PreParams P, double* __restrict__ c_vert, double* __restrict__ c_dist, unsigned char* __restrict__ c_rm, unsigned char* __restrict__ c_sel,
+                   unsigned* __restrict__ c_cnt, double* __restrict__ c_az, double* __restrict__ ring_dist, int* __restrict__ ring_ent, unsigned* __restrict__ err) {
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned ncol = *ncol_dev, nrun = *nrun_dev;
     if (c >= ncol) return;
     const unsigned j0 = col_first[c], j1 = (c + 1 < ncol) ? col_first[c + 1] : nrun;
     double vk[PRE_LMAX + 1], dk[PRE_LMAX + 1];
-    unsigned char rm[PRE_LMAX + 1];
+    unsigned char rm[PRE_LMAX + 1], sl[PRE_LMAX + 1];   // sl: selmap (readFrame :58-67), a later return overwrites it too
     int m = 0;
     const double az = azr[run_start[run_idx[j0]]];
     // rimg[azimuth][vertical] = distance: std::map semantics = sorted by key, a later return with the same key wins
@@ -205,10 +206,11 @@ pre_columns_kernel(const double* __restrict__ azr, const double* __restrict__ ve
             const double v = vert_deg[i] * PRE_PI / 180.0, d = (double)dist_u16[i] * 2.0;   // :46,:48
             int pos = 0;
             while (pos < m && vk[pos] < v) ++pos;
-            if (pos < m && vk[pos] == v) { dk[pos] = d; continue; }
+            const unsigned char sv = sel_in ? sel_in[i] : (unsigned char)1;
+            if (pos < m && vk[pos] == v) { dk[pos] = d; sl[pos] = sv; continue; }
             if (m >= PRE_LMAX) { *err = 2u; return; }
-            for (int q = m; q > pos; --q) { vk[q] = vk[q - 1]; dk[q] = dk[q - 1]; }
-            vk[pos] = v; dk[pos] = d; ++m;
+            for (int q = m; q > pos; --q) { vk[q] = vk[q - 1]; dk[q] = dk[q - 1]; sl[q] = sl[q - 1]; }
+            vk[pos] = v; dk[pos] = d; sl[pos] = sv; ++m;
         }
     }
     {   // rimg[azimuth][vert_init_] = 2450 / sin(vert_init_), rmmap = 1 (:55-57), written last: it wins over an equal key
@@ -217,8 +219,8 @@ pre_columns_kernel(const double* __restrict__ azr, const double* __restrict__ ve
         while (pos < m && vk[pos] < v) ++pos;
         if (pos < m && vk[pos] == v) dk[pos] = d;
         else {
-            for (int j = m; j > pos; --j) { vk[j] = vk[j - 1]; dk[j] = dk[j - 1]; }
-            vk[pos] = v; dk[pos] = d; ++m;
+            for (int j = m; j > pos; --j) { vk[j] = vk[j - 1]; dk[j] = dk[j - 1]; sl[j] = sl[j - 1]; }
+            vk[pos] = v; dk[pos] = d; sl[pos] = 0; ++m;
         }
     }
     for (int j = 0; j < m; ++j) rm[j] = (vk[j] == P.vert_init) ? 1 : 0;
@@ -258,7 +260,7 @@ pre_columns_kernel(const double* __restrict__ azr, const double* __restrict__ ve
         }
     }
     const size_t base = (size_t)c * (PRE_LMAX + 1);
-    for (int j = 0; j < m; ++j) { c_vert[base + j] = vk[j]; c_dist[base + j] = dk[j]; c_rm[base + j] = rm[j]; }
+    for (int j = 0; j < m; ++j) { c_vert[base + j] = vk[j]; c_dist[base + j] = dk[j]; c_rm[base + j] = rm[j]; c_sel[base + j] = sl[j]; }
     c_cnt[c] = (unsigned)m;
     c_az[c] = az;
     // ring table for removeOccluded: rimg[col][v] of every ring key (0 when the column has no such entry)
@@ -314,18 +316,19 @@ pre_rings_kernel(const double* __restrict__ ring_dist, const int* __restrict__ r
 }
 
 __global__ void pre_count_kernel(const double* __restrict__ c_vert, const double* __restrict__ c_dist, const unsigned char* __restrict__ c_rm,
-                                 const unsigned* __restrict__ c_cnt, const unsigned* __restrict__ ncol_dev, double vert_init, unsigned* __restrict__ keep) {
+                                 const unsigned char* __restrict__ c_sel, unsigned char save_sel, const unsigned* __restrict__ c_cnt,
+                                 const unsigned* __restrict__ ncol_dev, double vert_init, unsigned* __restrict__ keep) {
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= *ncol_dev) return;
     const size_t base = (size_t)c * (PRE_LMAX + 1);
     unsigned k = 0;
     for (unsigned j = 0; j < c_cnt[c]; ++j)
-        if (c_dist[base + j] != 0.0 && c_vert[base + j] != vert_init && c_rm[base + j] == 0) ++k;   // :201-207
+        if (c_dist[base + j] != 0.0 && c_vert[base + j] != vert_init && c_rm[base + j] == 0 && c_sel[base + j] == save_sel) ++k;   // :201-209
     keep[c] = k;
 }
 
 __global__ void pre_write_kernel(const double* __restrict__ c_vert, const double* __restrict__ c_dist, const unsigned char* __restrict__ c_rm,
-                                 const unsigned* __restrict__ c_cnt, const double* __restrict__ c_az, const unsigned* __restrict__ ncol_dev, double vert_init,
+                                 const unsigned char* __restrict__ c_sel, unsigned char save_sel, const unsigned* __restrict__ c_cnt, const double* __restrict__ c_az, const unsigned* __restrict__ ncol_dev, double vert_init,
                                  const unsigned* __restrict__ off, float* __restrict__ xyz, unsigned cap) {
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= *ncol_dev) return;
@@ -334,7 +337,7 @@ __global__ void pre_write_kernel(const double* __restrict__ c_vert, const double
     unsigned o = off[c];
     for (unsigned j = 0; j < c_cnt[c]; ++j) {
         const double dist = c_dist[base + j], vert = c_vert[base + j];
-        if (dist == 0.0 || vert == vert_init || c_rm[base + j] != 0) continue;
+        if (dist == 0.0 || vert == vert_init || c_rm[base + j] != 0 || c_sel[base + j] != save_sel) continue;
         if (o < cap) {
             xyz[3 * (size_t)o] = (float)(dist * cos(vert) * sin(az));
             xyz[3 * (size_t)o + 1] = (float)(dist * cos(vert) * cos(az));
@@ -365,7 +368,7 @@ struct Carver {
 // host inputs -> host output (xyz_out holds cap points).  Synchronous: two stream synchronisations (the number of columns
 // sizes the per-column scratch; the number of kept points sizes the copy back).
 int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const unsigned short* dist, size_t n, const double* ring_deg, size_t nv,
-                   double vert_init, double lowpt_th, float* xyz_out, size_t cap, size_t* n_out) {
+                   double vert_init, double lowpt_th, const unsigned char* sel, int save_sel, float* xyz_out, size_t cap, size_t* n_out) {
     if (n_out) *n_out = 0;
     if (n == 0) return BSHOT_OK;
     if (nv > 256) { set_error("bshot_preprocess: more than 256 rings"); return BSHOT_E_INVALID; }
@@ -376,9 +379,10 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     for (size_t i = 0; i < nv; ++i) ring[i] = ring_deg[i] * PRE_PI / 180.0;   // removeOccluded :171
     const unsigned nn = (unsigned)n;
     const size_t pad = 256 * 16;
-    BSHOT_TRY(scratch_reserve(c, 0, n * (8 + 8 + 2 + 8 + 4 + 4 + 4 + 8 + 4 + 8 + 4 + 4 + 4 + 4) + 8 * 256 + 12 * cap + pad));
+    BSHOT_TRY(scratch_reserve(c, 0, n * (8 + 8 + 2 + 1 + 8 + 4 + 4 + 4 + 8 + 4 + 8 + 4 + 4 + 4 + 4) + 8 * 256 + 12 * cap + pad));
     Carver A{(char*)c->d_pre[0]};
     double* d_az = A.take<double>(n); double* d_vert = A.take<double>(n); unsigned short* d_dist = A.take<unsigned short>(n);
+    unsigned char* d_sel = A.take<unsigned char>(n);
     double* d_azr = A.take<double>(n);
     unsigned* d_flag = A.take<unsigned>(n); unsigned* d_excl = A.take<unsigned>(n); unsigned* d_run_start = A.take<unsigned>(n);
     unsigned long long* d_key_a = A.take<unsigned long long>(n); unsigned* d_idx_a = A.take<unsigned>(n);
@@ -395,6 +399,7 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     BSHOT_CUDA_TRY(cudaMemcpyAsync(d_az, az_deg, 8 * n, cudaMemcpyHostToDevice, c->stream));
     BSHOT_CUDA_TRY(cudaMemcpyAsync(d_vert, vert_deg, 8 * n, cudaMemcpyHostToDevice, c->stream));
     BSHOT_CUDA_TRY(cudaMemcpyAsync(d_dist, dist, 2 * n, cudaMemcpyHostToDevice, c->stream));
+    if (sel) BSHOT_CUDA_TRY(cudaMemcpyAsync(d_sel, sel, n, cudaMemcpyHostToDevice, c->stream));
     BSHOT_CUDA_TRY(cudaMemcpyAsync(d_ring, ring.data(), 8 * ring.size(), cudaMemcpyHostToDevice, c->stream));
     BSHOT_CUDA_TRY(cudaMemsetAsync(ctl, 0, 32, c->stream));
     const unsigned gb = (nn + 255) / 256;
@@ -412,19 +417,19 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     BSHOT_CUDA_TRY(cudaStreamSynchronize(c->stream));
     const unsigned ncol = h_ctl[3];
     const size_t cw = (size_t)ncol * (PRE_LMAX + 1), rw = std::max<size_t>(nv, 1) * ncol;
-    BSHOT_TRY(scratch_reserve(c, 1, cw * (8 + 8 + 1) + (size_t)ncol * (4 + 8 + 4 + 4) + rw * (8 + 4) + pad));
+    BSHOT_TRY(scratch_reserve(c, 1, cw * (8 + 8 + 1 + 1) + (size_t)ncol * (4 + 8 + 4 + 4) + rw * (8 + 4) + pad));
     Carver B{(char*)c->d_pre[1]};
-    double* c_vert = B.take<double>(cw); double* c_dist = B.take<double>(cw); unsigned char* c_rm = B.take<unsigned char>(cw);
+    double* c_vert = B.take<double>(cw); double* c_dist = B.take<double>(cw); unsigned char* c_rm = B.take<unsigned char>(cw); unsigned char* c_sel = B.take<unsigned char>(cw);
     unsigned* c_cnt = B.take<unsigned>(ncol); double* c_az = B.take<double>(ncol);
     unsigned* d_keep = B.take<unsigned>(ncol); unsigned* d_off = B.take<unsigned>(ncol);
     double* d_rd = B.take<double>(rw); int* d_re = B.take<int>(rw);
     const unsigned* ncol_dev = ctl + 3;
-    pre_columns_kernel<<<(ncol + 63) / 64, 64, 0, c->stream>>>(d_azr, d_vert, d_dist, nn, d_run_start, d_idx_a, ctl, d_col_first, ncol_dev, d_ring, (unsigned)nv, P,
-                                                             c_vert, c_dist, c_rm, c_cnt, c_az, d_rd, d_re, ctl + 1);
+    pre_columns_kernel<<<(ncol + 63) / 64, 64, 0, c->stream>>>(d_azr, d_vert, d_dist, sel ? d_sel : nullptr, nn, d_run_start, d_idx_a, ctl, d_col_first, ncol_dev, d_ring, (unsigned)nv, P,
+                                                             c_vert, c_dist, c_rm, c_sel, c_cnt, c_az, d_rd, d_re, ctl + 1);
     if (nv) pre_rings_kernel<<<(unsigned)((nv * 32 + 127) / 128), 128, 0, c->stream>>>(d_rd, d_re, c_az, ncol_dev, (unsigned)nv, P, c_rm);
-    pre_count_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(c_vert, c_dist, c_rm, c_cnt, ncol_dev, vert_init, d_keep);
+    pre_count_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(c_vert, c_dist, c_rm, c_sel, (unsigned char)(save_sel ? 1 : 0), c_cnt, ncol_dev, vert_init, d_keep);
     pre_scan_kernel<<<1, 1024, 0, c->stream>>>(d_keep, ncol, nullptr, d_off, ctl + 2);
-    pre_write_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(c_vert, c_dist, c_rm, c_cnt, c_az, ncol_dev, vert_init, d_off, d_out, (unsigned)cap);
+    pre_write_kernel<<<(ncol + 255) / 256, 256, 0, c->stream>>>(c_vert, c_dist, c_rm, c_sel, (unsigned char)(save_sel ? 1 : 0), c_cnt, c_az, ncol_dev, vert_init, d_off, d_out, (unsigned)cap);
     count_launch(c, nv ? 5 : 4);
     BSHOT_TRY(check_launch("preprocess kernels"));
     BSHOT_CUDA_TRY(cudaMemcpyAsync(h_ctl, ctl, 32, cudaMemcpyDeviceToHost, c->stream));

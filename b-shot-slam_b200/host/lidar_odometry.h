@@ -1,7 +1,7 @@
-// lidar_odometry.h -- the three front-end stage methods of the reference's LidarOdometry
-// (include/lidar_odometry.h:22-25, src/lidar_odometry.cpp:51-265) over the B200 C ABI.  Only the hot
-// path is here: RANSAC rejection, ICP, pose bookkeeping and the viewer stay in the reference's own
-// CPU code and consume `corresp` exactly as before.
+// lidar_odometry.h -- the per-frame stage methods of the reference's LidarOdometry (include/lidar_odometry.h:22-31,
+// src/lidar_odometry.cpp:51-376) over the B200 C ABI: extractKeypoints, computeDescriptors, featureMatching (mutual
+// Hamming matching + RANSAC rejection), evaluateEstimation (gate + ICP), poseEstimation, updateMap -- the call order of
+// test/odometry_test.cpp:174-192.  The viewer, the ISS evaluation path and the printing are not carried over.
 #ifndef BSHOT_B200_HOST_LIDAR_ODOMETRY_H
 #define BSHOT_B200_HOST_LIDAR_ODOMETRY_H
 
@@ -89,6 +89,68 @@ public:
             c.index_match = pairs[2 * i + 1];
             corresp.push_back(c);
         }
+        // RANSAC based correspondence rejection (:251-261): 2000 iterations, inlier threshold 1500 mm
+        corr.clear();
+        if (last_status_ != BSHOT_OK) return;
+        std::vector<float> s = flat(cb.cloud1_keypoints), t = flat(cb.cloud2_keypoints);
+        std::vector<int> kept(2 * (size_t)n + 2);
+        int n_kept = 0, iters = 0;
+        float T[16];
+        last_status_ = bshot_ransac(cb.context(), s.data(), cb.cloud1_keypoints.size(), t.data(), cb.cloud2_keypoints.size(), pairs.data(), (size_t)n, 2000,
+                                    1500.0f, kept.data(), &n_kept, T, &iters);
+        if (last_status_ != BSHOT_OK) return;
+        for (int i = 0; i < n_kept; ++i) {
+            pcl::Correspondence c;
+            c.index_query = kept[2 * i];
+            c.index_match = kept[2 * i + 1];
+            corr.push_back(c);
+        }
+        T_ransac_ = from_row_major(T);
+    }
+
+    void evaluateEstimation() {  // :267-301 (its evaluate_corr_ statistics are prints only)
+        float Tj[16], Ti[16], Tb[16];
+        to_row_major(T_ransac_, Tj);
+        to_row_major(ref_->getPose(), Ti);
+        std::vector<float> s = flat(cb.cloud1_keypoints), t = flat(cb.cloud2_keypoints);
+        int upd = 0;
+        last_status_ = bshot_evaluate_estimation(cb.context(), Tj, Ti, (int)corr.size(), s.data(), cb.cloud1_keypoints.size(), t.data(),
+                                                 cb.cloud2_keypoints.size(), run_icp_ ? 1 : 0, Tb, &upd, &h_diff_, &t_diff_, &icp_iterations_);
+        if (last_status_ != BSHOT_OK) return;
+        shouldUpdateMap = upd != 0;
+        T_best_ = from_row_major(Tb);
+    }
+
+    void poseEstimation() { src_->setPose(T_best_); }  // :333-341, frame-to-localmap
+
+    void updateMap() {  // :344-376: every keypoint of the frame, moved by T_best_
+        Frame::PCPtr kps = src_->getKeypoints();
+        for (size_t i = 0; i < cb.cloud1_bshot.size() && i < kps->size(); ++i) {
+            // R * p + T in Eigen's order: the three products summed left to right, then the translation
+            const Vector3f& p = (*kps)[i];
+            Vector3f w((T_best_(0, 0) * p[0] + T_best_(0, 1) * p[1] + T_best_(0, 2) * p[2]) + T_best_(0, 3),
+                       (T_best_(1, 0) * p[0] + T_best_(1, 1) * p[1] + T_best_(1, 2) * p[2]) + T_best_(1, 3),
+                       (T_best_(2, 0) * p[0] + T_best_(2, 1) * p[1] + T_best_(2, 2) * p[2]) + T_best_(2, 3));
+            globalMap_.addKeypoint(Keypoint::createKeypoint(w, seg_ratios_[i], cb.cloud1_bshot[i]));
+        }
+        status_ = RUN;
+    }
+    void setRunICP(bool run_icp) { run_icp_ = run_icp; }
+    Matrix4f getBestTransformation() const { return T_best_; }
+    Matrix4f getRansacTransformation() const { return T_ransac_; }
+
+    static std::vector<float> flat(const pcl::PointCloud<pcl::PointXYZ>& c) {
+        std::vector<float> o(3 * c.size() + 3);
+        for (size_t i = 0; i < c.size(); ++i) { o[3 * i] = c.points[i].x; o[3 * i + 1] = c.points[i].y; o[3 * i + 2] = c.points[i].z; }
+        return o;
+    }
+    static void to_row_major(const Matrix4f& M, float* o) {
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) o[4 * r + c] = M(r, c);
+    }
+    static Matrix4f from_row_major(const float* a) {
+        Matrix4f M;
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) M(r, c) = a[4 * r + c];
+        return M;
     }
 
     pcl::PointCloud<pcl::PointXYZ> eigen2pcl(Frame::PCPtr pc) {
@@ -102,7 +164,11 @@ public:
     int last_status() const { return last_status_ != BSHOT_OK ? last_status_ : cb.last_status(); }
 
     bshot cb;
-    pcl::Correspondences corresp;   // output of featureMatching, input of the reference's RANSAC rejector
+    pcl::Correspondences corresp;   // mutual nearest neighbours (:234-242)
+    pcl::Correspondences corr;      // after RANSAC rejection (:253-261)
+    bool shouldUpdateMap = true;
+    float h_diff_ = 0, t_diff_ = 0;
+    int icp_iterations_ = 0;
     std::vector<float> seg_ratios_;
 
 private:
@@ -113,6 +179,8 @@ private:
     int top_k_;
     Map globalMap_;
     int last_status_ = BSHOT_OK;
+    bool run_icp_ = true;           // src/lidar_odometry.cpp:6
+    Matrix4f T_ransac_ = Matrix4f::Identity(), T_best_ = Matrix4f::Identity();
 };
 
 }  // namespace myslam

@@ -236,6 +236,15 @@ int bshot_preprocess(bshot_ctx* ctx, const double* azimuth_deg, const double* ve
                      size_t n, const double* ring_deg, size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out,
                      size_t cap, size_t* n_out);
 
+/* the same with the preprocessor's point selection (setSelectedPoints / haveSelectList / saveSelectPoints,
+ * include/preprocess.h:27-29): select_list holds indices into the returns; with have_select_list != 0 a return is
+ * "selected" when the list names it, otherwise every return is; only returns whose selection equals save_selected != 0
+ * are written (the reference's defaults: no list, save_selected = true). */
+int bshot_preprocess_select(bshot_ctx* ctx, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance,
+                            size_t n, const double* ring_deg, size_t nv, double vert_init_rad, double lowpt_th,
+                            const int* select_list, size_t n_select, int have_select_list, int save_selected, float* xyz_out,
+                            size_t cap, size_t* n_out);
+
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
  * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first

@@ -306,6 +306,8 @@ def ref_lib():
         L.ref_cb_compute_descriptors.argtypes = [C.c_void_p, fp, C.c_size_t, fp, C.c_size_t, C.c_float, up, fp, fp, fp]
         dp = C.POINTER(C.c_double)
         L.ref_preprocess.restype = C.c_size_t
+        L.ref_preprocess_select.restype = C.c_size_t
+        L.ref_preprocess_select.argtypes = [dp, dp, C.POINTER(C.c_ushort), C.c_size_t, dp, C.c_size_t, C.c_double, C.c_double, ip, C.c_size_t, C.c_int, C.c_int, fp, C.c_size_t]
         L.ref_preprocess.argtypes = [dp, dp, C.POINTER(C.c_ushort), C.c_size_t, dp, C.c_size_t, C.c_double, C.c_double, fp, C.c_size_t]
         _REF = L
     return _REF
@@ -337,7 +339,7 @@ def ref_feature_matching(q, t):
     return dict(left_idx=left, right_idx=right, pairs=pairs[:n].copy())
 
 
-def ref_preprocess(azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0):
+def ref_preprocess(azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6, lowpt_th=-1950.0, select=None, save_selected=True):
     """myslam::Preprocessor::run of the reference (src/preprocess.cpp:213-223, compiled unchanged) on one rotation of
     returns; vert_init / lowpt_th as the SLAM driver sets them (test/odometry_test.cpp:118-119)"""
     az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
@@ -346,8 +348,10 @@ def ref_preprocess(azimuth_deg, vertical_deg, distance, ring_deg, vert_init=-0.6
     ring = np.ascontiguousarray(ring_deg, dtype=np.float64)
     out = np.empty((max(az.size, 1), 3), np.float32)
     dp = C.POINTER(C.c_double)
-    n = ref_lib().ref_preprocess(az.ctypes.data_as(dp), ve.ctypes.data_as(dp), di.ctypes.data_as(C.POINTER(C.c_ushort)), az.size,
-                                 ring.ctypes.data_as(dp), ring.size, vert_init, lowpt_th, _f(out), out.shape[0])
+    sel = None if select is None else np.ascontiguousarray(select, dtype=np.int32)
+    n = ref_lib().ref_preprocess_select(az.ctypes.data_as(dp), ve.ctypes.data_as(dp), di.ctypes.data_as(C.POINTER(C.c_ushort)), az.size,
+                                        ring.ctypes.data_as(dp), ring.size, vert_init, lowpt_th, None if sel is None else _i(sel),
+                                        0 if sel is None else sel.size, 0 if sel is None else 1, 1 if save_selected else 0, _f(out), out.shape[0])
     return out[:n].copy()
 
 

@@ -101,8 +101,9 @@ void ref_cb_compute_descriptors(void* h, const float* xyz, size_t n, const float
 extern "C" {
 // Preprocessor::run() on one rotation: lasers (azimuth / vertical in degrees, distance in 2 mm units) -> kept points.
 // returns the number of points (written up to cap)
-size_t ref_preprocess(const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
-                      const double* vert_angles_deg, size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap) {
+size_t ref_preprocess_select(const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
+                             const double* vert_angles_deg, size_t nv, double vert_init_rad, double lowpt_th, const int* select_list, size_t n_select,
+                             int have_select_list, int save_selected, float* xyz_out, size_t cap) {
     std::vector<velodyne::Laser> lasers(n);
     for (size_t i = 0; i < n; ++i) {
         lasers[i].azimuth = azimuth_deg[i];
@@ -121,8 +122,22 @@ size_t ref_preprocess(const double* azimuth_deg, const double* vertical_deg, con
     pre.setLowPtThreshold(lowpt_th);
     pre.setPointCloud(pc);                                  // :125
     pre.setLasers(lasers);                                  // :143
+    if (have_select_list) {                                 // :144-157
+        std::vector<int> list(select_list, select_list + n_select);
+        pre.haveSelectList(true);
+        pre.saveSelectPoints(save_selected != 0);
+        pre.setSelectedPoints(list);
+    } else {
+        pre.haveSelectList(false);
+        pre.saveSelectPoints(save_selected != 0);
+    }
     pre.run();
     for (size_t i = 0; i < pc->size() && i < cap; ++i) { xyz_out[3 * i] = (*pc)[i][0]; xyz_out[3 * i + 1] = (*pc)[i][1]; xyz_out[3 * i + 2] = (*pc)[i][2]; }
     return pc->size();
+}
+
+size_t ref_preprocess(const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
+                      const double* vert_angles_deg, size_t nv, double vert_init_rad, double lowpt_th, float* xyz_out, size_t cap) {
+    return ref_preprocess_select(azimuth_deg, vertical_deg, distance, n, vert_angles_deg, nv, vert_init_rad, lowpt_th, nullptr, 0, 0, 1, xyz_out, cap);
 }
 }

@@ -9,6 +9,7 @@
 #include <fstream>
 
 #include "../b-shot-slam_b200/host/lidar_odometry.h"
+#include "../b-shot-slam_b200/host/preprocess.h"
 
 static myslam::Frame::PCPtr load(const char* path) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
@@ -58,6 +59,34 @@ int main(int argc, char** argv) {
         }
         std::printf("same-size reassignment ok\n");
     }
+    if (argc >= 6) {  // lasers.bin (n x {double az, double vert, u16 dist}) -> cloud.bin through the Preprocessor shim
+        std::ifstream lf(argv[4], std::ios::binary | std::ios::ate);
+        const size_t n = (size_t)lf.tellg() / 18;
+        lf.seekg(0);
+        std::vector<double> az(n), ve(n);
+        std::vector<unsigned short> di(n);
+        lf.read(reinterpret_cast<char*>(az.data()), (std::streamsize)(8 * n));
+        lf.read(reinterpret_cast<char*>(ve.data()), (std::streamsize)(8 * n));
+        lf.read(reinterpret_cast<char*>(di.data()), (std::streamsize)(2 * n));
+        std::vector<velodyne::Laser> lasers(n);
+        std::vector<double> ring;
+        for (size_t i = 0; i < n; ++i) {
+            lasers[i] = velodyne::Laser{az[i], ve[i], di[i], 0, (unsigned char)(i % 32), 0};
+            if (std::find(ring.begin(), ring.end(), ve[i]) == ring.end()) ring.push_back(ve[i]);
+        }
+        auto pc = std::make_shared<std::vector<Vector3f>>();
+        myslam::Preprocessor pre(lo.cb.context());       // test/odometry_test.cpp:114-125
+        pre.setVerticalAngles(ring);
+        pre.setVerticalInitial(-0.6);
+        pre.setLowPtThreshold(-1950);
+        pre.setPointCloud(pc);
+        pre.setLasers(lasers);
+        pre.run();
+        if (pre.last_status() != BSHOT_OK) { std::printf("preprocess: %s\n", bshot_last_error()); return 1; }
+        std::ofstream po(argv[5], std::ios::binary);
+        for (auto& p : *pc) po.write(reinterpret_cast<const char*>(p.v), 12);
+        std::printf("preprocessor: %zu returns -> %zu points\n", n, pc->size());
+    }
     std::ofstream out(argv[3], std::ios::binary);
     for (int fidx = 0; fidx < 2; ++fidx) {
         myslam::Frame::Ptr f = myslam::Frame::createFrame();
@@ -79,13 +108,22 @@ int main(int argc, char** argv) {
         const int nt = (int)lo.cb.cloud2_bshot.size();
         out.write(reinterpret_cast<const char*>(&nt), 4);
         out.write(reinterpret_cast<const char*>(lo.cb.cloud2_bshot.data()), (std::streamsize)nt * 48);
-        // the reference's updateMap (src/lidar_odometry.cpp:344-376): frame keypoints enter the global map
-        for (int i = 0; i < k; ++i) {
-            Vector3f pos = (*f->getKeypoints())[i];
-            lo.map().addKeypoint(myslam::Keypoint::createKeypoint(pos, lo.seg_ratios_[i], lo.cb.cloud1_bshot[i]));
-        }
-        lo.setRun();
-        std::printf("frame %d: %d keypoints, %d correspondences, map %d\n", fidx, k, nc, lo.map().size());
+        // ... and its positions, the correspondences RANSAC kept, the gate's verdict and the pose (test/odometry_test.cpp:178-181)
+        for (auto& p : lo.cb.cloud2_keypoints.points) out.write(reinterpret_cast<const char*>(p.data), 12);
+        lo.evaluateEstimation();
+        lo.poseEstimation();
+        lo.updateMap();
+        if (lo.last_status() != BSHOT_OK) { std::printf("frame %d (estimation): %s\n", fidx, bshot_last_error()); return 1; }
+        const int nr = (int)lo.corr.size(), upd = lo.shouldUpdateMap ? 1 : 0;
+        out.write(reinterpret_cast<const char*>(&nr), 4);
+        for (auto& c : lo.corr) { out.write(reinterpret_cast<const char*>(&c.index_query), 4); out.write(reinterpret_cast<const char*>(&c.index_match), 4); }
+        out.write(reinterpret_cast<const char*>(&upd), 4);
+        float Tr[16], Tb[16];
+        myslam::LidarOdometry::to_row_major(lo.getRansacTransformation(), Tr);
+        myslam::LidarOdometry::to_row_major(f->getPose(), Tb);
+        out.write(reinterpret_cast<const char*>(Tr), 64);
+        out.write(reinterpret_cast<const char*>(Tb), 64);
+        std::printf("frame %d: %d keypoints, %d correspondences, %d after RANSAC, map %d\n", fidx, k, nc, nr, lo.map().size());
     }
     return 0;
 }

@@ -39,10 +39,18 @@ def test_reference_call_order_two_frames(shim_binary, tmp_path, oracle, synth):
         s.tofile(p)
         paths.append(p)
     outp = str(tmp_path / "out.bin")
-    r = subprocess.run([shim_binary, paths[0], paths[1], outp], capture_output=True, text=True)
+    L = synth.make_lasers("hdl32e", 0, firings=500, start_deg=300.0)
+    lasers, pre_out = str(tmp_path / "lasers.bin"), str(tmp_path / "pre.bin")
+    with open(lasers, "wb") as fh:
+        fh.write(L["azimuth"].tobytes() + L["vertical"].tobytes() + L["distance"].tobytes())
+    r = subprocess.run([shim_binary, paths[0], paths[1], outp, lasers, pre_out], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    # myslam::Preprocessor shim == the reference's preprocess.cpp compiled unchanged
+    if oracle.ref_lib() is not None:
+        got = np.fromfile(pre_out, np.float32).reshape(-1, 3)
+        assert np.array_equal(got, oracle.ref_preprocess(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"]))
     raw = open(outp, "rb").read()
-    off, frames = 0, []
+    off, frames, rest = 0, [], []
     for _ in range(2):
         k, nc = struct.unpack_from("ii", raw, off); off += 8
         kp = np.frombuffer(raw, np.float32, 3 * k, off).reshape(k, 3); off += 12 * k
@@ -51,7 +59,14 @@ def test_reference_call_order_two_frames(shim_binary, tmp_path, oracle, synth):
         corr = np.frombuffer(raw, np.int32, 2 * nc, off).reshape(nc, 2); off += 8 * nc
         nt, = struct.unpack_from("i", raw, off); off += 4
         tgt = np.frombuffer(raw, np.uint64, 6 * nt, off).reshape(nt, 6); off += 48 * nt
+        tgt_xyz = np.frombuffer(raw, np.float32, 3 * nt, off).reshape(nt, 3); off += 12 * nt
+        nr, = struct.unpack_from("i", raw, off); off += 4
+        kept = np.frombuffer(raw, np.int32, 2 * nr, off).reshape(nr, 2); off += 8 * nr
+        upd, = struct.unpack_from("i", raw, off); off += 4
+        T_ransac = np.frombuffer(raw, np.float32, 16, off).reshape(4, 4); off += 64
+        pose = np.frombuffer(raw, np.float32, 16, off).reshape(4, 4); off += 64
         frames.append((kp, bits, rf, corr, tgt))
+        rest.append((tgt_xyz, kept, upd, T_ransac, pose))
     assert off == len(raw)
     assert "same-size reassignment ok" in r.stdout
     for (kp, bits, rf, corr, _), scan in zip(frames, scans):
@@ -71,3 +86,13 @@ def test_reference_call_order_two_frames(shim_binary, tmp_path, oracle, synth):
     assert len(t1) > 600 and np.array_equal(t1[-600:], b0)      # map subset first, then the 600 reference-frame records
     m1 = oracle.match(b1, t1)
     assert len(c1) > 0 and np.array_equal(c1, oracle.mutual(m1["left_idx"], m1["right_idx"]))
+    # RANSAC rejection, the gate + ICP and the pose (featureMatching :251-261, evaluateEstimation, poseEstimation):
+    # the oracle on the same keypoints / correspondences gives the same bits
+    pose_ref = np.eye(4, dtype=np.float32)
+    for (kp, _, _, c, _), (tgt_xyz, kept, upd, T_ransac, pose) in zip(frames, rest):
+        rs = oracle.ransac(kp, tgt_xyz, c)
+        assert np.array_equal(kept, rs["pairs"]) and np.array_equal(T_ransac, rs["transform"])
+        ev = oracle.evaluate_estimation(rs["transform"], pose_ref, len(rs["pairs"]), kp, tgt_xyz, run_icp=True)
+        assert bool(upd) == ev["should_update_map"]
+        assert np.array_equal(pose.view(np.uint32), ev["T_best"].view(np.uint32))
+        pose_ref = pose

@@ -162,6 +162,25 @@ def test_gpu_edge_cases(gpu_ctx, ref, bshot):
 
 
 @pytest.mark.gpu
+def test_gpu_point_selection(gpu_ctx, ref, synth):
+    """setSelectedPoints / haveSelectList / saveSelectPoints (test/odometry_test.cpp:144-160): selected returns only, or
+    everything but them; an unsorted list with a duplicate (the cursor of readFrame stops advancing at it)"""
+    L = synth.make_lasers("hdl32e", 1, firings=400, start_deg=200.0)
+    n = L["azimuth"].size
+    rng = np.random.default_rng(2)
+    args = (L["azimuth"], L["vertical"], L["distance"], L["ring_deg"])
+    everything = ref.ref_preprocess(*args)
+    for sel in (np.arange(0, n, 3), rng.permutation(n)[: n // 2], np.array([5, 900, 900, 4000, 7000]), np.zeros(0, np.int32), np.array([n + 5, -3, 10])):
+        for save in (True, False):
+            want = ref.ref_preprocess(*args, select=sel, save_selected=save)
+            same_points(gpu_ctx.preprocess(*args, select=sel, save_selected=save), want)
+        kept = len(ref.ref_preprocess(*args, select=sel, save_selected=True)) + len(ref.ref_preprocess(*args, select=sel, save_selected=False))
+        assert kept == len(everything)
+    # no list but "save the unselected": nothing is written
+    assert len(gpu_ctx.preprocess(*args, save_selected=False)) == len(ref.ref_preprocess(*args, save_selected=False)) == 0
+
+
+@pytest.mark.gpu
 def test_gpu_capacity_errors(gpu_ctx, bshot):
     import ctypes as C
     L = cat([column(10.0 + 0.2 * k, RING, [3000] * 6) for k in range(10)])
