@@ -118,6 +118,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("BSHOT_WARP_PATH")) c->force_warp_path = (atoi(e) != 0);
+    if (const char* e = getenv("BSHOT_DEFERRED_NORMALS")) c->no_deferred_normals = (atoi(e) == 0);
     if (const char* e = getenv("BSHOT_MAX_CELLS_LOG2")) {  // tuning knob: voxel table size (default 2^22 cells)
         const int v = atoi(e);
         if (v >= 10 && v <= 23) c->max_cells = 1u << v;
@@ -153,6 +154,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_nblocks, 8));
     A(dmalloc(&c->d_ovf, N));
     A(dmalloc(&c->d_rho_hint, N));
+    A(dmalloc(&c->d_qsums, 10 * N));
     A(dmalloc(&c->d_fb_list, N));
     A(dmalloc(&c->d_ratio, N));
     A(dmalloc(&c->d_keys, N));
@@ -228,7 +230,7 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     comm_free(c);
     gmap_free(c);
     void* ptrs[] = {c->d_raw, c->d_pts, c->d_sorted, c->d_cell_of, c->d_cell_start, c->d_cell_cursor, c->d_block_sums,
-                    c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
+                    c->d_grid, c->d_bbox, c->d_lvl, c->d_sorted_pos, c->d_kp_flag, c->d_blocks, c->d_blk_area, c->d_nblocks, c->d_ovf, c->d_rho_hint, c->d_qsums, c->d_fb_list, c->d_ratio, c->d_keys, c->d_kp_idx, c->d_kp_ratio, c->d_kp, c->d_kp_count,
                     c->d_tk_hist, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_normals, c->d_qnormals, c->d_shot, c->d_rf, c->d_nn, c->d_sum_nn, c->d_bits, c->d_prev_bits, c->d_prev_kp,
                     c->d_prev_count, c->d_q, c->d_t, c->d_map, c->d_partial, c->d_cand, c->d_cand2, c->d_gather,
                     c->d_left, c->d_right, c->d_pairs, c->d_pair_count, c->d_counters, c->d_pre[0], c->d_pre[1], c->d_pre[2]};
@@ -257,6 +259,7 @@ int bshot_ctx_reset(bshot_ctx* ctx) {
     ctx->have_normals = false;
     ctx->n_prev = 0;
     ctx->n_map = 0;
+    ctx->gate_top_k = 0;
     return sync(ctx);
 }
 
@@ -323,6 +326,7 @@ int bshot_set_keypoints(bshot_ctx* ctx, const float* kp_xyz, size_t k, size_t st
     ctx->n_kp = k;
     ctx->have_kp = true;
     ctx->kp_from_detector = false;
+    ctx->gate_top_k = 0;
     return sync(ctx);
 }
 

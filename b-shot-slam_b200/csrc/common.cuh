@@ -68,6 +68,15 @@ struct Comm {
     bool connected = false;
 };
 
+// which points get their covariance sums stored by the detector (deferred keypoint normals): the ones whose score reaches
+// the K-th score of the previous frame less a margin.  top_k == 0: every point.  A keypoint that was not predicted simply
+// has no sums and is searched on its own (exactness never depends on the prediction).
+struct SumGate {
+    const float* kth_ratio;  // d_kp_ratio: keypoints in ascending score order, [0] = the K-th best of the previous frame
+    const int* kth_count;    // d_kp_count
+    int top_k;
+};
+
 // GPU-resident global keypoint map (gmap.cu)
 struct Gmap {
     void* d_tab = nullptr;              // block hash table (GmapBlock[tab_cap])
@@ -90,6 +99,7 @@ struct Gmap {
 struct Ctx {
     int device = 0;
     int sm_count = 148;
+    bool no_deferred_normals = false;  // BSHOT_DEFERRED_NORMALS=0: keypoint normals by a second search (tile_keypoint_normals) instead of the detector's sums (tests)
     bool force_warp_path = false;  // BSHOT_WARP_PATH=1: skip the block-tiled kernels (tile.cuh), warp-per-query kernels everywhere (tests)
     unsigned max_cells = 1u << 22;  // voxel table size actually used (<= kMaxCells; BSHOT_MAX_CELLS_LOG2): zeroed and scanned every frame
     float yz_mul = 1.0f;  // cell_yz / cell (tuning knob BSHOT_YZ_MUL; 2 helps SHOT by ~3 %, costs the detector ~6 %)
@@ -115,6 +125,7 @@ struct Ctx {
     uint4* d_blocks = nullptr;         // N: query blocks {ix0, iy0, iz0, cells per edge | slice << 4} (tile.cuh)
     float* d_blk_area = nullptr;       // N: surface area per point around the block (radius prediction)
     unsigned* d_nblocks = nullptr;     // [0] heavy blocks, [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [5] light blocks
+    float* d_qsums = nullptr;          // N x 10: covariance sums + count of the detector's neighbourhood of every point (deferred normals)
     float* d_rho_hint = nullptr;       // N: radius of the detector's neighbourhood of every point (distance of its last member)
     uint2* d_ovf = nullptr;            // N: queries whose block tile overflowed {position in d_sorted, radius bits} (tilek.cu)
     unsigned* d_fb_list = nullptr;     // N: sorted positions of the queries the tiled kernels hand to the fallback
@@ -129,6 +140,11 @@ struct Ctx {
     bool sel_valid = false;                  // the detector ran on the current cloud with (sel_radius, sel_max_nn)
     float sel_radius = 0.0f;
     int sel_max_nn = 0;
+    int gate_top_k = 0;                      // the previous frame_extract ran with these detector parameters and left its K-th ratio in d_kp_ratio[0]
+    int gate_sr = -1;
+    float gate_radius = 0.0f;
+    int gate_max_nn = 0;
+    bool fused_sums = false;                 // d_qsums is valid for (fused_radius, fused_max_nn)
     bool fused_normals = false;              // d_normals already holds the FULL-mode normals for (fused_radius, fused_max_nn)
     float fused_radius = 0.0f;
     int fused_max_nn = 0;

@@ -333,10 +333,14 @@ static int seg_ratio_warp_launch(Ctx* c, float radius, int max_nn, int sr_type, 
     return check_launch("seg_ratio_kernel");
 }
 
-// fuse_normals: also compute the FULL-mode normal of every point from the same neighbourhoods (same radius / max_nn)
-int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_normals) {
+// fuse == 1: also compute the FULL-mode normal of every point from the same neighbourhoods (same radius / max_nn)
+// fuse == 2: also keep the nine covariance sums + count of every point's neighbourhood (d_qsums): the REFERENCE-mode normals
+//            of the points that become keypoints are then one small eigen-solve each, with no second neighbour search
+int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, int fuse, int gate_top_k) {
     const unsigned n = (unsigned)c->n_points;
+    bool fuse_normals = fuse == 1;
     c->fused_normals = false;
+    c->fused_sums = false;
     if (n == 0) return BSHOT_OK;
     if (sr_type < 0 || sr_type > 2) { set_error("bad sr_type %d", sr_type); return BSHOT_E_INVALID; }
     if (!(radius > 0.0f)) { set_error("bad radius"); return BSHOT_E_INVALID; }
@@ -344,7 +348,11 @@ int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_no
     count_launch(c);
     if (tile_path_ok(c, max_nn)) {
         fuse_normals = fuse_normals && !c->force_warp_path;
-        BSHOT_TRY(tile_neighbourhoods(c, sr_type, true, fuse_normals, radius, max_nn, nullptr, c->d_normals));
+        const bool sums = fuse == 2 && !c->force_warp_path && !c->no_deferred_normals;
+        // a point the tiles do not answer (fallback list) keeps a NaN count: its normal is searched on its own later
+        if (sums) BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_qsums, 0xFF, sizeof(float) * 10 * (size_t)n, c->stream));
+        BSHOT_TRY(tile_neighbourhoods(c, sr_type, true, fuse_normals ? 1 : (sums ? 2 : 0), radius, max_nn, nullptr, c->d_normals, sums ? gate_top_k : 0));
+        if (sums) { c->fused_sums = true; c->fused_radius = radius; c->fused_max_nn = max_nn; }
         // queries whose tile did not fit (device-side list, usually empty)
         BSHOT_TRY(seg_ratio_warp_launch(c, radius, max_nn, sr_type, (unsigned)c->sm_count * 4u, c->d_fb_list, c->d_nblocks + 1));
         if (fuse_normals) {
@@ -373,6 +381,7 @@ void knn_stats_dump() {
 #endif
 
 int detect_topk(Ctx* c, int top_k) {
+    c->gate_top_k = 0;  // d_kp_ratio is rewritten; frame_extract re-arms the gate for its own parameters
     const unsigned n = (unsigned)c->n_points;
     if (top_k < 0 || (size_t)top_k > c->max_kp) { set_error("top_k %d exceeds max_keypoints %zu", top_k, c->max_kp); return BSHOT_E_CAPACITY; }
     // keypoint ordinal per cell-sorted position, read by the tiled normals (REFERENCE mode): -1 = not a keypoint

@@ -33,10 +33,14 @@ int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, i
     BSHOT_TRY(grid_build(c, d_raw, n, stride_floats));
     mark(1);
     // FULL-mode normals use the detector's own neighbourhoods when the search parameters agree: one pass for both
-    const bool fuse = p->normals_mode == BSHOT_NORMALS_FULL && p->normal_radius == p->kp_radius && p->normal_max_nn == p->kp_max_nn;
-    BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type, fuse));
+    const bool same = p->normal_radius == p->kp_radius && p->normal_max_nn == p->kp_max_nn;
+    const int fuse = !same ? 0 : (p->normals_mode == BSHOT_NORMALS_FULL ? 1 : 2);
+    // sums for the deferred keypoint normals only where the previous frame's K-th score makes a keypoint likely
+    const int gate = (c->gate_top_k == p->top_k && c->gate_sr == p->sr_type && c->gate_radius == p->kp_radius && c->gate_max_nn == p->kp_max_nn) ? p->top_k : 0;
+    BSHOT_TRY(detect_seg_ratio(c, p->kp_radius, p->kp_max_nn, p->sr_type, fuse, gate));
     mark(2);
     BSHOT_TRY(detect_topk(c, p->top_k));
+    c->gate_top_k = p->top_k; c->gate_sr = p->sr_type; c->gate_radius = p->kp_radius; c->gate_max_nn = p->kp_max_nn;
     mark(3);
     BSHOT_TRY(normals_compute(c, p->normals_mode, p->normal_radius, p->normal_max_nn));
     mark(4);

@@ -350,6 +350,7 @@ int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats) {
     c->have_kp = false;
     c->kp_from_detector = false;
     c->sel_valid = false;
+    c->fused_sums = false;
     c->have_normals = c->normals_valid > 0;
     return BSHOT_OK;
 }

@@ -84,6 +84,35 @@ __global__ void place_normals_kernel(const float4* __restrict__ src, const int* 
     if (i < cap && (int)i < *count) dst[i] = src[i];
 }
 
+// REFERENCE-mode normals of the detector's keypoints from the covariance sums the detector kept for every point
+// (detect_seg_ratio, fuse == 2): one eigen-solve per keypoint, result at the keypoint's ordinal (include/bshot_bits.h:79-81).
+// A keypoint whose sums are missing (its query went to the warp fallback) is appended to the fallback list instead.
+__global__ void __launch_bounds__(128)
+normals_from_sums_kernel(const float* __restrict__ qsums, const float4* __restrict__ pts, const int* __restrict__ kp_idx, const int* __restrict__ kp_count,
+                         const unsigned* __restrict__ sorted_pos, float4* __restrict__ out, unsigned* __restrict__ fb_list, unsigned* __restrict__ fb_len,
+                         unsigned long long* __restrict__ counters) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt_n = 0;
+    if ((int)i < *kp_count) {
+        const int idx = kp_idx[i];
+        const float* s = qsums + 10 * (size_t)idx;
+        const float cnt = s[9];
+        if (cnt >= 1.0f) {
+            float a[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a[k] = s[k];
+            const float4 q = pts[idx];
+            out[i] = normal_from_sums(a, (int)cnt, q.x, q.y, q.z);
+            cnt_n = (int)cnt;
+        } else {
+            fb_list[atomicAdd(fb_len, 1u)] = sorted_pos[idx];
+            atomicAdd(&counters[6], 1ull);
+        }
+    }
+    cnt_n = warp_sum(cnt_n);
+    if ((threadIdx.x & 31) == 0 && cnt_n) atomicAdd(&counters[1], (unsigned long long)cnt_n);
+}
+
 // FULL mode: points that are not in the voxel table (non-finite coordinates) have no neighbourhood -> NaN normal
 __global__ void nan_unbinned_normals_kernel(const unsigned* __restrict__ cell_of, unsigned n, float4* __restrict__ normals) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,7 +164,15 @@ int normals_compute(Ctx* c, int mode, float radius, int max_nn) {
         c->fused_normals = false;  // keypoint normals overwrite the prefix of d_normals
         const size_t k = std::min(c->n_kp, c->n_points);  // keypoint ordinal idx lands at surface index idx
         if (k) {
-            if (tiled && c->kp_from_detector && c->sel_valid && c->sel_radius == radius && c->sel_max_nn == max_nn) {
+            if (tiled && c->kp_from_detector && c->sel_valid && c->fused_sums && c->fused_radius == radius && c->fused_max_nn == max_nn) {
+                // the detector kept the covariance sums of every point's neighbourhood: no second search
+                BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, sizeof(unsigned), c->stream));
+                normals_from_sums_kernel<<<(unsigned)((k + 127) / 128), 128, 0, c->stream>>>(c->d_qsums, c->d_pts, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos,
+                                                                                           c->d_normals, c->d_fb_list, c->d_nblocks + 1, c->d_counters);
+                count_launch(c);
+                BSHOT_TRY(check_launch("normals_from_sums_kernel"));
+                BSHOT_TRY(normals_fallback_list(c, radius, max_nn, c->d_kp_flag, c->d_normals));
+            } else if (tiled && c->kp_from_detector && c->sel_valid && c->sel_radius == radius && c->sel_max_nn == max_nn) {
                 // keypoints are cloud points the detector just searched with the same parameters: one private tile per
                 // keypoint with the radius kept for it, straight into d_normals[ordinal] (include/bshot_bits.h:79-81)
                 BSHOT_TRY(tile_keypoint_normals(c, radius, max_nn, c->d_normals));

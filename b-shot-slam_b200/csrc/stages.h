@@ -8,12 +8,12 @@ namespace bshot {
 int grid_build(Ctx* c, const float* d_raw, size_t n, int stride_floats);
 
 // a2/a3: seg-ratio for every point -> d_ratio, d_keys ; top-K -> d_kp_idx/d_kp_ratio/d_kp/d_kp_count (detect.cu)
-int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, bool fuse_normals = false);
+int detect_seg_ratio(Ctx* c, float radius, int max_nn, int sr_type, int fuse = 0, int gate_top_k = 0);  // fuse: 1 FULL normals, 2 covariance sums for the keypoint normals
 int detect_topk(Ctx* c, int top_k);
 
 // block-tiled exact neighbourhoods of cloud points (tilek.cu): seg-ratio scores and / or normals; d_flags = nullptr: every
 // point, else per cell-sorted position the output slot (>= 0) of the points that want a normal
-int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out);
+int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out, int gate_top_k = 0);
 bool tile_path_ok(const Ctx* c, int max_nn);
 // normals of the detector's keypoints at their ordinals, from the radii the detector kept (tilek.cu)
 int tile_keypoint_normals(Ctx* c, float radius, int max_nn, float4* d_nrm_out);

@@ -276,11 +276,12 @@ __device__ __forceinline__ float tile_seq_sum(const TileWarp& w, int row, int co
     return acc;
 }
 
-// sequential fp32 sum of products rowa[i] * rowb[i] (rowb < 0: plain sum of rowa) in neighbour order
+// sequential fp32 sum of products rowa[i] * rowb[i] (rowb < 0: plain sum of rowa, only when PLAIN) in neighbour order
+template <bool PLAIN = true>
 __device__ __forceinline__ float tile_seq_sum_prod(const TileWarp& w, int rowa, int rowb, int count) {
     const float4* a4 = reinterpret_cast<const float4*>(w.u.soa[rowa]);
-    const float4* b4 = reinterpret_cast<const float4*>(w.u.soa[rowb < 0 ? rowa : rowb]);
-    const bool plain = rowb < 0;
+    const float4* b4 = reinterpret_cast<const float4*>(w.u.soa[(PLAIN && rowb < 0) ? rowa : rowb]);
+    const bool plain = PLAIN && rowb < 0;
     float acc = 0.0f;
     const int n4 = (count + 3) >> 2;
 #pragma unroll 2

@@ -15,10 +15,19 @@ namespace bshot {
 // Everything that follows the selection of one query's neighbourhood (w.order[0..count) = tile slots in neighbour
 // order): coordinates into SoA, the reference's fp32 running sums replayed in that order, the score.  nsum (shared
 // memory, 10 floats) receives the nine accumulators of pcl::computeMeanAndCovarianceMatrix + the count when NRM.
-template <int SR, bool SEG, bool NRM>
+__device__ __forceinline__ float sum_gate_threshold(const SumGate& gate) {
+    float thr = -INFINITY;
+    if (gate.top_k > 0 && *gate.kth_count == gate.top_k) {
+        const float kth = gate.kth_ratio[0];
+        if (kth > 0.0f) thr = kth * 0.95f;
+    }
+    return thr;
+}
+
+template <int SR, bool SEG, int NRM>
 __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ tile, const float4& q, int count, TileWarp& w, unsigned lane,
                                                    float* __restrict__ ratio, unsigned long long* __restrict__ keys, float* nsum,
-                                                   float* __restrict__ rho_hint, int max_nn, float R) {
+                                                   float* __restrict__ rho_hint, int max_nn, float R, float* __restrict__ qsums = nullptr, float sum_thr = 0.0f) {
     const float nanf_ = __int_as_float(0x7FC00000);
     const unsigned qi = __float_as_uint(q.w);
     tile_gather(tile, count, w, lane);
@@ -30,14 +39,19 @@ __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ ti
         rho_hint[qi] = (count >= max_nn) ? sqrtf(sqdist_rn(q.x, q.y, q.z, w.u.soa[0][l], w.u.soa[1][l], w.u.soa[2][l])) * 1.0001f + 0.01f : R;
     }
     float sx, sy, sz;
-    if (NRM) {
+    constexpr bool GATED = NRM == 2 && SR == BSHOT_SR_CV;   // sums only where the score makes a keypoint likely (see SumGate)
+    if (NRM && !GATED) {
         // the nine accumulators, one lane each (6..8 = plain sums = the centroid sums of pcl::computeCentroid)
         const int c = (int)(lane % 9u);
         const int rowa = (c < 3) ? 0 : (c < 5 ? 1 : (c == 5 ? 2 : c - 6));
         const int rowb = (c < 3) ? c : (c < 5 ? c - 2 : (c == 5 ? 2 : -1));
         const float acc = tile_seq_sum_prod(w, rowa, rowb, count);
-        if (lane < 9) nsum[lane] = acc;
-        if (lane == 9) nsum[9] = fn;
+        if (NRM == 2) {  // deferred: the sums of every point go to global memory, the normal is solved later for the keypoints only
+            if (lane < 10) qsums[10 * (size_t)qi + lane] = (lane < 9) ? acc : fn;
+        } else {
+            if (lane < 9) nsum[lane] = acc;
+            if (lane == 9) nsum[9] = fn;
+        }
         sx = __shfl_sync(0xffffffffu, acc, 6);
         sy = __shfl_sync(0xffffffffu, acc, 7);
         sz = __shfl_sync(0xffffffffu, acc, 8);
@@ -47,7 +61,7 @@ __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ ti
         sy = __shfl_sync(0xffffffffu, acc, 1);
         sz = __shfl_sync(0xffffffffu, acc, 2);
     }
-    if (SEG && !(NRM && q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) {  // :63 the detector skips the origin
+    if (SEG && !(NRM == 1 && q.x == 0.0f && q.y == 0.0f && q.z == 0.0f)) {  // :63 the detector skips the origin
         const float vx = __fsub_rn(q.x, sx / fn), vy = __fsub_rn(q.y, sy / fn), vz = __fsub_rn(q.z, sz / fn);  // :79
         float seg;
         if (SR == BSHOT_SR_CV) {  // :83-97
@@ -62,6 +76,12 @@ __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ ti
             const float fp = (float)pos, fq = (float)neg;
             seg = 1.0f - fminf(fp, fq) / fmaxf(fp, fq);
             if (pos == 0 && neg == 0) seg = nanf_;  // 0/0 like the reference
+            if (GATED && seg >= sum_thr) {  // warp-uniform; the coordinates are still in w.u.soa
+                const int c = (int)(lane % 6u);  // xx xy xz yy yz zz
+                const int rowa = (c < 3) ? 0 : (c < 5 ? 1 : 2), rowb = (c < 3) ? c : (c < 5 ? c - 2 : 2);
+                const float acc2 = tile_seq_sum_prod<false>(w, rowa, rowb, count);
+                if (lane < 10) qsums[10 * (size_t)qi + lane] = (lane < 6) ? acc2 : (lane == 6 ? sx : (lane == 7 ? sy : (lane == 8 ? sz : fn)));
+            }
         } else {  // CVS :98-108 / CVSN :109-119: per-neighbour terms in parallel, fp32 running sum in neighbour order
             const float ctn = sqrtf(dot3_rn(vx, vy, vz, vx, vy, vz));
             __syncwarp();
@@ -95,13 +115,14 @@ __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ ti
 // keypoint ordinal >= 0, out index = ordinal: the reference's placement, include/bshot_bits.h:79-81).
 // One CTA per block of the grid's block list, one shared 1024-point tile, one warp per query.  Queries whose block tile
 // does not fit (very dense spots, density jumps) go to the overflow list {position, radius} for tile_single_kernel.
-template <int SR, bool SEG, bool NRM>
-__global__ void __launch_bounds__(TL_WARPS * 32, NRM ? BSHOT_TL_MINBLOCKS : BSHOT_TL_MINBLOCKS + 1)
+template <int SR, bool SEG, int NRM>
+__global__ void __launch_bounds__(TL_WARPS * 32, NRM == 1 ? BSHOT_TL_MINBLOCKS : BSHOT_TL_MINBLOCKS + 1)
 tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
             const uint4* __restrict__ blocks, const float* __restrict__ blk_area, unsigned* __restrict__ ctl, float radius, int max_nn,
             float* __restrict__ ratio, unsigned long long* __restrict__ keys, const int* __restrict__ flags, float4* __restrict__ nrm_out,
-            unsigned long long* __restrict__ counters, uint2* __restrict__ ovf, unsigned block_cap, float* __restrict__ rho_hint) {
-    using SM = TileShared<NRM, TL_CAP, TL_WARPS>;
+            unsigned long long* __restrict__ counters, uint2* __restrict__ ovf, unsigned block_cap, float* __restrict__ rho_hint,
+            float* __restrict__ qsums, SumGate gate) {
+    using SM = TileShared<NRM == 1, TL_CAP, TL_WARPS>;
     __shared__ SM sm;
     unsigned& s_block = sm.cur_block;
     unsigned& s_slot = sm.ovf_slot;
@@ -110,6 +131,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     const GridParams g = *gp;
     const float R = radius;
     const float R2 = (float)((double)R * (double)R);
+    const float sum_thr = sum_gate_threshold(gate);
     const unsigned n_heavy = ctl[0], nb = n_heavy + ctl[5];  // heavy blocks from the front of the list, light ones from its back
     unsigned long long st_staged = 0, st_swept = 0, st_attempts = 0, st_blocks = 0;  // thread 0 only
     for (;;) {
@@ -119,7 +141,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         if (s_block >= nb) break;
         const unsigned b = s_block < n_heavy ? s_block : block_cap - 1u - (s_block - n_heavy);
         const uint4 desc = __ldg(blocks + b);
-        tile_block_queries(g, cell_start, sorted, desc, SEG ? nullptr : flags, SEG && !NRM, sm, tid);
+        tile_block_queries(g, cell_start, sorted, desc, SEG ? nullptr : flags, SEG && NRM != 1, sm, tid);
         const unsigned nq = sm.nq;
         if (nq == 0) continue;
         ++st_blocks;
@@ -198,7 +220,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                         if (lane == 0) { sm.q_nin[k] = max(tq.n_in, 1); atomicMin(&sm.min_nin, tq.n_in); atomicAdd(&counters[5], 1ull); }
                         continue;
                     }
-                    tile_query_outputs<SR, SEG, NRM>(sm.tile, q, tq.count, w, lane, ratio, keys, NRM ? sm.nsum[k] : nullptr, rho_hint, max_nn, R);
+                    tile_query_outputs<SR, SEG, NRM>(sm.tile, q, tq.count, w, lane, ratio, keys, NRM == 1 ? sm.nsum[k] : nullptr, rho_hint, max_nn, R, qsums, sum_thr);
                     if (lane == 0) {
                         sm.q_nin[k] = -1;
                         atomicSub(&sm.pending, 1u);
@@ -213,7 +235,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             }
         }
         __syncthreads();
-        if (NRM) {  // eigen-solves of the block's queries in parallel
+        if (NRM == 1) {  // eigen-solves of the block's queries in parallel
             for (unsigned k = tid; k < nq; k += SM::kThreads) {
                 if (sm.q_nin[k] != -1) continue;
                 const float4 q = sm.q_pt[k];
@@ -238,6 +260,9 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
 // TS_CAP-point tile (row segments read by the warp, no CTA-wide step) and brackets the radius until the ball holds at
 // least max_nn and at most TS_CAP points -- always possible unless more than TS_CAP points coincide in distance, which
 // goes to the warp-per-query fallback list (knn.cuh).
+#ifndef BSHOT_TS_FLAT_BELOW
+#define BSHOT_TS_FLAT_BELOW 32u   // mean points per non-empty row segment below which the segments are read as one range
+#endif
 constexpr int TS_WARPS = 4;
 constexpr int TS_CAP = 640;
 
@@ -262,25 +287,60 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
             unsigned e;
             if (row_segment(g, cell_start, q.x, q.y, q.z, rs, iy, iz, s, e)) len = e - s;
         }
+        unsigned incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += up;
+        }
+        const unsigned excl = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
         unsigned m = __ballot_sync(0xffffffffu, len > 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1u;
-            const unsigned ss = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src);
-            for (unsigned j0 = 0; j0 < ll; j0 += 32) {
-                const unsigned j = j0 + lane;
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool keep = false;
-                if (j < ll) {
-                    p = __ldg(sorted + ss + j);
-                    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-                    keep = dx * dx + dy * dy + dz * dz <= rs2;
+        if (total >= BSHOT_TS_FLAT_BELOW * (unsigned)__popc(m)) {
+            // long segments (dense spots): one segment after the other, 32 points a step
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1u;
+                const unsigned ss = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src);
+                for (unsigned j0 = 0; j0 < ll; j0 += 32) {
+                    const unsigned j = j0 + lane;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bool keep = false;
+                    if (j < ll) {
+                        p = __ldg(sorted + ss + j);
+                        const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+                        keep = dx * dx + dy * dy + dz * dz <= rs2;
+                    }
+                    const unsigned km = __ballot_sync(0xffffffffu, keep);
+                    const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
+                    if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
+                    n += __popc(km);
                 }
-                const unsigned km = __ballot_sync(0xffffffffu, keep);
-                const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
-                if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
-                n += __popc(km);
             }
+            continue;
+        }
+        // short segments: the 32 of them are read as ONE concatenated index range (a round trip to memory per 32 points,
+        // not per segment) -- every lane finds the segment of its index by bisection over the exclusive prefix
+        for (unsigned j0 = 0; j0 < total; j0 += 32) {
+            const unsigned j = j0 + lane;
+            unsigned lo = 0;  // last segment whose first index is <= j (empty segments share the index of their successor)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const unsigned cand = lo + (unsigned)step;
+                const unsigned e = __shfl_sync(0xffffffffu, excl, cand & 31u);
+                if (cand < 32u && e <= j) lo = cand;
+            }
+            const unsigned ss = __shfl_sync(0xffffffffu, s, lo), se = __shfl_sync(0xffffffffu, excl, lo);
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool keep = false;
+            if (j < total) {
+                p = __ldg(sorted + ss + (j - se));
+                const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+                keep = dx * dx + dy * dy + dz * dz <= rs2;
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
+            if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
+            n += __popc(km);
         }
     }
     if (n <= (unsigned)TS_CAP) {
@@ -291,13 +351,14 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
     return n;
 }
 
-template <int SR, bool SEG, bool NRM>
+template <int SR, bool SEG, int NRM>
 __global__ void __launch_bounds__(TS_WARPS * 32, 3)
 tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
                    unsigned* __restrict__ ctl, float radius, int max_nn, float* __restrict__ ratio, unsigned long long* __restrict__ keys,
                    const int* __restrict__ flags, float4* __restrict__ nrm_out, unsigned long long* __restrict__ counters,
                    const uint2* __restrict__ ovf, unsigned* __restrict__ fb_list, float* __restrict__ rho_hint,
-                   const int* __restrict__ kp_idx, const int* __restrict__ kp_count, const unsigned* __restrict__ sorted_pos) {
+                   const int* __restrict__ kp_idx, const int* __restrict__ kp_count, const unsigned* __restrict__ sorted_pos,
+                   float* __restrict__ qsums, SumGate gate) {
     extern __shared__ __align__(16) unsigned char single_smem_raw[];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     SingleWarp& st = reinterpret_cast<SingleWarp*>(single_smem_raw)[wid];
@@ -306,6 +367,7 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
     const float R2 = (float)((double)R * (double)R);
     // items: the overflow queries of tile_kernel -- or (kp_idx != nullptr) the detector's keypoints, each with the radius
     // the detector kept for it; result slot = keypoint ordinal (the reference's placement, include/bshot_bits.h:79-81)
+    const float sum_thr = sum_gate_threshold(gate);
     const unsigned n_items = kp_idx ? (unsigned)max(*kp_count, 0) : ctl[4];
     unsigned long long nbr = 0;
     for (;;) {
@@ -339,8 +401,8 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
             if (at_R || S >= (unsigned)max_nn) {
                 const TileQuery tq = tile_select(st.tile, (S + 127u) & ~127u, q, rho2, at_R, max_nn, st.w, lane);
                 if (tq.count > 0) {
-                    tile_query_outputs<SR, SEG, NRM>(st.tile, q, tq.count, st.w, lane, ratio, keys, st.nsum, rho_hint, max_nn, R);
-                    if (NRM) {
+                    tile_query_outputs<SR, SEG, NRM>(st.tile, q, tq.count, st.w, lane, ratio, keys, st.nsum, rho_hint, max_nn, R, qsums, sum_thr);
+                    if (NRM == 1) {
                         __syncwarp();
                         if (lane == 0) {
                             float a[9];
@@ -369,7 +431,8 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
 
 bool tile_path_ok(const Ctx* c, int max_nn) { return !c->force_warp_path && max_nn > 0 && max_nn <= TL_MAXNN; }
 
-int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out) {
+int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, int max_nn, const int* d_flags, float4* d_nrm_out, int gate_top_k) {
+    const SumGate gate{c->d_kp_ratio, c->d_kp_count, gate_top_k};
     if (max_nn <= 0 || max_nn > TL_MAXNN) { set_error("tile_neighbourhoods: max_nn %d outside (0, %d]", max_nn, TL_MAXNN); return BSHOT_E_INVALID; }
     // persistent CTAs pulling blocks / queries from work counters; d_nblocks[1..4]: fallback-list length, work counters, overflow count
     BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, 4 * sizeof(unsigned), c->stream));
@@ -383,15 +446,23 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, bool nrm, float radius, i
         }                                                                                                                                  \
         tile_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * (BSHOT_TL_MINBLOCKS + 1), TL_WARPS * 32, 0, c->stream>>>(                       \
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_blocks, c->d_blk_area, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, \
-            d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points, c->d_rho_hint);                                                   \
+            d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points, c->d_rho_hint, c->d_qsums, gate);                                 \
         tile_single_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(                            \
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, d_nrm_out, c->d_counters,   \
-            c->d_ovf, c->d_fb_list, c->d_rho_hint, nullptr, nullptr, nullptr);                                                             \
+            c->d_ovf, c->d_fb_list, c->d_rho_hint, nullptr, nullptr, nullptr, c->d_qsums, gate);                                           \
     } while (0)
-    if (!seg) BSHOT_TILE(BSHOT_SR_CV, false, true);
-    else if (sr_type == BSHOT_SR_CV) { if (nrm) BSHOT_TILE(BSHOT_SR_CV, true, true); else BSHOT_TILE(BSHOT_SR_CV, true, false); }
-    else if (sr_type == BSHOT_SR_CVS) { if (nrm) BSHOT_TILE(BSHOT_SR_CVS, true, true); else BSHOT_TILE(BSHOT_SR_CVS, true, false); }
-    else { if (nrm) BSHOT_TILE(BSHOT_SR_CVSN, true, true); else BSHOT_TILE(BSHOT_SR_CVSN, true, false); }
+    // nrm: 0 none, 1 normals (d_nrm_out), 2 the nine covariance sums + count of every query into c->d_qsums (detector only)
+#define BSHOT_TILE_SR(SR)                                                              \
+    do {                                                                               \
+        if (nrm == 1) BSHOT_TILE(SR, true, 1);                                         \
+        else if (nrm == 2) BSHOT_TILE(SR, true, 2);                                    \
+        else BSHOT_TILE(SR, true, 0);                                                  \
+    } while (0)
+    if (!seg) BSHOT_TILE(BSHOT_SR_CV, false, 1);
+    else if (sr_type == BSHOT_SR_CV) BSHOT_TILE_SR(BSHOT_SR_CV);
+    else if (sr_type == BSHOT_SR_CVS) BSHOT_TILE_SR(BSHOT_SR_CVS);
+    else BSHOT_TILE_SR(BSHOT_SR_CVSN);
+#undef BSHOT_TILE_SR
 #undef BSHOT_TILE
     count_launch(c, 2);
     return check_launch("tile_kernel");
@@ -405,12 +476,12 @@ int tile_keypoint_normals(Ctx* c, float radius, int max_nn, float4* d_nrm_out) {
     const size_t single_smem = sizeof(SingleWarp) * TS_WARPS;
     static bool attr_set = false;
     if (!attr_set) {
-        BSHOT_CUDA_TRY(cudaFuncSetAttribute(tile_single_kernel<BSHOT_SR_CV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)single_smem));
+        BSHOT_CUDA_TRY(cudaFuncSetAttribute(tile_single_kernel<BSHOT_SR_CV, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)single_smem));
         attr_set = true;
     }
-    tile_single_kernel<BSHOT_SR_CV, false, true><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(
+    tile_single_kernel<BSHOT_SR_CV, false, 1><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(
         c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, nullptr, d_nrm_out, c->d_counters, c->d_ovf,
-        c->d_fb_list, c->d_rho_hint, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos);
+        c->d_fb_list, c->d_rho_hint, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos, nullptr, SumGate{nullptr, nullptr, 0});
     count_launch(c);
     return check_launch("tile_single_kernel (keypoints)");
 }

@@ -206,6 +206,61 @@ def test_tiled_and_warp_paths_agree(bshot, synth):
         assert np.array_equal(a, b, equal_nan=True)
 
 
+@pytest.mark.parametrize("sr_type", [0, 1, 2])
+def test_keypoint_normals_from_detector_sums_equal_a_second_search(bshot, synth, sr_type):
+    """frame path, REFERENCE normals: by default the detector keeps the covariance sums of every point and the keypoint
+    normals are one eigen-solve each; BSHOT_DEFERRED_NORMALS=0 searches the keypoints' neighbourhoods a second time
+    (tile_single_kernel).  Same neighbours, same summation order: identical bits, normals and descriptors."""
+    scan = synth.make_scan("hdl64e", 1)[::2].copy()
+    p = bshot.default_params(top_k=1500, sr_type=sr_type)
+    outs = []
+    for env in (None, "0"):
+        if env:
+            os.environ["BSHOT_DEFERRED_NORMALS"] = env
+        try:
+            with bshot.Context(0, 65536, 2048, 2048) as ctx:
+                f = ctx.extract_frame(scan, p)
+                outs.append((f["kp_idx"], f["bits"], ctx.compute_normals(bshot.NORMALS_REFERENCE, 3000.0, 300)[:1500], ctx.frame_counters()["normals_neighbours"]))
+        finally:
+            os.environ.pop("BSHOT_DEFERRED_NORMALS", None)
+    (ia, ba, na, ca), (ib, bb, nb, cb) = outs
+    assert np.array_equal(ia, ib) and np.array_equal(ba, bb)
+    assert np.array_equal(na.view(np.uint32), nb.view(np.uint32))
+    assert np.isfinite(na[:, :3]).mean() > 0.99 and ca == cb > 0
+
+
+def test_gated_sums_over_a_sequence(bshot, synth):
+    """from the second frame on the detector stores sums only for points whose score reaches 0.95 x the previous frame's
+    K-th score; a keypoint outside the prediction is searched on its own.  Frames 0-2 follow each other, frame 3 is a
+    different scene (scores shift: many keypoints are not predicted).  Same bits with and without the deferred path."""
+    scans = [synth.make_scan("hdl64e", f)[::2].copy() for f in range(3)]
+    rng = np.random.default_rng(4)
+    gx, gy = np.meshgrid(np.arange(180) * 80.0, np.arange(180) * 80.0)                         # one big plane: interior scores
+    odd = np.stack([gx.ravel() - 7000, gy.ravel() + 3000, np.full(gx.size, -1500.0)], 1)       # are near 0, far below the
+    odd = (odd + rng.normal(0, 4.0, odd.shape)).astype(np.float32)                             # street scene's K-th score
+    scans.append(odd)
+    p = bshot.default_params(top_k=1200)
+    outs, misses = [], []
+    for env in (None, "0"):
+        if env:
+            os.environ["BSHOT_DEFERRED_NORMALS"] = env
+        try:
+            with bshot.Context(0, 65536, 2048, 2048) as ctx:
+                res = []
+                for s in scans:
+                    f = ctx.extract_frame(s, p)
+                    res.append((f["kp_idx"], f["bits"]))
+                    if not env:
+                        misses.append(ctx.debug_counters()["fallback_queries"])
+                outs.append(res)
+        finally:
+            os.environ.pop("BSHOT_DEFERRED_NORMALS", None)
+    for (ia, ba), (ib, bb) in zip(*outs):
+        assert np.array_equal(ia, ib) and np.array_equal(ba, bb)
+    assert misses[0] == 0 and misses[1] < 60 and misses[2] < 60, misses   # consecutive frames: the prediction holds
+    assert misses[3] > 0, misses                                          # scene change: the unpredicted keypoints were searched
+
+
 def test_pile_of_equidistant_points(gpu_ctx, oracle):
     """400 invalid returns at (0,0,0) -- the reason for the reference's `skip the origin` test (:63) -- are all
     equidistant from any query: the max_nn-th neighbour falls inside the pile and must be cut by POINT INDEX"""
