@@ -8,6 +8,12 @@
 
 namespace bshot {
 
+#ifndef BSHOT_TL_SPLIT_MIN
+#define BSHOT_TL_SPLIT_MIN 8u   // a group with more pending queries than this is halved while its box is wider than the search radius
+#endif
+#ifndef BSHOT_TS_WIDE
+#define BSHOT_TS_WIDE 1000.0f   // overflow queries with at least this radius (mm) are processed first
+#endif
 #ifndef BSHOT_TL_MINBLOCKS
 #define BSHOT_TL_MINBLOCKS 5
 #endif
@@ -106,7 +112,7 @@ __device__ __forceinline__ void tile_query_outputs(const float4* __restrict__ ti
 }
 
 // ctl = {[0] heavy blocks (front of the list), [1] fallback-list length, [2] work counter (blocks), [3] work counter
-//        (overflow queries), [4] overflow queries, [5] light blocks (back of the list)}
+//        (overflow queries), [4] overflow queries, [5] light blocks (back of the list), [6] wide overflow queries (back of ovf)}
 // counters: [0] / [1] selected neighbours (detector / normals), [2] tiles staged, [3] tile points swept, [4] query
 // attempts, [5] attempts that found fewer than max_nn points, [6] queries handed to the fallback, [7] blocks.
 
@@ -147,17 +153,21 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
         ++st_blocks;
         // first radius: max_nn points on a surface of `area` mm^2 per point
         float rho = BSHOT_TL_SAFETY * sqrtf((float)max_nn * __ldg(blk_area + b) * 0.31830989f);
+        const float rho_block = rho;
         // sub-blocks still to do (bit g = group g)
         unsigned long long todo = 1ull;
         unsigned ngrp = 1;
         while (todo) {
             const unsigned grp = (unsigned)__ffsll((long long)todo) - 1u;
             todo &= todo - 1ull;
+#ifdef BSHOT_TL_GROUP_RHO
+            rho = rho_block;  // every group starts from the block's estimate, not from what a sparser group grew to
+#endif
             tile_block_bbox(sm, grp, tid);
             if (sm.pending == 0) continue;
             // a box much wider than the search radius makes every query sweep far more candidates than its own
             // neighbourhood: halve it first (the tile of each half is smaller; staging is cheap next to the sweeps)
-            if (sm.pending > 8u && ngrp < 64u) {
+            if (sm.pending > BSHOT_TL_SPLIT_MIN && ngrp < 64u) {
                 const float edge = fmaxf(fmaxf(sm.bbox[3] - sm.bbox[0], sm.bbox[4] - sm.bbox[1]), sm.bbox[5] - sm.bbox[2]);
                 if (edge > fminf(rho, R) && tile_block_split(sm, grp, ngrp, tid)) {
                     todo |= (1ull << grp) | (1ull << ngrp);
@@ -189,11 +199,14 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                     }
                     // does not fit a shared tile: every pending query gets its own tile (tile_single_kernel)
                     __syncthreads();
-                    if (tid == 0) { s_slot = atomicAdd(ctl + 4, sm.pending); sm.next_q = 0; }
+                    // wide balls (sparse spots: many rows to walk) are queued from the back of the list and taken first
+                    const bool wide = rr >= BSHOT_TS_WIDE;
+                    if (tid == 0) { s_slot = atomicAdd(ctl + (wide ? 6 : 4), sm.pending); sm.next_q = 0; }
                     __syncthreads();
                     for (unsigned k = tid; k < nq; k += SM::kThreads)
                         if (sm.q_nin[k] >= 0 && sm.q_grp[k] == grp) {
-                            ovf[s_slot + atomicAdd(&sm.next_q, 1u)] = make_uint2(sm.q_pos[k], __float_as_uint(fminf(rr, R)));
+                            const unsigned slot = s_slot + atomicAdd(&sm.next_q, 1u);
+                            ovf[wide ? block_cap - 1u - slot : slot] = make_uint2(sm.q_pos[k], __float_as_uint(fminf(rr, R)));
                             sm.q_nin[k] = -2;
                         }
                     break;
@@ -232,6 +245,9 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
                 if (sm.pending == 0) break;
                 // some spheres held fewer than max_nn points: grow by the density they saw (count ~ r^2 on surfaces)
                 rho = rr * fminf(fmaxf(sqrtf(1.35f * (float)max_nn / (float)max(sm.min_nin, 1)), 1.15f), 3.0f);
+#ifndef BSHOT_TL_NO_REBOX
+                tile_block_bbox(sm, grp, tid);  // the box of the queries that are left: the larger radius stages far less around it
+#endif
             }
         }
         __syncthreads();
@@ -273,20 +289,48 @@ struct SingleWarp {
 };
 
 // stages every point with distance <= rs of q into st.tile; returns the number found (may exceed TS_CAP: tile unusable)
+// stages the ball of radius rs around q into the warp's tile; returns the number of points inside (may exceed TS_CAP: then
+// the tile is unusable).  st.w.u.s.hist[0..63] receives the histogram of the squared distances in 64 equal steps of rs^2,
+// from which the caller picks a radius that fits when this one did not.
+constexpr int TS_HBINS = 64;
 __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
                                                  const float4& q, float rs, SingleWarp& st, unsigned lane) {
     const RowRange rr = row_range(g, q.y, q.z, rs);
-    const float rs2 = rs * rs;
+    const float rs2 = rs * rs, hscale = (float)TS_HBINS / rs2;
+    unsigned* const hist = st.w.u.s.hist;
+    hist[lane] = 0u; hist[lane + 32] = 0u;
+    __syncwarp();
     unsigned n = 0;
-    for (int r0 = 0; r0 < rr.nrows; r0 += 32) {
-        const int r = r0 + (int)lane;
-        unsigned s = 0, len = 0;
+    auto segment_of = [&](int r, unsigned& s_out, unsigned& len_out) {
+        s_out = 0; len_out = 0;
         if (r < rr.nrows) {
             int iy, iz;
             row_coords(rr, r, iy, iz);
             unsigned e;
-            if (row_segment(g, cell_start, q.x, q.y, q.z, rs, iy, iz, s, e)) len = e - s;
+            if (row_segment(g, cell_start, q.x, q.y, q.z, rs, iy, iz, s_out, e)) len_out = e - s_out;
         }
+    };
+    auto take = [&](const float4& p, bool valid) {
+        bool keep = false;
+        float d2 = 0.0f;
+        if (valid) {
+            const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+            d2 = dx * dx + dy * dy + dz * dz;
+            keep = d2 <= rs2;
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
+            if (pos < (unsigned)TS_CAP) st.tile[pos] = p;
+            atomicAdd(&hist[min((int)(d2 * hscale), TS_HBINS - 1)], 1u);
+        }
+        n += __popc(km);
+    };
+    unsigned s_next, len_next;
+    segment_of((int)lane, s_next, len_next);
+    for (int r0 = 0; r0 < rr.nrows; r0 += 32) {
+        const unsigned s = s_next, len = len_next;
+        if (r0 + 32 < rr.nrows) segment_of(r0 + 32 + (int)lane, s_next, len_next);  // the next batch's table reads fly during this one's gathers
         unsigned incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -296,32 +340,25 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
         const unsigned excl = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
         unsigned m = __ballot_sync(0xffffffffu, len > 0);
         if (total >= BSHOT_TS_FLAT_BELOW * (unsigned)__popc(m)) {
-            // long segments (dense spots): one segment after the other, 32 points a step
+            // long segments (dense spots): one segment after the other, 64 points a step
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1u;
                 const unsigned ss = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src);
-                for (unsigned j0 = 0; j0 < ll; j0 += 32) {
-                    const unsigned j = j0 + lane;
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    bool keep = false;
-                    if (j < ll) {
-                        p = __ldg(sorted + ss + j);
-                        const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-                        keep = dx * dx + dy * dy + dz * dz <= rs2;
-                    }
-                    const unsigned km = __ballot_sync(0xffffffffu, keep);
-                    const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
-                    if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
-                    n += __popc(km);
+                for (unsigned j0 = 0; j0 < ll; j0 += 64) {
+                    const unsigned j = j0 + lane, j2 = j + 32;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p;
+                    if (j < ll) p = __ldg(sorted + ss + j);
+                    if (j2 < ll) p2 = __ldg(sorted + ss + j2);
+                    take(p, j < ll);
+                    if (j0 + 32 < ll) take(p2, j2 < ll);
                 }
             }
             continue;
         }
-        // short segments: the 32 of them are read as ONE concatenated index range (a round trip to memory per 32 points,
+        // short segments: the 32 of them are read as ONE concatenated index range (a round trip to memory per 64 points,
         // not per segment) -- every lane finds the segment of its index by bisection over the exclusive prefix
-        for (unsigned j0 = 0; j0 < total; j0 += 32) {
-            const unsigned j = j0 + lane;
+        auto locate = [&](unsigned j) {
             unsigned lo = 0;  // last segment whose first index is <= j (empty segments share the index of their successor)
 #pragma unroll
             for (int step = 16; step > 0; step >>= 1) {
@@ -330,17 +367,16 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
                 if (cand < 32u && e <= j) lo = cand;
             }
             const unsigned ss = __shfl_sync(0xffffffffu, s, lo), se = __shfl_sync(0xffffffffu, excl, lo);
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool keep = false;
-            if (j < total) {
-                p = __ldg(sorted + ss + (j - se));
-                const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-                keep = dx * dx + dy * dy + dz * dz <= rs2;
-            }
-            const unsigned km = __ballot_sync(0xffffffffu, keep);
-            const unsigned pos = n + __popc(km & ((1u << lane) - 1u));
-            if (keep && pos < (unsigned)TS_CAP) st.tile[pos] = p;
-            n += __popc(km);
+            return ss + (j - se);
+        };
+        for (unsigned j0 = 0; j0 < total; j0 += 64) {
+            const unsigned j = j0 + lane, j2 = j + 32;
+            const unsigned a1 = locate(j), a2 = locate(j2);
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p;
+            if (j < total) p = __ldg(sorted + a1);
+            if (j2 < total) p2 = __ldg(sorted + a2);
+            take(p, j < total);
+            if (j0 + 32 < total) take(p2, j2 < total);
         }
     }
     if (n <= (unsigned)TS_CAP) {
@@ -351,6 +387,31 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
     return n;
 }
 
+// after a pass that found more than TS_CAP points: the largest radius (a bin edge of the pass's histogram) whose ball
+// holds at most `room` points; *count_out = how many it holds.  Warp-uniform.
+__device__ __forceinline__ float single_fit_radius(const SingleWarp& st, float rs, unsigned room, unsigned lane, unsigned* count_out) {
+    const unsigned* hist = st.w.u.s.hist;
+    const unsigned c0 = hist[2 * lane], c1 = hist[2 * lane + 1];
+    unsigned incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (unsigned)o) incl += up;
+    }
+    const unsigned cum1 = incl, cum0 = incl - c1;   // points in bins [0, 2 lane] / [0, 2 lane + 1]
+    const unsigned fit1 = __ballot_sync(0xffffffffu, cum1 <= room), fit0 = __ballot_sync(0xffffffffu, cum0 <= room);
+    // cumulative counts grow with the bin: the bins that fit are a prefix
+    const int nb = __popc(fit0) + __popc(fit1);   // number of leading bins whose cumulative count fits
+    unsigned cnt = 0;
+    if (nb > 0) {
+        const int last = nb - 1;
+        const unsigned v1 = __shfl_sync(0xffffffffu, cum1, last >> 1), v0 = __shfl_sync(0xffffffffu, cum0, last >> 1);
+        cnt = (last & 1) ? v1 : v0;
+    }
+    *count_out = cnt;
+    return rs * sqrtf((float)nb / (float)TS_HBINS);
+}
+
 template <int SR, bool SEG, int NRM>
 __global__ void __launch_bounds__(TS_WARPS * 32, 3)
 tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell_start, const float4* __restrict__ sorted,
@@ -358,7 +419,7 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
                    const int* __restrict__ flags, float4* __restrict__ nrm_out, unsigned long long* __restrict__ counters,
                    const uint2* __restrict__ ovf, unsigned* __restrict__ fb_list, float* __restrict__ rho_hint,
                    const int* __restrict__ kp_idx, const int* __restrict__ kp_count, const unsigned* __restrict__ sorted_pos,
-                   float* __restrict__ qsums, SumGate gate) {
+                   float* __restrict__ qsums, SumGate gate, unsigned ovf_cap) {
     extern __shared__ __align__(16) unsigned char single_smem_raw[];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     SingleWarp& st = reinterpret_cast<SingleWarp*>(single_smem_raw)[wid];
@@ -368,7 +429,8 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
     // items: the overflow queries of tile_kernel -- or (kp_idx != nullptr) the detector's keypoints, each with the radius
     // the detector kept for it; result slot = keypoint ordinal (the reference's placement, include/bshot_bits.h:79-81)
     const float sum_thr = sum_gate_threshold(gate);
-    const unsigned n_items = kp_idx ? (unsigned)max(*kp_count, 0) : ctl[4];
+    const unsigned n_wide = kp_idx ? 0u : ctl[6];
+    const unsigned n_items = kp_idx ? (unsigned)max(*kp_count, 0) : ctl[4] + n_wide;
     unsigned long long nbr = 0;
     for (;;) {
         unsigned i = 0;
@@ -380,19 +442,31 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
             const int idx = kp_idx[i];
             item = make_uint2(sorted_pos[idx], __float_as_uint(rho_hint[idx]));
         } else {
-            item = ovf[i];
+            item = i < n_wide ? ovf[ovf_cap - 1u - i] : ovf[i - n_wide];
         }
         const float4 q = __ldg(sorted + item.x);
         float rho = __uint_as_float(item.y), rho_lo = 0.0f, rho_hi = 3.0e38f;
         bool done = false;
+#ifdef BSHOT_TS_DEBUG
+        int dbg_it = 0; unsigned dbg_S = 0; float dbg_rr = 0.f;
+#endif
         for (int it = 0; it < 48 && !done; ++it) {
             const bool at_R = !(rho < R);
             const float rr = at_R ? R : rho;
             const float rs = rr * 1.0001f + 0.1f;
             const float rho2 = at_R ? R2 : __fmul_rn(rr, rr);
             const unsigned S = single_stage(g, cell_start, sorted, q, rs, st, lane);
-            if (S > (unsigned)TS_CAP) {  // too many: shrink (between the brackets when a smaller radius already failed)
+#ifdef BSHOT_TS_DEBUG
+            dbg_it = it + 1; dbg_S = S; dbg_rr = rr;
+#endif
+            if (S > (unsigned)TS_CAP) {  // too many: shrink
                 rho_hi = fminf(rho_hi, rr);
+                // the pass left the distance histogram: take the largest bin edge whose ball fits -- if that ball holds
+                // max_nn points the next pass is the last one
+                unsigned fit_count;
+                const float fit = single_fit_radius(st, rs, (unsigned)TS_CAP - 8u, lane, &fit_count) * 0.9999f;
+                if (fit_count >= (unsigned)max_nn && fit > rho_lo && fit < rho_hi) { rho = fit; continue; }
+                if (fit > rho_lo && fit < rho_hi && fit_count > 0u) rho_lo = fit;   // fewer than max_nn inside: the answer lies beyond it
                 if (rho_lo > 0.0f) { if (!(rho_hi > 1.0005f * rho_lo)) break; rho = sqrtf(rho_lo * rho_hi); }
                 else rho = rr * fminf(fmaxf(sqrtf(0.6f * (float)TS_CAP / (float)S), 0.3f), 0.9f);
                 continue;
@@ -423,6 +497,9 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
             rho = rr * fminf(fmaxf(sqrtf(1.35f * (float)max_nn / (float)max(n_in, 1)), 1.1f), 3.0f);
             if (rho >= rho_hi) { if (!(rho_hi > 1.0005f * rho_lo)) break; rho = sqrtf(rho_lo * rho_hi); }
         }
+#ifdef BSHOT_TS_DEBUG
+        if (lane == 0 && !kp_idx && (i % 97u) == 0u) printf("ovf %u/%u rho0 %.1f final %.1f it %d S %u done %d q %.0f %.0f %.0f\n", i, n_items, __uint_as_float(item.y), dbg_rr, dbg_it, dbg_S, (int)done, q.x, q.y, q.z);
+#endif
         if (!done && lane == 0) { fb_list[atomicAdd(ctl + 1, 1u)] = item.x; atomicAdd(&counters[6], 1ull); }
         __syncwarp();
     }
@@ -436,6 +513,7 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, in
     if (max_nn <= 0 || max_nn > TL_MAXNN) { set_error("tile_neighbourhoods: max_nn %d outside (0, %d]", max_nn, TL_MAXNN); return BSHOT_E_INVALID; }
     // persistent CTAs pulling blocks / queries from work counters; d_nblocks[1..4]: fallback-list length, work counters, overflow count
     BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, 4 * sizeof(unsigned), c->stream));
+    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 6, 0, sizeof(unsigned), c->stream));   // [5] = light blocks, written by the grid build
     const size_t single_smem = sizeof(SingleWarp) * TS_WARPS;
 #define BSHOT_TILE(SR, SEG, NRM)                                                                                                           \
     do {                                                                                                                                   \
@@ -449,7 +527,7 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, in
             d_nrm_out, c->d_counters, c->d_ovf, (unsigned)c->max_points, c->d_rho_hint, c->d_qsums, gate);                                 \
         tile_single_kernel<SR, SEG, NRM><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(                            \
             c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, d_flags, d_nrm_out, c->d_counters,   \
-            c->d_ovf, c->d_fb_list, c->d_rho_hint, nullptr, nullptr, nullptr, c->d_qsums, gate);                                           \
+            c->d_ovf, c->d_fb_list, c->d_rho_hint, nullptr, nullptr, nullptr, c->d_qsums, gate, (unsigned)c->max_points);                  \
     } while (0)
     // nrm: 0 none, 1 normals (d_nrm_out), 2 the nine covariance sums + count of every query into c->d_qsums (detector only)
 #define BSHOT_TILE_SR(SR)                                                              \
@@ -481,7 +559,7 @@ int tile_keypoint_normals(Ctx* c, float radius, int max_nn, float4* d_nrm_out) {
     }
     tile_single_kernel<BSHOT_SR_CV, false, 1><<<(unsigned)c->sm_count * 3u, TS_WARPS * 32, single_smem, c->stream>>>(
         c->d_grid, c->d_cell_start, c->d_sorted, c->d_nblocks, radius, max_nn, c->d_ratio, c->d_keys, nullptr, d_nrm_out, c->d_counters, c->d_ovf,
-        c->d_fb_list, c->d_rho_hint, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos, nullptr, SumGate{nullptr, nullptr, 0});
+        c->d_fb_list, c->d_rho_hint, c->d_kp_idx, c->d_kp_count, c->d_sorted_pos, nullptr, SumGate{nullptr, nullptr, 0}, (unsigned)c->max_points);
     count_launch(c);
     return check_launch("tile_single_kernel (keypoints)");
 }
