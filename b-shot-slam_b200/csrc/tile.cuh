@@ -36,6 +36,9 @@ constexpr int TL_MAXNN = 304;    // largest max_nn the tiled path handles
 constexpr int TL_ROW = 308;      // SoA row pitch in floats (rows 16-byte aligned, 3 rows on disjoint banks)
 constexpr int TL_SEGCAP = 768;   // row segments per tile
 
+#ifndef BSHOT_TL_STAGE_U
+#define BSHOT_TL_STAGE_U 2   // gathers in flight per lane while a block's tile is staged
+#endif
 #ifndef BSHOT_TL_SAFETY
 #define BSHOT_TL_SAFETY 1.15f    // first radius = density prediction x this
 #endif
@@ -483,23 +486,32 @@ __device__ __forceinline__ void tile_stage(const float4* __restrict__ sorted, fl
     const unsigned nseg = sm.nseg;
     for (unsigned k = wid; k < nseg; k += SM::kWarps) {
         const unsigned s = sm.u.st.seg_start[k], len = sm.u.st.seg_len[k];
-        for (unsigned j0 = 0; j0 < len; j0 += 32) {
-            const unsigned j = j0 + lane;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool keep = false;
-            if (j < len) {
-                p = __ldg(sorted + s + j);
-                const float dx = fmaxf(fmaxf(lox - p.x, p.x - hix), 0.0f), dy = fmaxf(fmaxf(loy - p.y, p.y - hiy), 0.0f),
-                            dz = fmaxf(fmaxf(loz - p.z, p.z - hiz), 0.0f);
-                keep = dx * dx + dy * dy + dz * dz <= rs2;
+        for (unsigned j0 = 0; j0 < len; j0 += 32 * BSHOT_TL_STAGE_U) {   // BSHOT_TL_STAGE_U gathers in flight per lane
+            float4 p[BSHOT_TL_STAGE_U];
+#pragma unroll
+            for (int u = 0; u < BSHOT_TL_STAGE_U; ++u) {
+                const unsigned j = j0 + 32u * u + lane;
+                p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < len) p[u] = __ldg(sorted + s + j);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&sm.tile_n, (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
-                if (keep && pos < (unsigned)SM::kCap) sm.tile[pos] = p;
+#pragma unroll
+            for (int u = 0; u < BSHOT_TL_STAGE_U; ++u) {
+                if (j0 + 32u * u >= len) break;
+                const unsigned j = j0 + 32u * u + lane;
+                bool keep = false;
+                if (j < len) {
+                    const float dx = fmaxf(fmaxf(lox - p[u].x, p[u].x - hix), 0.0f), dy = fmaxf(fmaxf(loy - p[u].y, p[u].y - hiy), 0.0f),
+                                dz = fmaxf(fmaxf(loz - p[u].z, p[u].z - hiz), 0.0f);
+                    keep = dx * dx + dy * dy + dz * dz <= rs2;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.tile_n, (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < (unsigned)SM::kCap) sm.tile[pos] = p[u];
+                }
             }
         }
     }

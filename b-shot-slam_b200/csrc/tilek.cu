@@ -279,6 +279,19 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
 #ifndef BSHOT_TS_FLAT_BELOW
 #define BSHOT_TS_FLAT_BELOW 32u   // mean points per non-empty row segment below which the segments are read as one range
 #endif
+#ifdef BSHOT_TS_DEBUG
+__device__ long long g_ts_dbg[8 * 8192];
+void ts_debug_dump() {
+    static long long h[8 * 8192];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_ts_dbg, sizeof(h));
+    long long t0 = 0x7fffffffffffffffll;
+    for (int i = 0; i < 8192; ++i) if (h[8 * i + 4] && h[8 * i + 6] < t0) t0 = h[8 * i + 6];
+    for (int i = 0; i < 8192; ++i) if (h[8 * i + 4]) fprintf(stderr, "TS %d rho0 %lld final %lld it %lld S %lld cyc %lld stage %lld start %lld warp %lld\n", i, h[8 * i] / 10, h[8 * i + 1] / 10, h[8 * i + 2], h[8 * i + 3], h[8 * i + 4], h[8 * i + 5], h[8 * i + 6] - t0, h[8 * i + 7]);
+    static long long z[8 * 8192];
+    cudaMemcpyToSymbol(g_ts_dbg, z, sizeof(z));
+}
+#endif
 constexpr int TS_WARPS = 4;
 constexpr int TS_CAP = 640;
 
@@ -345,13 +358,17 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
                 const int src = __ffs(m) - 1;
                 m &= m - 1u;
                 const unsigned ss = __shfl_sync(0xffffffffu, s, src), ll = __shfl_sync(0xffffffffu, len, src);
-                for (unsigned j0 = 0; j0 < ll; j0 += 64) {
-                    const unsigned j = j0 + lane, j2 = j + 32;
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p;
-                    if (j < ll) p = __ldg(sorted + ss + j);
-                    if (j2 < ll) p2 = __ldg(sorted + ss + j2);
-                    take(p, j < ll);
-                    if (j0 + 32 < ll) take(p2, j2 < ll);
+                for (unsigned j0 = 0; j0 < ll; j0 += 128) {   // four gathers in flight per lane
+                    float4 p[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const unsigned j = j0 + 32u * u + lane;
+                        p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j < ll) p[u] = __ldg(sorted + ss + j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + 32u * u < ll) take(p[u], j0 + 32u * u + lane < ll);
                 }
             }
             continue;
@@ -369,14 +386,18 @@ __device__ __forceinline__ unsigned single_stage(const GridParams& g, const unsi
             const unsigned ss = __shfl_sync(0xffffffffu, s, lo), se = __shfl_sync(0xffffffffu, excl, lo);
             return ss + (j - se);
         };
-        for (unsigned j0 = 0; j0 < total; j0 += 64) {
-            const unsigned j = j0 + lane, j2 = j + 32;
-            const unsigned a1 = locate(j), a2 = locate(j2);
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p;
-            if (j < total) p = __ldg(sorted + a1);
-            if (j2 < total) p2 = __ldg(sorted + a2);
-            take(p, j < total);
-            if (j0 + 32 < total) take(p2, j2 < total);
+        for (unsigned j0 = 0; j0 < total; j0 += 128) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + 32u * u + lane;
+                const unsigned a = locate(j);
+                p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < total) p[u] = __ldg(sorted + a);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + 32u * u < total) take(p[u], j0 + 32u * u + lane < total);
         }
     }
     if (n <= (unsigned)TS_CAP) {
@@ -449,15 +470,19 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
         bool done = false;
 #ifdef BSHOT_TS_DEBUG
         int dbg_it = 0; unsigned dbg_S = 0; float dbg_rr = 0.f;
+        const long long dbg_t0 = clock64(); long long dbg_stage = 0;
 #endif
         for (int it = 0; it < 48 && !done; ++it) {
             const bool at_R = !(rho < R);
             const float rr = at_R ? R : rho;
             const float rs = rr * 1.0001f + 0.1f;
             const float rho2 = at_R ? R2 : __fmul_rn(rr, rr);
+#ifdef BSHOT_TS_DEBUG
+            const long long dbg_s0 = clock64();
+#endif
             const unsigned S = single_stage(g, cell_start, sorted, q, rs, st, lane);
 #ifdef BSHOT_TS_DEBUG
-            dbg_it = it + 1; dbg_S = S; dbg_rr = rr;
+            dbg_it = it + 1; dbg_S = S; dbg_rr = rr; dbg_stage += clock64() - dbg_s0;
 #endif
             if (S > (unsigned)TS_CAP) {  // too many: shrink
                 rho_hi = fminf(rho_hi, rr);
@@ -498,7 +523,11 @@ tile_single_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict
             if (rho >= rho_hi) { if (!(rho_hi > 1.0005f * rho_lo)) break; rho = sqrtf(rho_lo * rho_hi); }
         }
 #ifdef BSHOT_TS_DEBUG
-        if (lane == 0 && !kp_idx && (i % 97u) == 0u) printf("ovf %u/%u rho0 %.1f final %.1f it %d S %u done %d q %.0f %.0f %.0f\n", i, n_items, __uint_as_float(item.y), dbg_rr, dbg_it, dbg_S, (int)done, q.x, q.y, q.z);
+        if (lane == 0 && !kp_idx && i < 8192u) {
+            long long* d = g_ts_dbg + 8 * (size_t)i;
+            d[0] = (long long)(__uint_as_float(item.y) * 10.f); d[1] = (long long)(dbg_rr * 10.f); d[2] = dbg_it; d[3] = dbg_S;
+            d[4] = clock64() - dbg_t0; d[5] = dbg_stage; d[6] = dbg_t0; d[7] = blockIdx.x * 4 + wid;
+        }
 #endif
         if (!done && lane == 0) { fb_list[atomicAdd(ctl + 1, 1u)] = item.x; atomicAdd(&counters[6], 1ull); }
         __syncwarp();
@@ -542,6 +571,9 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, in
     else BSHOT_TILE_SR(BSHOT_SR_CVSN);
 #undef BSHOT_TILE_SR
 #undef BSHOT_TILE
+#ifdef BSHOT_TS_DEBUG
+    ts_debug_dump();
+#endif
     count_launch(c, 2);
     return check_launch("tile_kernel");
 }
