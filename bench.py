@@ -294,7 +294,9 @@ def main():
     mean_n = float(np.mean(npts))
     kern = {"seg_ratio": ("tile_kernel + tile_single_kernel (seg-ratio detector stage)", 16.0 * counters_acc["detector_neighbours"] / K + 12.0 * mean_n),
             "shot_bshot": ("shot_kernel", 32.0 * counters_acc["shot_neighbours"] / K + 48.0 * n_desc),
-            "normals": ("tile_single_kernel (keypoint normals)", 16.0 * counters_acc["normals_neighbours"] / K + 16.0 * n_desc),
+            # REFERENCE normals of the frame path: the neighbour reads happened in the detector pass (covariance sums kept per point);
+            # what is left is 40 B of sums in + 16 B out per keypoint
+            "normals": ("normals_from_sums_kernel (sums kept by the detector pass)", 56.0 * n_desc),
             "voxel_build": ("grid_build", 2 * 16.0 * mean_n)}
     traffic_tab = {}
     try:
