@@ -35,7 +35,7 @@ EXPORTS = [
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
-    "bshot_preprocess", "bshot_preprocess_select", "bshot_icp", "bshot_evaluate_estimation",
+    "bshot_preprocess", "bshot_preprocess_select", "bshot_extract_scan", "bshot_icp", "bshot_evaluate_estimation",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
         L.bshot_icp.argtypes = [vp, vp, sz, vp, sz, vp, ci, vp, vp, vp, vp]
         L.bshot_evaluate_estimation.argtypes = [vp, vp, vp, ci, vp, sz, vp, sz, ci, vp, vp, vp, vp, vp]
         L.bshot_preprocess_select.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, ci, ci, vp, sz, C.POINTER(sz)]
+        L.bshot_extract_scan.argtypes = [vp, C.POINTER(Params), vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, C.POINTER(sz), vp, vp, vp, vp, vp]
         L.bshot_preprocess.argtypes = [vp, vp, vp, vp, sz, vp, sz, C.c_double, C.c_double, vp, sz, C.POINTER(sz)]
         L.bshot_comm_create.argtypes = [vp, ci, ci, sz]
         L.bshot_comm_export.argtypes = [vp, vp]
@@ -482,6 +483,23 @@ class Context:
         _chk(lib().bshot_preprocess_select(self.h, _p(az), _p(ve), _p(di), az.size, _p(ring), ring.size, vert_init, lowpt_th, _p(sel),
                                            0 if sel is None else sel.size, 0 if sel is None else 1, 1 if save_selected else 0, _p(out), out.shape[0], C.byref(n)))
         return out[:n.value].copy()
+
+    def extract_scan(self, azimuth_deg, vertical_deg, distance, ring_deg, params, vert_init=-0.6, lowpt_th=-1950.0, want_cloud=True):
+        """lasers -> preprocessed cloud (device resident) -> keypoints + descriptors in one call"""
+        az = np.ascontiguousarray(azimuth_deg, dtype=np.float64)
+        ve = np.ascontiguousarray(vertical_deg, dtype=np.float64)
+        di = np.ascontiguousarray(distance, dtype=np.uint16)
+        ring = np.ascontiguousarray(ring_deg, dtype=np.float64)
+        k = params.top_k
+        cloud = np.empty((max(az.size, 1), 3), np.float32) if want_cloud else None
+        idx, kp, ratio, bits = np.empty(k, np.int32), np.empty((k, 3), np.float32), np.empty(k, np.float32), np.empty((k, 6), np.uint64)
+        npts, nk = C.c_size_t(), C.c_int()
+        _chk(lib().bshot_extract_scan(self.h, C.byref(params), _p(az), _p(ve), _p(di), az.size, _p(ring), ring.size, vert_init, lowpt_th, _p(cloud),
+                                      0 if cloud is None else cloud.shape[0], C.byref(npts), _p(idx), _p(kp), _p(ratio), _p(bits), C.byref(nk)))
+        n = nk.value
+        self.n_points, self.n_kp = npts.value, n
+        return dict(cloud=None if cloud is None else cloud[:npts.value].copy(), n_points=npts.value, kp_idx=idx[:n].copy(), kp_xyz=kp[:n].copy(),
+                    seg_ratio=ratio[:n].copy(), bits=bits[:n].copy())
 
     def frame_commit(self):
         _chk(lib().bshot_frame_commit(self.h))

@@ -764,6 +764,36 @@ int bshot_extract_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz,
     return sync(ctx);
 }
 
+int bshot_extract_scan(bshot_ctx* ctx, const bshot_params* p, const double* azimuth_deg, const double* vertical_deg, const unsigned short* distance, size_t n,
+                       const double* ring_deg, size_t nv, double vert_init_rad, double lowpt_th, float* cloud_xyz_out, size_t cloud_cap,
+                       size_t* n_points_out, int* kp_idx_out, float* kp_xyz_out, float* seg_ratio_out, uint64_t* bits_out, int* n_kp_out) {
+    CHECK_CTX(ctx);
+    bshot_params dp;
+    if (!p) { bshot_params_default(&dp); p = &dp; }
+    if (n && (!azimuth_deg || !vertical_deg || !distance)) { set_error("bshot_extract_scan: null input"); return BSHOT_E_INVALID; }
+    if (nv && !ring_deg) { set_error("bshot_extract_scan: null ring table"); return BSHOT_E_INVALID; }
+    if (n > 0xFFFFFFFFull) { set_error("bshot_extract_scan: too many returns"); return BSHOT_E_CAPACITY; }
+    // Preprocessor::run; the cloud stays on the device and goes straight into the front end (no host round trip)
+    size_t kept = 0;
+    const float* d_cloud = nullptr;
+    BSHOT_TRY(preprocess_run(ctx, azimuth_deg, vertical_deg, distance, n, ring_deg, nv, vert_init_rad, lowpt_th, nullptr, 1, cloud_xyz_out,
+                             cloud_xyz_out ? cloud_cap : std::max<size_t>(n, 1), &kept, &d_cloud));
+    if (n_points_out) *n_points_out = kept;
+    if (cloud_xyz_out && kept > cloud_cap) { set_error("bshot_extract_scan: %zu points kept > capacity %zu", kept, cloud_cap); return BSHOT_E_CAPACITY; }
+    BSHOT_TRY(frame_args_ok(ctx, p, kept, 12, "bshot_extract_scan"));
+    BSHOT_TRY(frame_extract(ctx, p, d_cloud, kept, 3));
+    BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
+    BSHOT_TRY(sync(ctx));
+    const int k = std::min(ctx->h_scratch[0], p->top_k);
+    ctx->n_kp = (size_t)k;
+    if (n_kp_out) *n_kp_out = k;
+    if (kp_idx_out) BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * k));
+    if (seg_ratio_out) BSHOT_TRY(d2h(ctx, seg_ratio_out, ctx->d_kp_ratio, sizeof(float) * k));
+    if (bits_out) BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, 48 * (size_t)k));
+    if (kp_xyz_out && k) BSHOT_CUDA_TRY(cudaMemcpy2DAsync(kp_xyz_out, 12, ctx->d_kp, 16, 12, k, cudaMemcpyDeviceToHost, ctx->stream));
+    return sync(ctx);
+}
+
 int bshot_frame_commit(bshot_ctx* ctx) {
     CHECK_CTX(ctx);
     if (ctx->last_top_k == 0) { set_error("bshot_frame_commit: no extracted frame"); return BSHOT_E_STATE; }

@@ -368,7 +368,9 @@ struct Carver {
 // host inputs -> host output (xyz_out holds cap points).  Synchronous: two stream synchronisations (the number of columns
 // sizes the per-column scratch; the number of kept points sizes the copy back).
 int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const unsigned short* dist, size_t n, const double* ring_deg, size_t nv,
-                   double vert_init, double lowpt_th, const unsigned char* sel, int save_sel, float* xyz_out, size_t cap, size_t* n_out) {
+                   double vert_init, double lowpt_th, const unsigned char* sel, int save_sel, float* xyz_out, size_t cap, size_t* n_out,
+                   const float** d_xyz_out) {
+    if (d_xyz_out) *d_xyz_out = nullptr;
     if (n_out) *n_out = 0;
     if (n == 0) return BSHOT_OK;
     if (nv > 256) { set_error("bshot_preprocess: more than 256 rings"); return BSHOT_E_INVALID; }
@@ -437,6 +439,7 @@ int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const u
     if (h_ctl[1] == 2) { set_error("bshot_preprocess: more than %d returns in one azimuth column", PRE_LMAX); return BSHOT_E_CAPACITY; }
     const size_t kept = h_ctl[2];
     if (n_out) *n_out = kept;
+    if (d_xyz_out) *d_xyz_out = d_out;   // valid until the next preprocessor call on this context
     if (xyz_out && kept) {
         BSHOT_CUDA_TRY(cudaMemcpyAsync(xyz_out, d_out, 12 * std::min(kept, cap), cudaMemcpyDeviceToHost, c->stream));
         BSHOT_CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -70,7 +70,8 @@ int icp_run(Ctx* c, const float* src_xyz, size_t n_src, const float* tgt_xyz, si
 // scan preprocessor (preprocess.cu); scratch_reserve grows one of the context's on-demand scratch buffers
 int scratch_reserve(Ctx* c, int which, size_t bytes);
 int preprocess_run(Ctx* c, const double* az_deg, const double* vert_deg, const unsigned short* dist, size_t n, const double* ring_deg, size_t nv,
-                   double vert_init, double lowpt_th, const unsigned char* sel, int save_sel, float* xyz_out, size_t cap, size_t* n_out);
+                   double vert_init, double lowpt_th, const unsigned char* sel, int save_sel, float* xyz_out, size_t cap, size_t* n_out,
+                   const float** d_xyz_out = nullptr);
 
 // whole frame on the resident cloud (frame.cu)
 int frame_extract(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int stride_floats);

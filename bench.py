@@ -347,10 +347,11 @@ def main():
         map_match = bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks)
 
     # ---- extras at N = 1 ------------------------------------------------------------------------------
-    c2 = c3_sweep = None
+    c2 = c3_sweep = pose_loop = None
     if rank == 0 and world == 1 and not args.no_extras and not args.map_only:
         c2 = bench_c2_sequence(bs, synth, local_rank, flush)
         c3_sweep = bench_c3_sweep(bs, synth, local_rank, flush)
+        pose_loop = bench_pose_loop(bs, synth, local_rank)
 
     # ---- CPU baseline (rank 0, N = 1 only; bounded sample) --------------------------------------------
     cpu_baseline = None
@@ -378,7 +379,7 @@ def main():
                        "ms_per_step_distribution": percentile_summary(per_step), "descriptors_per_frame": n_desc,
                        "detector_mode": "exact: fp32 running sums replayed in neighbour order (scores / keypoint indices bit-identical to the oracle)"},
             "stages_ms": stages, "roofline": roofline, "roofline_others": roofline_others, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c2": c2, "c3_radius_sweep": c3_sweep,
+            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c2": c2, "c3_radius_sweep": c3_sweep, "pose_loop": pose_loop,
         }
         print(json.dumps(line))
     ctx.close()
@@ -506,6 +507,51 @@ def bench_c2_sequence(bs, synth, device, flush, n_frames=120, top_k=2048):
     ctx.close()
     return {"workload": "C2", "sensor": "hdl32e", "top_k": top_k, "points_per_frame": int(np.mean([len(f) for f in frames])),
             "ms_per_frame": percentile_summary(ms), "descriptors_per_s": top_k / (float(np.mean(ms)) * 1e-3), "stages_ms": acc}
+
+
+def bench_pose_loop(bs, synth, device, n_frames=12, top_k=600):
+    """the reference's whole per-frame loop (test/odometry_test.cpp:143-184) from raw laser returns to a pose, every stage
+    through the C ABI with HOST buffers: Preprocessor::run + extractKeypoints + computeDescriptors (bshot_extract_scan),
+    featureMatching against the device-resident map (bshot_match_frame_to_map + bshot_ransac), evaluateEstimation
+    (gate + ICP), updateMap.  Reference defaults: HDL-32E, K = 600.  Wall clock per frame (synchronous calls)."""
+    import time
+    rot = [synth.make_lasers("hdl32e", f) for f in range(n_frames)]
+    p = bs.default_params(top_k=top_k)
+    ctx = bs.Context(device, max_points=131072, max_keypoints=1024, max_targets=1 << 16)
+    ctx.gmap_create(1 << 16, 4096)
+    stage = {k: [] for k in ("extract_scan", "match_to_map", "ransac", "gate_icp", "map_update", "frame")}
+    pose_ref, poses = np.eye(4, dtype=np.float32), []
+    for rep in range(2):                                  # first pass warms up (scratch growth, module load)
+        ctx.reset(); ctx.gmap_reset()
+        pose_ref, poses = np.eye(4, dtype=np.float32), []
+        for k, L in enumerate(rot):
+            t0 = time.perf_counter()
+            f = ctx.extract_scan(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"], p, want_cloud=False)
+            t1 = time.perf_counter()
+            if k == 0:
+                pairs, tgt = ctx.match_mutual(f["bits"], f["bits"])[0], f["kp_xyz"]
+            else:
+                r = ctx.match_frame_to_map(pose_ref[:3, 3], 100000.0, pose_ref[:3], target_cap=1 << 16)
+                pairs, tgt = r["pairs"], r["target_xyz"]
+            t2 = time.perf_counter()
+            rs = ctx.ransac(f["kp_xyz"], tgt, pairs)
+            t3 = time.perf_counter()
+            ev = ctx.evaluate_estimation(rs["transform"], pose_ref, len(rs["pairs"]), f["kp_xyz"], tgt, run_icp=True)
+            t4 = time.perf_counter()
+            ctx.gmap_update_from_frame(ev["T_best"][:3]); ctx.frame_commit(); ctx.sync()
+            t5 = time.perf_counter()
+            pose_ref = ev["T_best"]
+            poses.append(pose_ref[:3, 3].tolist())
+            if rep == 1 and k > 0:
+                for name, a, b in (("extract_scan", t0, t1), ("match_to_map", t1, t2), ("ransac", t2, t3), ("gate_icp", t3, t4),
+                                   ("map_update", t4, t5), ("frame", t0, t5)):
+                    stage[name].append((b - a) * 1e3)
+    n_map = ctx.gmap_size()[0]
+    ctx.close()
+    return {"workload": "lasers -> pose, HDL-32E rotations (69 440 returns), K = 600, frame-to-map", "frames": n_frames - 1,
+            "ms_per_frame_wall": {k: float(np.median(v)) for k, v in stage.items()}, "map_keypoints": int(n_map),
+            "last_position_mm": poses[-1], "truth_last_position_mm": [500.0 * (n_frames - 1), 0.0, 0.0],
+            "note": "medians of synchronous host-buffer calls incl. Python/ctypes overhead; the sensor moves 500 mm per frame along x"}
 
 
 def bench_c3_sweep(bs, synth, device, flush, top_k=10000):

@@ -245,6 +245,16 @@ int bshot_preprocess_select(bshot_ctx* ctx, const double* azimuth_deg, const dou
                             const int* select_list, size_t n_select, int have_select_list, int save_selected, float* xyz_out,
                             size_t cap, size_t* n_out);
 
+/* Preprocessor::run + extractKeypoints + computeDescriptors of one rotation (test/odometry_test.cpp:143-177) in one call:
+ * the preprocessed cloud stays on the device and feeds the front end directly.  cloud_xyz_out (cloud_cap x 3 floats) may be
+ * NULL when the host does not need the cloud; the keypoint outputs are those of bshot_extract_frame (kp_idx indexes the
+ * preprocessed cloud).  Follow with bshot_match_frame_to_map / bshot_ransac / bshot_evaluate_estimation /
+ * bshot_gmap_update_from_frame / bshot_frame_commit as after bshot_extract_frame. */
+int bshot_extract_scan(bshot_ctx* ctx, const bshot_params* p, const double* azimuth_deg, const double* vertical_deg,
+                       const unsigned short* distance, size_t n, const double* ring_deg, size_t nv, double vert_init_rad,
+                       double lowpt_th, float* cloud_xyz_out, size_t cloud_cap, size_t* n_points_out, int* kp_idx_out,
+                       float* kp_xyz_out, float* seg_ratio_out, uint64_t* bits_out, int* n_kp_out);
+
 /* ---- sharded map matching (north_star multi-GPU piece) -------------------------------------- */
 /* The accumulated map descriptors (Map::getKeypoints output, include/mymap.h:34-38) are split
  * across ranks; each rank keeps its shard resident.  global_base = index of the shard's first

@@ -57,3 +57,21 @@ def test_lasers_to_pose_four_frames(bshot, oracle, synth):
     for k, T in enumerate(poses):
         assert np.allclose(T[:3, :3], np.eye(3), atol=0.02), (k, T)
         assert abs(T[0, 3] - 500.0 * k) < 350.0 and abs(T[1, 3]) < 350.0 and abs(T[2, 3]) < 350.0, (k, T[:3, 3])
+
+
+def test_extract_scan_equals_preprocess_then_extract_frame(bshot, synth):
+    """bshot_extract_scan keeps the preprocessed cloud on the device: same cloud, keypoints and descriptors as the two calls"""
+    p = bshot.default_params(top_k=600)
+    L = synth.make_lasers("hdl32e", 2)
+    with bshot.Context(0, 131072, 1024, 1024) as a, bshot.Context(0, 131072, 1024, 1024) as b:
+        cloud = a.preprocess(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"])
+        fa = a.extract_frame(cloud, p)
+        fb = b.extract_scan(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"], p)
+        assert np.array_equal(fb["cloud"], cloud) and fb["n_points"] == len(cloud)
+        for key in ("kp_idx", "kp_xyz", "seg_ratio", "bits"):
+            assert np.array_equal(fa[key], fb[key]), key
+        fc = b.extract_scan(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"], p, want_cloud=False)
+        assert fc["cloud"] is None and np.array_equal(fc["bits"], fa["bits"])
+        with pytest.raises(bshot.BshotError):   # more points than the context was created for
+            with bshot.Context(0, 1024, 64, 64) as small:
+                small.extract_scan(L["azimuth"], L["vertical"], L["distance"], L["ring_deg"], bshot.default_params(top_k=64))
