@@ -31,7 +31,7 @@ EXPORTS = [
     "bshot_stage_times", "bshot_frame_counters", "bshot_map_reset", "bshot_map_append",
     "bshot_map_size", "bshot_match_shard_dev", "bshot_match_dev", "bshot_merge_cands_dev",
     "bshot_match_map", "bshot_reverse_owned_dev", "bshot_apply_rq_dev", "bshot_push_cands_dev",
-    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev", "bshot_comm_create", "bshot_comm_export", "bshot_comm_import",
+    "bshot_reverse_owned_push_dev", "bshot_peer_barrier_dev", "bshot_peer_barrier_timeouts", "bshot_peer_barrier_reset", "bshot_launch_count", "bshot_popc_peak", "bshot_debug_counters", "bshot_map_append_dev", "bshot_comm_create", "bshot_comm_export", "bshot_comm_import",
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
@@ -134,6 +134,7 @@ def lib():
         L.bshot_push_cands_dev.argtypes = [vp, vp, sz, vp, ci, ci]
         L.bshot_peer_barrier_dev.argtypes = [vp, vp, ci, ci]
         L.bshot_peer_barrier_timeouts.argtypes = [vp, C.POINTER(C.c_uint)]
+        L.bshot_peer_barrier_reset.argtypes = [vp]
         L.bshot_reverse_owned_push_dev.argtypes = [vp, vp, sz, C.c_uint64, vp, vp, ci, ci]
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
@@ -570,6 +571,9 @@ class Context:
 
     def peer_barrier_dev(self, d_peer_flag_ptrs, nranks, rank):
         _chk(lib().bshot_peer_barrier_dev(self.h, d_peer_flag_ptrs, nranks, rank))
+
+    def peer_barrier_reset(self):
+        _chk(lib().bshot_peer_barrier_reset(self.h))
 
     def peer_barrier_timeouts(self):
         e = C.c_uint()

@@ -647,6 +647,14 @@ int bshot_peer_barrier_dev(bshot_ctx* ctx, const void* d_peer_flag_ptrs, int nra
     return hamming_peer_barrier(ctx, d_peer_flag_ptrs, (unsigned)nranks, (unsigned)rank);
 }
 
+int bshot_peer_barrier_reset(bshot_ctx* ctx) {
+    CHECK_CTX(ctx);
+    BSHOT_TRY(sync(ctx));
+    ctx->peer_epoch = 0;   // the epoch belongs to the (freshly zeroed) flag array the caller is about to use
+    BSHOT_CUDA_TRY(cudaMemsetAsync(ctx->d_pair_count + 3, 0, sizeof(int), ctx->stream));
+    return sync(ctx);
+}
+
 int bshot_peer_barrier_timeouts(bshot_ctx* ctx, unsigned* epoch_out) {
     CHECK_CTX(ctx);
     if (!epoch_out) { set_error("bshot_peer_barrier_timeouts: null output"); return BSHOT_E_INVALID; }

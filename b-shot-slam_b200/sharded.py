@@ -185,6 +185,7 @@ class DeviceShardedMatcher:
                 f = symm_mem.empty(64, dtype=torch.int32, device=dev)
                 g.zero_(); r.fill_(-1); f.zero_()
                 torch.cuda.synchronize()
+                ctx.peer_barrier_reset()   # the barrier epoch belongs to this (zeroed) flag array
                 hs = [symm_mem.rendezvous(t, dist.group.WORLD) for t in (g, r, f)]
                 self.peer = dict(g=g, r=r, f=f, handles=hs, pg=int(hs[0].buffer_ptrs_dev), pr=int(hs[1].buffer_ptrs_dev),
                                  pf=int(hs[2].buffer_ptrs_dev))

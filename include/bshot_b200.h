@@ -300,6 +300,10 @@ int bshot_push_cands_dev(bshot_ctx* ctx, const void* d_cands, size_t nq, const v
  * before the first barrier).  Every rank must issue the same sequence of barriers.  A rank that never arrives makes the
  * others give up after ~2 s instead of hanging; bshot_peer_barrier_timeouts then reports the epoch (0 = none). */
 int bshot_peer_barrier_dev(bshot_ctx* ctx, const void* d_peer_flag_ptrs, int nranks, int rank);
+/* start a new flag array: every rank calls this (collectively) right after its zeroed flag array is allocated, so the
+ * barrier epoch always matches the flags -- a second matcher on the same context, or one created after a failed call,
+ * starts in step.  Also clears the timeout record. */
+int bshot_peer_barrier_reset(bshot_ctx* ctx);
 int bshot_peer_barrier_timeouts(bshot_ctx* ctx, unsigned* epoch_out);
 int bshot_reverse_owned_push_dev(bshot_ctx* ctx, const void* d_q, size_t nq, uint64_t global_base,
                                  const void* d_merged, const void* d_peer_rq_ptrs, int nranks, int rank);
