@@ -382,6 +382,8 @@ static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void*
         set_error("hamming_top2: sizes exceed 32-bit index range");
         return BSHOT_E_INVALID;
     }
+    // the distance matrix on the tensor cores (hamming_tc.cu); the fused column minima stay with the POPC kernel
+    if (c->match_tc && !d_colmin) return hamming_tc_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);
     // whole waves: the grid is a multiple of (SMs x resident CTAs per SM) whenever the problem is big enough,
@@ -535,7 +537,7 @@ namespace bshot {
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                      bshot_cand* d_out, const unsigned* d_nq, const unsigned* d_nt) {
     if (nq == 0) return BSHOT_OK;
-    if (nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
+    if (!c->match_tc && nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
         return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right), d_nq, d_nt);
     BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr, d_nq, d_nt));
     return hamming_reverse(c, d_q, nq, d_t, global_base, d_out, d_nq);

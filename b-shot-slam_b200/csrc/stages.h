@@ -51,6 +51,10 @@ int comm_set_peers(Ctx* c, void* const* region_ptrs);
 int hamming_preload_sharded();
 int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long global_base, bshot_cand* d_out);
 
+// tensor-core distance matrix (hamming_tc.cu): per-split top-2 partials in c->d_partial
+int hamming_tc_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
+                        const unsigned* d_nt, unsigned* nsplit_out);
+
 // GPU-resident global map (gmap.cu)
 int gmap_create(Ctx* c, size_t max_entries, size_t max_blocks);
 void gmap_free(Ctx* c);

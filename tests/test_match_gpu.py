@@ -1,9 +1,27 @@
 """a10/a11 parity: CUDA Hamming search (through the C ABI) vs the oracle restatement of
 src/lidar_odometry.cpp:212-242 + minVect (include/bshot_bits.h:6-20). Bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["popc", "tensor-core"])
+def mctx(request, gpu_ctx, bshot):
+    """the same checks on both distance-matrix kernels: XOR + POPC (hamming.cu) and tcgen05 int8 dot products
+    (hamming_tc.cu, selected when a context is created with BSHOT_MATCH_TC=1)"""
+    if request.param == "popc":
+        yield gpu_ctx
+        return
+    os.environ["BSHOT_MATCH_TC"] = "1"
+    try:
+        ctx = bshot.Context(0, 131072, 16384, 1 << 21)
+    finally:
+        os.environ.pop("BSHOT_MATCH_TC", None)
+    yield ctx
+    ctx.close()
 
 
 def _check(ctx, oracle, q, t):
@@ -19,20 +37,20 @@ def _check(ctx, oracle, q, t):
 
 @pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (7, 5), (600, 600), (600, 1337), (2048, 2048),
                                    (257, 129), (1025, 4097), (3000, 20000)])
-def test_random(gpu_ctx, oracle, synth, nq, nt):
+def test_random(mctx, oracle, synth, nq, nt):
     q = synth.random_descriptors(nq, seed=nq)
     t = synth.random_descriptors(nt, seed=1000 + nt)
-    _check(gpu_ctx, oracle, q, t)
+    _check(mctx, oracle, q, t)
 
 
-def test_sparse_reference_like(gpu_ctx, oracle, synth):
+def test_sparse_reference_like(mctx, oracle, synth):
     # <= 40 bits set (what the reference's normals quirk yields): many distance ties
     q = synth.random_descriptors(2048, seed=3, density=33)
     t = synth.random_descriptors(5000, seed=4, density=33)
-    _check(gpu_ctx, oracle, q, t)
+    _check(mctx, oracle, q, t)
 
 
-def test_duplicates_and_ties(gpu_ctx, oracle, synth):
+def test_duplicates_and_ties(mctx, oracle, synth):
     rng = np.random.default_rng(11)
     t = synth.random_descriptors(4096, seed=5)
     # planted exact duplicates at several indices: lowest index must win
@@ -46,16 +64,16 @@ def test_duplicates_and_ties(gpu_ctx, oracle, synth):
         for b in rng.integers(0, 352, rng.integers(1, 4)):
             bits[i, b] ^= True
     q = synth.pack_bits(bits)
-    _check(gpu_ctx, oracle, q, t)
+    _check(mctx, oracle, q, t)
 
 
-def test_self_match_initial_frame(gpu_ctx, oracle, synth):
+def test_self_match_initial_frame(mctx, oracle, synth):
     # src/lidar_odometry.cpp:187-194: the first frame is matched against itself
     d = synth.random_descriptors(600, seed=9, density=33)
-    _check(gpu_ctx, oracle, d, d)
+    _check(mctx, oracle, d, d)
 
 
-def test_all_ones_invalid_descriptors(gpu_ctx, oracle, synth):
+def test_all_ones_invalid_descriptors(mctx, oracle, synth):
     # NaN SHOT binarises to all 352 bits set (include/bshot_bits.h:166-260)
     q = synth.random_descriptors(300, seed=21)
     t = synth.random_descriptors(700, seed=22)
@@ -64,28 +82,28 @@ def test_all_ones_invalid_descriptors(gpu_ctx, oracle, synth):
     q[5] = ones
     t[17] = ones
     t[400] = ones
-    _check(gpu_ctx, oracle, q, t)
+    _check(mctx, oracle, q, t)
 
 
-def test_empty_inputs(gpu_ctx, synth):
+def test_empty_inputs(mctx, synth):
     q = synth.random_descriptors(10, seed=1)
     e = np.zeros((0, 6), np.uint64)
-    g = gpu_ctx.match(q, e)
+    g = mctx.match(q, e)
     assert (g["left_idx"] == -1).all() and (g["left_dist"] == -1).all()
-    g = gpu_ctx.match(e, q)
+    g = mctx.match(e, q)
     assert (g["right_idx"] == -1).all()
-    pairs, dist = gpu_ctx.match_mutual(q, e)
+    pairs, dist = mctx.match_mutual(q, e)
     assert pairs.shape[0] == 0
 
 
-def test_single_target_has_no_runner_up(gpu_ctx, synth):
+def test_single_target_has_no_runner_up(mctx, synth):
     q = synth.random_descriptors(33, seed=1)
     t = synth.random_descriptors(1, seed=2)
-    g = gpu_ctx.match(q, t)
+    g = mctx.match(q, t)
     assert (g["left_idx"] == 0).all() and (g["left_idx2"] == -1).all() and (g["left_dist2"] == -1).all()
 
 
-def test_sharded_merge_equals_single(gpu_ctx, bshot, oracle, synth):
+def test_sharded_merge_equals_single(mctx, bshot, oracle, synth):
     """8 emulated shards on one GPU: per-shard candidates + merge == single-pass result."""
     import torch
     nq, nt, shards = 1000, 40000, 8
@@ -102,9 +120,9 @@ def test_sharded_merge_equals_single(gpu_ctx, bshot, oracle, synth):
     torch.cuda.synchronize()
     for r in range(shards):
         lo, hi = r * per, min(nt, (r + 1) * per)
-        gpu_ctx.match_dev(dq.data_ptr(), nq, dt[lo:hi].data_ptr(), hi - lo, lo, True, cands[r].data_ptr())
-    gpu_ctx.merge_cands_dev(cands.data_ptr(), shards, nq, merged.data_ptr())
-    gpu_ctx.sync()
+        mctx.match_dev(dq.data_ptr(), nq, dt[lo:hi].data_ptr(), hi - lo, lo, True, cands[r].data_ptr())
+    mctx.merge_cands_dev(cands.data_ptr(), shards, nq, merged.data_ptr())
+    mctx.sync()
     rec = merged.cpu().numpy().view(bshot.CAND_DTYPE).reshape(nq)
     u = bshot.unpack_cands(rec)
     o = oracle.match(q, t, want_right=True)
