@@ -118,7 +118,7 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("BSHOT_WARP_PATH")) c->force_warp_path = (atoi(e) != 0);
-    if (const char* e = getenv("BSHOT_MATCH_TC")) c->match_tc = (atoi(e) != 0);
+    if (const char* e = getenv("BSHOT_MATCH_TC")) c->match_tc = atoi(e);
     if (const char* e = getenv("BSHOT_DEFERRED_NORMALS")) c->no_deferred_normals = (atoi(e) == 0);
     if (const char* e = getenv("BSHOT_MAX_CELLS_LOG2")) {  // tuning knob: voxel table size (default 2^22 cells)
         const int v = atoi(e);

@@ -383,6 +383,7 @@ static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void*
         return BSHOT_E_INVALID;
     }
     // the distance matrix on the tensor cores (hamming_tc.cu); the fused column minima stay with the POPC kernel
+    if (c->match_tc == 2 && !d_colmin) return hamming_tc2_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     if (c->match_tc && !d_colmin) return hamming_tc_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);

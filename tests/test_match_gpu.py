@@ -8,14 +8,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["popc", "tensor-core"])
+@pytest.fixture(scope="module", params=["popc", "tensor-core", "tensor-core-pipelined"])
 def mctx(request, gpu_ctx, bshot):
     """the same checks on both distance-matrix kernels: XOR + POPC (hamming.cu) and tcgen05 int8 dot products
-    (hamming_tc.cu, selected when a context is created with BSHOT_MATCH_TC=1)"""
+    (hamming_tc.cu, selected when a context is created with BSHOT_MATCH_TC=1; hamming_tc2.cu, the warp-specialised
+    pipeline whose multiply leaves the packed (distance, column) key, with BSHOT_MATCH_TC=2)"""
     if request.param == "popc":
         yield gpu_ctx
         return
-    os.environ["BSHOT_MATCH_TC"] = "1"
+    os.environ["BSHOT_MATCH_TC"] = "1" if request.param == "tensor-core" else "2"
     try:
         ctx = bshot.Context(0, 131072, 16384, 1 << 21)
     finally:
