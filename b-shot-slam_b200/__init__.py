@@ -35,7 +35,7 @@ EXPORTS = [
     "bshot_comm_region", "bshot_comm_import_ptrs", "bshot_comm_destroy", "bshot_comm_check", "bshot_match_map_sharded_dev",
     "bshot_match_map_sharded", "bshot_gmap_create", "bshot_gmap_reset", "bshot_gmap_size", "bshot_gmap_add",
     "bshot_gmap_update_from_frame", "bshot_gmap_get_keypoints", "bshot_extract_frame", "bshot_match_frame_to_map", "bshot_frame_commit", "bshot_ransac",
-    "bshot_preprocess", "bshot_preprocess_select", "bshot_extract_scan", "bshot_icp", "bshot_evaluate_estimation",
+    "bshot_preprocess", "bshot_preprocess_select", "bshot_extract_scan", "bshot_icp", "bshot_evaluate_estimation", "bshot_set_matcher",
 ]
 
 
@@ -139,6 +139,7 @@ def lib():
         L.bshot_launch_count.argtypes = [vp]
         L.bshot_launch_count.restype = C.c_ulonglong
         L.bshot_popc_peak.argtypes = [vp, C.POINTER(C.c_double)]
+        L.bshot_set_matcher.argtypes = [vp, ci]
         L.bshot_debug_counters.argtypes = [vp, C.POINTER(C.c_ulonglong * 8)]
         _LIB = L
     return _LIB
@@ -214,6 +215,10 @@ class Context:
 
     def launch_count(self):
         return int(lib().bshot_launch_count(self.h))
+
+    def set_matcher(self, kind):
+        """-1 by problem size (default), 0 XOR + POPC, 1 tensor cores, 2 / 3 pipelined tensor-core kernel"""
+        _chk(lib().bshot_set_matcher(self.h, int(kind)))
 
     def popc_peak(self):
         v = C.c_double()

@@ -266,6 +266,13 @@ int bshot_ctx_reset(bshot_ctx* ctx) {
 
 unsigned long long bshot_launch_count(bshot_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 
+int bshot_set_matcher(bshot_ctx* ctx, int kind) {
+    CHECK_CTX(ctx);
+    if (kind < -1 || kind > 3) { set_error("bshot_set_matcher: kind %d (expected -1 .. 3)", kind); return BSHOT_E_INVALID; }
+    ctx->match_tc = kind;
+    return BSHOT_OK;
+}
+
 int bshot_popc_peak(bshot_ctx* ctx, double* out) {
     CHECK_CTX(ctx);
     if (!out) { set_error("null output"); return BSHOT_E_INVALID; }

@@ -99,7 +99,7 @@ struct Gmap {
 struct Ctx {
     int device = 0;
     int sm_count = 148;
-    int match_tc = 0;                  // BSHOT_MATCH_TC=1: Hamming distance matrix on the tensor cores (hamming_tc.cu); 2: the pipelined kernel (hamming_tc2.cu)
+    int match_tc = -1;                 // bshot_set_matcher / BSHOT_MATCH_TC: -1 by problem size, 0 XOR + POPC (hamming.cu), 1 tensor cores (hamming_tc.cu), 2 / 3 pipelined tensor-core kernel (hamming_tc2.cu)
     bool no_deferred_normals = false;  // BSHOT_DEFERRED_NORMALS=0: keypoint normals by a second search (tile_keypoint_normals) instead of the detector's sums (tests)
     bool force_warp_path = false;  // BSHOT_WARP_PATH=1: skip the block-tiled kernels (tile.cuh), warp-per-query kernels everywhere (tests)
     unsigned max_cells = 1u << 22;  // voxel table size actually used (<= kMaxCells; BSHOT_MAX_CELLS_LOG2): zeroed and scanned every frame

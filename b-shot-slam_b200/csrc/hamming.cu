@@ -374,6 +374,17 @@ static int pick_qpt(size_t nq, size_t nt, int sm_count) {
     return best;
 }
 
+// which distance-matrix kernel runs a nq x nt search: the caller's choice (bshot_set_matcher / BSHOT_MATCH_TC), otherwise the
+// tensor-core pipeline once the problem fills its tiles.  Measured crossover (tools/match_sweep.py, left top-2 + reverse):
+// 2 Mi pairs, or 8 Mi pairs when the POPC kernel can fuse the column minima into its single pass (nt <= 4 nq: 2048 x 2048
+// 0.024 ms POPC vs 0.029 ms tensor cores, 4096 x 4096 0.050 vs 0.037 ms)
+static int matcher_for(const Ctx* c, size_t nq, size_t nt) {
+    if (c->match_tc >= 0) return c->match_tc;
+    const unsigned long long pairs = (unsigned long long)nq * nt;
+    const bool fused = nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS);
+    return (nq >= 64 && nt >= 256 && pairs >= (fused ? (1ull << 23) : (1ull << 21))) ? 2 : 0;
+}
+
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
 // the distance-matrix pass alone: per-split top-2 candidates in c->d_partial ([nsplit][nq][2]); *nsplit_out splits
 static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
@@ -383,8 +394,9 @@ static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void*
         return BSHOT_E_INVALID;
     }
     // the distance matrix on the tensor cores (hamming_tc.cu); the fused column minima stay with the POPC kernel
-    if (c->match_tc == 2 && !d_colmin) return hamming_tc2_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
-    if (c->match_tc && !d_colmin) return hamming_tc_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+    const int kind = d_colmin ? 0 : matcher_for(c, nq, nt);
+    if (kind >= 2) return hamming_tc2_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+    if (kind == 1) return hamming_tc_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);
     // whole waves: the grid is a multiple of (SMs x resident CTAs per SM) whenever the problem is big enough,
@@ -538,7 +550,7 @@ namespace bshot {
 int hamming_match_rq(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
                      bshot_cand* d_out, const unsigned* d_nq, const unsigned* d_nt) {
     if (nq == 0) return BSHOT_OK;
-    if (!c->match_tc && nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
+    if (matcher_for(c, nq, nt) == 0 && nt <= 4 * nq && nt <= c->max_targets && nq <= (1u << HM_IDX_BITS))
         return hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, reinterpret_cast<unsigned*>(c->d_right), d_nq, d_nt);
     BSHOT_TRY(hamming_top2(c, d_q, nq, d_t, nt, global_base, d_out, nullptr, d_nq, d_nt));
     return hamming_reverse(c, d_q, nq, d_t, global_base, d_out, d_nq);

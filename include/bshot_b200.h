@@ -354,6 +354,20 @@ int bshot_frame_counters(bshot_ctx* ctx, unsigned long long out[4]);
  * [5] attempts whose sphere held fewer than max_nn points (retried with a larger tile), [6] queries handed to the
  * warp-per-query fallback, [7] query blocks processed (all tiled launches of the frame together) */
 int bshot_debug_counters(bshot_ctx* ctx, unsigned long long out[8]);
+/* Which kernel computes the Hamming distance matrix of every search on this context (all of them return the same
+ * bit-exact (distance, lowest index) winners as minVect, include/bshot_bits.h:6-20):
+ *   BSHOT_MATCHER_AUTO (default)  by problem size: tensor-core pipeline for searches of >= 2^21 pairs, XOR + POPC below
+ *   BSHOT_MATCHER_POPC            XOR + POPC top-2 kernel, query tile in registers, targets through TMA (hamming.cu)
+ *   BSHOT_MATCHER_TC              tcgen05 kind::i8, one CTA-serial tile at a time (hamming_tc.cu)
+ *   BSHOT_MATCHER_TC_PIPELINED    warp-specialised tcgen05 pipeline, query tiles in tensor memory (hamming_tc2.cu)
+ *   BSHOT_MATCHER_TC_PIPELINED_SMEM  the same with the query tiles in shared memory
+ * The environment variable BSHOT_MATCH_TC=<kind> sets the initial value at bshot_ctx_create. */
+#define BSHOT_MATCHER_AUTO (-1)
+#define BSHOT_MATCHER_POPC 0
+#define BSHOT_MATCHER_TC 1
+#define BSHOT_MATCHER_TC_PIPELINED 2
+#define BSHOT_MATCHER_TC_PIPELINED_SMEM 3
+int bshot_set_matcher(bshot_ctx* ctx, int kind);
 /* POPC-pipe microbenchmark: returns measured POPC32 instructions/s over the whole GPU */
 int bshot_popc_peak(bshot_ctx* ctx, double* popc_per_s_out);
 

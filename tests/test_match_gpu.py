@@ -8,19 +8,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["popc", "tensor-core", "tensor-core-pipelined"])
-def mctx(request, gpu_ctx, bshot):
-    """the same checks on both distance-matrix kernels: XOR + POPC (hamming.cu) and tcgen05 int8 dot products
-    (hamming_tc.cu, selected when a context is created with BSHOT_MATCH_TC=1; hamming_tc2.cu, the warp-specialised
-    pipeline whose multiply leaves the packed (distance, column) key, with BSHOT_MATCH_TC=2)"""
-    if request.param == "popc":
-        yield gpu_ctx
-        return
-    os.environ["BSHOT_MATCH_TC"] = "1" if request.param == "tensor-core" else "2"
-    try:
-        ctx = bshot.Context(0, 131072, 16384, 1 << 21)
-    finally:
-        os.environ.pop("BSHOT_MATCH_TC", None)
+MATCHERS = {"popc": 0, "tensor-core": 1, "tensor-core-pipelined": 2, "tensor-core-pipelined-smem": 3, "by-size": -1}
+
+
+@pytest.fixture(scope="module", params=list(MATCHERS))
+def mctx(request, bshot):
+    """the same checks on every distance-matrix kernel (bshot_set_matcher): XOR + POPC (hamming.cu), tcgen05 int8 dot products
+    (hamming_tc.cu), the warp-specialised tensor-core pipeline whose multiply leaves the packed (distance, column) key
+    (hamming_tc2.cu; query tiles in tensor memory or in shared memory) and the default choice by problem size"""
+    ctx = bshot.Context(0, 131072, 16384, 1 << 21)
+    ctx.set_matcher(MATCHERS[request.param])
     yield ctx
     ctx.close()
 
@@ -230,8 +227,17 @@ def test_sharded_peer_push_equals_single(bshot, oracle, synth):
     assert bshot.unpack_cands(recs[0])["idx1"][5] == 12
 
 
-def test_full_size_properties(gpu_ctx, bshot, synth):
+@pytest.mark.parametrize("kind", [0, 2], ids=["popc", "tensor-core-pipelined"])
+def test_full_size_properties(gpu_ctx, bshot, synth, kind):
     """C4-sized shard (Q=10000 x T=1M): size-independent properties instead of the O(QT) oracle."""
+    gpu_ctx.set_matcher(kind)
+    try:
+        _full_size_properties(gpu_ctx, bshot, synth)
+    finally:
+        gpu_ctx.set_matcher(-1)
+
+
+def _full_size_properties(gpu_ctx, bshot, synth):
     nq, nt = 10000, 1 << 20
     t = synth.random_descriptors(nt, seed=7)
     rng = np.random.default_rng(5)
