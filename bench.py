@@ -18,7 +18,9 @@ whole path.  The detector / normals run in the only mode there is: the reference
            frame stream, no data-path collective, weak scaling.  The part of the path that DOES shard -- frame-to-
            map Hamming search against a map split over the ranks -- is timed in the same run and reported under
            "map_match" (C4: Q = 10 000 / 2 048 / 600 queries vs T = 1 048 576 map descriptors, with the single-GPU
-           time of the same search measured in the same run -> efficiency_vs_1gpu; C5: T = 16 777 216 when 8 ranks).
+           time of the same search measured in the same run -> efficiency_vs_1gpu; C5: T = 16 777 216 when 8 ranks)
+           for the north_star's XOR + POPC kernel, and under "map_match_tc" for the tensor-core pipeline (tcgen05
+           kind::i8, hamming_tc2.cu) that the library picks by itself for searches of this size -- same bit-exact result.
  * extra objects at N = 1: "c2" (BASELINE.json configs[1]: HDL-32E sequence, K = 2 048, per-frame p50 / p99 over
            >= 100 distinct frames), "c3_radius_sweep" (extraction throughput over the SHOT radius, FULL normals).
  * --impl reference: the oracle port of the reference's CPU path on all host cores, same config / frames / metric.
@@ -54,6 +56,16 @@ def peaks():
         except Exception:
             pass
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def int8_peak_tops():
+    """dense int8 tensor peak in TOP/s: twice the measured cuBLAS bf16 burst figure (int8 is nominally 2 x bf16 on B200; the
+    pool has no measured int8 GEMM), else twice the profiling guide's fallback"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return 2.0 * float(json.load(open(p))["bf16_tflops"]), "2 x measured bf16 burst (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -342,9 +354,11 @@ def main():
            "api": "bshot_process_frame (C ABI, pinned host buffers, synchronous)"}
 
     # ---- sharded frame-to-map matching (the part of the path that shards) -----------------------------
-    map_match = None
+    map_match = map_match_tc = None
     if not args.no_map:
-        map_match = bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks)
+        map_match = bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks, kind=0)
+        map_match_tc = bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks, kind=2)
+        ctx.set_matcher(-1)
 
     # ---- extras at N = 1 ------------------------------------------------------------------------------
     c2 = c3_sweep = pose_loop = None
@@ -368,7 +382,7 @@ def main():
                                                 "normals_shot_threads": min(12, cores), "sample": "1 frame"}}
 
     if rank == 0 and args.map_only:
-        print(json.dumps(map_match))
+        print(json.dumps({"map_match": map_match, "map_match_tc": map_match_tc}))
     elif rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
@@ -379,7 +393,7 @@ def main():
                        "ms_per_step_distribution": percentile_summary(per_step), "descriptors_per_frame": n_desc,
                        "detector_mode": "exact: fp32 running sums replayed in neighbour order (scores / keypoint indices bit-identical to the oracle)"},
             "stages_ms": stages, "roofline": roofline, "roofline_others": roofline_others, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "c2": c2, "c3_radius_sweep": c3_sweep, "pose_loop": pose_loop,
+            "gpu_launches": int(launches), "clocks": clocks, "map_match": map_match, "map_match_tc": map_match_tc, "c2": c2, "c3_radius_sweep": c3_sweep, "pose_loop": pose_loop,
         }
         print(json.dumps(line))
     ctx.close()
@@ -387,13 +401,16 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks):
+def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_over_ranks, kind=0):
     """C4 / C5: Q queries vs a T-descriptor map split over the ranks; per-call device time (max over ranks), the single-GPU
-    time of the SAME search in the same run (-> efficiency_vs_1gpu) and the POPC roofline."""
+    time of the SAME search in the same run (-> efficiency_vs_1gpu) and the roofline of the distance-matrix kernel:
+    kind 0 = XOR + POPC (POPC pipe), kind 2 = tensor-core pipeline (int8 tensor peak)."""
     import torch
     sharded = load_sharded()
     dev = torch.device("cuda", local_rank)
+    ctx.set_matcher(kind)
     popc_peak = ctx.popc_peak()
+    i8_peak, i8_src = int8_peak_tops()
     rows = []
 
     def timed(fn, reps):
@@ -458,12 +475,18 @@ def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_ov
         mm_ms, per_call = timed(lambda: matcher.match(dq.data_ptr(), lo), args.map_steps)
         matcher.check()
         pairs = float(Q) * float(T)
-        row = {"workload": name, "Q": Q, "T": T, "shards": world, "ms_per_call": mm_ms, "pairs_per_s": pairs / (mm_ms * 1e-3),
-               "target_GBps": T * 48 / (mm_ms * 1e-3) / 1e9,
-               "roofline": {"bound": "popc", "achieved": 11 * pairs / (mm_ms * 1e-3) / 1e12, "peak": world * popc_peak / 1e12,
-                            "unit": "TPOPC32/s", "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
-                            "issued_popc_per_pair": 6, "frac_of_issued": 6 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
-                            "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"},
+        if kind == 0:
+            roof = {"bound": "popc", "achieved": 11 * pairs / (mm_ms * 1e-3) / 1e12, "peak": world * popc_peak / 1e12,
+                    "unit": "TPOPC32/s", "frac": 11 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
+                    "issued_popc_per_pair": 6, "frac_of_issued": 6 * pairs / (mm_ms * 1e-3) / (world * popc_peak),
+                    "peak_source": "measured live (bshot_popc_peak microbenchmark) x shards"}
+        else:   # 352 multiply-adds per pair are the algorithm; the kernel issues 384 (one extra K step carries |q|, |t| and the column)
+            roof = {"bound": "tensor", "achieved": 2 * 352 * pairs / (mm_ms * 1e-3) / 1e12, "peak": world * i8_peak, "unit": "TOP/s (int8)",
+                    "frac": 2 * 352 * pairs / (mm_ms * 1e-3) / 1e12 / (world * i8_peak), "issued_k_per_pair": 384,
+                    "frac_of_issued": 2 * 384 * pairs / (mm_ms * 1e-3) / 1e12 / (world * i8_peak), "peak_source": i8_src + " x shards"}
+        row = {"workload": name, "Q": Q, "T": T, "shards": world, "kernel": "hamming_top2_kernel (XOR + POPC)" if kind == 0 else "hamming_tc2_kernel (tcgen05 kind::i8)",
+               "ms_per_call": mm_ms, "pairs_per_s": pairs / (mm_ms * 1e-3),
+               "target_GBps": T * 48 / (mm_ms * 1e-3) / 1e9, "roofline": roof,
                "collective": matcher.describe(), "gpu_launches_per_call": per_call}
         if world == 1:
             row["ms_per_call_1gpu"], row["efficiency_vs_1gpu"] = mm_ms, 1.0
