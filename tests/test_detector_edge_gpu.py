@@ -280,15 +280,18 @@ def test_pile_of_equidistant_points(gpu_ctx, oracle):
     assert np.array_equal(np.isnan(ng), np.isnan(no)) and np.nanmax(np.abs(ng - no)) <= 1e-6
 
 
-def test_fewer_keypoints_than_top_k(bshot, oracle, synth):
+@pytest.mark.parametrize("matcher", [-1, 0, 1, 2], ids=["by-size", "popc", "tensor-core", "tensor-core-pipelined"])
+def test_fewer_keypoints_than_top_k(bshot, oracle, synth, matcher):
     """the reference's `< 600` branch (src/lidar_odometry.cpp:144-151): a frame that yields fewer valid points than
-    top_k, followed by a smaller one.  Only the real keypoints may take part in the matching (no stale records)."""
+    top_k, followed by a smaller one.  Only the real keypoints may take part in the matching (no stale records) --
+    with every distance-matrix kernel: they all trim queries and targets by the device-side counts."""
     rng = np.random.default_rng(9)
     f0 = synth.make_scan("hdl32e", 0)[::200].copy()                      # ~300 points
     f1 = synth.make_scan("hdl32e", 1)[::350].copy()                      # fewer
     f0[::7] = 0.0                                                        # origin points never become keypoints
     p = bshot.default_params(top_k=600)
     with bshot.Context(0, 4096, 600, 600) as ctx:
+        ctx.set_matcher(matcher)
         r0 = ctx.process_frame(f0, p)
         r1 = ctx.process_frame(f1, p)
         r2 = ctx.process_frame(f0, p)
