@@ -22,7 +22,7 @@ whole path.  The detector / normals run in the only mode there is: the reference
            for the north_star's XOR + POPC kernel, and under "map_match_tc" for the tensor-core pipeline (tcgen05
            kind::i8, hamming_tc2.cu) that the library picks by itself for searches of this size -- same bit-exact result.
  * extra objects at N = 1: "c2" (BASELINE.json configs[1]: HDL-32E sequence, K = 2 048, per-frame p50 / p99 over
-           >= 100 distinct frames), "c3_radius_sweep" (extraction throughput over the SHOT radius, FULL normals).
+           500 distinct frames), "c3_radius_sweep" (extraction throughput over the SHOT radius, FULL normals).
  * --impl reference: the oracle port of the reference's CPU path on all host cores, same config / frames / metric.
 """
 import argparse
@@ -320,9 +320,20 @@ def main():
         kname, alg = kern[name]
         ach = alg / (stages[name] * 1e-3) / 1e9
         t = traffic_tab.get(name, {})
-        return {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": t.get("dram_bytes_per_launch"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                "ms_per_launch": stages[name], "ncu": t.get("ncu")}
+        r = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+             "traffic": t.get("dram_bytes_per_launch"), "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+             "ms_per_launch": stages[name], "ncu": t.get("ncu")}
+        if t.get("warp_instructions_per_launch") and args.workload == "C3":
+            # what actually bounds the kernel: warp instructions (counted by ncu on this workload) against the issue slots
+            # of the launch's live duration (4 schedulers per SM, one instruction per clock)
+            sm_clock = (clock_probe or {}).get("sm_max_mhz") or 1965.0
+            peak_issue = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * sm_clock * 1e6
+            wi = float(t["warp_instructions_per_launch"])
+            r["issue"] = {"warp_instructions_per_launch": wi, "achieved_warp_inst_per_s": wi / (stages[name] * 1e-3),
+                          "peak_warp_inst_per_s": peak_issue, "frac": wi / (stages[name] * 1e-3) / peak_issue,
+                          "source": "instruction count: ncu smsp__inst_executed.sum (profiles/r2i_ncu_full.txt); time: this run"}
+        return r
+    clock_probe = {"sm_max_mhz": sampler.max_mhz} if sampler and sampler.max_mhz else None
     dom = max(kern, key=lambda k: stages[k])
     roofline = roof(dom)
     roofline["note"] = ("the cloud (< 2 MB) is L2 resident and the neighbourhood tiles are staged once per block in shared memory: "
@@ -499,11 +510,26 @@ def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_ov
     return out
 
 
-def bench_c2_sequence(bs, synth, device, flush, n_frames=120, top_k=2048):
-    """C2 (BASELINE.json configs[1]): frame-to-frame odometry front end over a synthetic HDL-32E sequence -- per-frame device
-    times over >= 100 DISTINCT frames (pose k = 500 mm * k along x, yaw 0.5 deg * k), L2 flushed before every frame"""
+def _scan_worker(job):
+    sensor, f = job
+    return load_synth().make_scan(sensor, f)
+
+
+def make_sequence(sensor, n_frames):
+    """n_frames distinct synthetic scans (pose k = 500 mm * k along x, yaw 0.5 deg * k); the numpy ray caster runs on a pool of
+    host processes (spawned: the parent already holds a CUDA context)"""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    workers = max(1, min(16, os.cpu_count() or 1))
+    with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+        return list(ex.map(_scan_worker, [(sensor, f) for f in range(n_frames)], chunksize=4))
+
+
+def bench_c2_sequence(bs, synth, device, flush, n_frames=500, top_k=2048):
+    """C2 (BASELINE.json configs[1]): frame-to-frame odometry front end over a 500-frame synthetic HDL-32E sequence -- per-frame
+    device times over 500 DISTINCT frames (pose k = 500 mm * k along x, yaw 0.5 deg * k), L2 flushed before every frame"""
     import torch
-    frames = [synth.make_scan("hdl32e", f) for f in range(n_frames)]
+    frames = make_sequence("hdl32e", n_frames)
     ctx = bs.Context(device, max_points=max(len(f) for f in frames) + 1024, max_keypoints=top_k, max_targets=top_k)
     st = torch.cuda.ExternalStream(ctx.stream)
     p = bs.default_params(top_k=top_k)

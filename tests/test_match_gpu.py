@@ -83,6 +83,27 @@ def test_all_ones_invalid_descriptors(mctx, oracle, synth):
     _check(mctx, oracle, q, t)
 
 
+def test_extreme_popcounts_and_constant_targets(mctx, oracle, synth):
+    """the corners of the key range: empty and full descriptors on both sides (distances 0 and 352), and a target set of
+    identical records -- every distance ties, so the winner and the runner-up must be targets 0 and 1 whatever tile or
+    split they fall into (first minimum of minVect, include/bshot_bits.h:6-20)"""
+    ones = np.full(6, 0xFFFFFFFFFFFFFFFF, np.uint64)
+    ones[5] = 0xFFFFFFFF
+    q = synth.random_descriptors(300, seed=31)
+    q[0] = 0
+    q[1] = ones
+    t = synth.random_descriptors(1000, seed=32)
+    t[999] = 0
+    t[128] = ones
+    t[127] = ones
+    _check(mctx, oracle, q, t)
+    same = np.repeat(synth.random_descriptors(1, seed=33), 5000, axis=0)
+    g = mctx.match(q, same)
+    assert (g["left_idx"] == 0).all() and (g["left_idx2"] == 1).all()
+    assert np.array_equal(g["left_dist"], g["left_dist2"])
+    _check(mctx, oracle, q[:64], same[:700])
+
+
 def test_empty_inputs(mctx, synth):
     q = synth.random_descriptors(10, seed=1)
     e = np.zeros((0, 6), np.uint64)
