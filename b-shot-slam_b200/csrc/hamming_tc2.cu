@@ -406,7 +406,9 @@ int hamming_tc2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, si
         if (nq > 128) return t2_launch<2, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
         return t2_launch<1, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     }
-    if (nq > 128) return t2_launch<2, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+    // two query tiles per CTA halve the expansion work per pair; one tile per CTA when that pads >= 10 % fewer rows
+    const size_t rows1 = (nq + 127) / 128 * 128, rows2 = (nq + 255) / 256 * 256;
+    if (rows1 * 10 > rows2 * 9) return t2_launch<2, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     return t2_launch<1, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
 }
 
