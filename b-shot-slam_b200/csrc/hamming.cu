@@ -872,7 +872,7 @@ int hamming_preload_sharded() {
     BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, wait_merge_select_kernel));
     BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, merge_push_rq_kernel));
     BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, wait_apply_rq_kernel));
-    return BSHOT_OK;
+    return hamming_tc2_preload();
 }
 
 // region of one rank: [gather: nranks x max_q records][rq: max_q u32][flags: 64 u32]

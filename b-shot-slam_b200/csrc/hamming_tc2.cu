@@ -146,6 +146,16 @@ hamming_tc2_kernel(const uint4* __restrict__ q, unsigned nq, const unsigned* __r
     const unsigned t1 = min(nt_live, t0 + chunk);
     const unsigned ntiles = t1 > t0 ? (t1 - t0 + 127u) / 128u : 0u;
 
+    if (q0 >= nq_live) {   // a query block beyond the device-side count (reverse pass of the sharded call: few owned winners)
+        for (unsigned x = tid; x < 128u * MT; x += Cfg::THREADS) {
+            if (q0 + x < nq) {
+                unsigned long long* p = partial + ((size_t)blockIdx.y * nq + q0 + x) * 2;
+                p[0] = T2_NONE;
+                p[1] = T2_NONE;
+            }
+        }
+        return;
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(t2_smem(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -396,6 +406,16 @@ static int t2_launch(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t
     count_launch(c);
     *nsplit_out = (unsigned)nsplit;
     return check_launch("hamming_tc2_kernel");
+}
+
+// see hamming_preload_sharded (hamming.cu): every kernel a sharded call may launch is loaded before the first call
+int hamming_tc2_preload() {
+    cudaFuncAttributes a;
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_tc2_kernel<1, true>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_tc2_kernel<2, true>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_tc2_kernel<1, false>));
+    BSHOT_CUDA_TRY(cudaFuncGetAttributes(&a, hamming_tc2_kernel<2, false>));
+    return BSHOT_OK;
 }
 
 // per-split top-2 candidates in c->d_partial ([nsplit][nq][2]) like hamming_top2_partials (hamming.cu)

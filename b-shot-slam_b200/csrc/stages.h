@@ -54,6 +54,7 @@ int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long
 // tensor-core distance matrix (hamming_tc.cu): per-split top-2 partials in c->d_partial
 int hamming_tc_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
                         const unsigned* d_nt, unsigned* nsplit_out);
+int hamming_tc2_preload();
 int hamming_tc2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
                         const unsigned* d_nt, unsigned* nsplit_out);
 

@@ -154,7 +154,8 @@ def test_sharded_merge_equals_single(mctx, bshot, oracle, synth):
     assert np.array_equal(mutual_gpu, opairs[:, 0])
 
 
-def test_sharded_reverse_owned_equals_single(bshot, oracle, synth):
+@pytest.mark.parametrize("kind", [0, 2], ids=["popc", "tensor-core-pipelined"])
+def test_sharded_reverse_owned_equals_single(bshot, oracle, synth, kind):
     """4 emulated ranks (4 contexts on one GPU): shard search without rq, merge, reverse pass for the owned
     winners only, MAX-combine -> records identical to the single-pass oracle result."""
     import torch
@@ -167,6 +168,8 @@ def test_sharded_reverse_owned_equals_single(bshot, oracle, synth):
     per = (nt + ranks - 1) // ranks
     ctxs = [bshot.Context(0, 1024, 1024, per) for _ in range(ranks)]
     try:
+        for c in ctxs:
+            c.set_matcher(kind)
         cands = torch.empty((ranks, nq, 3), dtype=torch.int64, device="cuda")
         torch.cuda.synchronize()
         for r, c in enumerate(ctxs):
@@ -198,7 +201,8 @@ def test_sharded_reverse_owned_equals_single(bshot, oracle, synth):
     assert u["idx1"][3] == 10
 
 
-def test_sharded_peer_push_equals_single(bshot, oracle, synth):
+@pytest.mark.parametrize("kind", [0, 2], ids=["popc", "tensor-core-pipelined"])
+def test_sharded_peer_push_equals_single(bshot, oracle, synth, kind):
     """the peer-memory exchange on 4 emulated ranks (4 contexts on one GPU, every 'peer' buffer is a local
     buffer): every rank pushes its records into slot r of every rank's gather buffer, merges its own copy, runs the
     reverse pass for the winners it owns and pushes rq into every rank's array -> every rank ends with records
@@ -213,6 +217,8 @@ def test_sharded_peer_push_equals_single(bshot, oracle, synth):
     per = (nt + ranks - 1) // ranks
     ctxs = [bshot.Context(0, 1024, 1024, per) for _ in range(ranks)]
     try:
+        for c in ctxs:
+            c.set_matcher(kind)
         gather = [torch.zeros((ranks, nq, 3), dtype=torch.int64, device="cuda") for _ in range(ranks)]
         rqbuf = [torch.full((nq,), -7, dtype=torch.int32, device="cuda") for _ in range(ranks)]
         peer_g = torch.tensor([g.data_ptr() for g in gather], dtype=torch.int64, device="cuda")
