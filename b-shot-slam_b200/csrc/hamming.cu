@@ -388,14 +388,14 @@ static int matcher_for(const Ctx* c, size_t nq, size_t nt) {
 // d_q (nq records) vs d_t (nt records): top-2 candidates per query into d_out (rq untouched = none)
 // the distance-matrix pass alone: per-split top-2 candidates in c->d_partial ([nsplit][nq][2]); *nsplit_out splits
 static int hamming_top2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base,
-                                 unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt, unsigned* nsplit_out) {
+                                 unsigned* d_colmin, const unsigned* d_nq, const unsigned* d_nt, unsigned* nsplit_out, size_t live_q = 0) {
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) {
         set_error("hamming_top2: sizes exceed 32-bit index range");
         return BSHOT_E_INVALID;
     }
     // the distance matrix on the tensor cores (hamming_tc.cu); the fused column minima stay with the POPC kernel
     const int kind = d_colmin ? 0 : matcher_for(c, nq, nt);
-    if (kind >= 2) return hamming_tc2_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+    if (kind >= 2) return hamming_tc2_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out, live_q);
     if (kind == 1) return hamming_tc_partials(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
     const int qpt = pick_qpt(nq, nt, c->sm_count);
     const unsigned qblocks = qblocks_for(nq, qpt);
@@ -929,7 +929,8 @@ int hamming_match_sharded(Ctx* c, const void* d_q, size_t nq, unsigned long long
     count_launch(c, 2);
     BSHOT_TRY(check_launch("sharded exchange kernels"));
     // 4 + 5: best query of every owned winner, pushed to every rank
-    BSHOT_TRY(hamming_top2_partials(c, c->d_gather, nq, d_q, nq, 0, nullptr, count, nullptr, &nsplit));
+    // (about nq / nranks of the rows are live: the grid of the tensor-core kernel is sized for that many)
+    BSHOT_TRY(hamming_top2_partials(c, c->d_gather, nq, d_q, nq, 0, nullptr, count, nullptr, &nsplit, (nq + nranks - 1) / nranks));
     merge_push_rq_kernel<<<mb, 256, 0, c->stream>>>(c->d_partial, nsplit, (unsigned)nq, count, owner_q, m.d_peer_rq, m.d_peer_flags, nranks, rank, epoch,
                                                    m.d_ticket + 1);
     // 6

@@ -372,7 +372,7 @@ hamming_tc2_kernel(const uint4* __restrict__ q, unsigned nq, const unsigned* __r
 
 template <int MT, bool ATM>
 static int t2_launch(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
-                     const unsigned* d_nt, unsigned* nsplit_out) {
+                     const unsigned* d_nt, unsigned* nsplit_out, size_t live_q) {
     using Cfg = T2Cfg<MT, ATM>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -383,16 +383,17 @@ static int t2_launch(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t
     const size_t ntile = (nt + 127) / 128;
     const size_t cap_splits = std::min<size_t>(c->partial_cap / (nq * 2), 65535);
     if (cap_splits == 0) { set_error("hamming_tc2: partial buffer too small for %zu queries", nq); return BSHOT_E_CAPACITY; }
-    // one CTA per SM: the grid fills k whole waves as closely as it can while a CTA keeps >= 16 tiles (the query tile is
-    // expanded once per CTA)
+    // one CTA per SM: the grid fills k whole waves as closely as it can; a CTA pays about three tiles' worth of prologue
+    // live_q: how many of the nq rows the caller expects to be live under the device-side count (dead blocks leave at once)
+    const size_t qblocks_live = std::max<size_t>(1, std::min(qblocks, (std::min(live_q, nq) + 128 * MT - 1) / (128 * MT)));
     const size_t sms = (size_t)c->sm_count;
     size_t best_split = 1;
     double best_cost = 1e30;
     for (size_t k = 1; k <= 16; ++k) {
-        size_t ns = std::max<size_t>(1, k * sms / qblocks);
+        size_t ns = std::max<size_t>(1, k * sms / qblocks_live);
         ns = std::min(ns, std::min(cap_splits, std::max<size_t>(1, ntile)));
         const size_t tiles = (ntile + ns - 1) / ns;                       // tiles per CTA
-        const size_t waves = (qblocks * ((ntile + tiles - 1) / tiles) + sms - 1) / sms;
+        const size_t waves = (qblocks_live * ((ntile + tiles - 1) / tiles) + sms - 1) / sms;
         const double cost = (double)waves * ((double)tiles + 3.0);          // ~3 tiles' worth of prologue per CTA
         if (cost < best_cost) { best_cost = cost; best_split = ns; }
     }
@@ -420,16 +421,17 @@ int hamming_tc2_preload() {
 
 // per-split top-2 candidates in c->d_partial ([nsplit][nq][2]) like hamming_top2_partials (hamming.cu)
 int hamming_tc2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
-                         const unsigned* d_nt, unsigned* nsplit_out) {
+                         const unsigned* d_nt, unsigned* nsplit_out, size_t live_q) {
+    if (live_q == 0 || !d_nq) live_q = nq;
     if (nq > 0xFFFFFFFFull || nt > 0xFFFFFFFFull || global_base + nt > 0x100000000ull) { set_error("hamming_tc2: sizes exceed 32-bit index range"); return BSHOT_E_INVALID; }
     if (c->match_tc == 3) {   // query tiles in shared memory (kept for comparison; never chosen by size)
-        if (nq > 128) return t2_launch<2, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
-        return t2_launch<1, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+        if (nq > 128) return t2_launch<2, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out, live_q);
+        return t2_launch<1, false>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out, live_q);
     }
     // two query tiles per CTA halve the expansion work per pair; one tile per CTA when that pads >= 10 % fewer rows
     const size_t rows1 = (nq + 127) / 128 * 128, rows2 = (nq + 255) / 256 * 256;
-    if (rows1 * 10 > rows2 * 9) return t2_launch<2, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
-    return t2_launch<1, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out);
+    if (rows1 * 10 > rows2 * 9) return t2_launch<2, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out, live_q);
+    return t2_launch<1, true>(c, d_q, nq, d_t, nt, global_base, d_nq, d_nt, nsplit_out, live_q);
 }
 
 }  // namespace bshot

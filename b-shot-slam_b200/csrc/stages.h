@@ -56,7 +56,7 @@ int hamming_tc_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, siz
                         const unsigned* d_nt, unsigned* nsplit_out);
 int hamming_tc2_preload();
 int hamming_tc2_partials(Ctx* c, const void* d_q, size_t nq, const void* d_t, size_t nt, unsigned long long global_base, const unsigned* d_nq,
-                        const unsigned* d_nt, unsigned* nsplit_out);
+                         const unsigned* d_nt, unsigned* nsplit_out, size_t live_q = 0);
 
 // GPU-resident global map (gmap.cu)
 int gmap_create(Ctx* c, size_t max_entries, size_t max_blocks);

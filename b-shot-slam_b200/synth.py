@@ -82,12 +82,13 @@ def _raycast(o, d, boxes, cyls):
     return t
 
 
-def make_scan(sensor="hdl32e", frame=0, noise_mm=20.0, scene_seed=SCENE_SEED, max_points=None):
-    """Return float32 (N,3) points in the SENSOR frame, in firing order (azimuth-major)."""
+def make_scan(sensor="hdl32e", frame=0, noise_mm=20.0, scene_seed=SCENE_SEED, max_points=None, pos=None, yaw_deg=None):
+    """Return float32 (N,3) points in the SENSOR frame, in firing order (azimuth-major).  Default pose of frame k: 500 mm * k
+    along x, yaw 0.5 deg * k (the scene ends after ~150 such frames); `pos` / `yaw_deg` place the sensor elsewhere."""
     vert, steps, max_range = SENSORS[sensor]
     boxes, cyls = _scene(scene_seed)
-    yaw = np.deg2rad(0.5 * frame)
-    pos = np.array([500.0 * frame, 0.0, 0.0])
+    yaw = np.deg2rad(0.5 * frame if yaw_deg is None else yaw_deg)
+    pos = np.array([500.0 * frame, 0.0, 0.0]) if pos is None else np.asarray(pos, dtype=np.float64)
     az = np.arange(steps) * (2 * np.pi / steps)
     el = np.deg2rad(vert)
     A, E = np.meshgrid(az, el, indexing="ij")

@@ -511,23 +511,32 @@ def bench_map(args, bs, synth, ctx, st, world, rank, local_rank, barrier, max_ov
 
 
 def _scan_worker(job):
-    sensor, f = job
-    return load_synth().make_scan(sensor, f)
+    sensor, f, pos, yaw = job
+    return load_synth().make_scan(sensor, f, pos=pos, yaw_deg=yaw)
+
+
+def loop_pose(k, n):
+    """closed loop through the synthetic scene: out to x = 75 m and back with a 3 m sideways swing, <= 471 mm per frame at
+    n = 500 (the reference drives ~500 mm per HDL-32E rotation), yaw 0.5 deg per frame"""
+    a = 2.0 * np.pi * k / n
+    return (37500.0 * (1.0 - np.cos(a)), 3000.0 * np.sin(a), 0.0), 0.5 * k
 
 
 def make_sequence(sensor, n_frames):
-    """n_frames distinct synthetic scans (pose k = 500 mm * k along x, yaw 0.5 deg * k); the numpy ray caster runs on a pool of
-    host processes (spawned: the parent already holds a CUDA context)"""
+    """n_frames distinct synthetic scans along loop_pose; the numpy ray caster runs on a pool of host processes (spawned:
+    the parent already holds a CUDA context)"""
     import multiprocessing as mp
     from concurrent.futures import ProcessPoolExecutor
     workers = max(1, min(16, os.cpu_count() or 1))
+    jobs = [(sensor, f) + loop_pose(f, n_frames) for f in range(n_frames)]
     with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
-        return list(ex.map(_scan_worker, [(sensor, f) for f in range(n_frames)], chunksize=4))
+        return list(ex.map(_scan_worker, jobs, chunksize=4))
 
 
 def bench_c2_sequence(bs, synth, device, flush, n_frames=500, top_k=2048):
     """C2 (BASELINE.json configs[1]): frame-to-frame odometry front end over a 500-frame synthetic HDL-32E sequence -- per-frame
-    device times over 500 DISTINCT frames (pose k = 500 mm * k along x, yaw 0.5 deg * k), L2 flushed before every frame"""
+    device times over 500 DISTINCT frames (a closed loop through the scene, <= 471 mm and 0.5 deg of yaw per frame), L2 flushed
+    before every frame"""
     import torch
     frames = make_sequence("hdl32e", n_frames)
     ctx = bs.Context(device, max_points=max(len(f) for f in frames) + 1024, max_keypoints=top_k, max_targets=top_k)
