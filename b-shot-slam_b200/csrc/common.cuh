@@ -128,6 +128,7 @@ struct Ctx {
     unsigned* d_nblocks = nullptr;     // [0] heavy blocks, [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [5] light blocks
     float* d_qsums = nullptr;          // N x 10: covariance sums + count of the detector's neighbourhood of every point (deferred normals)
     float* d_rho_hint = nullptr;       // N: radius of the detector's neighbourhood of every point (distance of its last member)
+    unsigned* d_shot_order = nullptr;  // K: order in which shot_kernel takes the keypoints (densest neighbourhoods first)
     uint2* d_ovf = nullptr;            // N: queries whose block tile overflowed {position in d_sorted, radius bits} (tilek.cu)
     unsigned* d_fb_list = nullptr;     // N: sorted positions of the queries the tiled kernels hand to the fallback
 

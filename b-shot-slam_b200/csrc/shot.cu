@@ -169,11 +169,11 @@ shot_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             const float4* __restrict__ sorted, const float4* __restrict__ kp, const int* __restrict__ kp_count,
             const float4* __restrict__ normals, unsigned normals_limit, float radius, int lrf_only,
             float* __restrict__ rf_out, int* __restrict__ nn_out, float* __restrict__ shot_out,
-            uint64_t* __restrict__ bits_out, unsigned long long* __restrict__ sum_nn) {
+            uint64_t* __restrict__ bits_out, unsigned long long* __restrict__ sum_nn, const unsigned* __restrict__ order) {
     __shared__ ShotSmem sm;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int k = blockIdx.x;
-    if (k >= *kp_count) return;
+    if ((int)blockIdx.x >= *kp_count) return;
+    const int k = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
     const GridParams g = *gp;
     const float4 q = kp[k];
     const float R = radius;
@@ -653,16 +653,61 @@ binarize_kernel(const float* __restrict__ shot, unsigned k, uint64_t* __restrict
     if (lane < 6) bits[(size_t)warp * 6 + lane] = ((uint64_t)hi << 32) | lo;
 }
 
+// Keypoints differ ten-fold in cost (126 .. 2800 neighbours) and a CTA per keypoint in index order leaves the SMs idle for
+// ~11 % of the launch while the last heavy ones finish.  Longest-processing-time-first: the keypoints are taken in the
+// order of the radius that held max_nn neighbours in the detector pass (small radius = dense = expensive).  One CTA,
+// 256-bin counting sort; the order only decides WHEN a keypoint is processed, never what is computed.
+__global__ void __launch_bounds__(1024)
+shot_order_kernel(const float4* __restrict__ kp, const int* __restrict__ kp_count, unsigned kcap, const float* __restrict__ rho_hint, unsigned n_points,
+                  float R, unsigned* __restrict__ order) {
+    __shared__ unsigned hist[256];
+    const unsigned tid = threadIdx.x;
+    const unsigned K = min(kcap, (unsigned)max(*kp_count, 0));
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    auto bin_of = [&](unsigned k) {
+        const unsigned idx = __float_as_uint(kp[k].w);
+        const float rho = idx < n_points ? rho_hint[idx] : R;
+        return (rho > 0.0f) ? min(255u, (unsigned)(rho / R * 255.0f)) : 255u;
+    };
+    for (unsigned k = tid; k < K; k += 1024) atomicAdd(&hist[bin_of(k)], 1u);
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of 256 bins by one warp: 8 bins per lane
+        unsigned h[8], s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h[i] = hist[tid * 8 + i]; s += h[i]; }
+        unsigned inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= (unsigned)o) inc += up;
+        }
+        unsigned run = inc - s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { hist[tid * 8 + i] = run; run += h[i]; }
+    }
+    __syncthreads();
+    for (unsigned k = tid; k < K; k += 1024) order[atomicAdd(&hist[bin_of(k)], 1u)] = k;
+}
+
 int shot_compute(Ctx* c, float radius, bool lrf_only, bool write_shot) {
     const size_t k = c->n_kp;
     if (k == 0) return BSHOT_OK;
     if (!lrf_only) BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_sum_nn, 0, sizeof(unsigned long long), c->stream));
     const unsigned limit = (unsigned)std::min(c->normals_valid, c->n_points);
+    // processing order: only when the keypoints are the detector's (d_kp[i].w = surface index) and its radii are at hand
+    static const bool lpt = [] { const char* e = getenv("BSHOT_SHOT_LPT"); return !e || atoi(e) != 0; }();
+    const unsigned* order = nullptr;
+    if (lpt && c->kp_from_detector && c->sel_valid && k >= 512) {
+        shot_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_kp, c->d_kp_count, (unsigned)k, c->d_rho_hint, (unsigned)c->n_points, c->sel_radius, c->d_shot_order);
+        count_launch(c);
+        order = c->d_shot_order;
+    }
     static const int nthreads = [] { const char* e = getenv("BSHOT_SHOT_THREADS"); const int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
 #define BSHOT_LAUNCH_SHOT(NT)                                                                                              \
     shot_kernel<NT><<<(unsigned)k, NT, 0, c->stream>>>(c->d_grid, c->d_cell_start, c->d_sorted, c->d_kp, c->d_kp_count,   \
                                                       c->d_normals, limit, radius, lrf_only ? 1 : 0, c->d_rf, c->d_nn,   \
-                                                      write_shot ? c->d_shot : nullptr, c->d_bits, c->d_sum_nn)
+                                                      write_shot ? c->d_shot : nullptr, c->d_bits, c->d_sum_nn, order)
     if (nthreads == 64) BSHOT_LAUNCH_SHOT(64);
     else if (nthreads == 256) BSHOT_LAUNCH_SHOT(256);
     else BSHOT_LAUNCH_SHOT(128);

@@ -31,10 +31,13 @@ def test_driver_compiles_and_fails_loudly_without_gpu(ipc_binary):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nranks,T,Q", [(2, 6000, 700), (3, 5000, 257), (4, 40000, 1024)])
-def test_multi_process_sharded_match(ipc_binary, nranks, T, Q):
+@pytest.mark.parametrize("nranks,T,Q,matcher", [(2, 6000, 700, None), (3, 5000, 257, None), (4, 40000, 1024, None), (2, 6000, 700, "2")],
+                         ids=["2-ranks", "3-ranks", "4-ranks", "2-ranks-tensor-core-pipelined"])
+def test_multi_process_sharded_match(ipc_binary, nranks, T, Q, matcher):
     import torch
     env = dict(os.environ, BSHOT_TEST_NDEV=str(torch.cuda.device_count()))
+    if matcher is not None:
+        env["BSHOT_MATCH_TC"] = matcher      # every search of the call on the tensor-core pipeline, whatever its size
     r = subprocess.run([ipc_binary, str(nranks), str(T), str(Q)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "all ranks ok" in r.stdout, r.stdout + r.stderr
 
