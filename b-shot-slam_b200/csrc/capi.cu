@@ -150,9 +150,9 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
     A(dmalloc(&c->d_lvl, (size_t)kMaxCells + 16));
     A(dmalloc(&c->d_sorted_pos, N));
     A(dmalloc(&c->d_kp_flag, N));
-    A(dmalloc(&c->d_blocks, N));
-    A(dmalloc(&c->d_blk_area, N));
-    A(dmalloc(&c->d_nblocks, 8));
+    A(dmalloc(&c->d_blocks, (size_t)kBlockClasses * N));
+    A(dmalloc(&c->d_blk_area, (size_t)kBlockClasses * N));
+    A(dmalloc(&c->d_nblocks, 32));
     A(dmalloc(&c->d_ovf, N));
     A(dmalloc(&c->d_rho_hint, N));
     A(dmalloc(&c->d_shot_order, K));

@@ -96,6 +96,9 @@ struct Gmap {
     size_t entries_upper = 0;           // host-side upper bound of the number of entries (sizes the match grid without a sync)
 };
 
+// query blocks are listed by weight class (class c: kBlockClasses regions of max_points entries in d_blocks / d_blk_area)
+constexpr int kBlockClasses = 8;
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
@@ -125,7 +128,7 @@ struct Ctx {
     int* d_kp_flag = nullptr;          // N: per sorted position, keypoint ordinal or -1 (reset by the grid build)
     uint4* d_blocks = nullptr;         // N: query blocks {ix0, iy0, iz0, cells per edge | slice << 4} (tile.cuh)
     float* d_blk_area = nullptr;       // N: surface area per point around the block (radius prediction)
-    unsigned* d_nblocks = nullptr;     // [0] heavy blocks, [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [5] light blocks
+    unsigned* d_nblocks = nullptr;     // [1] fallback-list length, [2],[3] work counters, [4] overflow queries, [6] wide overflow queries, [16 + c] blocks of weight class c
     float* d_qsums = nullptr;          // N x 10: covariance sums + count of the detector's neighbourhood of every point (deferred normals)
     float* d_rho_hint = nullptr;       // N: radius of the detector's neighbourhood of every point (distance of its last member)
     unsigned* d_shot_order = nullptr;  // K: order in which shot_kernel takes the keypoints (densest neighbourhoods first)

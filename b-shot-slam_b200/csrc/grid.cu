@@ -134,7 +134,7 @@ __global__ void zero_cells_kernel(const GridParams* __restrict__ g, unsigned* __
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cursor[i] = 0;
     const unsigned nl = lvl_total(*g);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += gridDim.x * blockDim.x) lvl[i] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { nblocks[0] = 0; nblocks[5] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)kBlockClasses) nblocks[16 + threadIdx.x] = 0;
 }
 
 // one atomicAdd per RUN of equal keys inside a warp: lidar points arrive in firing order, neighbouring lanes mostly
@@ -315,11 +315,13 @@ scatter_kernel(const float4* __restrict__ pts, unsigned n, const unsigned* __res
     else { const float s2 = side * (float)(2 << leaf); area = s2 * s2 / (float)cnt[leaf + 1]; }
     const unsigned nb = (leaf == 0) ? (c0 + TL_QCAP - 1) / TL_QCAP : 1u;
     const int L = 1 << leaf;
-    // blocks with many queries are listed from the front, light ones from the back: the kernels walk the list front
-    // to back, so the expensive blocks start first (longest-processing-time-first keeps the tail short)
+    // blocks are listed by weight class (class 0: the most queries); the kernels walk class after class, so the expensive
+    // blocks start first and the launch ends on blocks of a few queries (longest-processing-time-first: a 64-query block takes
+    // a third of the whole launch, with two classes the last block pulled could still hold 31 queries)
     for (unsigned sidx = 0; sidx < nb; ++sidx) {
         const unsigned weight = (leaf == 0) ? min(c0 - sidx * TL_QCAP, (unsigned)TL_QCAP) : cnt[leaf];
-        const unsigned slot = (weight >= (unsigned)(TL_QCAP / 2)) ? atomicAdd(nblocks, 1u) : block_cap - 1u - atomicAdd(nblocks + 5, 1u);
+        const unsigned cls = ((unsigned)TL_QCAP - min(max(weight, 1u), (unsigned)TL_QCAP)) * (unsigned)kBlockClasses / (unsigned)TL_QCAP;
+        const unsigned slot = cls * block_cap + atomicAdd(nblocks + 16 + cls, 1u);
         blocks[slot] = make_uint4((unsigned)(ix & ~(L - 1)), (unsigned)(iy & ~(L - 1)), (unsigned)(iz & ~(L - 1)), (unsigned)L | (sidx << 4));
         blk_area[slot] = area;
     }

@@ -138,14 +138,24 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
     const float R = radius;
     const float R2 = (float)((double)R * (double)R);
     const float sum_thr = sum_gate_threshold(gate);
-    const unsigned n_heavy = ctl[0], nb = n_heavy + ctl[5];  // heavy blocks from the front of the list, light ones from its back
+    unsigned cum[kBlockClasses + 1];  // blocks by weight class, heaviest class first
+    cum[0] = 0;
+#pragma unroll
+    for (int cl = 0; cl < kBlockClasses; ++cl) cum[cl + 1] = cum[cl] + ctl[16 + cl];
+    const unsigned nb = cum[kBlockClasses];
     unsigned long long st_staged = 0, st_swept = 0, st_attempts = 0, st_blocks = 0;  // thread 0 only
     for (;;) {
         __syncthreads();  // previous block's epilogue is done with the shared state
         if (tid == 0) s_block = atomicAdd(work, 1u);  // blocks differ widely in cost: dynamic assignment, heavy blocks first
         __syncthreads();
         if (s_block >= nb) break;
-        const unsigned b = s_block < n_heavy ? s_block : block_cap - 1u - (s_block - n_heavy);
+        unsigned cls = 0;
+#pragma unroll
+        for (int cl = 1; cl < kBlockClasses; ++cl) cls += (s_block >= cum[cl]) ? 1u : 0u;
+        unsigned base = 0;
+#pragma unroll
+        for (int cl = 1; cl < kBlockClasses; ++cl) base = (cls == (unsigned)cl) ? cum[cl] : base;
+        const unsigned b = cls * block_cap + (s_block - base);
         const uint4 desc = __ldg(blocks + b);
         tile_block_queries(g, cell_start, sorted, desc, SEG ? nullptr : flags, SEG && NRM != 1, sm, tid);
         const unsigned nq = sm.nq;
@@ -542,7 +552,7 @@ int tile_neighbourhoods(Ctx* c, int sr_type, bool seg, int nrm, float radius, in
     if (max_nn <= 0 || max_nn > TL_MAXNN) { set_error("tile_neighbourhoods: max_nn %d outside (0, %d]", max_nn, TL_MAXNN); return BSHOT_E_INVALID; }
     // persistent CTAs pulling blocks / queries from work counters; d_nblocks[1..4]: fallback-list length, work counters, overflow count
     BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 1, 0, 4 * sizeof(unsigned), c->stream));
-    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 6, 0, sizeof(unsigned), c->stream));   // [5] = light blocks, written by the grid build
+    BSHOT_CUDA_TRY(cudaMemsetAsync(c->d_nblocks + 6, 0, sizeof(unsigned), c->stream));   // [16 ..] = blocks per weight class, written by the grid build
     const size_t single_smem = sizeof(SingleWarp) * TS_WARPS;
 #define BSHOT_TILE(SR, SEG, NRM)                                                                                                           \
     do {                                                                                                                                   \
