@@ -657,6 +657,7 @@ binarize_kernel(const float* __restrict__ shot, unsigned k, uint64_t* __restrict
 // ~11 % of the launch while the last heavy ones finish.  Longest-processing-time-first: the keypoints are taken in the
 // order of the radius that held max_nn neighbours in the detector pass (small radius = dense = expensive).  One CTA,
 // 256-bin counting sort; the order only decides WHEN a keypoint is processed, never what is computed.
+constexpr int SO_PER = 16;  // keypoints per thread held in registers (1024 threads: 16 384 keypoints in one sweep)
 __global__ void __launch_bounds__(1024)
 shot_order_kernel(const float4* __restrict__ kp, const int* __restrict__ kp_count, unsigned kcap, const float* __restrict__ rho_hint, unsigned n_points,
                   float R, unsigned* __restrict__ order) {
@@ -665,29 +666,54 @@ shot_order_kernel(const float4* __restrict__ kp, const int* __restrict__ kp_coun
     const unsigned K = min(kcap, (unsigned)max(*kp_count, 0));
     if (tid < 256) hist[tid] = 0u;
     __syncthreads();
-    auto bin_of = [&](unsigned k) {
-        const unsigned idx = __float_as_uint(kp[k].w);
-        const float rho = idx < n_points ? rho_hint[idx] : R;
-        return (rho > 0.0f) ? min(255u, (unsigned)(rho / R * 255.0f)) : 255u;
-    };
-    for (unsigned k = tid; k < K; k += 1024) atomicAdd(&hist[bin_of(k)], 1u);
-    __syncthreads();
-    if (tid < 32) {   // exclusive scan of 256 bins by one warp: 8 bins per lane
-        unsigned h[8], s = 0;
+    const float scale = 255.0f / R;
+    for (unsigned k0 = 0; k0 < K; k0 += 1024 * SO_PER) {   // one round unless K > 16 384
+        // all loads of a thread are independent: the two dependent round trips (keypoint -> its radius) overlap 16-fold
+        unsigned idx[SO_PER], bin[SO_PER];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { h[i] = hist[tid * 8 + i]; s += h[i]; }
-        unsigned inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= (unsigned)o) inc += up;
+        for (int j = 0; j < SO_PER; ++j) {
+            const unsigned k = k0 + tid + 1024u * j;
+            idx[j] = k < K ? __float_as_uint(kp[k].w) : 0xFFFFFFFFu;
         }
-        unsigned run = inc - s;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { hist[tid * 8 + i] = run; run += h[i]; }
+        for (int j = 0; j < SO_PER; ++j) {
+            const float rho = idx[j] < n_points ? rho_hint[idx[j]] : R;
+            bin[j] = (rho > 0.0f) ? min(255u, (unsigned)(rho * scale)) : 255u;
+        }
+        if (k0 == 0 && K <= 1024 * SO_PER) {   // the common case: histogram, scan and scatter from registers
+#pragma unroll
+            for (int j = 0; j < SO_PER; ++j)
+                if (k0 + tid + 1024u * j < K) atomicAdd(&hist[bin[j]], 1u);
+            __syncthreads();
+            if (tid < 32) {   // exclusive scan of 256 bins by one warp: 8 bins per lane
+                unsigned h[8], sum = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { h[i] = hist[tid * 8 + i]; sum += h[i]; }
+                unsigned inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (tid >= (unsigned)o) inc += up;
+                }
+                unsigned run = inc - sum;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { hist[tid * 8 + i] = run; run += h[i]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < SO_PER; ++j) {
+                const unsigned k = k0 + tid + 1024u * j;
+                if (k < K) order[atomicAdd(&hist[bin[j]], 1u)] = k;
+            }
+            return;
+        }
+        // more keypoints than one sweep holds: plain index order for this launch (correct, only the schedule differs)
+#pragma unroll
+        for (int j = 0; j < SO_PER; ++j) {
+            const unsigned k = k0 + tid + 1024u * j;
+            if (k < K) order[k] = k;
+        }
     }
-    __syncthreads();
-    for (unsigned k = tid; k < K; k += 1024) order[atomicAdd(&hist[bin_of(k)], 1u)] = k;
 }
 
 int shot_compute(Ctx* c, float radius, bool lrf_only, bool write_shot) {
