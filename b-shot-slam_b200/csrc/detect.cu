@@ -149,6 +149,7 @@ __global__ void mark_unscored_kernel(const float4* __restrict__ pts, const unsig
 constexpr int TK_THREADS = 256;
 constexpr int TK_BINS = 4096;
 constexpr int TK_TILE = 2048;
+constexpr int TK_ITEMS = 16;   // items ranked per CTA pass (tk_rank_kernel)
 enum { TKS_VALID = 0, TKS_TICKET = 1, TKS_BIN = 2, TKS_KEFF = 3, TKS_NSURE = 4, TKS_NTIE = 5, TKS_NEED = 6 };
 
 // monotone (non-decreasing in the key) bin: ratios in [0,1] -- all CV scores -- are spread uniformly over
@@ -275,15 +276,17 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
                const unsigned long long* __restrict__ tie, const float4* __restrict__ pts, const unsigned* __restrict__ sorted_pos,
                int* __restrict__ kp_flag, int* __restrict__ kp_idx, float* __restrict__ kp_ratio, float4* __restrict__ kp) {
     __shared__ unsigned long long s_keys[TK_TILE];
-    __shared__ unsigned s_cnt[8][32];
-    const unsigned tid = threadIdx.x, slot = tid & 31, part = tid >> 5;  // 32 items per CTA, every warp counts one eighth of a tile
+    __shared__ unsigned s_cnt[16][TK_ITEMS];
+    // TK_ITEMS items per CTA; every warp counts one eighth of a tile, its two half warps one sixteenth each (16 items per
+    // CTA instead of 32 doubles the number of CTAs with work: K = 10 000 used to keep only half of the GPU busy)
+    const unsigned tid = threadIdx.x, slot = tid & (TK_ITEMS - 1), part = tid / TK_ITEMS;
     const unsigned n_sure = state[TKS_NSURE], n_tie = state[TKS_NTIE], need = state[TKS_NEED];
-    const unsigned nb_a = (n_sure + 31) / 32, nb_b = (n_tie + 31) / 32;
+    const unsigned nb_a = (n_sure + TK_ITEMS - 1) / TK_ITEMS, nb_b = (n_tie + TK_ITEMS - 1) / TK_ITEMS;
     for (unsigned ib = blockIdx.x; ib < nb_a + nb_b; ib += gridDim.x) {
         const bool is_a = ib < nb_a;
         const unsigned long long* list = is_a ? sure : tie;
         const unsigned len = is_a ? n_sure : n_tie;
-        const unsigned item = (is_a ? ib : ib - nb_a) * 32 + slot;
+        const unsigned item = (is_a ? ib : ib - nb_a) * TK_ITEMS + slot;
         const unsigned long long x = (item < len) ? list[item] : 0ull;
         unsigned cnt = 0;
         for (unsigned t0 = 0; t0 < len; t0 += TK_TILE) {
@@ -291,7 +294,7 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
             __syncthreads();
             for (unsigned t = tid; t < tl; t += TK_THREADS) s_keys[t] = list[t0 + t];
             __syncthreads();
-            const unsigned lo = part * (TK_TILE / 8), hi = min(lo + TK_TILE / 8, tl);
+            const unsigned lo = part * (TK_TILE / 16), hi = min(lo + TK_TILE / 16, tl);
             if (is_a) {  // sure keys: position among the sure keys, ascending
                 for (unsigned j = lo; j < hi; ++j) cnt += (s_keys[j] < x) ? 1u : 0u;
             } else {     // tie keys: number of larger tie keys
@@ -301,8 +304,9 @@ tk_rank_kernel(const unsigned* __restrict__ state, const unsigned long long* __r
         s_cnt[part][slot] = cnt;
         __syncthreads();
         if (part == 0 && item < len) {
-            const unsigned c = s_cnt[0][slot] + s_cnt[1][slot] + s_cnt[2][slot] + s_cnt[3][slot] + s_cnt[4][slot] + s_cnt[5][slot] +
-                               s_cnt[6][slot] + s_cnt[7][slot];
+            unsigned c = 0;
+#pragma unroll
+            for (int pp = 0; pp < 16; ++pp) c += s_cnt[pp][slot];
             const bool keep = is_a || c < need;
             if (keep) {
                 const unsigned pos = is_a ? need + c : need - 1u - c;
@@ -389,7 +393,7 @@ int detect_topk(Ctx* c, int top_k) {
     const unsigned hist_ctas = std::max(1u, std::min((n + TK_THREADS * 16 - 1) / (TK_THREADS * 16), (unsigned)c->sm_count));
     tk_hist_kernel<<<hist_ctas, TK_THREADS, 0, c->stream>>>(c->d_keys, n, top_k, c->d_tk_hist, c->d_tk_state, c->d_kp_count);
     if (n) tk_compact_kernel<<<(n + TK_THREADS - 1) / TK_THREADS, TK_THREADS, 0, c->stream>>>(c->d_keys, n, c->d_tk_state, c->d_tk_sure, c->d_tk_tie, (unsigned)c->max_kp);
-    tk_rank_kernel<<<(unsigned)c->sm_count * 4u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_sorted_pos,
+    tk_rank_kernel<<<(unsigned)c->sm_count * 8u, TK_THREADS, 0, c->stream>>>(c->d_tk_state, c->d_tk_sure, c->d_tk_tie, c->d_pts, c->d_sorted_pos,
                                                                              c->d_kp_flag, c->d_kp_idx, c->d_kp_ratio, c->d_kp);
     count_launch(c, n ? 3 : 2);
 #ifdef BSHOT_KNN_STATS
