@@ -11,6 +11,9 @@ namespace bshot {
 #ifndef BSHOT_TL_SPLIT_MIN
 #define BSHOT_TL_SPLIT_MIN 8u   // a group with more pending queries than this is halved while its box is wider than the search radius
 #endif
+#ifndef BSHOT_TL_SPLIT_EDGE
+#define BSHOT_TL_SPLIT_EDGE 1.0f   // a block's box is halved while its longest edge exceeds this x the search radius
+#endif
 #ifndef BSHOT_TS_WIDE
 #define BSHOT_TS_WIDE 1000.0f   // overflow queries with at least this radius (mm) are processed first
 #endif
@@ -179,7 +182,7 @@ tile_kernel(const GridParams* __restrict__ gp, const unsigned* __restrict__ cell
             // neighbourhood: halve it first (the tile of each half is smaller; staging is cheap next to the sweeps)
             if (sm.pending > BSHOT_TL_SPLIT_MIN && ngrp < 64u) {
                 const float edge = fmaxf(fmaxf(sm.bbox[3] - sm.bbox[0], sm.bbox[4] - sm.bbox[1]), sm.bbox[5] - sm.bbox[2]);
-                if (edge > fminf(rho, R) && tile_block_split(sm, grp, ngrp, tid)) {
+                if (edge > BSHOT_TL_SPLIT_EDGE * fminf(rho, R) && tile_block_split(sm, grp, ngrp, tid)) {
                     todo |= (1ull << grp) | (1ull << ngrp);
                     ++ngrp;
                     continue;
