@@ -14,11 +14,12 @@
 //     (three VIMNMX.U16x2 per two pairs) and merged.
 //   * ROLES.  warp 0: one thread issues the MMAs; warps 1-8: expand target records into the K-major byte tile (half a row
 //     per thread, next tile's records prefetched); 4 warps per query tile: epilogue.  mbarriers: full/empty per target stage,
-//     full/empty per accumulator (two accumulators per query tile in tensor memory, released as soon as they are in
-//     registers).  MT = 2 query tiles share every expanded target tile (expansion per pair halves).
+//     full/empty per accumulator (in tensor memory, released as soon as it is in registers).  MT = 2 query tiles share
+//     every expanded target tile (expansion per pair halves); MT = 1 when that pads >= 10 % fewer query rows.
 //
-// Shared memory: MT x 48 KB query tiles (24 K chunks: 22 data, extras, zeros) + STAGES x 46 KB target tiles (23 chunks; the
-// 24th chunk of the last K step aliases the bytes that follow and is multiplied by the query tile's zeros).
+// A query tile is 24 K chunks of 16 bytes per row (22 data, extras, zeros): 96 tensor-memory columns, or 48 KB of shared
+// memory when ATM = false.  A target tile is 23 chunks (46 KB per stage): the 24th chunk of the last K step aliases the bytes
+// that follow and is multiplied by the query tile's zeros.
 // Output = per-split partial top-2 records like hamming_top2_kernel (hamming.cu); the merge kernels take over.
 #include "common.cuh"
 #include "stages.h"
@@ -36,10 +37,13 @@ constexpr unsigned long long T2_NONE = 0xFFFFFFFFFFFFFFFFull;
 constexpr int T2_XWARPS = 8;                      // expander warps (256 threads: half a target row each)
 
 // ATM: the query tiles live in TENSOR MEMORY (96 columns each: 384 K bytes, four per column) instead of shared memory.
-// Every tcgen05.mma re-reads its A operand; from shared memory that is as much traffic as the target tile itself and the
-// kernel ends up bound by shared-memory bandwidth (measured: tensor pipe 66 % busy).  With A in tensor memory shared memory
-// only carries the target tiles (written once, read once per query tile) and holds four stages of them.  Two query tiles then
+// Every tcgen05.mma re-reads its A operand, and the query rows never change: each epilogue thread expands its own row in
+// registers and stores it once (tcgen05.st), the multiply then reads A from tensor memory ([a_tmem] operand form).  Shared
+// memory only carries the target tiles (written once, read once per query tile) and holds four stages of them; two query tiles
 // take turns on ONE accumulator each (the multiply of the other tile covers the time the epilogue needs to read it out).
+// Measured: 2.48 -> 2.44 ms on C4 -- operand bandwidth was not the limit (the chain of multiplies alone takes 2.25 ms); kept as
+// the default because it frees 96 KB of shared memory for deeper target staging.  ATM = false (BSHOT_MATCH_TC=3) keeps the
+// query tiles in shared memory, two accumulators per query tile.
 template <int MT, bool ATM> struct T2Cfg {
     static constexpr int STAGES = ATM ? 4 : (MT == 2 ? 2 : 3);
     static constexpr int NACC = (ATM && MT == 2) ? 1 : 2;            // accumulators per query tile
