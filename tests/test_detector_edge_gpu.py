@@ -179,6 +179,23 @@ def test_hdl64e_full_scan_index_equality(bshot, oracle, synth):
     check_scan_against_oracle(bshot, oracle, synth, synth.make_scan("hdl64e", 1), 10000, 131072)
 
 
+def test_hdl64e_full_normals_chain(bshot, oracle, synth):
+    """C3 workload with FULL normals COMPUTED BY THE GPU (one normal per surface point, fused into the detector pass) ->
+    SHOT -> B-SHOT against the oracle's FULL chain: same keypoint indices, >= 99.9 % of the bits, normals to the last ulp
+    of the closed-form eigen-solver at scan scale (|x| ~ 1e5 mm)"""
+    top_k = 10000
+    scan = synth.make_scan("hdl64e", 2)
+    oc = oracle.Cloud(scan)
+    idx_o, _ = oracle.select_keypoints(oc.seg_ratio(3000.0, 300, 0), top_k, oracle.TIE_DETERMINISTIC)
+    with bshot.Context(0, 131072, top_k, top_k) as ctx:
+        f = ctx.process_frame(scan, bshot.default_params(top_k=top_k, normals_mode=bshot.NORMALS_FULL))
+    assert np.array_equal(f["kp_idx"], idx_o)
+    od = oc.compute_descriptors(scan[idx_o], 3000.0, 300, oracle.MODE_FULL)
+    same = synth.unpack_bits(f["bits"]) == synth.unpack_bits(od["bits"])
+    assert same.mean() >= 0.999, same.mean()
+    assert (same.all(axis=1)).mean() >= 0.95, (same.all(axis=1)).mean()   # whole descriptors identical
+
+
 @pytest.mark.parametrize("sr_type", [0, 1, 2])
 def test_all_score_types_bit_identical(gpu_ctx, oracle, synth, sr_type):
     scan = synth.make_scan("hdl32e", 5)[::2].copy()
