@@ -312,7 +312,7 @@ def main():
             "voxel_build": ("grid_build", 2 * 16.0 * mean_n)}
     traffic_tab = {}
     try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_r3.json")))
     except Exception:
         pass
 
@@ -331,7 +331,7 @@ def main():
             wi = float(t["warp_instructions_per_launch"])
             r["issue"] = {"warp_instructions_per_launch": wi, "achieved_warp_inst_per_s": wi / (stages[name] * 1e-3),
                           "peak_warp_inst_per_s": peak_issue, "frac": wi / (stages[name] * 1e-3) / peak_issue,
-                          "source": "instruction count: ncu smsp__inst_executed.sum (profiles/r2i_ncu_full.txt); time: this run"}
+                          "source": "instruction count: ncu smsp__inst_executed.sum (profiles/r3z_ncu_full.txt); time: this run"}
         return r
     clock_probe = {"sm_max_mhz": sampler.max_mhz} if sampler and sampler.max_mhz else None
     dom = max(kern, key=lambda k: stages[k])
