@@ -212,6 +212,8 @@ int bshot_ctx_create(bshot_ctx** out, int device, size_t max_points, size_t max_
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_sum_nn, 0, 2 * sizeof(unsigned long long), c->stream);
         for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_desc, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { set_error("context init failed: %s", cudaGetErrorString(e)); r = BSHOT_E_CUDA; }
     }
@@ -242,6 +244,8 @@ void bshot_ctx_destroy(bshot_ctx* c) {
     if (c->h_pairs) cudaFreeHost(c->h_pairs);
     for (int i = 0; i < 8; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_desc) cudaEventDestroy(c->ev_desc);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -510,8 +514,18 @@ int bshot_process_frame_dev(bshot_ctx* ctx, const bshot_params* p, const void* d
     return frame_run(ctx, p, reinterpret_cast<const float*>(d_xyz), n, (int)(stride_bytes / 4));
 }
 
+static int fetch_frame_impl(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out,
+                            int* n_pairs_out, bool payload_early);
+
 int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out,
                       int* n_pairs_out) {
+    return fetch_frame_impl(ctx, top_k, kp_idx_out, bits_out, n_kp_out, pairs_out, n_pairs_out, false);
+}
+
+// payload_early: keypoint indices and descriptors go over the copy stream as soon as the descriptors are complete (event
+// recorded by frame_run), i.e. while the match stage still runs; only the counts and the pairs wait for the end of the frame
+static int fetch_frame_impl(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits_out, int* n_kp_out, int* pairs_out,
+                            int* n_pairs_out, bool payload_early) {
     CHECK_CTX(ctx);
     if (top_k <= 0 || (size_t)top_k > ctx->max_kp) { set_error("bshot_fetch_frame: bad top_k"); return BSHOT_E_INVALID; }
     if (ctx->last_top_k == 0) { set_error("bshot_fetch_frame: no frame has been processed"); return BSHOT_E_STATE; }
@@ -520,11 +534,14 @@ int bshot_fetch_frame(bshot_ctx* ctx, int top_k, int* kp_idx_out, uint64_t* bits
     // counts + payload in one stream-ordered batch, a single synchronisation
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[0], ctx->d_kp_count, sizeof(int)));
     BSHOT_TRY(d2h(ctx, &ctx->h_scratch[1], ctx->d_pair_count, sizeof(int)));
-    BSHOT_TRY(d2h(ctx, kp_idx_out, ctx->d_kp_idx, sizeof(int) * kmax));
-    BSHOT_TRY(d2h(ctx, bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * kmax));
+    cudaStream_t ps = payload_early ? ctx->copy_stream : ctx->stream;
+    if (payload_early) BSHOT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_desc, 0));
+    if (kp_idx_out) BSHOT_CUDA_TRY(cudaMemcpyAsync(kp_idx_out, ctx->d_kp_idx, sizeof(int) * kmax, cudaMemcpyDeviceToHost, ps));
+    if (bits_out) BSHOT_CUDA_TRY(cudaMemcpyAsync(bits_out, ctx->d_bits, sizeof(uint64_t) * 6 * kmax, cudaMemcpyDeviceToHost, ps));
     int* tmp = ctx->h_pairs;  // pinned, max_keypoints x 3: no per-frame host allocation, a true async copy
     if (pairs_out) BSHOT_CUDA_TRY(cudaMemcpyAsync(tmp, ctx->d_pairs, sizeof(int) * 3 * kmax, cudaMemcpyDeviceToHost, ctx->stream));
     BSHOT_TRY(sync(ctx));
+    if (payload_early) BSHOT_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     const int k = std::min(ctx->h_scratch[0], (int)kmax), np = std::min(ctx->h_scratch[1], k);
     ctx->n_kp = (size_t)k;
     if (n_kp_out) *n_kp_out = k;
@@ -543,7 +560,7 @@ int bshot_process_frame(bshot_ctx* ctx, const bshot_params* p, const float* xyz,
     BSHOT_TRY(frame_args_ok(ctx, p, n, stride_bytes, "bshot_process_frame"));
     BSHOT_TRY(h2d(ctx, ctx->d_raw, xyz, n * stride_bytes));
     BSHOT_TRY(frame_run(ctx, p, ctx->d_raw, n, (int)(stride_bytes / 4)));
-    return bshot_fetch_frame(ctx, p->top_k, kp_idx_out, bits_out, n_kp_out, pairs_out, n_pairs_out);
+    return fetch_frame_impl(ctx, p->top_k, kp_idx_out, bits_out, n_kp_out, pairs_out, n_pairs_out, true);
 }
 
 int bshot_ctx_enable_timing(bshot_ctx* ctx, int on) {

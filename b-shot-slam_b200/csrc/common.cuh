@@ -208,6 +208,8 @@ struct Ctx {
     unsigned long long* d_counters = nullptr;  // 8 work counters (see bshot_frame_counters)
     bool timing = false;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;   // bshot_process_frame: keypoints + descriptors travel to the host while the frame is still being matched
+    cudaEvent_t ev_desc = nullptr;        // recorded when the descriptors of the frame are complete
     bool ev_valid = false;
 };
 

@@ -55,6 +55,7 @@ int frame_run(Ctx* c, const bshot_params* p, const float* d_raw, size_t n, int s
         if (c->timing) cudaEventRecord(c->ev[i], c->stream);
     };
     BSHOT_TRY(frame_extract(c, p, d_raw, n, stride_floats));
+    if (c->ev_desc) BSHOT_CUDA_TRY(cudaEventRecord(c->ev_desc, c->stream));   // descriptors complete: bshot_process_frame starts their copy here
     // featureMatching: the initial frame is matched against itself (src/lidar_odometry.cpp:187-194),
     // later frames against the previous frame's descriptors.  Host-side counts are upper bounds
     // (top_k); the kernels trim queries AND targets by the device-side keypoint counts, so a frame that

@@ -314,9 +314,26 @@ mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq_cap, const 
     const unsigned per = (nq + blockDim.x - 1) / blockDim.x;
     const unsigned q0 = tid * per, q1 = min(nq, q0 + per);
     unsigned mine = 0;
-    for (unsigned qi = q0; qi < q1; ++qi) {
-        const bshot_cand c = cand[qi];
-        mine += ((c.k1 != HM_NONE) && (c.rq == qi)) ? 1u : 0u;
+    // up to MP_PER queries per thread (16 384 queries): the records are read once, all loads of a thread in flight together
+    constexpr int MP_PER = 16;
+    const bool in_regs = per <= (unsigned)MP_PER;
+    unsigned long long rk[MP_PER];
+    unsigned hit = 0;   // bit j: query q0 + j is a mutual pair
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < MP_PER; ++j) {
+            const unsigned qi = q0 + j;
+            rk[j] = HM_NONE;
+            unsigned rq = 0xFFFFFFFFu;
+            if (qi < q1) { rk[j] = cand[qi].k1; rq = cand[qi].rq; }
+            hit |= ((rk[j] != HM_NONE) && (rq == qi)) ? (1u << j) : 0u;
+        }
+        mine = (unsigned)__popc(hit);
+    } else {
+        for (unsigned qi = q0; qi < q1; ++qi) {
+            const bshot_cand c = cand[qi];
+            mine += ((c.k1 != HM_NONE) && (c.rq == qi)) ? 1u : 0u;
+        }
     }
     unsigned inc = mine;
 #pragma unroll
@@ -339,6 +356,17 @@ mutual_pairs_kernel(const bshot_cand* __restrict__ cand, unsigned nq_cap, const 
     }
     __syncthreads();
     unsigned pos = warp_tot[wid] + inc - mine;
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < MP_PER; ++j)
+            if (hit & (1u << j)) {
+                pairs[3 * pos] = (int)(q0 + j);
+                pairs[3 * pos + 1] = (int)(rk[j] & 0xFFFFFFFFull);
+                pairs[3 * pos + 2] = (int)(rk[j] >> 32);
+                ++pos;
+            }
+        return;
+    }
     for (unsigned qi = q0; qi < q1; ++qi) {
         const bshot_cand c = cand[qi];
         if ((c.k1 != HM_NONE) && (c.rq == qi)) {
